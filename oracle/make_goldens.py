@@ -1,0 +1,224 @@
+"""ORACLE (test infrastructure only).  Mints tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):   python -m oracle.make_goldens
+
+Every vector is produced by the reference's own Python code on CPU — i.e. the `impl='ref'`
+branch of its ops (upfirdn2d.py:162-164, bias_act.py:87-89), F.conv2d for the contractions
+(conv2d_gradfix.py:51-52) and the reference network classes — with fixed seeds.  The reference's
+test-suite has no vectors for this path, so these files are the parity pin.
+"""
+import json
+import os
+import numpy as np
+import torch
+
+from . import ref_loader
+from . import synthesis_ref as sr
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+UPFIRDN_CASES = [
+    # (N, C, H, W, filter, up, down, padding, flip, gain, channels_last)
+    dict(shape=[2, 3, 9, 9], f=[1, 3, 3, 1], up=1, down=1, padding=1, flip=False, gain=4),          # G up-layer FIR (2h+1 -> 2h)
+    dict(shape=[2, 3, 8, 8], f=[1, 3, 3, 1], up=2, down=1, padding=[2, 1, 2, 1], flip=False, gain=4),  # img upsample2d
+    dict(shape=[1, 4, 8, 8], f=[1, 3, 3, 1], up=1, down=2, padding=1, flip=False, gain=1),          # D skip downsample
+    dict(shape=[1, 4, 8, 8], f=[1, 3, 3, 1], up=1, down=1, padding=2, flip=False, gain=1),          # D blur before stride-2 conv
+    dict(shape=[2, 2, 8, 8], f=[1, 3, 3, 1], up=1, down=1, padding=2, flip=True, gain=4),           # backward of case 0
+    dict(shape=[1, 2, 7, 5], f=[[1, 2, 3], [4, 5, 6]], up=[2, 3], down=[3, 2], padding=[1, 2, 0, 3], flip=False, gain=1.5),
+    dict(shape=[1, 2, 7, 5], f=[[1, 2, 3], [4, 5, 6]], up=[2, 3], down=[3, 2], padding=[1, 2, 0, 3], flip=True, gain=1.5),
+    dict(shape=[1, 3, 10, 12], f=[1, 3, 3, 1], up=1, down=1, padding=[-1, 2, 1, -2], flip=False, gain=1),   # negative padding = crop
+    dict(shape=[1, 2, 6, 6], f=None, up=2, down=1, padding=0, flip=False, gain=1),                  # identity filter
+    dict(shape=[1, 2, 16, 16], f='sym6', up=2, down=1, padding=[6, 5, 6, 5], flip=False, gain=4),   # separable 12-tap (augment.py path)
+    dict(shape=[1, 2, 16, 16], f='sym6', up=1, down=2, padding=[5, 5, 5, 5], flip=True, gain=1),
+    dict(shape=[2, 8, 9, 9], f=[1, 3, 3, 1], up=1, down=1, padding=1, flip=False, gain=4, channels_last=True),
+    dict(shape=[1, 5, 6, 7], f=[1, 2, 1], up=2, down=2, padding=[1, 1, 1, 1], flip=False, gain=2, channels_last=True),
+    dict(shape=[1, 1, 1, 1], f=[1, 3, 3, 1], up=1, down=1, padding=[2, 1, 2, 1], flip=False, gain=1),  # minimal extent
+]
+SYM6 = [0.015404109327027373, 0.0034907120842174702, -0.11799011114819057, -0.048311742585633, 0.4910559419267466, 0.787641141030194]
+
+
+def _filter(ref, spec):
+    if spec is None:
+        return None
+    if spec == 'sym6':
+        taps = np.asarray(SYM6 + SYM6[::-1])
+        return ref.upfirdn2d.setup_filter(taps)      # >= 8 taps -> separable (upfirdn2d.py:100-101)
+    return ref.upfirdn2d.setup_filter(spec)
+
+
+def gen_upfirdn2d(ref):
+    out = {}
+    meta = []
+    for i, c in enumerate(UPFIRDN_CASES):
+        g = torch.Generator().manual_seed(100 + i)
+        x = torch.randn(c['shape'], generator=g, dtype=torch.float64)
+        if c.get('channels_last'):
+            x = x.contiguous(memory_format=torch.channels_last)
+        f = _filter(ref, c['f'])
+        x.requires_grad_(True)
+        y = ref.upfirdn2d.upfirdn2d(x, f, up=c['up'], down=c['down'], padding=c['padding'], flip_filter=c['flip'], gain=c['gain'], impl='ref')
+        dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+        dx, = torch.autograd.grad(y, x, dy)
+        out[f'c{i}_x'] = x.detach().numpy()
+        out[f'c{i}_y'] = y.detach().numpy()
+        out[f'c{i}_dy'] = dy.numpy()
+        out[f'c{i}_dx'] = dx.numpy()
+        if f is not None:
+            out[f'c{i}_f'] = f.numpy()
+        meta.append({k: v for k, v in c.items() if k != 'f'} | {'has_f': f is not None})
+    out['meta'] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, 'upfirdn2d_cases.npz'), **out)
+
+
+def gen_bias_act(ref):
+    out = {}
+    meta = []
+    i = 0
+    for act in ref.bias_act.activation_funcs.keys():
+        for (gain, clamp, alpha, use_b, dim, shape) in [
+            (None, None, None, True, 1, [2, 5, 4, 3]),
+            (0.7, 0.9, 0.3, True, 1, [2, 5, 4, 3]),
+            (2.0, None, None, False, 1, [3, 7]),
+            (None, 0.5, None, True, 0, [4, 6]),
+        ]:
+            g = torch.Generator().manual_seed(200 + i)
+            x = (torch.randn(shape, generator=g, dtype=torch.float64) * 2).requires_grad_(True)
+            b = torch.randn(shape[dim], generator=g, dtype=torch.float64).requires_grad_(True) if use_b else None
+            y = ref.bias_act.bias_act(x, b, dim=dim, act=act, alpha=alpha, gain=gain, clamp=clamp, impl='ref')
+            dy = torch.randn(shape, generator=g, dtype=torch.float64).requires_grad_(True)
+            ins = [x] + ([b] if use_b else [])
+            grads = torch.autograd.grad(y, ins, dy, create_graph=True)
+            ddx = torch.randn(shape, generator=g, dtype=torch.float64)
+            # second order: d(<dx, ddx>)/d(dy) and /d(x)
+            g2 = torch.autograd.grad(grads[0], [dy, x], ddx, allow_unused=True)
+            out[f'c{i}_x'] = x.detach().numpy()
+            if use_b:
+                out[f'c{i}_b'] = b.detach().numpy()
+                out[f'c{i}_db'] = grads[1].detach().numpy()
+            out[f'c{i}_y'] = y.detach().numpy()
+            out[f'c{i}_dy'] = dy.detach().numpy()
+            out[f'c{i}_dx'] = grads[0].detach().numpy()
+            out[f'c{i}_ddx'] = ddx.numpy()
+            out[f'c{i}_g2_dy'] = g2[0].numpy()
+            out[f'c{i}_g2_x'] = (g2[1] if g2[1] is not None else torch.zeros(shape, dtype=torch.float64)).numpy()
+            meta.append(dict(act=act, gain=gain, clamp=clamp, alpha=alpha, use_b=use_b, dim=dim, shape=shape))
+            i += 1
+    out['meta'] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, 'bias_act_cases.npz'), **out)
+
+
+MODCONV_CASES = [
+    dict(N=2, I=8, O=6, H=6, k=3, up=1, demod=True, fused=False),
+    dict(N=2, I=8, O=6, H=6, k=3, up=1, demod=True, fused=True),
+    dict(N=2, I=8, O=6, H=5, k=3, up=2, demod=True, fused=False),
+    dict(N=2, I=8, O=6, H=5, k=3, up=2, demod=True, fused=True),
+    dict(N=3, I=8, O=3, H=6, k=1, up=1, demod=False, fused=False),      # ToRGB
+    dict(N=2, I=32, O=32, H=16, k=3, up=1, demod=True, fused=False),     # tensor-core friendly sizes
+    dict(N=2, I=32, O=32, H=8, k=3, up=2, demod=True, fused=False),
+    dict(N=2, I=64, O=3, H=16, k=1, up=1, demod=False, fused=False),
+]
+
+
+def gen_modconv(ref):
+    out = {}
+    f = ref.upfirdn2d.setup_filter([1, 3, 3, 1])
+    for i, c in enumerate(MODCONV_CASES):
+        g = torch.Generator().manual_seed(300 + i)
+        x = torch.randn(c['N'], c['I'], c['H'], c['H'], generator=g).requires_grad_(True)
+        w = torch.randn(c['O'], c['I'], c['k'], c['k'], generator=g).requires_grad_(True)
+        s = (torch.randn(c['N'], c['I'], generator=g) + 1).requires_grad_(True)
+        y = ref.networks.modulated_conv2d(x=x, weight=w, styles=s, up=c['up'], padding=c['k'] // 2, resample_filter=f,
+                                          demodulate=c['demod'], flip_weight=(c['up'] == 1), fused_modconv=c['fused'])
+        dy = torch.randn(y.shape, generator=g)
+        dx, dw, ds = torch.autograd.grad(y, [x, w, s], dy)
+        for k, v in dict(x=x, w=w, s=s, y=y, dy=dy, dx=dx, dw=dw, ds=ds).items():
+            out[f'c{i}_{k}'] = v.detach().numpy()
+    out['f'] = f.numpy()
+    out['meta'] = np.frombuffer(json.dumps(MODCONV_CASES).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, 'modconv_cases.npz'), **out)
+
+
+RESAMPLE_CASES = [
+    dict(N=1, I=4, O=5, H=8, k=3, up=1, down=1, flip_weight=True),
+    dict(N=1, I=4, O=5, H=8, k=3, up=2, down=1, flip_weight=False),
+    dict(N=1, I=4, O=5, H=8, k=3, up=1, down=2, flip_weight=True),
+    dict(N=1, I=4, O=5, H=8, k=1, up=1, down=2, flip_weight=True),
+    dict(N=1, I=4, O=5, H=8, k=1, up=2, down=1, flip_weight=True),
+    dict(N=2, I=3, O=8, H=8, k=1, up=1, down=1, flip_weight=True),
+]
+
+
+def gen_conv2d_resample(ref):
+    out = {}
+    f = ref.upfirdn2d.setup_filter([1, 3, 3, 1])
+    for i, c in enumerate(RESAMPLE_CASES):
+        g = torch.Generator().manual_seed(400 + i)
+        x = torch.randn(c['N'], c['I'], c['H'], c['H'], generator=g).requires_grad_(True)
+        w = torch.randn(c['O'], c['I'], c['k'], c['k'], generator=g).requires_grad_(True)
+        y = ref.conv2d_resample.conv2d_resample(x=x, w=w, f=f, up=c['up'], down=c['down'], padding=c['k'] // 2, flip_weight=c['flip_weight'])
+        dy = torch.randn(y.shape, generator=g)
+        dx, dw = torch.autograd.grad(y, [x, w], dy)
+        for k, v in dict(x=x, w=w, y=y, dy=dy, dx=dx, dw=dw).items():
+            out[f'c{i}_{k}'] = v.detach().numpy()
+    out['f'] = f.numpy()
+    out['meta'] = np.frombuffer(json.dumps(RESAMPLE_CASES).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, 'conv2d_resample_cases.npz'), **out)
+
+
+TINY = dict(img_resolution=32, w_dim=64, channel_base=1024, channel_max=32, motion_z_dim=32, motion_v_dim=32, time_enc_dim=16)
+
+
+def gen_synthesis(ref):
+    cfg = sr.SynthesisConfig(**TINY)
+    rcfg = ref_loader.to_cfg(cfg.reference_generator_cfg())
+    torch.manual_seed(0)
+    S = ref.networks.SynthesisNetwork(w_dim=cfg.w_dim, img_resolution=cfg.img_resolution, img_channels=3,
+                                      channel_base=cfg.channel_base, channel_max=cfg.channel_max, cfg=rcfg)
+    # give biases non-trivial values so they are exercised
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for n, p in S.named_parameters():
+            if n.endswith('.bias') and 'affine' not in n:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    B, Fr = 2, 3
+    ws = torch.randn(B, S.num_ws, cfg.w_dim, generator=g).requires_grad_(True)
+    t = torch.tensor([[0.0, 5.25, 9.0], [100.5, 101.0, 130.75]])
+    c = torch.zeros(B, 0)
+    L = sr.max_traj_len(cfg, float(t.max()))
+    mz = torch.randn(B, L, cfg.motion_z_dim, generator=g)
+    out = {}
+    S.train()   # => fused_modconv=False (networks.py:232)
+    motion_v = S.motion_encoder(c, t, motion_z=mz)['motion_v']
+    img = S(ws, t=t, c=c, motion_z=mz)
+    dimg = torch.randn(img.shape, generator=g)
+    params = dict(S.named_parameters())
+    names = sorted(params.keys())
+    grads = torch.autograd.grad(img, [ws] + [params[n] for n in names], dimg)
+    S.eval()    # => fused_modconv=True for fp32
+    with torch.no_grad():
+        img_eval = S(ws, t=t, c=c, motion_z=mz)
+    for k, v in S.state_dict().items():
+        out['p:' + k] = v.detach().numpy()
+    out.update(ws=ws.detach().numpy(), t=t.numpy(), motion_z=mz.numpy(), motion_v=motion_v.detach().numpy(),
+               img_train=img.detach().numpy(), img_eval=img_eval.numpy(), dimg=dimg.numpy(), d_ws=grads[0].numpy())
+    for n, gr in zip(names, grads[1:]):
+        out['g:' + n] = gr.numpy()
+    out['meta'] = np.frombuffer(json.dumps(TINY).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, 'synthesis_tiny.npz'), **out)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_loader.load()
+    torch.set_num_threads(4)
+    gen_upfirdn2d(ref)
+    gen_bias_act(ref)
+    gen_modconv(ref)
+    gen_conv2d_resample(ref)
+    gen_synthesis(ref)
+    for fn in sorted(os.listdir(OUT)):
+        print(fn, os.path.getsize(os.path.join(OUT, fn)))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,98 @@
+"""ctypes binding of libsgv_b200.so (the C ABI declared in include/sgv_b200.h).
+
+There is no CPU implementation behind this module: if the shared library is missing, or was built
+without an entry point the header declares, importing a kernel raises immediately.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libsgv_b200.so')
+
+c_int, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+SGV_F32, SGV_F16, SGV_F64 = 0, 1, 2
+ABI_VERSION = 1
+
+
+class UpfirdnParams(ctypes.Structure):
+    """struct sgv_upfirdn2d_params"""
+    _fields_ = [
+        ('x', c_vp), ('f', c_vp), ('y', c_vp), ('dtype', c_int),
+        ('up_x', c_int), ('up_y', c_int), ('down_x', c_int), ('down_y', c_int),
+        ('pad_x0', c_int), ('pad_x1', c_int), ('pad_y0', c_int), ('pad_y1', c_int),
+        ('flip', c_int), ('gain', c_f32),
+        ('in_w', c_int), ('in_h', c_int), ('in_c', c_int), ('in_n', c_int),
+        ('in_stride_x', c_i64), ('in_stride_y', c_i64), ('in_stride_c', c_i64), ('in_stride_n', c_i64),
+        ('f_w', c_int), ('f_h', c_int), ('f_stride_x', c_i64), ('f_stride_y', c_i64),
+        ('out_w', c_int), ('out_h', c_int),
+        ('out_stride_x', c_i64), ('out_stride_y', c_i64), ('out_stride_c', c_i64), ('out_stride_n', c_i64),
+        ('epi_scale', c_vp), ('epi_bias', c_vp), ('epi_act', c_int),
+        ('epi_alpha', c_f32), ('epi_gain', c_f32), ('epi_clamp', c_f32),
+    ]
+
+
+class BiasActParams(ctypes.Structure):
+    """struct sgv_bias_act_params"""
+    _fields_ = [
+        ('x', c_vp), ('b', c_vp), ('xref', c_vp), ('yref', c_vp), ('dy', c_vp), ('y', c_vp),
+        ('dtype', c_int), ('grad', c_int), ('act', c_int),
+        ('alpha', c_f32), ('gain', c_f32), ('clamp', c_f32),
+        ('size_x', c_int), ('size_b', c_int), ('step_b', c_int),
+        ('db_accum', c_vp),
+    ]
+
+
+# every symbol include/sgv_b200*.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ('sgv_abi_version', c_int, []),
+    ('sgv_last_error', ctypes.c_char_p, []),
+    ('sgv_device_check', c_int, []),
+    ('sgv_kernel_launch_count', c_i64, []),
+    ('sgv_upfirdn2d_out_size', c_int, [c_int] * 6),
+    ('sgv_upfirdn2d', c_int, [ctypes.POINTER(UpfirdnParams), c_vp]),
+    ('sgv_bias_act', c_int, [ctypes.POINTER(BiasActParams), c_vp]),
+]
+
+_lib = None
+_lock = threading.Lock()
+
+
+class SgvError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads (once) and returns the shared library; raises if it is absent or incomplete."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise SgvError(f'{LIB_PATH} not found: build it with `python -m stylegan_v_b200.build` '
+                           '(there is no CPU or PyTorch fallback for the CUDA ops)')
+        L = ctypes.CDLL(LIB_PATH)
+        for name, restype, argtypes in SYMBOLS:
+            try:
+                fn = getattr(L, name)
+            except AttributeError as e:
+                raise SgvError(f'{LIB_PATH} does not export {name}; rebuild the library') from e
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if L.sgv_abi_version() != ABI_VERSION:
+            raise SgvError(f'ABI mismatch: library {L.sgv_abi_version()} vs binding {ABI_VERSION}')
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().sgv_last_error()
+        raise SgvError(f'{what} failed (status {rc}): {msg.decode() if msg else "?"}')
+
+
+def launch_count() -> int:
+    return int(lib().sgv_kernel_launch_count())

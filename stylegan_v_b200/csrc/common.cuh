@@ -1,0 +1,40 @@
+// Shared host/device helpers for libsgv_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include "../../include/sgv_b200.h"
+
+namespace sgv {
+
+// thread-local error text returned by sgv_last_error()
+char* error_buffer();
+int fail(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define SGV_CHECK_ARG(cond, ...) do { if (!(cond)) return ::sgv::fail(SGV_ERR_INVALID, __VA_ARGS__); } while (0)
+#define SGV_CUDA_OK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) \
+    return ::sgv::fail(SGV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+
+// Launch-error check that does not synchronise.
+#define SGV_LAUNCH_OK(name) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) \
+    return ::sgv::fail(SGV_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); ::sgv::count_launch(); } while (0)
+
+int num_sms();   // SM count of the current device (cached per device)
+
+template <class T> struct acc_type            { typedef float  type; };
+template <>        struct acc_type<double>    { typedef double type; };
+
+// Same floor division as the reference kernels (upfirdn2d.cu:20-24); exact for b > 0 and any a.
+__host__ __device__ __forceinline__ int floor_div(int a, int b)
+{
+    int t = 1 - a / b;
+    return (a + t * b) / b - t;
+}
+
+__host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+} // namespace sgv
