@@ -1,0 +1,62 @@
+/*
+ * sgv_b200 — C ABI, part 2: the dense contraction of the hot path on tcgen05 tensor cores.
+ *
+ * Replaces the library calls the reference makes for the contraction — torch.nn.functional.conv2d /
+ * conv_transpose2d -> cuDNN (src/torch_utils/ops/conv2d_gradfix.py:35-43,108-116) and
+ * aten::cudnn_convolution_backward_weight (conv2d_gradfix.py:140-148) — and fuses into it what the
+ * reference runs as separate elementwise passes around the contraction in modulated_conv2d
+ * (src/training/networks.py:64-74: x*styles before, *dcoefs after) and bias_act (bias_act.cu:23-147).
+ *
+ * Layout: activations are NHWC fp32 (torch channels_last); weights are pre-arranged once per call by
+ * sgv_conv_prep_weights into [tap][out_channel][in_channel] fp32 rounded to TF32 (round-to-nearest).
+ * Arithmetic: TF32 x TF32 products, fp32 accumulation in TMEM (tcgen05.mma.kind::tf32).
+ * Same contract as include/sgv_b200.h: caller-owned buffers, no allocation, no synchronisation, work is
+ * enqueued on `stream`, 0 on success.
+ */
+#ifndef SGV_B200_CONV_H
+#define SGV_B200_CONV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGV_CONV_MAX_TAPS 16
+
+/* Gathers + rounds weights:  wp[t][r][k] = tf32_rn( w[r*stride_row + k*stride_col + tap_ky[t]*stride_ky + tap_kx[t]*stride_kx] )
+ * for t < ntaps, r < rows, k < cols.  (rows = GEMM N = output channels of the contraction, cols = GEMM K.) */
+int sgv_conv_prep_weights(const float* w, int64_t stride_row, int64_t stride_col, int64_t stride_ky, int64_t stride_kx,
+                          int32_t rows, int32_t cols, int32_t ntaps, const int32_t* tap_ky, const int32_t* tap_kx,
+                          float* wp, void* stream);
+
+/* y[n, oy, ox, o] = epilogue( sum_{t, i}  x[n, oy*in_stride + tap_dy[t], ox*in_stride + tap_dx[t], i] * a_scale[n, i] * wp[t][o][i] )
+ *   epilogue(v) = clamp( act( v * o_scale[n, o] + bias[o] ) * gain )        (each piece optional)
+ * Out-of-range input pixels read as zero.  Output element (n, oy, ox, o) lives at
+ *   y + n*out_stride_n + oy*out_stride_y + ox*out_stride_x + o        (element strides; lets one call write a
+ *   polyphase sub-lattice of a larger tensor, which is how the stride-2 transposed convolution is issued).
+ * Requirements: cin % 32 == 0, cout % 64 == 0 (or cout in {16, 32}), x and wp 16-byte aligned, y and strides multiples of 4 elements.
+ */
+typedef struct sgv_conv_params {
+    const float* x;            /* [n, h, w, cin] NHWC */
+    const float* wp;           /* [ntaps, cout, cin] from sgv_conv_prep_weights */
+    float*       y;
+    int32_t n, h, w, cin, cout;
+    int32_t out_h, out_w;
+    int64_t out_stride_n, out_stride_y, out_stride_x;
+    int32_t in_stride;         /* 1 or 2 */
+    int32_t ntaps;
+    int32_t tap_dy[SGV_CONV_MAX_TAPS], tap_dx[SGV_CONV_MAX_TAPS];
+    const float* a_scale;      /* [n, cin]  or NULL : StyleGAN modulation (styles), dcoefs for the data gradient */
+    const float* o_scale;      /* [n, cout] or NULL : demodulation coefficients, styles for the data gradient */
+    const float* bias;         /* [cout] or NULL */
+    int32_t act;               /* 1 = linear, 3 = lrelu (bias_act cuda_idx numbering) */
+    float   alpha, gain, clamp;/* clamp < 0 disables */
+} sgv_conv_params;
+
+int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGV_B200_CONV_H */

@@ -44,6 +44,25 @@ class BiasActParams(ctypes.Structure):
     ]
 
 
+CONV_MAX_TAPS = 16
+
+
+class ConvParams(ctypes.Structure):
+    """struct sgv_conv_params (include/sgv_b200_conv.h)"""
+    _fields_ = [
+        ('x', c_vp), ('wp', c_vp), ('y', c_vp),
+        ('n', c_int), ('h', c_int), ('w', c_int), ('cin', c_int), ('cout', c_int),
+        ('out_h', c_int), ('out_w', c_int),
+        ('out_stride_n', c_i64), ('out_stride_y', c_i64), ('out_stride_x', c_i64),
+        ('in_stride', c_int), ('ntaps', c_int),
+        ('tap_dy', c_int * CONV_MAX_TAPS), ('tap_dx', c_int * CONV_MAX_TAPS),
+        ('a_scale', c_vp), ('o_scale', c_vp), ('bias', c_vp),
+        ('act', c_int), ('alpha', c_f32), ('gain', c_f32), ('clamp', c_f32),
+    ]
+
+
+STRUCTS = {'sgv_upfirdn2d_params': UpfirdnParams, 'sgv_bias_act_params': BiasActParams, 'sgv_conv_params': ConvParams}
+
 # every symbol include/sgv_b200*.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ('sgv_abi_version', c_int, []),
@@ -53,6 +72,9 @@ SYMBOLS = [
     ('sgv_upfirdn2d_out_size', c_int, [c_int] * 6),
     ('sgv_upfirdn2d', c_int, [ctypes.POINTER(UpfirdnParams), c_vp]),
     ('sgv_bias_act', c_int, [ctypes.POINTER(BiasActParams), c_vp]),
+    ('sgv_conv_prep_weights', c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int,
+                                      ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_vp, c_vp]),
+    ('sgv_conv2d_tf32', c_int, [ctypes.POINTER(ConvParams), c_vp]),
 ]
 
 _lib = None

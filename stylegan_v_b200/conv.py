@@ -1,0 +1,89 @@
+"""Tensor-level interface to the tcgen05 implicit-GEMM convolution of libsgv_b200 (include/sgv_b200_conv.h).
+
+Activations are NHWC in memory = torch tensors of logical shape [N, C, H, W] with channels_last strides.
+`igemm_conv` is the raw kernel call; the autograd-aware layers that use it live in stylegan_v_b200/synthesis.py.
+"""
+import ctypes
+import torch
+
+from . import _lib
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _req(cond, msg):
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def prep_weights(w, taps, rows_dim=0, cols_dim=1):
+    """[rows, cols, kh, kw]-like weight (any strides) -> [ntaps, rows, cols] TF32-rounded slab for the kernel.
+
+    taps: list of (ky, kx) kernel positions; rows_dim / cols_dim say which weight dims play GEMM-N (output
+    channels of the contraction) and GEMM-K (its input channels)."""
+    _req(w.is_cuda and w.dtype == torch.float32 and w.ndim == 4, 'weight must be a CUDA float32 4-D tensor')
+    L = _lib.lib()
+    rows, cols = w.shape[rows_dim], w.shape[cols_dim]
+    nt = len(taps)
+    wp = torch.empty([nt, rows, cols], dtype=torch.float32, device=w.device)
+    ky = (ctypes.c_int32 * nt)(*[int(t[0]) for t in taps])
+    kx = (ctypes.c_int32 * nt)(*[int(t[1]) for t in taps])
+    with torch.cuda.device(w.device):
+        _lib.check(L.sgv_conv_prep_weights(w.data_ptr(), w.stride(rows_dim), w.stride(cols_dim), w.stride(2), w.stride(3),
+                                           rows, cols, nt, ky, kx, wp.data_ptr(), _stream(w.device)), 'sgv_conv_prep_weights')
+    return wp
+
+
+def igemm_conv(x, wp, tap_offsets, out=None, out_hw=None, out_view=None, in_stride=1,
+               a_scale=None, o_scale=None, bias=None, act='linear', alpha=0.2, gain=1.0, clamp=None):
+    """y[n,oy,ox,o] = epi(sum_{t,i} x[n, oy*in_stride+dy_t, ox*in_stride+dx_t, i] * a_scale[n,i] * wp[t,o,i]).
+
+    x: [N, Cin, H, W] channels_last fp32.  wp: [ntaps, Cout, Cin] from prep_weights.  tap_offsets: [(dy, dx)].
+    Output: a new channels_last [N, Cout, out_h, out_w] tensor, or — for polyphase writes — `out_view`, a strided
+    view [N, Cout, out_h, out_w] (channel stride 1) of a larger channels_last tensor."""
+    _req(x.is_cuda and x.dtype == torch.float32 and x.ndim == 4, 'x must be a CUDA float32 [N,C,H,W] tensor')
+    N, Cin, H, W = x.shape
+    _req(x.stride(1) == 1 and x.stride(3) == Cin and x.stride(2) == W * Cin and x.stride(0) == H * W * Cin, 'x must be dense channels_last (NHWC)')
+    nt, Cout, Cin2 = wp.shape
+    _req(Cin2 == Cin and nt == len(tap_offsets) and wp.is_contiguous(), 'wp does not match x / taps')
+    if out_view is not None:
+        y = out_view
+        oh, ow = y.shape[2], y.shape[3]
+        _req(y.shape[0] == N and y.shape[1] == Cout and y.stride(1) == 1, 'out_view must be [N,Cout,oh,ow] with unit channel stride')
+    else:
+        oh, ow = out_hw if out_hw is not None else (H, W)
+        y = torch.empty([N, Cout, oh, ow], dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+        if Cout == 1 or (oh == 1 and ow == 1):
+            y = torch.empty([N, oh, ow, Cout], dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
+    L = _lib.lib()
+    p = _lib.ConvParams()
+    p.x, p.wp, p.y = x.data_ptr(), wp.data_ptr(), y.data_ptr()
+    p.n, p.h, p.w, p.cin, p.cout = N, H, W, Cin, Cout
+    p.out_h, p.out_w = oh, ow
+    p.out_stride_n, p.out_stride_y, p.out_stride_x = y.stride(0), y.stride(2), y.stride(3)
+    p.in_stride, p.ntaps = in_stride, nt
+    for i, (dy, dx) in enumerate(tap_offsets):
+        p.tap_dy[i], p.tap_dx[i] = int(dy), int(dx)
+    keep = []
+    for name, t, shape in (('a_scale', a_scale, (N, Cin)), ('o_scale', o_scale, (N, Cout)), ('bias', bias, (Cout,))):
+        if t is not None:
+            t = t.to(torch.float32).contiguous()
+            _req(tuple(t.shape) == shape and t.device == x.device, f'{name} must be a float32 {shape} tensor on the same device')
+            keep.append(t)
+            setattr(p, name, t.data_ptr())
+    p.act = {'linear': 1, 'lrelu': 3}[act]
+    p.alpha, p.gain = float(alpha), float(gain)
+    p.clamp = float(clamp) if clamp is not None else -1.0
+    with torch.cuda.device(x.device):
+        _lib.check(L.sgv_conv2d_tf32(ctypes.byref(p), _stream(x.device)), 'sgv_conv2d_tf32')
+    return y
+
+
+TAPS_3x3 = [(ky, kx) for ky in range(3) for kx in range(3)]
+
+
+def conv3x3_taps():
+    """Correlation with padding 1: tap (ky,kx) reads input offset (ky-1, kx-1)."""
+    return TAPS_3x3, [(ky - 1, kx - 1) for ky, kx in TAPS_3x3]

@@ -17,15 +17,20 @@ struct BiasActArgs
     int grad; float alpha, gain, clamp;
     int size_x, size_b, step_b;
     float* db;
+    FastDiv div_step, div_size;
 };
 
-template <class S, int A>
-__device__ __forceinline__ S bias_act_elem(S x, S b, S xref, S yref, S dy, int G, S alpha, S gain, S clamp)
+template <class S, int A, int G>
+__device__ __forceinline__ S bias_act_elem(S x, S b, S xref, S yref, S dy, S alpha, S gain, S clamp)
 {
     const S one = 1, two = 2, expRange = 80, halfExpRange = 40;
     const S seluScale = (S)1.0507009873554804934193349852946;
     const S seluAlpha = (S)1.6732632423543772848170429916717;
-    S yy = (gain != 0) ? yref / gain : 0;
+    // yy = yref / gain is only consumed by the gradient formulas; relu/lrelu need just its sign, which is
+    // sign(yref) * sign(gain) (no division on the hot path; differs from the quotient only if it underflows).
+    S yy = 0;
+    if (G >= 1 && A >= 4 && A <= 8) yy = (gain != 0) ? yref / gain : 0;
+    if (G >= 1 && (A == 2 || A == 3)) yy = (gain > 0) ? yref : (gain < 0) ? -yref : 0;
     S y = 0;
     if (G == 0) x += b; else xref += b;
     if (A == 1) { y = x; if (G == 2) y = 0; }
@@ -84,7 +89,7 @@ __device__ __forceinline__ S bias_act_elem(S x, S b, S xref, S yref, S dy, int G
 }
 
 // ---- scalar kernel: any dtype ----
-template <class T, int A>
+template <class T, int A, int G>
 __global__ void __launch_bounds__(256) bias_act_scalar(BiasActArgs p)
 {
     typedef typename acc_type<T>::type S;
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(256) bias_act_scalar(BiasActArgs p)
         S xref = p.xref ? (S)((const T*)p.xref)[xi] : (S)0;
         S yref = p.yref ? (S)((const T*)p.yref)[xi] : (S)0;
         S dy = p.dy ? (S)((const T*)p.dy)[xi] : (S)1;
-        S y = bias_act_elem<S, A>(x, b, xref, yref, dy, p.grad, alpha, gain, clamp);
+        S y = bias_act_elem<S, A, G>(x, b, xref, yref, dy, alpha, gain, clamp);
         ((T*)p.y)[xi] = (T)y;
         if (p.db) atomicAdd(p.db + bi, (float)y);
     }
@@ -106,7 +111,7 @@ __global__ void __launch_bounds__(256) bias_act_scalar(BiasActArgs p)
 // ---- vector kernel: fp32, size_x % 4 == 0, 16-byte aligned pointers ----
 // BMODE 0: no bias; 1: the 4 elements share one bias (step_b % 4 == 0); 2: step_b == 1 and size_b % 4 == 0
 // (bias is itself a float4); 3: general per-element index.
-template <int A, int BMODE>
+template <int A, int G, int BMODE>
 __global__ void __launch_bounds__(256) bias_act_vec4(BiasActArgs p)
 {
     extern __shared__ float sdb[];
@@ -124,54 +129,70 @@ __global__ void __launch_bounds__(256) bias_act_vec4(BiasActArgs p)
     const float* B = (const float*)p.b;
     float4* Y = (float4*)p.y;
     const float alpha = p.alpha, gain = p.gain, clamp = p.clamp;
-    const int G = p.grad;
-    for (int base = blockIdx.x * blockDim.x; base < nvec; base += gridDim.x * blockDim.x)   // block-uniform trip count
+    constexpr int U = 4;   // independent 128-bit loads in flight per thread and operand (HBM latency hiding)
+    for (int base = blockIdx.x * blockDim.x * U; base < nvec; base += gridDim.x * blockDim.x * U)   // block-uniform trip count
     {
-        const int vi = base + threadIdx.x;
-        const bool valid = vi < nvec;
-        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-        int bi0 = -1, bi1 = -1, bi2 = -1, bi3 = -1;
-        if (valid)
-        {
-            const int xi = vi << 2;
-            float4 x = __ldg(X + vi);
-            float4 xr = XR ? __ldg(XR + vi) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 yr = YR ? __ldg(YR + vi) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 dy = DY ? __ldg(DY + vi) : make_float4(1.f, 1.f, 1.f, 1.f);
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (BMODE == 1) { bi0 = bi1 = bi2 = bi3 = (xi / p.step_b) % p.size_b; if (B) b.x = b.y = b.z = b.w = __ldg(B + bi0); }
-            if (BMODE == 2) { bi0 = xi % p.size_b; bi1 = bi0 + 1; bi2 = bi0 + 2; bi3 = bi0 + 3; if (B) b = __ldg((const float4*)(B + bi0)); }
-            if (BMODE == 3)
-            {
-                bi0 = ((xi + 0) / p.step_b) % p.size_b; bi1 = ((xi + 1) / p.step_b) % p.size_b;
-                bi2 = ((xi + 2) / p.step_b) % p.size_b; bi3 = ((xi + 3) / p.step_b) % p.size_b;
-                if (B) { b.x = __ldg(B + bi0); b.y = __ldg(B + bi1); b.z = __ldg(B + bi2); b.w = __ldg(B + bi3); }
-            }
-            y.x = bias_act_elem<float, A>(x.x, b.x, xr.x, yr.x, dy.x, G, alpha, gain, clamp);
-            y.y = bias_act_elem<float, A>(x.y, b.y, xr.y, yr.y, dy.y, G, alpha, gain, clamp);
-            y.z = bias_act_elem<float, A>(x.z, b.z, xr.z, yr.z, dy.z, G, alpha, gain, clamp);
-            y.w = bias_act_elem<float, A>(x.w, b.w, xr.w, yr.w, dy.w, G, alpha, gain, clamp);
-            Y[vi] = y;
-        }
-        if (reduce)
-        {
-            if (BMODE == 1)
-            {
-                // the 4 values of a lane share a channel; merge across the warp when every valid lane agrees
-                float s = (y.x + y.y) + (y.z + y.w);
-                const int lead = __shfl_sync(0xffffffffu, bi0, 0);
-                const bool uniform = __all_sync(0xffffffffu, !valid || bi0 == lead);
-                if (uniform)
-                {
+        float4 x[U], xr[U], yr[U], dy[U];
+        bool valid[U];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-                    if ((threadIdx.x & 31) == 0 && lead >= 0) atomicAdd(sdb + lead, s);
-                }
-                else if (valid) atomicAdd(sdb + bi0, s);
-            }
-            else if (valid)
+        for (int u = 0; u < U; u++)
+        {
+            const int vi = base + u * blockDim.x + threadIdx.x;
+            valid[u] = vi < nvec;
+            x[u] = xr[u] = yr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            dy[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (valid[u])
             {
-                atomicAdd(sdb + bi0, y.x); atomicAdd(sdb + bi1, y.y); atomicAdd(sdb + bi2, y.z); atomicAdd(sdb + bi3, y.w);
+                x[u] = __ldcs(X + vi);
+                if (XR) xr[u] = __ldcs(XR + vi);
+                if (YR) yr[u] = __ldcs(YR + vi);
+                if (DY) dy[u] = __ldcs(DY + vi);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+        {
+            const int vi = base + u * blockDim.x + threadIdx.x;
+            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+            int bi0 = -1, bi1 = -1, bi2 = -1, bi3 = -1;
+            if (valid[u])
+            {
+                const int xi = vi << 2;
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (BMODE == 1) { uint32_t q_, r_; p.div_size.divmod(p.div_step.div((uint32_t)xi), q_, r_); bi0 = bi1 = bi2 = bi3 = (int)r_; if (B) b.x = b.y = b.z = b.w = __ldg(B + bi0); }
+                if (BMODE == 2) { uint32_t q_, r_; p.div_size.divmod((uint32_t)xi, q_, r_); bi0 = (int)r_; bi1 = bi0 + 1; bi2 = bi0 + 2; bi3 = bi0 + 3; if (B) b = __ldg((const float4*)(B + bi0)); }
+                if (BMODE == 3)
+                {
+                    bi0 = ((xi + 0) / p.step_b) % p.size_b; bi1 = ((xi + 1) / p.step_b) % p.size_b;
+                    bi2 = ((xi + 2) / p.step_b) % p.size_b; bi3 = ((xi + 3) / p.step_b) % p.size_b;
+                    if (B) { b.x = __ldg(B + bi0); b.y = __ldg(B + bi1); b.z = __ldg(B + bi2); b.w = __ldg(B + bi3); }
+                }
+                y.x = bias_act_elem<float, A, G>(x[u].x, b.x, xr[u].x, yr[u].x, dy[u].x, alpha, gain, clamp);
+                y.y = bias_act_elem<float, A, G>(x[u].y, b.y, xr[u].y, yr[u].y, dy[u].y, alpha, gain, clamp);
+                y.z = bias_act_elem<float, A, G>(x[u].z, b.z, xr[u].z, yr[u].z, dy[u].z, alpha, gain, clamp);
+                y.w = bias_act_elem<float, A, G>(x[u].w, b.w, xr[u].w, yr[u].w, dy[u].w, alpha, gain, clamp);
+                __stcs(Y + vi, y);
+            }
+            if (reduce)
+            {
+                if (BMODE == 1)
+                {
+                    // the 4 values of a lane share a channel; merge across the warp when every valid lane agrees
+                    float s = (y.x + y.y) + (y.z + y.w);
+                    const int lead = __shfl_sync(0xffffffffu, bi0, 0);
+                    const bool uniform = __all_sync(0xffffffffu, !valid[u] || bi0 == lead);
+                    if (uniform)
+                    {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+                        if ((threadIdx.x & 31) == 0 && lead >= 0) atomicAdd(sdb + lead, s);
+                    }
+                    else if (valid[u]) atomicAdd(sdb + bi0, s);
+                }
+                else if (valid[u])
+                {
+                    atomicAdd(sdb + bi0, y.x); atomicAdd(sdb + bi1, y.y); atomicAdd(sdb + bi2, y.z); atomicAdd(sdb + bi3, y.w);
+                }
             }
         }
     }
@@ -186,8 +207,8 @@ __global__ void __launch_bounds__(256) bias_act_vec4(BiasActArgs p)
     }
 }
 
-template <int A>
-static int launch_act(const BiasActArgs& a, int dtype, cudaStream_t stream)
+template <int A, int G>
+static int launch_act_g(const BiasActArgs& a, int dtype, cudaStream_t stream)
 {
     const int sms = num_sms();
     if (dtype == SGV_F32)
@@ -205,23 +226,31 @@ static int launch_act(const BiasActArgs& a, int dtype, cudaStream_t stream)
                 else mode = 3;
             }
             const int nvec = a.size_x / 4;
-            const unsigned grid = (unsigned)min((long long)sms * 16, ((long long)nvec + 255) / 256);
+            const unsigned grid = (unsigned)min((long long)sms * 8, ((long long)nvec + 1023) / 1024);
             const size_t smem = a.db ? (size_t)a.size_b * sizeof(float) : 0;
             switch (mode)
             {
-                case 0: bias_act_vec4<A, 0><<<grid, 256, smem, stream>>>(a); break;
-                case 1: bias_act_vec4<A, 1><<<grid, 256, smem, stream>>>(a); break;
-                case 2: bias_act_vec4<A, 2><<<grid, 256, smem, stream>>>(a); break;
-                default: bias_act_vec4<A, 3><<<grid, 256, smem, stream>>>(a); break;
+                case 0: bias_act_vec4<A, G, 0><<<grid, 256, smem, stream>>>(a); break;
+                case 1: bias_act_vec4<A, G, 1><<<grid, 256, smem, stream>>>(a); break;
+                case 2: bias_act_vec4<A, G, 2><<<grid, 256, smem, stream>>>(a); break;
+                default: bias_act_vec4<A, G, 3><<<grid, 256, smem, stream>>>(a); break;
             }
             return 0;
         }
     }
     const unsigned grid = (unsigned)min((long long)sms * 16, ((long long)a.size_x + 255) / 256);
-    if (dtype == SGV_F32) bias_act_scalar<float, A><<<grid, 256, 0, stream>>>(a);
-    else if (dtype == SGV_F64) bias_act_scalar<double, A><<<grid, 256, 0, stream>>>(a);
-    else bias_act_scalar<__half, A><<<grid, 256, 0, stream>>>(a);
+    if (dtype == SGV_F32) bias_act_scalar<float, A, G><<<grid, 256, 0, stream>>>(a);
+    else if (dtype == SGV_F64) bias_act_scalar<double, A, G><<<grid, 256, 0, stream>>>(a);
+    else bias_act_scalar<__half, A, G><<<grid, 256, 0, stream>>>(a);
     return 0;
+}
+
+template <int A>
+static int launch_act(const BiasActArgs& a, int dtype, cudaStream_t stream)
+{
+    if (a.grad == 0) return launch_act_g<A, 0>(a, dtype, stream);
+    if (a.grad == 1) return launch_act_g<A, 1>(a, dtype, stream);
+    return launch_act_g<A, 2>(a, dtype, stream);
 }
 
 } // namespace sgv
@@ -247,6 +276,8 @@ extern "C" int sgv_bias_act(const sgv_bias_act_params* p, void* stream_)
     a.grad = p->grad; a.alpha = p->alpha; a.gain = p->gain; a.clamp = p->clamp;
     a.size_x = p->size_x; a.size_b = p->b || p->db_accum ? p->size_b : 1; a.step_b = p->b || p->db_accum ? p->step_b : 1;
     a.db = p->db_accum;
+    a.div_step = FastDiv((uint32_t)a.step_b);
+    a.div_size = FastDiv((uint32_t)a.size_b);
     // the reduction needs a channel index even when no bias is added: keep b NULL but index via size_b/step_b
     switch (p->act)
     {

@@ -37,4 +37,19 @@ __host__ __device__ __forceinline__ int floor_div(int a, int b)
 
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Division of 0 <= n < 2^31 by a runtime-constant d >= 1 with one mulhi + add + shift (Granlund-Montgomery).
+struct FastDiv
+{
+    uint32_t d, m, s;
+    __host__ __device__ FastDiv() : d(1), m(1), s(0) {}
+    __host__ __device__ explicit FastDiv(uint32_t div) : d(div)
+    {
+        s = 0;
+        while ((1ull << s) < div) s++;
+        m = (uint32_t)(((1ull << 32) * ((1ull << s) - div)) / div + 1);
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return (__umulhi(n, m) + n) >> s; }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
 } // namespace sgv

@@ -1,0 +1,387 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a) with StyleGAN modulation and bias/activation fused.
+//
+//   y[n,p,o] = epi( sum_{t,i} (x[n, p*stride + d_t, i] * a[n,i]) * W[t][o][i] )          (include/sgv_b200_conv.h)
+//
+// GEMM view: M = 128 output pixels per CTA (a TW x TH x TN box of the NHWC tensor), N = BN output channels,
+// K = taps x Cin walked in chunks of 32 channels (= one 128-byte swizzle row of TF32).
+//
+// Warp roles (192 threads):
+//   warp 0     TMA producer: per k-step one 4-D tile load of the activation box shifted by the tap offset
+//              (out-of-image pixels are zero-filled by TMA = convolution padding for free) and one 2-D load of
+//              the [BN x 32] weight slab; both land 128B-swizzled in shared memory and signal full[stage].
+//   warps 2-5  operand transform: multiply the staged activation rows by the per-sample modulation
+//              a[n, c..c+31] and round to TF32 (round-to-nearest; the tensor core would truncate), in place, then
+//              fence.proxy.async and signal ready[stage].  After the k-loop the same warps run the epilogue:
+//              tcgen05.ld the fp32 accumulator rows, apply o_scale[n,o] / bias / lrelu / gain / clamp, store NHWC.
+//   warp 1     allocates TMEM, issues tcgen05.mma.kind::tf32 (one elected thread, 4 x K=8 per k-step) with the
+//              accumulator in TMEM, releases stages with tcgen05.commit -> empty[stage].
+//
+// Replaces cuDNN for the reference's conv2d_gradfix.conv2d / conv_transpose2d on the hot-path shapes
+// (conv2d_gradfix.py:35-43) plus the x*styles, *dcoefs and bias_act passes around it (networks.py:64-74,141-143).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/sgv_b200_conv.h"
+
+namespace sgv {
+
+using namespace ptx;
+
+constexpr int kConvThreads = 192;
+constexpr int kBM = 128;
+constexpr int kBK = 32;                       // fp32/TF32 elements per k-step = 128 bytes
+constexpr int kATileBytes = kBM * kBK * 4;    // 16 KB
+
+struct ConvArgs
+{
+    float* y; const float* a_scale; const float* o_scale; const float* bias;
+    int n, cin, cout, out_h, out_w;
+    long long osn, osy, osx;
+    int in_stride, ntaps;
+    int tap_dy[SGV_CONV_MAX_TAPS], tap_dx[SGV_CONV_MAX_TAPS];
+    int tw, th, tn;                   // activation box: tw*th*tn == 128
+    int tiles_x, tiles_y, tiles_nb;
+    int act; float alpha, gain, clamp;
+};
+
+template <int BN, int STAGES>
+struct ConvSmem
+{
+    static constexpr int kBTileBytes = BN * kBK * 4;
+    static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kTotal = kBarOffset + (3 * STAGES + 1) * 8 + 16 + 1024;   // + barriers + tmem ptr + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const ConvArgs p)
+{
+    using L = ConvSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* ready_bar = full_bar + STAGES;
+    uint64_t* empty_bar = ready_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates
+    int mt = blockIdx.x;
+    const int tile_x = mt % p.tiles_x; mt /= p.tiles_x;
+    const int tile_y = mt % p.tiles_y; mt /= p.tiles_y;
+    const int n0 = mt * p.tn;
+    const int ox0 = tile_x * p.tw, oy0 = tile_y * p.th;
+    const int nb0 = blockIdx.y * BN;                 // first output channel of this CTA
+    const int kchunks = p.cin / kBK;
+    const int ksteps = kchunks * p.ntaps;
+
+    if (threadIdx.x == 0)
+    {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_w);
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 1); mbar_init(ready_bar + s, 4); mbar_init(empty_bar + s, 1); }
+        mbar_init(accum_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1)
+    {
+        tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0)
+    {
+        // ===== TMA producer =====
+        if (elect_one())
+        {
+            int stage = 0; uint32_t phase = 0;
+            for (int kc = 0; kc < kchunks; kc++)
+                for (int t = 0; t < p.ntaps; t++)
+                {
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    uint8_t* sa = smem + stage * L::kStageBytes;
+                    uint8_t* sb = sa + kATileBytes;
+                    mbar_expect_tx(full_bar + stage, L::kStageBytes);
+                    tma_load_4d(sa, &tmap_x, full_bar + stage, kc * kBK, ox0 * p.in_stride + p.tap_dx[t], oy0 * p.in_stride + p.tap_dy[t], n0);
+                    tma_load_2d(sb, &tmap_w, full_bar + stage, kc * kBK, t * p.cout + nb0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+        }
+    }
+    else if (warp == 1)
+    {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+        int stage = 0; uint32_t phase = 0;
+        for (int ks = 0; ks < ksteps; ks++)
+        {
+            mbar_wait(ready_bar + stage, phase);
+            tc_fence_after();
+            if (elect_one())
+            {
+                const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+                const uint64_t da = umma_desc_k_sw128(sa);
+                const uint64_t db = umma_desc_k_sw128(sa + kATileBytes);
+#pragma unroll
+                for (int k = 0; k < kBK / 8; k++)      // K = 8 TF32 per instruction = 32 bytes along the swizzled row
+                    mma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks > 0 || k > 0) ? 1u : 0u);
+                mma_commit(empty_bar + stage);
+                if (ks == ksteps - 1) mma_commit(accum_bar);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+    else
+    {
+        // ===== operand transform, then epilogue =====
+        const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;                 // accumulator row = A-tile row = pixel index inside the box
+        const int box_hw = p.th * p.tw;
+        const int tn_i = row / box_hw;
+        const int rem = row - tn_i * box_hw;
+        const int ty = rem / p.tw, tx = rem - ty * p.tw;
+        const int n = n0 + tn_i;
+        const int oy = oy0 + ty, ox = ox0 + tx;
+        const bool valid = (n < p.n) && (oy < p.out_h) && (ox < p.out_w);
+        const int nc = n < p.n ? n : p.n - 1;
+
+        {
+            int stage = 0; uint32_t phase = 0;
+            float sv[kBK];
+            for (int kc = 0; kc < kchunks; kc++)
+            {
+                if (p.a_scale)
+                {
+                    const float4* sp = reinterpret_cast<const float4*>(p.a_scale + (long long)nc * p.cin + kc * kBK);
+#pragma unroll
+                    for (int j = 0; j < kBK / 4; j++) { float4 v = __ldg(sp + j); sv[4 * j] = v.x; sv[4 * j + 1] = v.y; sv[4 * j + 2] = v.z; sv[4 * j + 3] = v.w; }
+                }
+                else
+                {
+#pragma unroll
+                    for (int j = 0; j < kBK; j++) sv[j] = 1.f;
+                }
+                for (int t = 0; t < p.ntaps; t++)
+                {
+                    mbar_wait(full_bar + stage, phase);
+                    uint8_t* arow = smem + stage * L::kStageBytes + row * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                    {
+                        float4* ptr = reinterpret_cast<float4*>(arow + ((j ^ (row & 7)) << 4));   // logical 16-byte chunk j
+                        float4 v = *ptr;
+                        v.x = tf32_rn(v.x * sv[4 * j + 0]); v.y = tf32_rn(v.y * sv[4 * j + 1]);
+                        v.z = tf32_rn(v.z * sv[4 * j + 2]); v.w = tf32_rn(v.w * sv[4 * j + 3]);
+                        *ptr = v;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(ready_bar + stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+
+        // ---- epilogue ----
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        float* yrow = p.y + (long long)nc * p.osn + (long long)oy * p.osy + (long long)ox * p.osx + nb0;
+        const float* osc = p.o_scale ? p.o_scale + (long long)nc * p.cout + nb0 : nullptr;
+        const float* bia = p.bias ? p.bias + nb0 : nullptr;
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 32; cc++)
+        {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
+            tmem_ld_wait();
+            if (valid)
+            {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                {
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                    {
+                        const int col = cc * 32 + j * 4 + e;
+                        float f = __uint_as_float(v[j * 4 + e]);
+                        if (osc) f = __fmul_rn(f, __ldg(osc + col));
+                        if (bia) f = __fadd_rn(f, __ldg(bia + col));
+                        if (p.act == 3) f = (f > 0.f) ? f : f * p.alpha;
+                        f *= p.gain;
+                        if (p.clamp >= 0.f) f = (f > -p.clamp && f < p.clamp) ? f : (f >= 0.f ? p.clamp : -p.clamp);
+                        o[e] = f;
+                    }
+                    *reinterpret_cast<float4*>(yrow + cc * 32 + j * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+}
+
+// ---- weight preparation ----
+struct TapTable { int ky[SGV_CONV_MAX_TAPS]; int kx[SGV_CONV_MAX_TAPS]; };
+
+__global__ void __launch_bounds__(256) conv_prep_weights_kernel(const float* __restrict__ w, long long sr, long long sc, long long sky, long long skx,
+                                                                  int rows, int cols, int ntaps, TapTable taps, float* __restrict__ wp)
+{
+    const long long total = (long long)ntaps * rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    {
+        const int k = (int)(i % cols);
+        const int r = (int)((i / cols) % rows);
+        const int t = (int)(i / ((long long)cols * rows));
+        wp[i] = ptx::tf32_rn(w[r * sr + k * sc + taps.ky[t] * sky + taps.kx[t] * skx]);
+    }
+}
+
+// ---- host ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn)
+    {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, const uint32_t* elem_strides)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(SGV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base),
+                    reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
+                    reinterpret_cast<const cuuint32_t*>(box), reinterpret_cast<const cuuint32_t*>(elem_strides),
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SGV_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SGV_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvArgs& a, dim3 grid, cudaStream_t stream)
+{
+    using L = ConvSmem<BN, STAGES>;
+    auto kern = conv_tf32_kernel<BN, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        SGV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        attr_set = true;
+    }
+    kern<<<grid, kConvThreads, L::kTotal, stream>>>(tx, tw, a);
+    SGV_LAUNCH_OK("conv_tf32_kernel");
+    return SGV_OK;
+}
+
+} // namespace sgv
+
+extern "C" int sgv_conv_prep_weights(const float* w, int64_t stride_row, int64_t stride_col, int64_t stride_ky, int64_t stride_kx,
+                                     int32_t rows, int32_t cols, int32_t ntaps, const int32_t* tap_ky, const int32_t* tap_kx,
+                                     float* wp, void* stream_)
+{
+    using namespace sgv;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SGV_CHECK_ARG(w && wp && tap_ky && tap_kx, "sgv_conv_prep_weights: NULL argument");
+    SGV_CHECK_ARG(ntaps >= 1 && ntaps <= SGV_CONV_MAX_TAPS, "ntaps must be in [1, %d]", SGV_CONV_MAX_TAPS);
+    SGV_CHECK_ARG(rows >= 1 && cols >= 1, "rows/cols must be positive");
+    int rc = sgv_device_check();
+    if (rc != SGV_OK) return rc;
+    TapTable taps;
+    for (int t = 0; t < SGV_CONV_MAX_TAPS; t++) { taps.ky[t] = t < ntaps ? tap_ky[t] : 0; taps.kx[t] = t < ntaps ? tap_kx[t] : 0; }
+    const long long total = (long long)ntaps * rows * cols;
+    const unsigned grid = (unsigned)min((long long)num_sms() * 8, (total + 255) / 256);
+    conv_prep_weights_kernel<<<grid, 256, 0, stream>>>(w, stride_row, stride_col, stride_ky, stride_kx, rows, cols, ntaps, taps, wp);
+    SGV_LAUNCH_OK("conv_prep_weights_kernel");
+    return SGV_OK;
+}
+
+static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
+
+extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
+{
+    using namespace sgv;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SGV_CHECK_ARG(p != nullptr, "sgv_conv2d_tf32: params is NULL");
+    SGV_CHECK_ARG(p->x && p->wp && p->y, "sgv_conv2d_tf32: x, wp and y must be non-NULL");
+    SGV_CHECK_ARG(p->n >= 1 && p->h >= 1 && p->w >= 1 && p->out_h >= 1 && p->out_w >= 1, "extents must be positive");
+    SGV_CHECK_ARG(p->cin >= 32 && p->cin % 32 == 0, "cin must be a multiple of 32 (got %d)", p->cin);
+    SGV_CHECK_ARG(p->cout % 64 == 0 || p->cout == 32 || p->cout == 16, "cout must be a multiple of 64, or 16/32 (got %d)", p->cout);
+    SGV_CHECK_ARG(p->ntaps >= 1 && p->ntaps <= SGV_CONV_MAX_TAPS, "ntaps must be in [1, %d]", SGV_CONV_MAX_TAPS);
+    SGV_CHECK_ARG(p->in_stride == 1 || p->in_stride == 2, "in_stride must be 1 or 2");
+    SGV_CHECK_ARG(p->act == 1 || p->act == 3, "act must be 1 (linear) or 3 (lrelu)");
+    SGV_CHECK_ARG((reinterpret_cast<uintptr_t>(p->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->wp) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(p->y) & 15) == 0, "x, wp and y must be 16-byte aligned");
+    SGV_CHECK_ARG(p->out_stride_n % 4 == 0 && p->out_stride_y % 4 == 0 && p->out_stride_x % 4 == 0, "output strides must be multiples of 4 elements");
+    SGV_CHECK_ARG((long long)p->n * p->h * p->w * p->cin <= 0x7fffffffLL, "x is too large");
+    int rc = sgv_device_check();
+    if (rc != SGV_OK) return rc;
+
+    ConvArgs a;
+    a.y = p->y; a.a_scale = p->a_scale; a.o_scale = p->o_scale; a.bias = p->bias;
+    a.n = p->n; a.cin = p->cin; a.cout = p->cout; a.out_h = p->out_h; a.out_w = p->out_w;
+    a.osn = p->out_stride_n; a.osy = p->out_stride_y; a.osx = p->out_stride_x;
+    a.in_stride = p->in_stride; a.ntaps = p->ntaps;
+    for (int t = 0; t < SGV_CONV_MAX_TAPS; t++) { a.tap_dy[t] = p->tap_dy[t]; a.tap_dx[t] = p->tap_dx[t]; }
+    a.act = p->act; a.alpha = p->alpha; a.gain = p->gain; a.clamp = p->clamp;
+
+    // activation box of 128 output pixels: as square as the plane allows, spilling into the batch dimension for tiny planes
+    int tw = pow2_floor(p->out_w < 16 ? p->out_w : 16);
+    if (tw < p->out_w && tw < 16 && pow2_ceil(p->out_w) <= 16) tw = pow2_ceil(p->out_w);
+    int th = 128 / tw;
+    if (th > pow2_ceil(p->out_h)) th = pow2_ceil(p->out_h);
+    int tn = 128 / (tw * th);
+    a.tw = tw; a.th = th; a.tn = tn;
+    a.tiles_x = ceil_div(p->out_w, tw); a.tiles_y = ceil_div(p->out_h, th); a.tiles_nb = ceil_div(p->n, tn);
+
+    const int bn = (p->cout % 256 == 0) ? 256 : (p->cout % 128 == 0) ? 128 : (p->cout % 64 == 0) ? 64 : p->cout;
+
+    CUtensorMap tmx, tmw;
+    {
+        const uint64_t dims[4] = {(uint64_t)p->cin, (uint64_t)p->w, (uint64_t)p->h, (uint64_t)p->n};
+        const uint64_t strides[3] = {(uint64_t)p->cin * 4, (uint64_t)p->w * p->cin * 4, (uint64_t)p->h * p->w * p->cin * 4};
+        const uint32_t box[4] = {(uint32_t)kBK, (uint32_t)(tw * p->in_stride), (uint32_t)(th * p->in_stride), (uint32_t)tn};
+        const uint32_t es[4] = {1, (uint32_t)p->in_stride, (uint32_t)p->in_stride, 1};
+        SGV_CHECK_ARG(box[1] <= 256 && box[2] <= 256, "activation box too large");
+        rc = make_tmap_f32(&tmx, p->x, 4, dims, strides, box, es);
+        if (rc != SGV_OK) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)p->cin, (uint64_t)p->ntaps * p->cout};
+        const uint64_t strides[1] = {(uint64_t)p->cin * 4};
+        const uint32_t box[2] = {(uint32_t)kBK, (uint32_t)bn};
+        const uint32_t es[2] = {1, 1};
+        rc = make_tmap_f32(&tmw, p->wp, 2, dims, strides, box, es);
+        if (rc != SGV_OK) return rc;
+    }
+    dim3 grid((unsigned)(a.tiles_x * a.tiles_y * a.tiles_nb), (unsigned)(p->cout / bn), 1);
+    switch (bn)
+    {
+        case 256: return launch_conv<256, 4>(tmx, tmw, a, grid, stream);
+        case 128: return launch_conv<128, 6>(tmx, tmw, a, grid, stream);
+        case 64:  return launch_conv<64, 8>(tmx, tmw, a, grid, stream);
+        case 32:  return launch_conv<32, 8>(tmx, tmw, a, grid, stream);
+        default:  return launch_conv<16, 8>(tmx, tmw, a, grid, stream);
+    }
+}

@@ -30,12 +30,18 @@ struct FirArgs
     const float* escale; const float* ebias; int eact; float ealpha, egain, eclamp;
 };
 
-template <class A>
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+template <class A, bool EPI = true>
 __device__ __forceinline__ A fir_epilogue(A v, const FirArgs& p, int n, int c)
 {
-    if (p.eact == 0) return v;
-    if (p.escale) v *= (A)p.escale[(long long)n * p.in_c + c];
-    if (p.ebias) v += (A)p.ebias[c];
+    if (!EPI || p.eact == 0) return v;
+    // separate roundings (no FMA contraction) so the fused result equals the unfused op sequence bit for bit
+    if (p.escale) v = mul_rn(v, (A)p.escale[(long long)n * p.in_c + c]);
+    if (p.ebias) v = add_rn(v, (A)p.ebias[c]);
     if (p.eact == 3) v = (v > 0) ? v : v * (A)p.ealpha;
     v *= (A)p.egain;
     if (p.eclamp >= 0) { A cl = (A)p.eclamp; v = (v > -cl && v < cl) ? v : (v >= 0 ? cl : -cl); }
@@ -95,10 +101,10 @@ __global__ void __launch_bounds__(256) fir_generic(FirArgs p, int channels_fast,
 //------------------------------------------------------------------------------------------------
 // Tiled kernel for dense NCHW fp32.
 //   block = 256 threads = lanes_x (power of two, <= 32) x (256 / lanes_x) thread rows;
-//   each thread: 4 consecutive outputs in x, RPT = 2 output rows.
+//   each thread: 4 consecutive outputs in x, RPT = 4 output rows.
 
 constexpr int kFirThreads = 256;
-constexpr int kFirRPT = 2;
+constexpr int kFirRPT = 4;
 constexpr int kFirMaxTaps = 32;   // per dimension, for the runtime-sized filter variants
 
 struct FirTile
@@ -110,9 +116,10 @@ struct FirTile
     int tiles_x, tiles_y;
     long long in_total;   // numel of x (for vector-load bounds)
     int out_vec_ok;       // 128-bit stores allowed
+    FastDiv div_vpr;      // division by vecs_per_row
 };
 
-template <int UPX, int UPY, int DOWNX, int DOWNY, int FW_T, int FH_T>
+template <int UPX, int UPY, int DOWNX, int DOWNY, int FW_T, int FH_T, bool EPI>
 __global__ void __launch_bounds__(kFirThreads) fir_nchw_tiled(FirArgs p, FirTile t)
 {
     extern __shared__ __align__(16) float smem[];
@@ -155,32 +162,53 @@ __global__ void __launch_bounds__(kFirThreads) fir_nchw_tiled(FirArgs p, FirTile
     // ---- stage the input tile: aligned 128-bit loads, each row keeps its global 16-byte phase ----
     const float* xg = (const float*)p.x;
     const long long plane_off = plane * (long long)p.in_h * p.in_w;
-    for (int i = tid; i < t.tile_in_h * t.vecs_per_row; i += kFirThreads)
+    constexpr int LDU = 4;     // independent 128-bit loads in flight per thread
+    const int nvec_tile = t.tile_in_h * t.vecs_per_row;
+    for (int base = 0; base < nvec_tile; base += kFirThreads * LDU)
     {
-        const int r = i / t.vecs_per_row, v = i - r * t.vecs_per_row;
-        const int inY = tileInY + r;
-        const long long rowbase = plane_off + (long long)inY * p.in_w + tileInX;
-        const int phase = (int)(rowbase & 3);
-        const long long e0 = rowbase - phase + 4 * v;
-        const int x0 = tileInX - phase + 4 * v;
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (inY >= 0 && inY < p.in_h && x0 + 3 >= 0 && x0 < p.in_w)
+        float4 val[LDU];
+        int xs[LDU], so[LDU];
+#pragma unroll
+        for (int u = 0; u < LDU; u++)
         {
-            if (e0 >= 0 && e0 + 3 < t.in_total)
-                val = __ldg(reinterpret_cast<const float4*>(xg + e0));
-            else
+            const int i = base + u * kFirThreads + tid;
+            val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            so[u] = -1;
+            if (i < nvec_tile)
             {
-                if (e0 + 0 >= 0 && e0 + 0 < t.in_total) val.x = __ldg(xg + e0 + 0);
-                if (e0 + 1 >= 0 && e0 + 1 < t.in_total) val.y = __ldg(xg + e0 + 1);
-                if (e0 + 2 >= 0 && e0 + 2 < t.in_total) val.z = __ldg(xg + e0 + 2);
-                if (e0 + 3 >= 0 && e0 + 3 < t.in_total) val.w = __ldg(xg + e0 + 3);
+                const int r = (int)t.div_vpr.div((uint32_t)i), v = i - r * t.vecs_per_row;
+                const int inY = tileInY + r;
+                const long long rowbase = plane_off + (long long)inY * p.in_w + tileInX;
+                const int phase = (int)(rowbase & 3);
+                const long long e0 = rowbase - phase + 4 * v;
+                const int x0 = tileInX - phase + 4 * v;
+                xs[u] = x0;
+                so[u] = r * pitch + 4 * v;
+                if (inY >= 0 && inY < p.in_h && x0 + 3 >= 0 && x0 < p.in_w)
+                {
+                    if (e0 >= 0 && e0 + 3 < t.in_total)
+                        val[u] = __ldg(reinterpret_cast<const float4*>(xg + e0));
+                    else
+                    {
+                        if (e0 + 0 >= 0 && e0 + 0 < t.in_total) val[u].x = __ldg(xg + e0 + 0);
+                        if (e0 + 1 >= 0 && e0 + 1 < t.in_total) val[u].y = __ldg(xg + e0 + 1);
+                        if (e0 + 2 >= 0 && e0 + 2 < t.in_total) val[u].z = __ldg(xg + e0 + 2);
+                        if (e0 + 3 >= 0 && e0 + 3 < t.in_total) val[u].w = __ldg(xg + e0 + 3);
+                    }
+                }
             }
-            if (x0 + 0 < 0 || x0 + 0 >= p.in_w) val.x = 0.f;
-            if (x0 + 1 < 0 || x0 + 1 >= p.in_w) val.y = 0.f;
-            if (x0 + 2 < 0 || x0 + 2 >= p.in_w) val.z = 0.f;
-            if (x0 + 3 < 0 || x0 + 3 >= p.in_w) val.w = 0.f;
         }
-        *reinterpret_cast<float4*>(sx + r * pitch + 4 * v) = val;
+#pragma unroll
+        for (int u = 0; u < LDU; u++)
+        {
+            if (so[u] < 0) continue;
+            const int x0 = xs[u];
+            if (x0 + 0 < 0 || x0 + 0 >= p.in_w) val[u].x = 0.f;
+            if (x0 + 1 < 0 || x0 + 1 >= p.in_w) val[u].y = 0.f;
+            if (x0 + 2 < 0 || x0 + 2 >= p.in_w) val[u].z = 0.f;
+            if (x0 + 3 < 0 || x0 + 3 >= p.in_w) val[u].w = 0.f;
+            *reinterpret_cast<float4*>(sx + so[u]) = val[u];
+        }
     }
     __syncthreads();
 
@@ -278,10 +306,10 @@ __global__ void __launch_bounds__(kFirThreads) fir_nchw_tiled(FirArgs p, FirTile
         if (relOutY0 + r >= t.tile_out_h || outY >= p.out_h) continue;
         float o[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) o[k] = fir_epilogue<float>(acc[r][k] * p.gain, p, n, c);
+        for (int k = 0; k < 4; k++) o[k] = fir_epilogue<float, EPI>(acc[r][k] * p.gain, p, n, c);
         float* dst = yg + (plane * p.out_h + outY) * (long long)p.out_w + outX0;
         if (t.out_vec_ok && outX0 + 3 < p.out_w && relOutX0 + 3 < t.tile_out_w)
-            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
         else
         {
 #pragma unroll
@@ -303,25 +331,25 @@ __device__ __forceinline__ void vfma(float& a, const float& x, float f) { a = fm
 __device__ __forceinline__ void vzero(float4& a) { a = make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void vzero(float& a) { a = 0.f; }
 
-template <int VEC>
+template <int VEC, bool EPI>
 __device__ __forceinline__ void nhwc_store(const FirArgs& p, typename vec_t<VEC>::type v, int n, int c0, int outY, int outX)
 {
     float* dst = (float*)p.y + n * p.osn + outY * p.osy + outX * p.osx + c0;
     if constexpr (VEC == 4)
     {
         float4 o;
-        o.x = fir_epilogue<float>(v.x * p.gain, p, n, c0 + 0);
-        o.y = fir_epilogue<float>(v.y * p.gain, p, n, c0 + 1);
-        o.z = fir_epilogue<float>(v.z * p.gain, p, n, c0 + 2);
-        o.w = fir_epilogue<float>(v.w * p.gain, p, n, c0 + 3);
-        *reinterpret_cast<float4*>(dst) = o;
+        o.x = fir_epilogue<float, EPI>(v.x * p.gain, p, n, c0 + 0);
+        o.y = fir_epilogue<float, EPI>(v.y * p.gain, p, n, c0 + 1);
+        o.z = fir_epilogue<float, EPI>(v.z * p.gain, p, n, c0 + 2);
+        o.w = fir_epilogue<float, EPI>(v.w * p.gain, p, n, c0 + 3);
+        __stcs(reinterpret_cast<float4*>(dst), o);
     }
     else
-        *dst = fir_epilogue<float>(v * p.gain, p, n, c0);
+        *dst = fir_epilogue<float, EPI>(v * p.gain, p, n, c0);
 }
 
 // FAST: up = 1 in both dims, compile-time FWxFH filter, ROWS = 2 output rows per thread.
-template <int VEC, int DOWN, int FW_T, int FH_T>
+template <int VEC, int DOWN, int FW_T, int FH_T, bool EPI>
 __global__ void __launch_bounds__(256) fir_nhwc_fast(FirArgs p, long long total)
 {
     typedef typename vec_t<VEC>::type V;
@@ -376,8 +404,8 @@ __global__ void __launch_bounds__(256) fir_nhwc_fast(FirArgs p, long long total)
                 for (int x = 0; x < FW_T; x++) vfma(acc1, win[x], sf[(wr - DOWN) * FW_T + x]);
             }
         }
-        nhwc_store<VEC>(p, acc0, n, c0, outY0, outX);
-        if (outY0 + 1 < p.out_h) nhwc_store<VEC>(p, acc1, n, c0, outY0 + 1, outX);
+        nhwc_store<VEC, EPI>(p, acc0, n, c0, outY0, outX);
+        if (outY0 + 1 < p.out_h) nhwc_store<VEC, EPI>(p, acc1, n, c0, outY0 + 1, outX);
     }
 }
 
@@ -417,7 +445,7 @@ __global__ void __launch_bounds__(256) fir_nhwc_any(FirArgs p, long long total)
             xp += p.isy;
             fp += stepY;
         }
-        nhwc_store<VEC>(p, acc, n, c0, outY, outX);
+        nhwc_store<VEC, true>(p, acc, n, c0, outY, outX);
     }
 }
 
@@ -441,7 +469,8 @@ static int launch_tiled(const FirArgs& a, cudaStream_t stream)
     FirTile t;
     int need_lanes = ceil_div(a.out_w, 4);
     int lg = 0;
-    while ((1 << lg) < need_lanes && lg < 5) lg++;
+    const int lg_max = (DOWNX > 1) ? 4 : 5;      // keep the staged tile of decimating variants under 48 KB
+    while ((1 << lg) < need_lanes && lg < lg_max) lg++;
     t.lanes_x_log2 = lg;
     const int lanes_x = 1 << lg;
     t.tile_out_w = 4 * lanes_x;
@@ -454,6 +483,7 @@ static int launch_tiled(const FirArgs& a, cudaStream_t stream)
     t.tile_in_w = ((t.tile_out_w - 1) * DOWNX + fwp - 1) / UPX + 1;
     t.tile_in_h = ((t.tile_out_h - 1) * DOWNY + fhp - 1) / UPY + 1;
     t.vecs_per_row = (t.tile_in_w + 3 + 3) / 4;
+    t.div_vpr = FastDiv((uint32_t)t.vecs_per_row);
     t.tiles_x = ceil_div(a.out_w, t.tile_out_w);
     t.tiles_y = ceil_div(a.out_h, t.tile_out_h);
     t.in_total = (long long)a.in_n * a.in_c * a.in_h * a.in_w;
@@ -462,7 +492,7 @@ static int launch_tiled(const FirArgs& a, cudaStream_t stream)
     if (smem > 96 * 1024) return -1;
     long long blocks = (long long)a.in_n * a.in_c * t.tiles_x * t.tiles_y;
     if (blocks > 0x7fffffffLL) return -1;
-    auto kern = fir_nchw_tiled<UPX, UPY, DOWNX, DOWNY, FW_T, FH_T>;
+    auto kern = (a.eact != 0) ? fir_nchw_tiled<UPX, UPY, DOWNX, DOWNY, FW_T, FH_T, true> : fir_nchw_tiled<UPX, UPY, DOWNX, DOWNY, FW_T, FH_T, false>;
     if (smem > 48 * 1024)
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     kern<<<(unsigned)blocks, kFirThreads, smem, stream>>>(a, t);
@@ -547,10 +577,14 @@ extern "C" int sgv_upfirdn2d(const sgv_upfirdn2d_params* p, void* stream_)
             {
                 const long long work = (long long)a.in_n * ((oh + 1) / 2) * ow * cvecs;
                 const unsigned grid = (unsigned)min((long long)sms * 32, (work + 255) / 256);
-                if (v4 && a.downx == 1) fir_nhwc_fast<4, 1, 4, 4><<<grid, 256, 0, stream>>>(a, work);
-                else if (v4) fir_nhwc_fast<4, 2, 4, 4><<<grid, 256, 0, stream>>>(a, work);
-                else if (a.downx == 1) fir_nhwc_fast<1, 1, 4, 4><<<grid, 256, 0, stream>>>(a, work);
-                else fir_nhwc_fast<1, 2, 4, 4><<<grid, 256, 0, stream>>>(a, work);
+                const bool epi = a.eact != 0;
+#define SGV_NHWC_FAST(V, D) do { if (epi) fir_nhwc_fast<V, D, 4, 4, true><<<grid, 256, 0, stream>>>(a, work); \
+                                 else fir_nhwc_fast<V, D, 4, 4, false><<<grid, 256, 0, stream>>>(a, work); } while (0)
+                if (v4 && a.downx == 1) SGV_NHWC_FAST(4, 1);
+                else if (v4) SGV_NHWC_FAST(4, 2);
+                else if (a.downx == 1) SGV_NHWC_FAST(1, 1);
+                else SGV_NHWC_FAST(1, 2);
+#undef SGV_NHWC_FAST
                 SGV_LAUNCH_OK("fir_nhwc_fast");
                 return SGV_OK;
             }

@@ -1,0 +1,108 @@
+"""tcgen05 implicit-GEMM convolution (through the C ABI) vs fp32/fp64 convolution of the same operands.
+
+Tolerance: the kernel multiplies TF32-rounded operands (10-bit mantissa, round-to-nearest) and accumulates in
+fp32, so against a true-fp32 contraction we require normwise relative error <= 1e-3 (BASELINE north_star);
+against a reference fed the SAME TF32-rounded operands the only difference is accumulation order: <= 2e-5."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+from stylegan_v_b200 import conv as C
+
+pytestmark = pytest.mark.gpu
+
+
+def tf32_round(t):
+    """round-to-nearest (ties away) to 10 explicit mantissa bits, like cvt.rna.tf32.f32"""
+    i = t.contiguous().view(torch.int32)
+    i = (i + 0x1000) & ~0x1FFF
+    return i.view(torch.float32)
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize('N,Cin,Cout,H,W', [(2, 32, 64, 16, 16), (1, 64, 128, 8, 8), (3, 64, 64, 20, 12), (2, 128, 256, 16, 16),
+                                            (8, 32, 64, 4, 4), (1, 32, 512, 8, 8), (2, 96, 64, 33, 17)])
+def test_conv3x3_plain(N, Cin, Cout, H, W):
+    g = torch.Generator().manual_seed(N * 1000 + Cin)
+    x = torch.randn(N, Cin, H, W, generator=g).cuda()
+    w = torch.randn(Cout, Cin, 3, 3, generator=g).cuda()
+    taps, offs = C.conv3x3_taps()
+    wp = C.prep_weights(w, taps)
+    assert torch.equal(wp, tf32_round(w).permute(2, 3, 0, 1).reshape(9, Cout, Cin))
+    y = C.igemm_conv(_cl(x), wp, offs)
+    assert y.shape == (N, Cout, H, W)
+    ref_same = F.conv2d(tf32_round(x).double(), tf32_round(w).double(), padding=1)
+    ref_fp32 = F.conv2d(x.double(), w.double(), padding=1)
+    assert rel_err(y, ref_same) < 2e-5
+    assert rel_err(y, ref_fp32) < 1e-3
+
+
+def test_conv1x1_and_modulated_epilogue():
+    g = torch.Generator().manual_seed(7)
+    N, Cin, Cout, H = 4, 64, 64, 16
+    x = torch.randn(N, Cin, H, H, generator=g).cuda()
+    w = torch.randn(Cout, Cin, 3, 3, generator=g).cuda()
+    s = (torch.randn(N, Cin, generator=g) + 1).cuda()
+    d = (torch.rand(N, Cout, generator=g) + 0.5).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    taps, offs = C.conv3x3_taps()
+    wp = C.prep_weights(w, taps)
+    y = C.igemm_conv(_cl(x), wp, offs, a_scale=s, o_scale=d, bias=b, act='lrelu', gain=float(np.sqrt(2)), clamp=None)
+    xs = (x * s[:, :, None, None])
+    ref = F.conv2d(xs.double(), w.double(), padding=1) * d.double()[:, :, None, None] + b.double()[None, :, None, None]
+    ref = F.leaky_relu(ref, 0.2) * np.sqrt(2)
+    assert rel_err(y, ref) < 1e-3
+    ref_same = F.conv2d(tf32_round(xs).double(), tf32_round(w).double(), padding=1) * d.double()[:, :, None, None] + b.double()[None, :, None, None]
+    ref_same = F.leaky_relu(ref_same, 0.2) * np.sqrt(2)
+    assert rel_err(y, ref_same) < 2e-5
+    # 1x1
+    w1 = torch.randn(Cout, Cin, 1, 1, generator=g).cuda()
+    y1 = C.igemm_conv(_cl(x), C.prep_weights(w1, [(0, 0)]), [(0, 0)], clamp=2.0)
+    ref1 = F.conv2d(tf32_round(x).double(), tf32_round(w1).double()).clamp(-2, 2)
+    assert rel_err(y1, ref1) < 2e-5
+
+
+def test_transposed_conv_as_four_phases():
+    """conv_transpose2d(stride 2, pad 0) written as 4 polyphase stride-1 launches into one [2h+1, 2w+1] tensor."""
+    g = torch.Generator().manual_seed(3)
+    N, Cin, Cout, h = 2, 64, 64, 12
+    x = torch.randn(N, Cin, h, h, generator=g).cuda()
+    w = torch.randn(Cout, Cin, 3, 3, generator=g).cuda()        # layer weight [O, I, 3, 3]; conv_transpose2d takes w.transpose(0,1)
+    u = torch.zeros(N, Cout, 2 * h + 1, 2 * h + 1, device='cuda').contiguous(memory_format=torch.channels_last)
+    for a in (0, 1):
+        for b in (0, 1):
+            kys = [a + 2 * m for m in range(2) if a + 2 * m <= 2]
+            kxs = [b + 2 * m for m in range(2) if b + 2 * m <= 2]
+            taps = [(ky, kx) for ky in kys for kx in kxs]
+            offs = [(-(ky - a) // 2, -(kx - b) // 2) for ky, kx in taps]
+            view = u[:, :, a::2, b::2]
+            C.igemm_conv(_cl(x), C.prep_weights(w, taps), offs, out_view=view)
+    ref = F.conv_transpose2d(tf32_round(x).double(), tf32_round(w).double().transpose(0, 1), stride=2)
+    assert rel_err(u, ref) < 2e-5
+
+
+def test_stride2_input():
+    """data gradient of the transposed conv = stride-2 correlation (TMA element strides)."""
+    g = torch.Generator().manual_seed(5)
+    N, Cin, Cout, h = 2, 64, 64, 10
+    du = torch.randn(N, Cin, 2 * h + 1, 2 * h + 1, generator=g).cuda()
+    w = torch.randn(Cout, Cin, 3, 3, generator=g).cuda()
+    taps = C.TAPS_3x3
+    y = C.igemm_conv(_cl(du), C.prep_weights(w, taps), taps, out_hw=(h, h), in_stride=2)
+    ref = F.conv2d(tf32_round(du).double(), tf32_round(w).double(), stride=2)
+    assert ref.shape == y.shape
+    assert rel_err(y, ref) < 2e-5
+
+
+def test_argument_errors():
+    x = torch.randn(1, 24, 8, 8).cuda().contiguous(memory_format=torch.channels_last)
+    with pytest.raises(RuntimeError):
+        C.igemm_conv(x, torch.zeros(1, 64, 24, device='cuda'), [(0, 0)])        # cin % 32 != 0
+    x = torch.randn(1, 32, 8, 8).cuda()
+    with pytest.raises(RuntimeError):
+        C.igemm_conv(x, torch.zeros(1, 64, 32, device='cuda'), [(0, 0)])        # not channels_last
