@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Benchmark of the StyleGAN-V synthesis hot path on B200 (contract: see DESIGN.md §Measurement).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+Workload (BASELINE.json metric "256x256 synthesis frames/sec (fwd+bwd)"): one step = forward + backward of the
+256x256 SynthesisNetwork (fmaps 0.5, fp32 storage, random-init weights) on 32 synthetic frames per GPU
+(32 latents x 1 frame, BASELINE configs[1] batch), gradients w.r.t. all parameters and ws; for N > 1 ranks each
+rank runs its own 32 frames (weak scaling) and gradients are averaged with one NCCL all-reduce per step.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES_PER_GPU = 32
+RES = 256
+
+
+def load_peaks():
+    try:
+        pk = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        return dict(hbm_gbs=float(pk['hbm_gbs']), bf16_tflops=float(pk['bf16_tflops']),
+                    bf16_tflops_sustained=float(pk.get('bf16_tflops_sustained', pk['bf16_tflops'])), source='measured')
+    except Exception:
+        return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source='fallback')
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100', '-i', str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_reference_step(frames, threads):
+    """One forward+backward of the reference's CPU path (oracle port: torch_utils.ops 'ref' formulations + F.conv2d,
+    training-mode non-fused modconv) on `frames` frames at 256x256.  Returns seconds."""
+    from oracle import synthesis_ref as sr
+    torch.set_num_threads(threads)
+    cfg = sr.SynthesisConfig(img_resolution=RES)
+    P = {k: v.requires_grad_(True) for k, v in sr.init_params(cfg, seed=0).items()}
+    g = torch.Generator().manual_seed(1)
+    ws = torch.randn(frames, cfg.num_ws, cfg.w_dim, generator=g).requires_grad_(True)
+    t = torch.zeros(frames, 1)
+    mz = torch.randn(frames, sr.max_traj_len(cfg, 0.0), cfg.motion_z_dim, generator=g)
+
+    def step():
+        t0 = time.perf_counter()
+        img = sr.synthesis_forward(P, cfg, ws, t, motion_z=mz, fused_modconv=False)
+        dimg = torch.ones_like(img)
+        torch.autograd.grad(img, [ws] + list(P.values()), dimg, allow_unused=True)
+        return time.perf_counter() - t0
+    return step
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port) on the host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = min(os.cpu_count() or 1, 32)
+    sample_frames = 1
+    step = cpu_reference_step(sample_frames, threads)
+    step()
+    times = [step() for _ in range(max(1, min(args.steps, 3)))]
+    sec = sorted(times)[len(times) // 2]
+    fps = sample_frames / sec
+    line = dict(metric='synthesis_fwd_bwd_frames_per_sec_256', value=fps, unit='frames/s', n_gpus=args.gpus, steps=len(times), warmup=1,
+                ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+                config=dict(workload='256x256 SynthesisNetwork fwd+bwd (oracle CPU port of the reference path, fused_modconv=False)',
+                            frames_per_step=sample_frames, note='bounded sample of the 32-frame workload; CPU frames/s is batch-size insensitive'),
+                cpu_baseline=dict(value=fps, unit='frames/s', cores=threads, kind='port', sample=f'{sample_frames} frames fwd+bwd, median of {len(times)}'),
+                e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device: the b200 implementation has no CPU path'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    from stylegan_v_b200 import _lib, conv as C, plugin
+    from stylegan_v_b200.synthesis import SynthesisNetwork
+    from stylegan_v_b200.ddp import FlatGradReducer
+    from stylegan_v_b200.ops import upfirdn2d as U
+    from oracle import synthesis_ref as sr     # FLOP model + cpu_baseline only
+
+    torch.manual_seed(rank)
+    net = SynthesisNetwork(img_resolution=RES).to(dev).train()
+    reducer = FlatGradReducer(net.parameters())
+    N = FRAMES_PER_GPU
+    L = net.motion_encoder.traj_len()
+    # host-side (pinned) inputs for the end-to-end measurement
+    h_ws = torch.randn(N, net.num_ws, net.w_dim).pin_memory()
+    h_t = torch.zeros(N, 1).pin_memory()
+    h_mz = torch.randn(N, L, net.motion_encoder.z_dim).pin_memory()
+    d_ws, d_t, d_mz = h_ws.to(dev), h_t.to(dev), h_mz.to(dev)
+    dimg = torch.randn(N, 3, RES, RES, device=dev)
+    h_out = torch.zeros(1).pin_memory()
+
+    def step(ws, t, mz):
+        reducer.zero()
+        ws = ws.requires_grad_(True)
+        img = net(ws, t, motion_z=mz)
+        loss = (img * dimg).sum()
+        loss.backward()
+        reducer.all_reduce()
+        return loss
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), _lib.launch_count() - l0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # (1) device-resident inputs
+    ms_total, launches = timed(lambda: step(d_ws.detach(), d_t, d_mz), args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # (2) end to end: H2D of the step's inputs from pinned memory, D2H of the loss, every step
+    def e2e_step():
+        ws = h_ws.to(dev, non_blocking=True); t = h_t.to(dev, non_blocking=True); mz = h_mz.to(dev, non_blocking=True)
+        loss = step(ws, t, mz)
+        h_out.copy_(loss.detach().reshape(1), non_blocking=True)
+    ms_e2e, _ = timed(e2e_step, args.steps, 1)
+
+    ms_step = ms_total / args.steps
+    frames = N * world
+    value = frames / (ms_step * 1e-3)
+    e2e_value = frames / (ms_e2e / args.steps * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    # ---- roofline of the dominant kernel (largest share of the step): the implicit-GEMM conv at its heaviest layer shape,
+    #      and the stand-alone upfirdn2d kernel the metric names ----
+    def kernel_ms(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); evs.append((a, b))
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in evs)
+        return sum(ts) / len(ts)
+    taps, offs = C.conv3x3_taps()
+    conv_shapes = [('b32.conv1', 512, 512, 32), ('b64.conv1', 256, 256, 64), ('b128.conv1', 128, 128, 128), ('b256.conv1', 64, 64, 256)]
+    per_layer = []
+    for name, ci, co, r in conv_shapes:
+        x = torch.randn(N, ci, r, r, device=dev).contiguous(memory_format=torch.channels_last)
+        wp = C.prep_weights(torch.randn(co, ci, 3, 3, device=dev), taps)
+        s = torch.rand(N, ci, device=dev) + 0.5; d = torch.rand(N, co, device=dev) + 0.5; b = torch.zeros(co, device=dev)
+        ms = kernel_ms(lambda: C.igemm_conv(x, wp, offs, a_scale=s, o_scale=d, bias=b, act='lrelu', gain=1.4142135))
+        fl = 2.0 * N * r * r * ci * co * 9
+        per_layer.append(dict(layer=name, ms=ms, tflops=fl / ms / 1e9, flops=fl))
+        del x, wp
+    dom = max(per_layer, key=lambda z: z['ms'])
+    roofline = dict(bound='tensor', kernel=f"conv_tf32_kernel @ {dom['layer']} (N={N})", achieved=dom['tflops'], peak=peaks['bf16_tflops'],
+                    unit='TFLOP/s', frac=dom['tflops'] / peaks['bf16_tflops'], traffic=None, peak_source=peaks['source'] + ' (dense bf16 cuBLAS; the kernel runs kind::tf32 = half that rate)',
+                    algorithmic_flops_per_launch=dom['flops'], per_layer=per_layer)
+    f = U.setup_filter([1, 3, 3, 1], device=dev)
+    xf = torch.randn(N, 64, 257, 257, device=dev)
+    fir_ms = kernel_ms(lambda: plugin.upfirdn2d(xf, f, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0))
+    fir_bytes = (xf.numel() + N * 64 * 256 * 256) * 4
+    upfirdn = dict(bound='hbm', kernel='fir_nchw_tiled [32,64,257,257]->[32,64,256,256]', achieved=fir_bytes / fir_ms / 1e6, peak=peaks['hbm_gbs'], unit='GB/s',
+                   frac=fir_bytes / fir_ms / 1e6 / peaks['hbm_gbs'], traffic=None, algorithmic_bytes_per_launch=fir_bytes, peak_source=peaks['source'])
+    del xf
+
+    cfg = sr.SynthesisConfig(img_resolution=RES)
+    conv_gflop_fwd = sr.conv_flops_per_frame(cfg) / 1e9
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        threads = min(os.cpu_count() or 1, 32)
+        cstep = cpu_reference_step(1, threads)
+        cstep()
+        ts = sorted(cstep() for _ in range(2))
+        cpu_baseline = dict(value=1 / ts[0], unit='frames/s', cores=threads, kind='port',
+                            sample='1 frame fwd+bwd at 256x256 (oracle port of the reference CPU path, fused_modconv=False), best of 2 after 1 warm-up; '
+                                   f'{threads} torch threads of {os.cpu_count()} host cores')
+
+    line = dict(metric='synthesis_fwd_bwd_frames_per_sec_256', value=value, unit='frames/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='tf32 (fp32 storage, TF32 tensor-core products, fp32 accumulate)',
+                data='synthetic',
+                config=dict(workload='256x256 SynthesisNetwork forward+backward, 32 frames/GPU (32 latents x 1 frame), fmaps 0.5, random-init weights',
+                            frames_per_gpu=N, parallelism=f'dp{world}', l2='activation working set per step (>= 134 MB per layer at res >= 64, ~6 GB total) exceeds the 126 MB L2; no explicit flush',
+                            conv_gflop_per_frame_fwd=conv_gflop_fwd),
+                e2e=dict(value=e2e_value, unit='frames/s', h2d_bytes_per_step=(h_ws.numel() + h_t.numel() + h_mz.numel()) * 4, d2h_bytes_per_step=4),
+                gpu_launches=launches, clocks=clocks, roofline=roofline, upfirdn2d=upfirdn, cpu_baseline=cpu_baseline,
+                model_tflops_fwd_bwd=3 * conv_gflop_fwd * frames / ms_step / 1e3 / world)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

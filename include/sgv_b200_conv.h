@@ -56,6 +56,32 @@ typedef struct sgv_conv_params {
 
 int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream);
 
+/* Weight gradient of the same contraction (replaces aten::cudnn_convolution_backward_weight /
+ * cudnn_convolution_transpose_backward_weight, conv2d_gradfix.py:140-148), with both per-sample scalings fused:
+ *
+ *   dw[t][o][i] += sum_{n, p}  g[n, p*g_stride + g_dy[t], ..., o] * g_scale[n, o]  *  x[n, p*x_stride + x_dy[t], ..., i] * x_scale[n, i]
+ *
+ * p runs over an out_h x out_w lattice per sample.  stride-1 3x3 correlation (padding 1): g unshifted, x shifted by
+ * (ky-1, kx-1).  stride-2 transposed 3x3: g = gradient of the (2h+1)x(2w+1) map sampled with g_stride = 2 at offset
+ * (ky, kx), x unshifted.  Out-of-range pixels read as zero.  `dw` is a float32 [ntaps, cout, cin] accumulation buffer the
+ * caller zeroes (split-K partial sums are added with atomics).  Requirements: cin % 32 == 0, cout % 32 == 0.
+ */
+typedef struct sgv_wgrad_params {
+    const float* g;            /* [n, gh, gw, cout] NHWC gradient w.r.t. the contraction output */
+    const float* x;            /* [n, xh, xw, cin]  NHWC contraction input */
+    float*       dw;           /* [ntaps, cout, cin] */
+    int32_t n, gh, gw, xh, xw, cin, cout;
+    int32_t out_h, out_w;      /* lattice summed over, per sample */
+    int32_t g_stride, x_stride;
+    int32_t ntaps;
+    int32_t g_dy[SGV_CONV_MAX_TAPS], g_dx[SGV_CONV_MAX_TAPS];
+    int32_t x_dy[SGV_CONV_MAX_TAPS], x_dx[SGV_CONV_MAX_TAPS];
+    const float* g_scale;      /* [n, cout] or NULL */
+    const float* x_scale;      /* [n, cin]  or NULL */
+} sgv_wgrad_params;
+
+int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

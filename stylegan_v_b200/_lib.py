@@ -61,7 +61,19 @@ class ConvParams(ctypes.Structure):
     ]
 
 
-STRUCTS = {'sgv_upfirdn2d_params': UpfirdnParams, 'sgv_bias_act_params': BiasActParams, 'sgv_conv_params': ConvParams}
+class WgradParams(ctypes.Structure):
+    """struct sgv_wgrad_params (include/sgv_b200_conv.h)"""
+    _fields_ = [
+        ('g', c_vp), ('x', c_vp), ('dw', c_vp),
+        ('n', c_int), ('gh', c_int), ('gw', c_int), ('xh', c_int), ('xw', c_int), ('cin', c_int), ('cout', c_int),
+        ('out_h', c_int), ('out_w', c_int), ('g_stride', c_int), ('x_stride', c_int), ('ntaps', c_int),
+        ('g_dy', c_int * CONV_MAX_TAPS), ('g_dx', c_int * CONV_MAX_TAPS), ('x_dy', c_int * CONV_MAX_TAPS), ('x_dx', c_int * CONV_MAX_TAPS),
+        ('g_scale', c_vp), ('x_scale', c_vp),
+    ]
+
+
+STRUCTS = {'sgv_upfirdn2d_params': UpfirdnParams, 'sgv_bias_act_params': BiasActParams, 'sgv_conv_params': ConvParams,
+           'sgv_wgrad_params': WgradParams}
 
 # every symbol include/sgv_b200*.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -75,6 +87,7 @@ SYMBOLS = [
     ('sgv_conv_prep_weights', c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int,
                                       ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_vp, c_vp]),
     ('sgv_conv2d_tf32', c_int, [ctypes.POINTER(ConvParams), c_vp]),
+    ('sgv_conv2d_wgrad_tf32', c_int, [ctypes.POINTER(WgradParams), c_vp]),
 ]
 
 _lib = None

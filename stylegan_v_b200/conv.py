@@ -87,3 +87,37 @@ TAPS_3x3 = [(ky, kx) for ky in range(3) for kx in range(3)]
 def conv3x3_taps():
     """Correlation with padding 1: tap (ky,kx) reads input offset (ky-1, kx-1)."""
     return TAPS_3x3, [(ky - 1, kx - 1) for ky, kx in TAPS_3x3]
+
+
+def igemm_wgrad(g, x, taps_g, taps_x, out_hw, g_stride=1, x_stride=1, g_scale=None, x_scale=None):
+    """dw[t,o,i] = sum_{n,p} g[n, p*gs + dg_t, o] * g_scale[n,o] * x[n, p*xs + dx_t, i] * x_scale[n,i]  ->  [ntaps, Cout, Cin].
+
+    g: [N, Cout, gh, gw], x: [N, Cin, xh, xw], both channels_last fp32; taps_*: per-tap (dy, dx) pixel offsets."""
+    for name, t in (('g', g), ('x', x)):
+        _req(t.is_cuda and t.dtype == torch.float32 and t.ndim == 4, f'{name} must be a CUDA float32 [N,C,H,W] tensor')
+        _req(t.stride(1) == 1 and t.stride(3) == t.shape[1] and t.stride(2) == t.shape[3] * t.shape[1] and t.stride(0) == t.shape[1] * t.shape[2] * t.shape[3],
+             f'{name} must be dense channels_last (NHWC)')
+    N, Cout, gh, gw = g.shape
+    N2, Cin, xh, xw = x.shape
+    _req(N == N2 and len(taps_g) == len(taps_x), 'g / x / taps mismatch')
+    nt = len(taps_g)
+    dw = torch.zeros([nt, Cout, Cin], dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    p = _lib.WgradParams()
+    p.g, p.x, p.dw = g.data_ptr(), x.data_ptr(), dw.data_ptr()
+    p.n, p.gh, p.gw, p.xh, p.xw, p.cin, p.cout = N, gh, gw, xh, xw, Cin, Cout
+    p.out_h, p.out_w = out_hw
+    p.g_stride, p.x_stride, p.ntaps = g_stride, x_stride, nt
+    for i in range(nt):
+        p.g_dy[i], p.g_dx[i] = int(taps_g[i][0]), int(taps_g[i][1])
+        p.x_dy[i], p.x_dx[i] = int(taps_x[i][0]), int(taps_x[i][1])
+    keep = []
+    for name, t, shape in (('g_scale', g_scale, (N, Cout)), ('x_scale', x_scale, (N, Cin))):
+        if t is not None:
+            t = t.to(torch.float32).contiguous()
+            _req(tuple(t.shape) == shape, f'{name} must be {shape}')
+            keep.append(t)
+            setattr(p, name, t.data_ptr())
+    with torch.cuda.device(x.device):
+        _lib.check(L.sgv_conv2d_wgrad_tf32(ctypes.byref(p), _stream(x.device)), 'sgv_conv2d_wgrad_tf32')
+    return dw

@@ -20,6 +20,7 @@
 // (conv2d_gradfix.py:35-43) plus the x*styles, *dcoefs and bias_act passes around it (networks.py:64-74,141-143).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 #include "../../include/sgv_b200_conv.h"
 
 namespace sgv {
@@ -265,14 +266,14 @@ static EncodeTiledFn encode_tiled_fn()
 }
 
 int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, const uint32_t* elem_strides)
+                  const uint32_t* box, const uint32_t* elem_strides, bool atom32)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(SGV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base),
                     reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
                     reinterpret_cast<const cuuint32_t*>(box), reinterpret_cast<const cuuint32_t*>(elem_strides),
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SGV_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return SGV_OK;

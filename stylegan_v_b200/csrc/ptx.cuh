@@ -67,6 +67,12 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
                  :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4)
+{
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
 // ---- tcgen05 / TMEM ----
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols)   // whole warp
 {
@@ -133,6 +139,20 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
+    return d;
+}
+// Shared-memory operand, MN-major, 32-bit elements: SWIZZLE_128B_BASE32B (layout type 1) — 128-byte rows hold 32 consecutive
+// M/N elements of one k, the swizzle atom is 4 k-rows (512 B) with 32-byte chunks XOR-ed by (row % 4); this is the only
+// MN-major layout tcgen05 accepts for TF32 (probe: profiles/umma_probe_r1.txt; CUTLASS sm100_common.inl:92).
+// LBO = bytes between 32-element blocks along M/N, SBO = bytes between 4-row groups along K.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
     return d;
 }
 // Instruction descriptor for kind::tf32, fp32 accumulate, M x N tile; a_mn / b_mn = 1 for MN-major operands.

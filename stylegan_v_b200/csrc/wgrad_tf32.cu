@@ -1,0 +1,288 @@
+// Weight gradient of the modulated convolution on tcgen05 tensor cores (sm_100a), split-K over pixels.
+//
+//   dw[t][o][i] += sum_{n,p} (g[n, p*gs + dg_t, o] * g_scale[n,o]) * (x[n, p*xs + dx_t, i] * x_scale[n,i])     (include/sgv_b200_conv.h)
+//
+// GEMM view per tap t: D[o][i] (M = 128 output channels, N = BN input channels) accumulated over K = pixels.  With NHWC
+// tensors both operands are "MN-major" (channels contiguous, pixels strided): a TMA box {32 channels x 32 pixels} lands as
+// 32 rows of 128 bytes = eight 4-pixel x 32-channel swizzle atoms (TMA SWIZZLE_128B_ATOM_32B), the canonical MN-major
+// SWIZZLE_128B_BASE32B layout of the UMMA descriptor (the only MN-major layout for 32-bit operands).  A 5-D tensor map {32, W, H, N, C/32} delivers all channel blocks of a stage with ONE bulk load
+// ([c_blk][pixel][32 ch] in shared memory); taps are shifted / strided boxes with TMA zero fill at the borders.
+//
+// Same warp roles as conv_tf32.cu: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-5 scale the staged rows
+// by g_scale / x_scale and round to TF32 in place, then run the epilogue (TMEM -> red.global.add.v4.f32 into dw).
+// Grid: (M tiles x N tiles, taps, K splits).  Replaces aten::cudnn_convolution_backward_weight (conv2d_gradfix.py:140-148).
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+#include "../../include/sgv_b200_conv.h"
+
+namespace sgv {
+
+using namespace ptx;
+
+constexpr int kWgThreads = 192;
+constexpr int kWgM = 128;
+constexpr int kWgKc = 32;                       // pixels per k-step
+constexpr int kWgATile = kWgM * kWgKc * 4;      // 16 KB: [4 channel blocks][32 pixels][32 ch]
+
+struct WgArgs
+{
+    float* dw; const float* g_scale; const float* x_scale;
+    int n, cin, cout, out_h, out_w;
+    int g_stride, x_stride, ntaps;
+    int g_dy[SGV_CONV_MAX_TAPS], g_dx[SGV_CONV_MAX_TAPS], x_dy[SGV_CONV_MAX_TAPS], x_dx[SGV_CONV_MAX_TAPS];
+    int tw, th, tn;                   // pixel box: tw*th*tn == 32
+    int tiles_x, tiles_y, tiles_nb;
+    int mtiles, ktiles, ksplit;
+};
+
+template <int BN, int STAGES>
+struct WgSmem
+{
+    static constexpr int kBTile = BN * kWgKc * 4;
+    static constexpr int kStage = kWgATile + kBTile;
+    static constexpr int kBarOffset = STAGES * kStage;
+    static constexpr int kTotal = kBarOffset + (3 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+// scales one staged 128-byte row (32 channels of one pixel) by sc[0..31] and rounds to TF32, in place
+__device__ __forceinline__ void wg_transform_row(uint8_t* rowp, int row, const float* __restrict__ sc)
+{
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+    {
+        // SWIZZLE_128B_ATOM_32B: logical 32-byte chunk (j >> 1) lives at physical chunk (j >> 1) ^ (row & 3)
+        float4* ptr = reinterpret_cast<float4*>(rowp + (((((j >> 1) ^ (row & 3)) << 1) | (j & 1)) << 4));
+        float4 v = *ptr;
+        float4 s = sc ? __ldg(reinterpret_cast<const float4*>(sc) + j) : make_float4(1.f, 1.f, 1.f, 1.f);
+        v.x = tf32_rn(v.x * s.x); v.y = tf32_rn(v.y * s.y); v.z = tf32_rn(v.z * s.z); v.w = tf32_rn(v.w * s.w);
+        *ptr = v;
+    }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x, const WgArgs p)
+{
+    using L = WgSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* ready_bar = full_bar + STAGES;
+    uint64_t* empty_bar = ready_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = blockIdx.x % p.mtiles, nt = blockIdx.x / p.mtiles;
+    const int m0 = mt * kWgM;                 // first output channel (rows of dw)
+    const int c0 = nt * BN;                   // first input channel (cols of dw)
+    const int tap = blockIdx.y;
+    const int per = (p.ktiles + p.ksplit - 1) / p.ksplit;
+    const int kt0 = blockIdx.z * per;
+    const int kt1 = min(kt0 + per, p.ktiles);
+    const int ksteps = kt1 - kt0;             // may be <= 0 for trailing splits
+
+    if (threadIdx.x == 0)
+    {
+        prefetch_tmap(&tmap_g);
+        prefetch_tmap(&tmap_x);
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 1); mbar_init(ready_bar + s, 4); mbar_init(empty_bar + s, 1); }
+        mbar_init(accum_bar, 1);
+        fence_mbar_init();
+    }
+    constexpr int kTmemCols = BN < 32 ? 32 : BN;
+    if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (ksteps > 0)
+    {
+        if (warp == 0)
+        {
+            if (elect_one())
+            {
+                int stage = 0; uint32_t phase = 0;
+                for (int kt = kt0; kt < kt1; kt++)
+                {
+                    int r = kt;
+                    const int tx = r % p.tiles_x; r /= p.tiles_x;
+                    const int ty = r % p.tiles_y; r /= p.tiles_y;
+                    const int px0 = tx * p.tw, py0 = ty * p.th, nb0 = r * p.tn;
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    uint8_t* sa = smem + stage * L::kStage;
+                    mbar_expect_tx(full_bar + stage, L::kStage);
+                    tma_load_5d(sa, &tmap_g, full_bar + stage, 0, px0 * p.g_stride + p.g_dx[tap], py0 * p.g_stride + p.g_dy[tap], nb0, m0 / 32);
+                    tma_load_5d(sa + kWgATile, &tmap_x, full_bar + stage, 0, px0 * p.x_stride + p.x_dx[tap], py0 * p.x_stride + p.x_dy[tap], nb0, c0 / 32);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        else if (warp == 1)
+        {
+            constexpr uint32_t idesc = umma_idesc_tf32(kWgM, BN, 1, 1);     // both operands MN-major
+            int stage = 0; uint32_t phase = 0;
+            for (int ks = 0; ks < ksteps; ks++)
+            {
+                mbar_wait(ready_bar + stage, phase);
+                tc_fence_after();
+                if (elect_one())
+                {
+                    const uint32_t sa = smem_u32(smem + stage * L::kStage);
+#pragma unroll
+                    for (int k = 0; k < kWgKc / 8; k++)         // one 8-pixel swizzle atom (1024 B) per instruction
+                    {
+                        const uint64_t da = umma_desc_mn_sw128_32b(sa + k * 1024, kWgKc * 128, 512);
+                        const uint64_t db = umma_desc_mn_sw128_32b(sa + kWgATile + k * 1024, kWgKc * 128, 512);
+                        mma_tf32(tmem_base, da, db, idesc, (ks > 0 || k > 0) ? 1u : 0u);
+                    }
+                    mma_commit(empty_bar + stage);
+                    if (ks == ksteps - 1) mma_commit(accum_bar);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        else
+        {
+            const int tid = threadIdx.x - 64;                  // 0..127
+            const int box_hw = p.tw * p.th;
+            {
+                int stage = 0; uint32_t phase = 0;
+                for (int kt = kt0; kt < kt1; kt++)
+                {
+                    const int nb0 = (kt / (p.tiles_x * p.tiles_y)) * p.tn;
+                    mbar_wait(full_bar + stage, phase);
+                    uint8_t* sa = smem + stage * L::kStage;
+                    {   // gradient rows: row = blk*32 + pixel, 128 rows = one per thread
+                        const int blk = tid >> 5, pix = tid & 31;
+                        const int n = min(nb0 + pix / box_hw, p.n - 1);
+                        const int ch = m0 + blk * 32;
+                        const float* sc = (p.g_scale && ch < p.cout) ? p.g_scale + (long long)n * p.cout + ch : nullptr;
+                        if (ch < p.cout) wg_transform_row(sa + tid * 128, tid, sc);
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < (BN + 127) / 128; rr++)
+                    {
+                        const int row = rr * 128 + tid;
+                        if (row < BN)
+                        {
+                            const int blk = row >> 5, pix = row & 31;
+                            const int n = min(nb0 + pix / box_hw, p.n - 1);
+                            const int ch = c0 + blk * 32;
+                            const float* sc = (p.x_scale && ch < p.cin) ? p.x_scale + (long long)n * p.cin + ch : nullptr;
+                            if (ch < p.cin) wg_transform_row(sa + kWgATile + row * 128, row, sc);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(ready_bar + stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+            // ---- epilogue: accumulate the partial [128 x BN] block into dw[tap] ----
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+            const int q = warp & 3;
+            const int o = m0 + q * 32 + lane;
+            float* drow = p.dw + ((long long)tap * p.cout + o) * p.cin + c0;
+#pragma unroll 1
+            for (int cc = 0; cc < BN / 32; cc++)
+            {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
+                tmem_ld_wait();
+                if (o < p.cout && c0 + cc * 32 < p.cin)
+                {
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        atomicAdd(reinterpret_cast<float4*>(drow + cc * 32 + j * 4),
+                                  make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, const WgArgs& a, dim3 grid, cudaStream_t stream)
+{
+    using L = WgSmem<BN, STAGES>;
+    auto kern = wgrad_tf32_kernel<BN, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        SGV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        attr_set = true;
+    }
+    kern<<<grid, kWgThreads, L::kTotal, stream>>>(tg, tx, a);
+    SGV_LAUNCH_OK("wgrad_tf32_kernel");
+    return SGV_OK;
+}
+
+static int make_blocked_tmap(CUtensorMap* m, const float* base, int c, int w, int h, int n, int tw, int th, int tn, int stride, int blocks)
+{
+    const uint64_t dims[5] = {32, (uint64_t)w, (uint64_t)h, (uint64_t)n, (uint64_t)(c / 32)};
+    const uint64_t strides[4] = {(uint64_t)c * 4, (uint64_t)w * c * 4, (uint64_t)h * w * c * 4, 128};
+    const uint32_t box[5] = {32, (uint32_t)(tw * stride), (uint32_t)(th * stride), (uint32_t)tn, (uint32_t)blocks};
+    const uint32_t es[5] = {1, (uint32_t)stride, (uint32_t)stride, 1, 1};
+    return make_tmap_f32(m, base, 5, dims, strides, box, es, /*atom32=*/true);
+}
+
+} // namespace sgv
+
+extern "C" int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream_)
+{
+    using namespace sgv;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SGV_CHECK_ARG(p != nullptr, "sgv_conv2d_wgrad_tf32: params is NULL");
+    SGV_CHECK_ARG(p->g && p->x && p->dw, "sgv_conv2d_wgrad_tf32: g, x and dw must be non-NULL");
+    SGV_CHECK_ARG(p->cin >= 32 && p->cin % 32 == 0 && p->cout >= 32 && p->cout % 32 == 0, "cin and cout must be multiples of 32 (got %d, %d)", p->cin, p->cout);
+    SGV_CHECK_ARG(p->ntaps >= 1 && p->ntaps <= SGV_CONV_MAX_TAPS, "ntaps must be in [1, %d]", SGV_CONV_MAX_TAPS);
+    SGV_CHECK_ARG((p->g_stride == 1 || p->g_stride == 2) && (p->x_stride == 1 || p->x_stride == 2), "strides must be 1 or 2");
+    SGV_CHECK_ARG(p->n >= 1 && p->out_h >= 1 && p->out_w >= 1, "extents must be positive");
+    SGV_CHECK_ARG((reinterpret_cast<uintptr_t>(p->g) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(p->dw) & 15) == 0, "g, x and dw must be 16-byte aligned");
+    int rc = sgv_device_check();
+    if (rc != SGV_OK) return rc;
+
+    WgArgs a;
+    a.dw = p->dw; a.g_scale = p->g_scale; a.x_scale = p->x_scale;
+    a.n = p->n; a.cin = p->cin; a.cout = p->cout; a.out_h = p->out_h; a.out_w = p->out_w;
+    a.g_stride = p->g_stride; a.x_stride = p->x_stride; a.ntaps = p->ntaps;
+    for (int t = 0; t < SGV_CONV_MAX_TAPS; t++) { a.g_dy[t] = p->g_dy[t]; a.g_dx[t] = p->g_dx[t]; a.x_dy[t] = p->x_dy[t]; a.x_dx[t] = p->x_dx[t]; }
+    // 32-pixel box, spilling into the batch dimension for tiny planes
+    int tw = 1; while (tw * 2 <= p->out_w && tw < 8) tw *= 2;
+    int th = 32 / tw; { int ph = 1; while (ph < p->out_h) ph *= 2; if (th > ph) th = ph; }
+    int tn = 32 / (tw * th);
+    a.tw = tw; a.th = th; a.tn = tn;
+    a.tiles_x = ceil_div(p->out_w, tw); a.tiles_y = ceil_div(p->out_h, th); a.tiles_nb = ceil_div(p->n, tn);
+    a.ktiles = a.tiles_x * a.tiles_y * a.tiles_nb;
+    const int bn = (p->cin % 256 == 0) ? 256 : (p->cin % 128 == 0) ? 128 : (p->cin % 64 == 0) ? 64 : 32;
+    a.mtiles = ceil_div(p->cout, kWgM);
+    const int base_ctas = a.mtiles * (p->cin / bn) * p->ntaps;
+    int ksplit = ceil_div(2 * num_sms(), base_ctas);
+    if (ksplit > a.ktiles) ksplit = a.ktiles;
+    if (ksplit < 1) ksplit = 1;
+    a.ksplit = ksplit;
+
+    CUtensorMap tg, tx;
+    rc = make_blocked_tmap(&tg, p->g, p->cout, p->gw, p->gh, p->n, tw, th, tn, p->g_stride, kWgM / 32);
+    if (rc != SGV_OK) return rc;
+    rc = make_blocked_tmap(&tx, p->x, p->cin, p->xw, p->xh, p->n, tw, th, tn, p->x_stride, bn / 32);
+    if (rc != SGV_OK) return rc;
+    dim3 grid((unsigned)(a.mtiles * (p->cin / bn)), (unsigned)p->ntaps, (unsigned)ksplit);
+    switch (bn)
+    {
+        case 256: return launch_wgrad<256, 4>(tg, tx, a, grid, stream);
+        case 128: return launch_wgrad<128, 6>(tg, tx, a, grid, stream);
+        case 64:  return launch_wgrad<64, 8>(tg, tx, a, grid, stream);
+        default:  return launch_wgrad<32, 8>(tg, tx, a, grid, stream);
+    }
+}

@@ -1,0 +1,189 @@
+"""Fused modulated-convolution layer op for the native synthesis path (NHWC, fp32 storage, TF32 tensor-core math).
+
+One call covers what the reference runs as 4-6 kernels per layer in training mode
+(src/training/networks.py:64-74 + 141-143):
+
+    x * styles  ->  conv2d / conv_transpose2d(stride 2) [-> upfirdn2d 4x4]  ->  * dcoefs  ->  + bias -> lrelu -> * gain -> clamp
+
+  up = 1 : ONE tcgen05 implicit-GEMM launch (styles folded into the A-operand staging, dcoefs/bias/act in the epilogue)
+  up = 2 : four polyphase implicit-GEMM launches write the (2h+1)x(2w+1) transposed-conv result, then ONE FIR
+           launch whose epilogue applies dcoefs/bias/act (conv2d_resample.py:125-139 geometry: pad 1, gain 4).
+
+Backward (first order; second order is served by the unfused drop-in ops in stylegan_v_b200/ops):
+  activation gradient + bias gradient   bias_act CUDA kernel (grad=1) with the per-channel reduction fused
+  data gradient                         the same implicit-GEMM kernel with transposed weights; dcoefs are folded
+                                        into its A-operand staging (stride-2 variant for up = 2 via TMA element strides)
+  weight gradient                       implicit-GEMM weight-gradient kernel (stylegan_v_b200/csrc/wgrad_tf32.cu) when
+                                        available for the shape, else the cuDNN library call the reference uses
+                                        (conv2d_gradfix.py:140-148)
+  d styles, d dcoefs                    small reductions; dcoefs themselves are computed by differentiable torch ops
+                                        outside this Function (see demod_coefs), so their dependence on styles / weight
+                                        is handled by autograd on [N,C]-sized tensors.
+"""
+import numpy as np
+import torch
+
+from . import conv as _conv
+from . import plugin as _plugin
+
+_TAPS3 = _conv.TAPS_3x3
+_OFFS3_FWD = [(ky - 1, kx - 1) for ky, kx in _TAPS3]          # correlation, padding 1
+_OFFS3_DGRAD = [(1 - ky, 1 - kx) for ky, kx in _TAPS3]        # its adjoint
+_FIR_1331 = None
+
+
+def demod_coefs(weight, styles):
+    """dcoefs[n,o] = rsqrt(sum_{i,k} (W[o,i,k] * s[n,i])^2 + 1e-8)   (networks.py:57-59) without materialising [N,O,I,k,k]."""
+    wsq = weight.square().sum(dim=[2, 3])                  # [O, I]
+    return (styles.square() @ wsq.t() + 1e-8).rsqrt()      # [N, O]
+
+
+def _phase_taps(a, b):
+    """Taps of the stride-2 transposed 3x3 conv that land on output phase (a, b), with their input offsets."""
+    taps = [(ky, kx) for ky in range(a, 3, 2) for kx in range(b, 3, 2)]
+    offs = [(-((ky - a) // 2), -((kx - b) // 2)) for ky, kx in taps]
+    return taps, offs
+
+
+def _nhwc(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def _fir(device):
+    global _FIR_1331
+    if _FIR_1331 is None or _FIR_1331.device != device:
+        k = torch.tensor([1.0, 3.0, 3.0, 1.0], dtype=torch.float32)
+        k = torch.outer(k, k)
+        _FIR_1331 = (k / k.sum()).to(device)
+    return _FIR_1331
+
+
+def _wgrad_native(gout, x, styles, dscale, w_shape, up):
+    """Weight gradient on the tcgen05 split-K kernel (csrc/wgrad_tf32.cu) with styles / dcoefs folded into operand staging."""
+    O, I, kh, kw = w_shape
+    N, _, H, W = x.shape
+    if up == 1:
+        taps_x = _OFFS3_FWD if kh == 3 else [(0, 0)]
+        dw = _conv.igemm_wgrad(gout, x, [(0, 0)] * len(taps_x), taps_x, (H, W), g_scale=dscale, x_scale=styles)
+    else:
+        dw = _conv.igemm_wgrad(gout, x, _TAPS3, [(0, 0)] * 9, (H, W), g_stride=2, g_scale=dscale, x_scale=styles)
+    return dw.reshape(kh, kw, O, I).permute(2, 3, 0, 1)
+
+
+USE_NATIVE_WGRAD = True      # False -> cuDNN library call (kept for A/B measurements)
+
+
+def _wgrad_library(gout, xin, w_shape, transposed, stride):
+    """Weight gradient through the library call the reference uses (cuDNN), TF32 allowed to match the native kernels."""
+    w_like = torch.empty(w_shape, dtype=xin.dtype, device=xin.device)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=True):
+        _, gw, _ = torch.ops.aten.convolution_backward(gout, xin, w_like, None, [stride, stride], [0, 0] if transposed else [w_shape[2] // 2] * 2,
+                                                      [1, 1], transposed, [0, 0], 1, [False, True, False])
+    return gw
+
+
+class _FusedModConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, styles, dcoefs, bias, up, act, gain, flip_weight):
+        assert x.is_cuda and x.dtype == torch.float32, 'the fused layer op is CUDA / float32 only (no CPU path)'
+        x = _nhwc(x)
+        O, I, kh, kw = weight.shape
+        N, _, H, W = x.shape
+        assert kh == kw and kh in (1, 3)
+        wsrc = weight if flip_weight else weight.flip([2, 3])      # conv2d_resample.py:35-36
+        if up == 1:
+            taps = _TAPS3 if kh == 3 else [(0, 0)]
+            offs = _OFFS3_FWD if kh == 3 else [(0, 0)]
+            wp = _conv.prep_weights(wsrc, taps)
+            y = _conv.igemm_conv(x, wp, offs, a_scale=styles, o_scale=dcoefs, bias=bias, act=act, gain=gain)
+            u = None
+        else:
+            assert up == 2 and kh == 3
+            # conv2d_resample passes flip_weight = not flip_weight to the transposed conv (conv2d_resample.py:138);
+            # the synthesis layers call with flip_weight=False for up=2 (networks.py:136) => no flip is executed.
+            wsrc = weight if not flip_weight else weight.flip([2, 3])
+            u = torch.empty([N, O, 2 * H + 1, 2 * W + 1], dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+            for a in (0, 1):
+                for b in (0, 1):
+                    taps, offs = _phase_taps(a, b)
+                    _conv.igemm_conv(x, _conv.prep_weights(wsrc, taps), offs, a_scale=styles, out_view=u[:, :, a::2, b::2])
+            y = _plugin.upfirdn2d(u, _fir(x.device), 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0,
+                                  epilogue=dict(scale=dcoefs, bias=bias, act=act, alpha=0.2, gain=gain, clamp=None))
+        ctx.save_for_backward(x, weight, styles, dcoefs if dcoefs is not None else x.new_empty(0), bias if bias is not None else x.new_empty(0), y)
+        ctx.cfg = (up, act, gain, flip_weight, dcoefs is not None, bias is not None)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, weight, styles, dcoefs, bias, y = ctx.saved_tensors
+        up, act, gain, flip_weight, has_d, has_b = ctx.cfg
+        O, I, kh, kw = weight.shape
+        N, _, H, W = x.shape
+        dy = _nhwc(dy)
+        nil = x.new_empty(0)
+        # ---- activation (+ bias) gradient: dz = d(loss)/d(pre-activation) ----
+        db = torch.zeros([O], dtype=torch.float32, device=x.device) if has_b and ctx.needs_input_grad[4] else None
+        act_idx = {'linear': 1, 'lrelu': 3}[act]
+        if act != 'linear' or gain != 1:
+            dz = _plugin.bias_act(dy, nil, nil, y if act != 'linear' else nil, nil, 1, 1, act_idx, 0.2, gain, -1.0, db_accum=db)
+        else:
+            dz = dy
+            if db is not None:
+                db = dz.sum([0, 2, 3])
+        # ---- d dcoefs: needs the un-demodulated conv output, recovered from y (lrelu is invertible) ----
+        ddcoefs = None
+        if has_d and ctx.needs_input_grad[3]:
+            pre = y * (1.0 / gain)
+            if act == 'lrelu':
+                pre = torch.where(pre > 0, pre, pre * (1.0 / 0.2))
+            if has_b:
+                pre = pre - bias.reshape(1, -1, 1, 1)
+            ddcoefs = (dz * pre).sum(dim=[2, 3]) / dcoefs
+        dscale = dcoefs if has_d else None
+        wsrc_same = weight if flip_weight else weight.flip([2, 3])
+        # ---- data gradient (w.r.t. the modulated input x*s), then ds and dx ----
+        if up == 1:
+            gout = dz
+            if kh == 3:
+                wp = _conv.prep_weights(wsrc_same, _TAPS3, rows_dim=1, cols_dim=0)
+                dxs = _conv.igemm_conv(dz, wp, _OFFS3_DGRAD, a_scale=dscale)
+            else:
+                wp = _conv.prep_weights(wsrc_same, [(0, 0)], rows_dim=1, cols_dim=0)
+                dxs = _conv.igemm_conv(dz, wp, [(0, 0)], a_scale=dscale)
+        else:
+            wsrc_t = weight if not flip_weight else weight.flip([2, 3])
+            # adjoint of the FIR pass (upfirdn2d.py:246-261): padding (fw - p - 1) = 2, flipped filter, same gain
+            gout = _plugin.upfirdn2d(dz, _fir(x.device), 1, 1, 1, 1, 2, 2, 2, 2, True, 4.0)
+            wp = _conv.prep_weights(wsrc_t, _TAPS3, rows_dim=1, cols_dim=0)
+            dxs = _conv.igemm_conv(gout, wp, _TAPS3, out_hw=(H, W), in_stride=2, a_scale=dscale)
+        ds = (dxs * x).sum(dim=[2, 3]) if ctx.needs_input_grad[2] else None
+        dx = dxs * styles.reshape(N, I, 1, 1) if ctx.needs_input_grad[0] else None
+        # ---- weight gradient ----
+        dw = None
+        if ctx.needs_input_grad[1]:
+            if USE_NATIVE_WGRAD and I % 32 == 0 and O % 32 == 0:
+                dw = _wgrad_native(gout, x, styles, dscale, (O, I, kh, kw), up)
+            else:
+                xs = x * styles.reshape(N, I, 1, 1)
+                g = gout * dscale.reshape(N, O, 1, 1) if has_d else gout
+                if up == 1:
+                    dw = _wgrad_library(g, xs, (O, I, kh, kw), False, 1)
+                else:
+                    dw = _wgrad_library(g, xs, (I, O, kh, kw), True, 2).transpose(0, 1)
+            if up == 1 and not flip_weight:
+                dw = dw.flip([2, 3])
+            if up == 2 and flip_weight:
+                dw = dw.flip([2, 3])
+        return dx, dw, ds, ddcoefs, db, None, None, None, None
+
+
+def fused_modulated_conv(x, weight, styles, bias=None, up=1, demodulate=True, act='lrelu', gain=None, flip_weight=True):
+    """y = clamp-free bias_act(modulated_conv2d(x, weight, styles, up, demodulate), bias, act, gain) on NHWC fp32 tensors.
+
+    Equivalent (up to TF32 rounding of the contraction operands) to the reference's training-mode sequence
+    modulated_conv2d(..., fused_modconv=False) + bias_act (networks.py:30-86,141-143)."""
+    if gain is None:
+        gain = float(np.sqrt(2)) if act == 'lrelu' else 1.0
+    dcoefs = demod_coefs(weight, styles) if demodulate else None
+    return _FusedModConv.apply(x, weight, styles, dcoefs, bias, up, act, float(gain), flip_weight)

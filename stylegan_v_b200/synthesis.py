@@ -1,0 +1,187 @@
+"""Native (B200) synthesis network of StyleGAN-V: same parameters and results as the reference's
+SynthesisLayer / ToRGBLayer / SynthesisBlock / SynthesisNetwork (src/training/networks.py:90-366, 'skip'
+architecture, concat_const time conditioning, temporal input — the stylegan-v.yaml model), executed on the fused
+sm_100a kernels of libsgv_b200 with NHWC activations.
+
+State-dict keys equal the reference's (`b{res}.conv{0,1}.{weight,bias,affine.weight,affine.bias}`,
+`b{res}.torgb.*`, `b4.input.input.const`, `motion_encoder.*`, `*.resample_filter`), so a reference checkpoint's
+`G.synthesis.state_dict()` loads with `load_state_dict`.
+
+What differs from the reference is how a layer is executed (see stylegan_v_b200/modconv.py): per layer one
+implicit-GEMM launch (plus one FIR launch for up=2) instead of x*styles, cuDNN conv, upfirdn2d, *dcoefs, bias_act;
+all style affines of a forward pass are evaluated as ONE stacked GEMM up front.
+"""
+import numpy as np
+import torch
+
+from .modconv import fused_modulated_conv
+from .ops import upfirdn2d as _upfirdn2d
+from .time_encoder import EqualizedLinear, MotionMappingNetwork
+
+
+def _setup_filter(taps):
+    return _upfirdn2d.setup_filter(taps)
+
+
+class SynthesisLayer(torch.nn.Module):
+    def __init__(self, in_channels, out_channels, w_dim, resolution, kernel_size=3, up=1, resample_filter=(1, 3, 3, 1)):
+        super().__init__()
+        self.resolution, self.up = resolution, up
+        self.register_buffer('resample_filter', _setup_filter(list(resample_filter)))
+        self.affine = EqualizedLinear(w_dim, in_channels, bias_init=1)
+        self.weight = torch.nn.Parameter(torch.randn(out_channels, in_channels, kernel_size, kernel_size))
+        self.bias = torch.nn.Parameter(torch.zeros(out_channels))
+
+    def forward(self, x, w=None, styles=None, gain=1.0):
+        if styles is None:
+            styles = self.affine(w)
+        return fused_modulated_conv(x, self.weight, styles, self.bias, up=self.up, demodulate=True, act='lrelu',
+                                    gain=float(np.sqrt(2)) * gain, flip_weight=(self.up == 1))
+
+
+class ToRGBLayer(torch.nn.Module):
+    """1x1 modulated conv to RGB without demodulation + bias (networks.py:148-163).  With 3 output channels this is
+    memory-bound; it runs as one batched [HW, C] x [C, 3] product per sample straight from the NHWC activations."""
+
+    def __init__(self, in_channels, out_channels, w_dim):
+        super().__init__()
+        self.affine = EqualizedLinear(w_dim, in_channels, bias_init=1)
+        self.weight = torch.nn.Parameter(torch.randn(out_channels, in_channels, 1, 1))
+        self.bias = torch.nn.Parameter(torch.zeros(out_channels))
+        self.weight_gain = 1 / np.sqrt(in_channels)
+
+    def forward(self, x, w=None, styles=None):
+        if styles is None:
+            styles = self.affine(w)
+        styles = styles * self.weight_gain
+        N, C, H, W = x.shape
+        wmod = self.weight.reshape(1, -1, C) * styles.unsqueeze(1)                         # [N, 3, C]
+        xf = x.permute(0, 2, 3, 1).reshape(N, H * W, C)                                    # view of the NHWC storage
+        y = torch.baddbmm(self.bias.reshape(1, 1, -1), xf, wmod.transpose(1, 2))           # [N, HW, 3]
+        return y.reshape(N, H, W, -1).permute(0, 3, 1, 2).contiguous()                     # NCHW fp32 like the reference (networks.py:261)
+
+
+class _TemporalInput(torch.nn.Module):
+    def __init__(self, channel_dim, motion_v_dim):
+        super().__init__()
+        self.motion_v_dim = motion_v_dim
+        self.const = torch.nn.Parameter(torch.randn(1, channel_dim, 4, 4))
+
+    def get_dim(self):
+        return self.motion_v_dim + self.const.shape[1]
+
+    def forward(self, motion_v):
+        n = motion_v.shape[0]
+        x = torch.cat([self.const.expand(n, -1, -1, -1), motion_v[:, :, None, None].expand(-1, -1, 4, 4)], dim=1)
+        return x.contiguous(memory_format=torch.channels_last)
+
+
+class _GenInput(torch.nn.Module):
+    def __init__(self, channel_dim, motion_v_dim):
+        super().__init__()
+        self.input = _TemporalInput(channel_dim, motion_v_dim)
+        self.total_dim = self.input.get_dim()
+
+    def forward(self, motion_v):
+        return self.input(motion_v)
+
+
+class SynthesisBlock(torch.nn.Module):
+    def __init__(self, in_channels, out_channels, w_dim, motion_v_dim, resolution, img_channels, resample_filter=(1, 3, 3, 1)):
+        super().__init__()
+        self.in_channels, self.resolution = in_channels, resolution
+        self.register_buffer('resample_filter', _setup_filter(list(resample_filter)))
+        self.num_conv = 0
+        if in_channels == 0:
+            self.input = _GenInput(out_channels, motion_v_dim)
+            conv1_in = self.input.total_dim
+        else:
+            self.conv0 = SynthesisLayer(in_channels, out_channels, w_dim, resolution, up=2, resample_filter=resample_filter)
+            self.num_conv += 1
+            conv1_in = out_channels
+        self.conv1 = SynthesisLayer(conv1_in, out_channels, w_dim, resolution, resample_filter=resample_filter)
+        self.num_conv += 1
+        self.torgb = ToRGBLayer(out_channels, img_channels, w_dim)
+        self.num_torgb = 1
+
+    def layers(self):
+        return ([] if self.in_channels == 0 else [self.conv0]) + [self.conv1, self.torgb]
+
+    def forward(self, x, img, styles, motion_v=None):
+        """styles: list of per-layer style tensors in layer order (conv0?, conv1, torgb)."""
+        it = iter(styles)
+        if self.in_channels == 0:
+            x = self.input(motion_v)
+        else:
+            x = self.conv0(x, styles=next(it))
+        x = self.conv1(x, styles=next(it))
+        if img is not None:
+            img = _upfirdn2d.upsample2d(img, self.resample_filter)
+        y = self.torgb(x, styles=next(it))
+        img = img.add_(y) if img is not None else y
+        return x, img
+
+
+class SynthesisNetwork(torch.nn.Module):
+    def __init__(self, w_dim=512, img_resolution=256, img_channels=3, channel_base=16384, channel_max=512,
+                 motion_z_dim=512, motion_v_dim=512, motion_kernel_size=11, motion_z_distance=16, time_enc_dim=256,
+                 min_period_len=16, max_period_len=1024, max_num_frames=1024, resample_filter=(1, 3, 3, 1)):
+        assert img_resolution >= 4 and img_resolution & (img_resolution - 1) == 0
+        super().__init__()
+        self.w_dim, self.img_resolution, self.img_channels = w_dim, img_resolution, img_channels
+        self.block_resolutions = [2 ** i for i in range(2, int(np.log2(img_resolution)) + 1)]
+        self.motion_encoder = MotionMappingNetwork(motion_z_dim, motion_v_dim, motion_kernel_size, motion_z_distance,
+                                                   time_enc_dim, min_period_len, max_period_len, max_num_frames)
+        self.motion_v_dim = self.motion_encoder.get_dim()
+        ch = {res: min(channel_base // res, channel_max) for res in self.block_resolutions}
+        self.num_ws = 0
+        for res in self.block_resolutions:
+            block = SynthesisBlock(ch[res // 2] if res > 4 else 0, ch[res], w_dim, self.motion_v_dim, res, img_channels, resample_filter)
+            self.num_ws += block.num_conv
+            if res == img_resolution:
+                self.num_ws += block.num_torgb
+            setattr(self, f'b{res}', block)
+
+    @classmethod
+    def from_config(cls, cfg):
+        """cfg: anything with the attributes of oracle-side SynthesisConfig / the reference's yaml values."""
+        return cls(w_dim=cfg.w_dim, img_resolution=cfg.img_resolution, img_channels=cfg.img_channels, channel_base=cfg.channel_base,
+                   channel_max=cfg.channel_max, motion_z_dim=cfg.motion_z_dim, motion_v_dim=cfg.motion_v_dim,
+                   motion_kernel_size=cfg.motion_kernel_size, motion_z_distance=cfg.motion_z_distance, time_enc_dim=cfg.time_enc_dim,
+                   min_period_len=cfg.min_period_len, max_period_len=cfg.max_period_len, max_num_frames=cfg.max_num_frames,
+                   resample_filter=tuple(cfg.resample_filter))
+
+    def _all_styles(self, ws):
+        """Evaluates every style affine of the forward pass with one stacked GEMM per distinct w index.
+        Layer l of block b reads ws[:, w_idx(b) + l] (networks.py:350-357); layers sharing a w row share a GEMM."""
+        groups = {}
+        w_idx = 0
+        order = []
+        for res in self.block_resolutions:
+            block = getattr(self, f'b{res}')
+            for j, layer in enumerate(block.layers()):
+                groups.setdefault(w_idx + j, []).append(layer)
+                order.append((res, layer))
+            w_idx += block.num_conv
+        out = {}
+        for wi, layers in groups.items():
+            wcat = torch.cat([l.affine.weight for l in layers], dim=0) * layers[0].affine.weight_gain
+            bcat = torch.cat([l.affine.bias for l in layers], dim=0)
+            s = torch.addmm(bcat.unsqueeze(0), ws[:, wi], wcat.t())
+            for l, piece in zip(layers, s.split([l.affine.weight.shape[0] for l in layers], dim=1)):
+                out[id(l)] = piece
+        return out
+
+    def forward(self, ws, t, c=None, motion_z=None, motion_v=None, t_max=None):
+        """ws [B, num_ws, w_dim], t [B, F] -> img [B*F, 3, R, R] (fp32, NCHW) — networks.py:324-366 semantics."""
+        assert t.ndim == 2 and len(ws) == len(t)
+        assert ws.shape[1] == self.num_ws and ws.shape[2] == self.w_dim
+        if motion_v is None:
+            motion_v = self.motion_encoder(t, motion_z=motion_z, t_max=t_max)['motion_v']
+        ws = ws.to(torch.float32).repeat_interleave(t.shape[1], dim=0)
+        styles = self._all_styles(ws)
+        x = img = None
+        for res in self.block_resolutions:
+            block = getattr(self, f'b{res}')
+            x, img = block(x, img, [styles[id(l)] for l in block.layers()], motion_v=motion_v)
+        return img

@@ -1,0 +1,136 @@
+"""Continuous Fourier time-encoder of StyleGAN-V (motion codes), native-path module.
+
+Parameter names and shapes follow the reference's MotionMappingNetwork / AlignedTimeEncoder
+(src/training/motion.py:18-156,160-214) so reference checkpoints load: `conv.{0,1}.{weight,bias}`,
+`time_encoder.{periods,phase,aligners}_predictor.weight`, buffers `time_encoder.{freqs,phase_scales}`.
+
+Computation (same maths, reorganised):
+  trajectory     z ~ N(0,1) [B, L, 512]  ->  two equalised-lr Conv1d(k=11, no padding) + lrelu   (motion.py:55-58,100)
+  neighbours     left = floor(t / 16), right = left + 1, alpha = frac(t / 16)                    (motion.py:105-115)
+  embedding      emb(tau) = [sin, cos](freqs * (tanh(P u_L) + 1) * tau + (Phi u_L) * phase_scales)
+                 v = emb(t) - lerp(emb(t_L), emb(t_R), alpha) + lerp(A u_L, A u_R, alpha)         (motion.py:198-212)
+The three predictors on u_L share one stacked GEMM ([P; Phi; A]).  Arguments of sin/cos reach ~800 rad, so accurate
+(not fast-math) sin/cos are required for parity; the elementwise tail currently runs as PyTorch ops (it is <0.1% of a
+forward pass: [B*F, 512] elements).
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def linspaced_frequencies(num_freqs, min_period_len, max_period_len):
+    """2*pi / 2^linspace(log2 min, log2 max), highest frequency last (motion.py:218-222)."""
+    periods = 2.0 ** np.linspace(np.log2(min_period_len), np.log2(max_period_len), num_freqs)
+    return torch.from_numpy((2 * np.pi / periods)[::-1].copy().astype(np.float32)).unsqueeze(0)
+
+
+class EqualizedLinear(torch.nn.Module):
+    """Bias-free or biased dense layer with runtime weight scaling lr_mult / sqrt(fan_in) (layers.py:108-138)."""
+
+    def __init__(self, in_features, out_features, bias=True, lr_multiplier=1.0, bias_init=0.0):
+        super().__init__()
+        self.weight = torch.nn.Parameter(torch.randn(out_features, in_features) / lr_multiplier)
+        self.bias = torch.nn.Parameter(torch.full([out_features], float(bias_init))) if bias else None
+        self.weight_gain = lr_multiplier / np.sqrt(in_features)
+        self.bias_gain = lr_multiplier
+
+    def forward(self, x):
+        w = self.weight.to(x.dtype) * self.weight_gain
+        if self.bias is None:
+            return x.matmul(w.t())
+        b = self.bias.to(x.dtype)
+        if self.bias_gain != 1:
+            b = b * self.bias_gain
+        return torch.addmm(b.unsqueeze(0), x, w.t())
+
+
+class EqualizedConv1d(torch.nn.Module):
+    """Conv1d with equalised learning rate + leaky ReLU (layers.py:331-373)."""
+
+    def __init__(self, in_features, out_features, kernel_size, lr_multiplier=1.0):
+        super().__init__()
+        self.weight = torch.nn.Parameter(torch.randn(out_features, in_features, kernel_size) / lr_multiplier)
+        self.bias = torch.nn.Parameter(torch.zeros(out_features))
+        self.weight_gain = lr_multiplier / np.sqrt(in_features * kernel_size)
+        self.bias_gain = lr_multiplier
+
+    def forward(self, x):
+        # true fp32: the embedding multiplies these features by phase scales up to 64 and takes sin/cos, so TF32 rounding
+        # here (PyTorch's cuDNN default) would show up as ~1e-2 errors in motion_v; the reference trains with allow_tf32=False
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            y = F.conv1d(x, self.weight * self.weight_gain, self.bias * self.bias_gain)
+        return F.leaky_relu(y, 0.2)
+
+
+class AlignedTimeEncoder(torch.nn.Module):
+    def __init__(self, latent_dim, num_freqs, min_period_len, max_period_len):
+        super().__init__()
+        freqs = linspaced_frequencies(num_freqs, min_period_len, max_period_len)
+        self.register_buffer('freqs', freqs)
+        self.register_buffer('phase_scales', max_period_len / (2 * np.pi / freqs))
+        self.periods_predictor = EqualizedLinear(latent_dim, num_freqs, bias=False)
+        self.phase_predictor = EqualizedLinear(latent_dim, num_freqs, bias=False)
+        self.aligners_predictor = EqualizedLinear(latent_dim, num_freqs * 2, bias=False)
+
+    def get_dim(self):
+        return self.freqs.shape[1] * 2
+
+    def forward(self, t, u_left, u_right, alpha, t_left, t_right):
+        """t, t_left, t_right [M]; u_left, u_right [M, latent]; alpha [M, 1] -> [M, 2*num_freqs]."""
+        nf = self.freqs.shape[1]
+        # one stacked GEMM for the three heads on u_left, one for the aligners on u_right
+        heads = torch.cat([self.periods_predictor.weight, self.phase_predictor.weight, self.aligners_predictor.weight], dim=0)
+        gain = self.periods_predictor.weight_gain
+        hl = u_left.matmul((heads * gain).t())
+        periods = hl[:, :nf].tanh() + 1
+        phases = hl[:, nf:2 * nf]
+        al_left = hl[:, 2 * nf:]
+        al_right = self.aligners_predictor(u_right)
+        base = self.freqs * periods
+        shift = phases * self.phase_scales
+
+        def emb(tau):
+            raw = base * tau.reshape(-1, 1).float() + shift
+            return torch.cat([raw.sin(), raw.cos()], dim=1)
+        remove = emb(t_left) * (1 - alpha) + emb(t_right) * alpha
+        add = al_left * (1 - alpha) + al_right * alpha
+        return emb(t) - remove + add
+
+
+class MotionMappingNetwork(torch.nn.Module):
+    def __init__(self, z_dim=512, v_dim=512, kernel_size=11, motion_z_distance=16, time_enc_dim=256,
+                 min_period_len=16, max_period_len=1024, max_num_frames=1024):
+        super().__init__()
+        self.z_dim, self.v_dim = z_dim, v_dim
+        self.motion_z_distance = motion_z_distance
+        self.max_num_frames = max_num_frames
+        self.num_additional_codes = (kernel_size - 1) * 2
+        self.conv = torch.nn.Sequential(EqualizedConv1d(z_dim, z_dim, kernel_size, lr_multiplier=0.01),
+                                        EqualizedConv1d(z_dim, v_dim, kernel_size, lr_multiplier=0.01))
+        self.time_encoder = AlignedTimeEncoder(v_dim, time_enc_dim, min_period_len, max_period_len)
+
+    def get_dim(self):
+        return self.time_encoder.get_dim()
+
+    def traj_len(self, t_max=None):
+        """Trajectory length the reference derives from max(t) (motion.py:63-66,80).  Passing t_max=None assumes
+        t <= max_num_frames - 1 (true for the training sampler) and avoids the reference's host sync on t.max()."""
+        max_t = self.max_num_frames - 1 if t_max is None else max(self.max_num_frames - 1, t_max)
+        return int(np.ceil(max_t / self.motion_z_distance)) + 2 + self.num_additional_codes
+
+    def forward(self, t, motion_z=None, t_max=None):
+        """t [B, F] (float frame positions) -> dict(motion_v [B*F, dim], motion_z)."""
+        B, Fr = t.shape
+        L = self.traj_len(t_max)
+        if motion_z is None:
+            motion_z = torch.randn(B, L, self.z_dim, device=t.device)
+        trajs = self.conv(motion_z[:B, :L, :self.z_dim].permute(0, 2, 1)).permute(0, 2, 1)   # [B, L - 20, v_dim]
+        d = self.motion_z_distance
+        left = (t / d).floor().long()
+        rows = torch.arange(B, device=t.device).unsqueeze(1).expand(B, Fr)
+        u_left = trajs[rows, left].reshape(B * Fr, -1)
+        u_right = trajs[rows, left + 1].reshape(B * Fr, -1)
+        t_left = t - t % d
+        alpha = ((t % d) / d).reshape(-1, 1).to(torch.float32)
+        v = self.time_encoder(t.reshape(-1), u_left, u_right, alpha, t_left.reshape(-1), (t_left + d).reshape(-1))
+        return dict(motion_v=v, motion_z=motion_z)

@@ -99,6 +99,38 @@ def test_stride2_input():
     assert rel_err(y, ref) < 2e-5
 
 
+@pytest.mark.parametrize('N,Cin,Cout,H', [(2, 64, 128, 16), (3, 32, 64, 12), (8, 64, 64, 4), (2, 256, 128, 8), (1, 128, 32, 20)])
+def test_wgrad_stride1(N, Cin, Cout, H):
+    g_ = torch.Generator().manual_seed(N + Cin)
+    x = torch.randn(N, Cin, H, H, generator=g_).cuda()
+    gy = torch.randn(N, Cout, H, H, generator=g_).cuda()
+    s = (torch.rand(N, Cin, generator=g_) + 0.5).cuda()
+    d = (torch.rand(N, Cout, generator=g_) + 0.5).cuda()
+    taps = C.TAPS_3x3
+    dw = C.igemm_wgrad(_cl(gy), _cl(x), [(0, 0)] * 9, [(ky - 1, kx - 1) for ky, kx in taps], (H, H), g_scale=d, x_scale=s)
+    xs = tf32_round(x * s[:, :, None, None]).double().requires_grad_(False)
+    gs = tf32_round(gy * d[:, :, None, None]).double()
+    w = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float64, device='cuda', requires_grad=True)
+    ref, = torch.autograd.grad(F.conv2d(xs, w, padding=1), w, gs)
+    got = dw.reshape(3, 3, Cout, Cin).permute(2, 3, 0, 1)
+    assert rel_err(got, ref) < 2e-5
+    ref32, = torch.autograd.grad(F.conv2d((x * s[:, :, None, None]).double(), w, padding=1), w, (gy * d[:, :, None, None]).double())
+    assert rel_err(got, ref32) < 1e-3
+
+
+def test_wgrad_transposed_stride2():
+    g_ = torch.Generator().manual_seed(11)
+    N, Cin, Cout, h = 2, 64, 64, 9
+    x = torch.randn(N, Cin, h, h, generator=g_).cuda()
+    du = torch.randn(N, Cout, 2 * h + 1, 2 * h + 1, generator=g_).cuda()
+    taps = C.TAPS_3x3
+    dw = C.igemm_wgrad(_cl(du), _cl(x), taps, [(0, 0)] * 9, (h, h), g_stride=2)
+    wT = torch.zeros(Cin, Cout, 3, 3, dtype=torch.float64, device='cuda', requires_grad=True)
+    ref, = torch.autograd.grad(F.conv_transpose2d(tf32_round(x).double(), wT, stride=2), wT, tf32_round(du).double())
+    got = dw.reshape(3, 3, Cout, Cin).permute(3, 2, 0, 1)       # [Cin, Cout, ky, kx] like the conv_transpose2d weight
+    assert rel_err(got, ref) < 2e-5
+
+
 def test_argument_errors():
     x = torch.randn(1, 24, 8, 8).cuda().contiguous(memory_format=torch.channels_last)
     with pytest.raises(RuntimeError):

@@ -1,0 +1,93 @@
+"""Native synthesis network (fused sm_100a kernels, through the C ABI) vs the oracle / reference-minted goldens.
+
+Tolerances: every contraction multiplies TF32-rounded operands (unit roundoff 2^-11) with fp32 accumulation; per
+layer that is <= 1e-3 normwise (tests/test_conv_gpu.py).  Through the 7-conv tiny network errors compound roughly
+like sqrt(depth), so whole-network outputs are held to 3e-3 and gradients to 1e-2 (normwise, vs true-fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import synthesis_ref as sr
+from stylegan_v_b200.synthesis import SynthesisNetwork
+from stylegan_v_b200 import modconv
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _load(g, meta):
+    cfg = sr.SynthesisConfig(**meta)
+    net = SynthesisNetwork.from_config(cfg)
+    sd = {k[2:]: _t(g[k]) for k in g.files if k.startswith('p:')}
+    missing, unexpected = net.load_state_dict(sd, strict=True), None
+    return cfg, net.cuda()
+
+
+def test_state_dict_keys_equal_reference():
+    g, meta = load_golden('synthesis_tiny.npz')
+    cfg = sr.SynthesisConfig(**meta)
+    net = SynthesisNetwork.from_config(cfg)
+    ref_keys = sorted(k[2:] for k in g.files if k.startswith('p:'))
+    assert sorted(net.state_dict().keys()) == ref_keys
+    for k, v in net.state_dict().items():
+        assert tuple(v.shape) == g['p:' + k].shape, k
+    assert net.num_ws == cfg.num_ws
+
+
+def test_fused_layer_vs_golden_modconv():
+    g, meta = load_golden('modconv_cases.npz')
+    for i, m in enumerate(meta):
+        if m['I'] % 32 or m['O'] % 16 or m['fused']:
+            continue
+        x = _t(g[f'c{i}_x']).cuda().requires_grad_(True)
+        w = _t(g[f'c{i}_w']).cuda().requires_grad_(True)
+        s = _t(g[f'c{i}_s']).cuda().requires_grad_(True)
+        y = modconv.fused_modulated_conv(x, w, s, None, up=m['up'], demodulate=m['demod'], act='linear', gain=1.0, flip_weight=(m['up'] == 1))
+        dx, dw, ds = torch.autograd.grad(y, [x, w, s], _t(g[f'c{i}_dy']).cuda())
+        for a, k in ((y, 'y'), (dx, 'dx'), (dw, 'dw'), (ds, 'ds')):
+            assert rel_err(a, _t(g[f'c{i}_{k}'])) < 2e-3, (i, m, k, rel_err(a, _t(g[f'c{i}_{k}'])))
+
+
+def test_network_forward_backward_vs_golden():
+    g, meta = load_golden('synthesis_tiny.npz')
+    cfg, net = _load(g, meta)
+    ws = _t(g['ws']).cuda().requires_grad_(True)
+    t = _t(g['t']).cuda(); mz = _t(g['motion_z']).cuda()
+    mv = net.motion_encoder(t, motion_z=mz, t_max=float(t.max()))['motion_v']
+    assert rel_err(mv, _t(g['motion_v'])) < 1e-4
+    img = net(ws, t, motion_z=mz, t_max=float(t.max()))
+    assert img.shape == g['img_train'].shape and not img.is_contiguous(memory_format=torch.channels_last) or img.shape[1] == 1
+    e = rel_err(img, _t(g['img_train']))
+    assert e < 3e-3, e
+    names = sorted(k[2:] for k in g.files if k.startswith('g:'))
+    params = dict(net.named_parameters())
+    grads = torch.autograd.grad(img, [ws] + [params[n] for n in names], _t(g['dimg']).cuda())
+    assert rel_err(grads[0], _t(g['d_ws'])) < 1e-2
+    worst = max((rel_err(gr, _t(g['g:' + n])), n) for n, gr in zip(names, grads[1:]))
+    assert worst[0] < 1e-2, worst
+
+
+def test_network_vs_oracle_other_config():
+    """A second architecture (64x64, 64 channels) against the CPU oracle computed on the fly."""
+    cfg = sr.SynthesisConfig(img_resolution=64, w_dim=128, channel_base=2048, channel_max=64, motion_z_dim=64, motion_v_dim=64, time_enc_dim=32)
+    P = sr.init_params(cfg, seed=3)
+    net = SynthesisNetwork.from_config(cfg)
+    sd = net.state_dict()
+    for k in sd:
+        if k in P:
+            sd[k] = P[k]
+    net.load_state_dict(sd)
+    net = net.cuda()
+    gen = torch.Generator().manual_seed(5)
+    B, Fr = 2, 2
+    ws = torch.randn(B, cfg.num_ws, cfg.w_dim, generator=gen)
+    t = torch.tensor([[3.0, 40.5], [700.25, 701.0]])
+    mz = torch.randn(B, sr.max_traj_len(cfg, 1023.0), cfg.motion_z_dim, generator=gen)
+    ref = sr.synthesis_forward(P, cfg, ws, t, motion_z=mz, fused_modconv=False)
+    img = net(ws.cuda(), t.cuda(), motion_z=mz.cuda())
+    e = rel_err(img, ref)
+    assert e < 3e-3, e
