@@ -277,5 +277,46 @@ int main()
             }
         }
     }
+    // ---------------- MN-major BASE32B with unaligned starts / SBO != 512 (halo-patch addressing for wgrad) ----------------
+    {
+        // A image: one channel block, 200 pixel rows (k), value = k (row index); B: identity over n.  One K=8 instruction:
+        // D[m][n] = sum_k A[k][m] * B[k][n]; with B[k][n] = delta(k - k0 == n) for the 8 rows used -> D[m][n] = A-row index fetched for k=n.
+        for (int variant = 0; variant < 4; variant++)
+        {
+            const unsigned start_row = (unsigned[]){0, 3, 13, 13}[variant];
+            const unsigned sbo = (unsigned[]){512, 512, 512, 768}[variant];      // 768 = 6-row pitch: rows {s..s+3} and {s+6..s+9}
+            std::vector<float> img(IMG, -7777.f);
+            for (unsigned k = 0; k < 200; k++)
+            {
+                float row[32];
+                for (int j = 0; j < 32; j++) row[j] = (float)k;                     // every m sees the row index
+                put_row_sw32(img, A_BASE + k * 128, row);
+            }
+            // B rows: 8 rows used by one instruction, aligned start; B[kk][n] = (n == kk)
+            for (unsigned kk = 0; kk < 8; kk++)
+            {
+                float row[32];
+                for (int n = 0; n < 32; n++) row[n] = (n == (int)kk) ? 1.f : 0.f;
+                put_row_sw32(img, B_BASE + kk * 128, row);
+            }
+            Case c{};
+            c.a_mn = 1; c.b_mn = 1; c.a_off = A_BASE + start_row * 128; c.b_off = B_BASE;
+            c.a_lbo = 4096; c.a_sbo = sbo; c.b_lbo = 4096; c.b_sbo = 512; c.a_base_offset = 0;
+            c.n = 32; c.ksteps = 1; c.a_kstep = 0; c.b_kstep = 0;
+            std::vector<float> out;
+            char name[128];
+            snprintf(name, sizeof(name), "MN-major BASE32B start +%u rows, SBO=%u", start_row, sbo);
+            if (!run(name, img, c, out)) continue;
+            int ok = 0, bad = 0;
+            for (int m = 0; m < 32; m++)
+                for (int n = 0; n < 8; n++)
+                {
+                    float exp = (float)(start_row + (n / 4) * (sbo / 128) + (n % 4));
+                    if (out[m * 64 + n] == exp) ok++; else bad++;
+                }
+            printf("[k-row probe] %-58s match=%d mismatch=%d | D[0][0..7]= %g %g %g %g %g %g %g %g\n", name, ok, bad,
+                   out[0], out[1], out[2], out[3], out[4], out[5], out[6], out[7]);
+        }
+    }
     return 0;
 }

@@ -1,8 +1,16 @@
 """Native synthesis network (fused sm_100a kernels, through the C ABI) vs the oracle / reference-minted goldens.
 
 Tolerances: every contraction multiplies TF32-rounded operands (unit roundoff 2^-11) with fp32 accumulation; per
-layer that is <= 1e-3 normwise (tests/test_conv_gpu.py).  Through the 7-conv tiny network errors compound roughly
-like sqrt(depth), so whole-network outputs are held to 3e-3 and gradients to 1e-2 (normwise, vs true-fp32)."""
+layer that is <= 1e-3 normwise (tests/test_conv_gpu.py).  Whole-network OUTPUTS are held to 3e-3 (measured 6e-4).
+
+Gradients need care: a leaky-ReLU gradient is discontinuous in the forward value, so any forward that is not bit-equal
+to fp32 (TF32 here, cuDNN-TF32 or fp16 in the reference's own fast modes) flips the slope of the few activations whose
+pre-activation is within ~1e-3*sigma of zero.  In this tiny network a channel sums only 1.5k-6k pixels, so 1-3 flipped
+elements move a (random-sign) gradient sum by 1-4 %.  That is a property of the forward precision, not of the backward
+kernels, so the backward is validated in two ways:
+  * test_fused_layer_backward_with_matched_forward: the reference forward is fed the same TF32-rounded operands (masks
+    then agree) and every gradient of the fused layer (dx, dW, dstyles, ddcoefs, dbias) must agree to 2e-3;
+  * whole-network gradients vs the true-fp32 goldens: cosine similarity >= 0.998 and normwise error <= 6e-2."""
 import numpy as np
 import pytest
 import torch
@@ -66,9 +74,56 @@ def test_network_forward_backward_vs_golden():
     names = sorted(k[2:] for k in g.files if k.startswith('g:'))
     params = dict(net.named_parameters())
     grads = torch.autograd.grad(img, [ws] + [params[n] for n in names], _t(g['dimg']).cuda())
-    assert rel_err(grads[0], _t(g['d_ws'])) < 1e-2
+    def cos(a, b):
+        a, b = a.detach().double().cpu().flatten(), b.double().flatten()
+        return float((a @ b) / (a.norm() * b.norm()))
+    assert rel_err(grads[0], _t(g['d_ws'])) < 6e-2 and cos(grads[0], _t(g['d_ws'])) > 0.998
     worst = max((rel_err(gr, _t(g['g:' + n])), n) for n, gr in zip(names, grads[1:]))
-    assert worst[0] < 1e-2, worst
+    assert worst[0] < 6e-2, worst
+    worst_cos = min((cos(gr, _t(g['g:' + n])), n) for n, gr in zip(names, grads[1:]))
+    assert worst_cos[0] > 0.998, worst_cos
+
+
+def _tf32_ste(t):
+    """TF32 rounding (round-to-nearest, ties away) with a straight-through gradient."""
+    r = ((t.detach().float().contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32).to(t.dtype)
+    return t + (r - t).detach()
+
+
+@pytest.mark.parametrize('up', [1, 2])
+def test_fused_layer_backward_with_matched_forward(up):
+    gen = torch.Generator().manual_seed(17 + up)
+    N, I, O, H = 3, 64, 64, 12
+    x = torch.randn(N, I, H, H, generator=gen).cuda().requires_grad_(True)
+    w = torch.randn(O, I, 3, 3, generator=gen).cuda().requires_grad_(True)
+    s = (torch.randn(N, I, generator=gen) + 1).cuda().requires_grad_(True)
+    d = (torch.rand(N, O, generator=gen) + 0.5).cuda().requires_grad_(True)
+    b = (0.3 * torch.randn(O, generator=gen)).cuda().requires_grad_(True)
+    gain = float(np.sqrt(2))
+    y = modconv._FusedModConv.apply(x, w, s, d, b, up, 'lrelu', gain, up == 1)
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).cuda()
+    got = torch.autograd.grad(y, [x, w, s, d, b], dy)
+    # reference: same rounded operands, fp64 arithmetic, autograd
+    X, W, S, D, B = (t.detach().double().requires_grad_(True) for t in (x, w, s, d, b))
+    xs = _tf32_ste((X * S[:, :, None, None]).float()).double() if False else None
+    xs32 = (x.detach() * s.detach()[:, :, None, None])
+    delta_x = (((xs32.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32) - xs32).double()
+    w32 = w.detach()
+    delta_w = (((w32.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32) - w32).double()
+    xs = X * S[:, :, None, None] + delta_x
+    wr = W + delta_w
+    F = torch.nn.functional
+    if up == 1:
+        c = F.conv2d(xs, wr, padding=1)
+    else:
+        u = F.conv_transpose2d(xs, wr.transpose(0, 1), stride=2)
+        f = modconv._fir(x.device).double()
+        c = F.conv2d(F.pad(u, [1, 1, 1, 1]), (f * 4).flip([0, 1])[None, None].repeat(O, 1, 1, 1), groups=O)
+    yr = F.leaky_relu(c * D[:, :, None, None] + B[None, :, None, None], 0.2) * gain
+    assert rel_err(y, yr) < 2e-5
+    ref = torch.autograd.grad(yr, [X, W, S, D, B], dy.double())
+    for name, a, r in zip(('dx', 'dw', 'dstyles', 'ddcoefs', 'dbias'), got, ref):
+        assert rel_err(a, r) < 2e-3, (up, name, rel_err(a, r))
 
 
 def test_network_vs_oracle_other_config():
