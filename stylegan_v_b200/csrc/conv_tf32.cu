@@ -23,9 +23,13 @@
 #include "tmap.cuh"
 #include "../../include/sgv_b200_conv.h"
 
+#include <stdlib.h>
+
 namespace sgv {
 
 using namespace ptx;
+
+int conv2d_tf32_v2(const sgv_conv_params* p, cudaStream_t stream);     // conv_tf32_v2.cu
 
 constexpr int kConvThreads = 192;
 constexpr int kBM = 128;
@@ -338,6 +342,14 @@ extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
     SGV_CHECK_ARG((long long)p->n * p->h * p->w * p->cin <= 0x7fffffffLL, "x is too large");
     int rc = sgv_device_check();
     if (rc != SGV_OK) return rc;
+
+    // v2 (halo patch + shifted descriptors, csrc/conv_tf32_v2.cu) covers stride-1 inputs on planes >= 12x12; SGV_CONV_V1=1 forces v1
+    static const bool force_v1 = getenv("SGV_CONV_V1") != nullptr;
+    if (!force_v1)
+    {
+        rc = conv2d_tf32_v2(p, stream);
+        if (rc != SGV_ERR_UNSUPPORTED) return rc;
+    }
 
     ConvArgs a;
     a.y = p->y; a.a_scale = p->a_scale; a.o_scale = p->o_scale; a.bias = p->bias;

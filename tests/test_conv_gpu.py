@@ -26,7 +26,8 @@ def _cl(t):
 
 
 @pytest.mark.parametrize('N,Cin,Cout,H,W', [(2, 32, 64, 16, 16), (1, 64, 128, 8, 8), (3, 64, 64, 20, 12), (2, 128, 256, 16, 16),
-                                            (8, 32, 64, 4, 4), (1, 32, 512, 8, 8), (2, 96, 64, 33, 17)])
+                                            (8, 32, 64, 4, 4), (1, 32, 512, 8, 8), (2, 96, 64, 33, 17),
+                                            (1, 64, 128, 40, 40), (2, 32, 256, 24, 31), (1, 128, 512, 16, 16)])
 def test_conv3x3_plain(N, Cin, Cout, H, W):
     g = torch.Generator().manual_seed(N * 1000 + Cin)
     x = torch.randn(N, Cin, H, W, generator=g).cuda()
