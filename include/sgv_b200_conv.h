@@ -82,6 +82,25 @@ typedef struct sgv_wgrad_params {
 
 int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream);
 
+/* ---- one-pass NHWC companions of the fused layer (csrc/layer_elementwise.cu) -------------------------------------------
+ * All tensors float32; activations [n, hw, c] (NHWC, c % 4 == 0, 256 % (c/4) == 0); accumulation outputs (db, dd, ds, dwmod)
+ * are ADDED to (caller zeroes them).
+ *
+ * sgv_modconv_act_bwd: gradient of  y = act(v + bias) * gain  w.r.t. v, from the saved OUTPUT y (bias_act.cu:69-73,133 for
+ *   act = linear(1) / lrelu(3)):  dz = act'(.) * dy * gain;  db[c] += sum_{n,hw} dz;  dd[n,c] += sum_hw dz * (v)   where
+ *   v = act^-1(y / gain) - bias is recovered from y (so the un-activated conv output never needs to be stored).
+ *   Replaces BiasActCudaGrad + dx.sum() (bias_act.py:161-186) and the reduction in the autograd of x*dcoefs (networks.py:68-71).
+ * sgv_modconv_scale_reduce:  dx = dxs * s[n,c] (dx may be NULL or alias dxs);  ds[n,c] += sum_hw dxs * x    (networks.py:66 autograd)
+ * sgv_torgb_fwd:  y[n,j,hw] = sum_c x[n,hw,c] * wmod[n,j,c] + bias[j],  j < 3, y in NCHW            (networks.py:159-163)
+ * sgv_torgb_bwd:  dx[n,hw,c] = sum_j dy[n,j,hw] * wmod[n,j,c];  dwmod[n,j,c] += sum_hw dy[n,j,hw] * x[n,hw,c]
+ */
+int sgv_modconv_act_bwd(const float* dy, const float* y, const float* bias, float* dz, float* db, float* dd,
+                        int32_t n, int32_t hw, int32_t c, int32_t act, float alpha, float gain, void* stream);
+int sgv_modconv_scale_reduce(const float* dxs, const float* x, const float* s, float* dx, float* ds,
+                             int32_t n, int32_t hw, int32_t c, void* stream);
+int sgv_torgb_fwd(const float* x, const float* wmod, const float* bias, float* y, int32_t n, int32_t hw, int32_t c, void* stream);
+int sgv_torgb_bwd(const float* dy, const float* x, const float* wmod, float* dx, float* dwmod, int32_t n, int32_t hw, int32_t c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

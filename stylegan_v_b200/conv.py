@@ -121,3 +121,69 @@ def igemm_wgrad(g, x, taps_g, taps_x, out_hw, g_stride=1, x_stride=1, g_scale=No
     with torch.cuda.device(x.device):
         _lib.check(L.sgv_conv2d_wgrad_tf32(ctypes.byref(p), _stream(x.device)), 'sgv_conv2d_wgrad_tf32')
     return dw
+
+
+# ---- one-pass NHWC companions of the fused layer (csrc/layer_elementwise.cu) ----
+
+def _is_nhwc(t):
+    N, C, H, W = t.shape
+    return t.stride(1) == 1 and t.stride(3) == C and t.stride(2) == W * C and t.stride(0) == H * W * C
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def act_bwd(dy, y, bias, act, gain, want_db, want_dd, alpha=0.2):
+    """dz, db[C], dd[N,C] (see sgv_modconv_act_bwd).  dy, y: [N,C,H,W] channels_last."""
+    _req(dy.is_cuda and dy.dtype == torch.float32 and _is_nhwc(dy) and _is_nhwc(y) and dy.shape == y.shape, 'dy / y must be matching NHWC float32 CUDA tensors')
+    N, C, H, W = dy.shape
+    dz = torch.empty_like(dy)
+    db = torch.zeros([C], dtype=torch.float32, device=dy.device) if want_db else None
+    dd = torch.zeros([N, C], dtype=torch.float32, device=dy.device) if want_dd else None
+    b = bias.to(torch.float32).contiguous() if bias is not None else None
+    L = _lib.lib()
+    with torch.cuda.device(dy.device):
+        _lib.check(L.sgv_modconv_act_bwd(dy.data_ptr(), y.data_ptr(), _ptr(b), dz.data_ptr(), _ptr(db), _ptr(dd), N, H * W, C,
+                                         {'linear': 1, 'lrelu': 3}[act], float(alpha), float(gain), _stream(dy.device)), 'sgv_modconv_act_bwd')
+    return dz, db, dd
+
+
+def scale_reduce(dxs, x, s, want_dx=True, want_ds=True):
+    """dx = dxs * s[n,c] (written IN PLACE into dxs), ds[N,C] = sum_hw dxs * x."""
+    _req(dxs.is_cuda and dxs.dtype == torch.float32 and _is_nhwc(dxs) and _is_nhwc(x) and dxs.shape == x.shape, 'dxs / x must be matching NHWC float32 CUDA tensors')
+    N, C, H, W = dxs.shape
+    s = s.to(torch.float32).contiguous()
+    ds = torch.zeros([N, C], dtype=torch.float32, device=x.device) if want_ds else None
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        _lib.check(L.sgv_modconv_scale_reduce(dxs.data_ptr(), x.data_ptr(), s.data_ptr(), dxs.data_ptr() if want_dx else None, _ptr(ds),
+                                              N, H * W, C, _stream(x.device)), 'sgv_modconv_scale_reduce')
+    return (dxs if want_dx else None), ds
+
+
+def torgb_fwd(x, wmod, bias):
+    """x [N,C,H,W] NHWC, wmod [N,3,C], bias [3] -> y [N,3,H,W] contiguous (NCHW)."""
+    _req(x.is_cuda and x.dtype == torch.float32 and _is_nhwc(x), 'x must be an NHWC float32 CUDA tensor')
+    N, C, H, W = x.shape
+    wmod = wmod.to(torch.float32).contiguous()
+    _req(tuple(wmod.shape) == (N, 3, C), 'wmod must be [N, 3, C]')
+    y = torch.empty([N, 3, H, W], dtype=torch.float32, device=x.device)
+    b = bias.to(torch.float32).contiguous() if bias is not None else None
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        _lib.check(L.sgv_torgb_fwd(x.data_ptr(), wmod.data_ptr(), _ptr(b), y.data_ptr(), N, H * W, C, _stream(x.device)), 'sgv_torgb_fwd')
+    return y
+
+
+def torgb_bwd(dy, x, wmod):
+    """dy [N,3,H,W] contiguous, x NHWC, wmod [N,3,C] -> dx (NHWC), dwmod [N,3,C]."""
+    N, C, H, W = x.shape
+    dy = dy.contiguous()
+    wmod = wmod.to(torch.float32).contiguous()
+    dx = torch.empty_like(x)
+    dwmod = torch.zeros([N, 3, C], dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        _lib.check(L.sgv_torgb_bwd(dy.data_ptr(), x.data_ptr(), wmod.data_ptr(), dx.data_ptr(), dwmod.data_ptr(), N, H * W, C, _stream(x.device)), 'sgv_torgb_bwd')
+    return dx, dwmod

@@ -16,9 +16,14 @@
 #include "tmap.cuh"
 #include "../../include/sgv_b200_conv.h"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace sgv {
 
 using namespace ptx;
+
+int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, cudaStream_t stream);
 
 constexpr int kWgThreads = 192;
 constexpr int kWgM = 128;
@@ -252,6 +257,13 @@ extern "C" int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream_)
     int rc = sgv_device_check();
     if (rc != SGV_OK) return rc;
 
+    static const bool force_v1 = getenv("SGV_WGRAD_V1") != nullptr;
+    if (!force_v1)
+    {
+        rc = conv2d_wgrad_tf32_v2(p, stream);
+        if (rc != SGV_ERR_UNSUPPORTED) return rc;
+    }
+
     WgArgs a;
     a.dw = p->dw; a.g_scale = p->g_scale; a.x_scale = p->x_scale;
     a.n = p->n; a.cin = p->cin; a.cout = p->cout; a.out_h = p->out_h; a.out_w = p->out_w;
@@ -286,3 +298,305 @@ extern "C" int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream_)
         default:  return launch_wgrad<32, 8>(tg, tx, a, grid, stream);
     }
 }
+
+// =====================================================================================================================
+// v2 (stride-1 correlations, e.g. 3x3 pad 1): one CTA owns a GROUP of taps that share dy (one kernel row: up to 3 taps).
+//   Each tap has its own NT-column TMEM accumulator (3 x 128 = 384 columns).  Per k-step (an 8x4 pixel tile) the gradient
+//   tile is loaded once and the input once as a (8 + dx-span) x 4 patch of NT channels; tap t's B operand is that patch
+//   addressed through a shifted MN-major descriptor (start row = y*PW + dx_t; 8 consecutive pixel rows = one image row).
+//   tcgen05 swizzles on absolute address bits, so unaligned starts are legal (profiles/umma_probe_r1.txt).
+//   Why groups of 3 and NT = 128: an SS-mode tcgen05.mma re-reads its A tile (128 x 8 x 4 B) from shared memory for every
+//   instruction, so N must be >= 128 for the 128 B/clk shared-memory port to keep up (measured: an all-9-taps variant with
+//   N = 32 ran at 110 TFLOP/s); TMEM (512 columns) then holds 3 taps.
+// =====================================================================================================================
+namespace sgv {
+
+constexpr int kW2GTile = 128 * 32 * 4;            // 16 KB
+constexpr int kW2MaxGroupTaps = 3;
+constexpr int kWg2Threads = 64 + 256;          // TMA warp, MMA warp, 8 transform/epilogue warps
+
+struct Wg2Args
+{
+    float* dw; const float* g_scale; const float* x_scale;
+    int n, cin, cout, out_h, out_w;
+    int ngroups;
+    int grp_ntaps[SGV_CONV_MAX_TAPS];                       // taps in group
+    int grp_dy[SGV_CONV_MAX_TAPS];                          // common dy of the group
+    int grp_tap[SGV_CONV_MAX_TAPS][kW2MaxGroupTaps];        // global tap index (row of dw)
+    int grp_col[SGV_CONV_MAX_TAPS][kW2MaxGroupTaps];        // dx_t - dx_min: column offset inside the patch
+    int dx_min, pw;
+    int tiles_x, tiles_y, mtiles, ktiles, ksplit;
+};
+
+template <int NT, int STAGES>
+struct Wg2Smem
+{
+    static constexpr int kXBlock = 10 * 4 * 128;                  // one 32-channel block of the (8+2) x 4 patch (5120 B, multiple of the 512 B swizzle atom)
+    static constexpr int kXTile = ((NT / 32) * kXBlock + 1023) & ~1023;
+    static constexpr int kStage = kW2GTile + kXTile;
+    static constexpr int kBarOffset = STAGES * kStage;
+    static constexpr int kTotal = kBarOffset + (3 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int NT, int STAGES>
+__global__ void __launch_bounds__(kWg2Threads, 1)
+wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x, const Wg2Args p)
+{
+    using L = Wg2Smem<NT, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* ready_bar = full_bar + STAGES;
+    uint64_t* empty_bar = ready_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = blockIdx.x % p.mtiles, nt = blockIdx.x / p.mtiles;
+    const int m0 = mt * kWgM, c0 = nt * NT;
+    const int grp = blockIdx.z;
+    const int gtaps = p.grp_ntaps[grp];
+    const int per = (p.ktiles + p.ksplit - 1) / p.ksplit;
+    const int kt0 = blockIdx.y * per;
+    const int kt1 = min(kt0 + per, p.ktiles);
+    const int ksteps = kt1 - kt0;
+    const int xblock = p.pw * 4 * 128;                         // bytes of one 32-channel block of the patch
+    const uint32_t x_bytes = (uint32_t)(xblock * (NT / 32));
+
+    if (threadIdx.x == 0)
+    {
+        prefetch_tmap(&tmap_g);
+        prefetch_tmap(&tmap_x);
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 1); mbar_init(ready_bar + s, 8); mbar_init(empty_bar + s, 1); }
+        mbar_init(accum_bar, 1);
+        fence_mbar_init();
+    }
+    constexpr int kCols = (kW2MaxGroupTaps * NT) <= 256 ? 256 : 512;
+    if (warp == 1) { tmem_alloc(tmem_slot, kCols); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (ksteps > 0)
+    {
+        if (warp == 0)
+        {
+            if (elect_one())
+            {
+                int stage = 0; uint32_t phase = 0;
+                for (int kt = kt0; kt < kt1; kt++)
+                {
+                    int r = kt;
+                    const int tx = r % p.tiles_x; r /= p.tiles_x;
+                    const int ty = r % p.tiles_y; r /= p.tiles_y;
+                    const int px0 = tx * 8, py0 = ty * 4, n = r;
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    uint8_t* sg = smem + stage * L::kStage;
+                    mbar_expect_tx(full_bar + stage, kW2GTile + x_bytes);
+                    tma_load_5d(sg, &tmap_g, full_bar + stage, 0, px0, py0, n, m0 / 32);
+                    tma_load_5d(sg + kW2GTile, &tmap_x, full_bar + stage, 0, px0 + p.dx_min, py0 + p.grp_dy[grp], n, c0 / 32);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        else if (warp == 1)
+        {
+            constexpr uint32_t idesc = umma_idesc_tf32(kWgM, NT, 1, 1);
+            int stage = 0; uint32_t phase = 0;
+            for (int ks = 0; ks < ksteps; ks++)
+            {
+                mbar_wait(ready_bar + stage, phase);
+                tc_fence_after();
+                if (elect_one())
+                {
+                    const uint32_t sg = smem_u32(smem + stage * L::kStage);
+                    const uint32_t sx = sg + kW2GTile;
+                    for (int t = 0; t < gtaps; t++)
+                    {
+#pragma unroll
+                        for (int k = 0; k < 4; k++)        // image row k of the 8x4 tile = 8 consecutive pixel rows
+                        {
+                            const uint64_t da = umma_desc_mn_sw128_32b(sg + k * 1024, 32 * 128, 512);
+                            const uint64_t db = umma_desc_mn_sw128_32b(sx + (uint32_t)(p.grp_col[grp][t] + k * p.pw) * 128u, (uint32_t)xblock, 512);
+                            mma_tf32(tmem_base + (uint32_t)(t * NT), da, db, idesc, (ks > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    mma_commit(empty_bar + stage);
+                    if (ks == ksteps - 1) mma_commit(accum_bar);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        else
+        {
+            // 8 transform warps.  Unified row space: rows [0,128) = gradient tile, rows [128, 128 + xrows) = input patch.
+            // A thread owns rows tid and tid + 256; their channel block is fixed, so the 32 scale factors stay in registers and
+            // are reloaded only when the sample index changes.
+            const int tid = threadIdx.x - 64;                   // 0..255
+            const int xrows_blk = p.pw * 4;
+            const int total_rows = 128 + xrows_blk * (NT / 32);
+            float sv[2][32];
+            int cur_n = -1;
+            int rr[2]; const float* sbase[2]; int sstride[2]; bool act[2];
+#pragma unroll
+            for (int s = 0; s < 2; s++)
+            {
+                rr[s] = tid + s * 256;
+                act[s] = rr[s] < total_rows;
+                sbase[s] = nullptr; sstride[s] = 0;
+                if (act[s])
+                {
+                    if (rr[s] < 128) { const int ch = m0 + (rr[s] >> 5) * 32; act[s] = ch < p.cout; if (p.g_scale) { sbase[s] = p.g_scale + ch; sstride[s] = p.cout; } }
+                    else { const int ch = c0 + ((rr[s] - 128) / xrows_blk) * 32; act[s] = ch < p.cin; if (p.x_scale) { sbase[s] = p.x_scale + ch; sstride[s] = p.cin; } }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j++) sv[s][j] = 1.f;
+            }
+            {
+                int stage = 0; uint32_t phase = 0;
+                for (int kt = kt0; kt < kt1; kt++)
+                {
+                    const int n = min(kt / (p.tiles_x * p.tiles_y), p.n - 1);
+                    if (n != cur_n)
+                    {
+                        cur_n = n;
+#pragma unroll
+                        for (int s = 0; s < 2; s++)
+                            if (act[s] && sbase[s])
+                            {
+                                const float4* sp = reinterpret_cast<const float4*>(sbase[s] + (long long)n * sstride[s]);
+#pragma unroll
+                                for (int j = 0; j < 8; j++) { float4 v = __ldg(sp + j); sv[s][4 * j] = v.x; sv[s][4 * j + 1] = v.y; sv[s][4 * j + 2] = v.z; sv[s][4 * j + 3] = v.w; }
+                            }
+                    }
+                    mbar_wait(full_bar + stage, phase);
+                    uint8_t* sg = smem + stage * L::kStage;
+#pragma unroll
+                    for (int s = 0; s < 2; s++)
+                    {
+                        if (!act[s]) continue;
+                        const int row = rr[s] < 128 ? rr[s] : rr[s] - 128;
+                        uint8_t* rowp = sg + (rr[s] < 128 ? 0 : kW2GTile) + row * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                        {
+                            float4* ptr = reinterpret_cast<float4*>(rowp + (((((j >> 1) ^ (row & 3)) << 1) | (j & 1)) << 4));
+                            float4 v = *ptr;
+                            v.x = tf32_rn(v.x * sv[s][4 * j + 0]); v.y = tf32_rn(v.y * sv[s][4 * j + 1]);
+                            v.z = tf32_rn(v.z * sv[s][4 * j + 2]); v.w = tf32_rn(v.w * sv[s][4 * j + 3]);
+                            *ptr = v;
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(ready_bar + stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+            const int q = warp & 3;
+            const int half = (warp - 2) >> 2;                   // two warps share a TMEM lane quarter and split the column chunks
+            const int o = m0 + q * 32 + lane;
+#pragma unroll 1
+            for (int t = 0; t < gtaps; t++)
+            {
+                float* drow = p.dw + ((long long)p.grp_tap[grp][t] * p.cout + o) * p.cin + c0;
+#pragma unroll 1
+                for (int cc = half; cc < NT / 32; cc += 2)
+                {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NT + cc * 32), v);
+                    tmem_ld_wait();
+                    if (o < p.cout && c0 + cc * 32 < p.cin)
+                    {
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            atomicAdd(reinterpret_cast<float4*>(drow + cc * 32 + j * 4),
+                                      make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kCols);
+}
+
+template <int NT, int STAGES>
+static int launch_wgrad_v2(const CUtensorMap& tg, const CUtensorMap& tx, const Wg2Args& a, dim3 grid, cudaStream_t stream)
+{
+    using L = Wg2Smem<NT, STAGES>;
+    auto kern = wgrad_tf32_v2_kernel<NT, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        SGV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        attr_set = true;
+    }
+    kern<<<grid, kWg2Threads, L::kTotal, stream>>>(tg, tx, a);
+    SGV_LAUNCH_OK("wgrad_tf32_v2_kernel");
+    return SGV_OK;
+}
+
+int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, cudaStream_t stream)
+{
+    if (p->g_stride != 1 || p->x_stride != 1 || p->out_w < 8 || p->out_h < 4) return SGV_ERR_UNSUPPORTED;
+    int dx_min = p->x_dx[0], dx_max = p->x_dx[0];
+    for (int t = 0; t < p->ntaps; t++)
+    {
+        if (p->g_dy[t] != 0 || p->g_dx[t] != 0) return SGV_ERR_UNSUPPORTED;
+        dx_min = min(dx_min, p->x_dx[t]); dx_max = max(dx_max, p->x_dx[t]);
+    }
+    if (dx_max - dx_min > 2) return SGV_ERR_UNSUPPORTED;
+    Wg2Args a;
+    memset(&a, 0, sizeof(a));
+    a.dw = p->dw; a.g_scale = p->g_scale; a.x_scale = p->x_scale;
+    a.n = p->n; a.cin = p->cin; a.cout = p->cout; a.out_h = p->out_h; a.out_w = p->out_w;
+    a.dx_min = dx_min; a.pw = 8 + (dx_max - dx_min);
+    // group taps by dy
+    a.ngroups = 0;
+    for (int t = 0; t < p->ntaps; t++)
+    {
+        int g = -1;
+        for (int j = 0; j < a.ngroups; j++) if (a.grp_dy[j] == p->x_dy[t] && a.grp_ntaps[j] < kW2MaxGroupTaps) { g = j; break; }
+        if (g < 0) { g = a.ngroups++; a.grp_dy[g] = p->x_dy[t]; a.grp_ntaps[g] = 0; }
+        a.grp_tap[g][a.grp_ntaps[g]] = t;
+        a.grp_col[g][a.grp_ntaps[g]] = p->x_dx[t] - dx_min;
+        a.grp_ntaps[g]++;
+    }
+    a.tiles_x = ceil_div(p->out_w, 8); a.tiles_y = ceil_div(p->out_h, 4);
+    a.ktiles = a.tiles_x * a.tiles_y * p->n;
+    a.mtiles = ceil_div(p->cout, kWgM);
+    const int nt = (p->cin % 128 == 0) ? 128 : (p->cin % 64 == 0) ? 64 : 32;
+    const int base_ctas = a.mtiles * (p->cin / nt) * a.ngroups;
+    int ksplit = ceil_div(2 * num_sms(), base_ctas);
+    if (ksplit > a.ktiles) ksplit = a.ktiles;
+    if (ksplit < 1) ksplit = 1;
+    a.ksplit = ksplit;
+
+    CUtensorMap tg, tx;
+    int rc = make_blocked_tmap(&tg, p->g, p->cout, p->gw, p->gh, p->n, 8, 4, 1, 1, kWgM / 32);
+    if (rc != SGV_OK) return rc;
+    {
+        const uint64_t dims[5] = {32, (uint64_t)p->xw, (uint64_t)p->xh, (uint64_t)p->n, (uint64_t)(p->cin / 32)};
+        const uint64_t strides[4] = {(uint64_t)p->cin * 4, (uint64_t)p->xw * p->cin * 4, (uint64_t)p->xh * p->xw * p->cin * 4, 128};
+        const uint32_t box[5] = {32, (uint32_t)a.pw, 4, 1, (uint32_t)(nt / 32)};
+        const uint32_t es[5] = {1, 1, 1, 1, 1};
+        rc = make_tmap_f32(&tx, p->x, 5, dims, strides, box, es, /*atom32=*/true);
+        if (rc != SGV_OK) return rc;
+    }
+    dim3 grid((unsigned)(a.mtiles * (p->cin / nt)), (unsigned)ksplit, (unsigned)a.ngroups);
+    switch (nt)
+    {
+        case 128: return launch_wgrad_v2<128, 5>(tg, tx, a, grid, stream);
+        case 64:  return launch_wgrad_v2<64, 7>(tg, tx, a, grid, stream);
+        default:  return launch_wgrad_v2<32, 8>(tg, tx, a, grid, stream);
+    }
+}
+
+} // namespace sgv

@@ -121,25 +121,11 @@ class _FusedModConv(torch.autograd.Function):
         O, I, kh, kw = weight.shape
         N, _, H, W = x.shape
         dy = _nhwc(dy)
-        nil = x.new_empty(0)
-        # ---- activation (+ bias) gradient: dz = d(loss)/d(pre-activation) ----
-        db = torch.zeros([O], dtype=torch.float32, device=x.device) if has_b and ctx.needs_input_grad[4] else None
-        act_idx = {'linear': 1, 'lrelu': 3}[act]
-        if act != 'linear' or gain != 1:
-            dz = _plugin.bias_act(dy, nil, nil, y if act != 'linear' else nil, nil, 1, 1, act_idx, 0.2, gain, -1.0, db_accum=db)
-        else:
-            dz = dy
-            if db is not None:
-                db = dz.sum([0, 2, 3])
-        # ---- d dcoefs: needs the un-demodulated conv output, recovered from y (lrelu is invertible) ----
-        ddcoefs = None
-        if has_d and ctx.needs_input_grad[3]:
-            pre = y * (1.0 / gain)
-            if act == 'lrelu':
-                pre = torch.where(pre > 0, pre, pre * (1.0 / 0.2))
-            if has_b:
-                pre = pre - bias.reshape(1, -1, 1, 1)
-            ddcoefs = (dz * pre).sum(dim=[2, 3]) / dcoefs
+        # ---- activation (+ bias) gradient dz, bias gradient and the dcoefs reduction in ONE pass over (dy, y) ----
+        want_db = has_b and ctx.needs_input_grad[4]
+        want_dd = has_d and ctx.needs_input_grad[3]
+        dz, db, dd = _conv.act_bwd(dy, y, bias if has_b else None, act, gain, want_db, want_dd)
+        ddcoefs = dd / dcoefs if want_dd else None
         dscale = dcoefs if has_d else None
         wsrc_same = weight if flip_weight else weight.flip([2, 3])
         # ---- data gradient (w.r.t. the modulated input x*s), then ds and dx ----
@@ -157,8 +143,8 @@ class _FusedModConv(torch.autograd.Function):
             gout = _plugin.upfirdn2d(dz, _fir(x.device), 1, 1, 1, 1, 2, 2, 2, 2, True, 4.0)
             wp = _conv.prep_weights(wsrc_t, _TAPS3, rows_dim=1, cols_dim=0)
             dxs = _conv.igemm_conv(gout, wp, _TAPS3, out_hw=(H, W), in_stride=2, a_scale=dscale)
-        ds = (dxs * x).sum(dim=[2, 3]) if ctx.needs_input_grad[2] else None
-        dx = dxs * styles.reshape(N, I, 1, 1) if ctx.needs_input_grad[0] else None
+        # dx = dxs * styles (in place) and dstyles = sum_hw dxs * x in ONE pass over (dxs, x)
+        dx, ds = _conv.scale_reduce(dxs, x, styles, want_dx=ctx.needs_input_grad[0], want_ds=ctx.needs_input_grad[2])
         # ---- weight gradient ----
         dw = None
         if ctx.needs_input_grad[1]:

@@ -14,6 +14,7 @@ all style affines of a forward pass are evaluated as ONE stacked GEMM up front.
 import numpy as np
 import torch
 
+from . import conv as _conv
 from .modconv import fused_modulated_conv
 from .ops import upfirdn2d as _upfirdn2d
 from .time_encoder import EqualizedLinear, MotionMappingNetwork
@@ -39,6 +40,23 @@ class SynthesisLayer(torch.nn.Module):
                                     gain=float(np.sqrt(2)) * gain, flip_weight=(self.up == 1))
 
 
+class _ToRGB(torch.autograd.Function):
+    """y[n,j,hw] = sum_c x[n,hw,c] * wmod[n,j,c] + b[j] on the NHWC activation (csrc/layer_elementwise.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, wmod, bias):
+        x = x.contiguous(memory_format=torch.channels_last)
+        ctx.save_for_backward(x, wmod)
+        return _conv.torgb_fwd(x, wmod, bias)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, wmod = ctx.saved_tensors
+        dx, dwmod = _conv.torgb_bwd(dy, x, wmod)
+        return dx, dwmod, dy.sum(dim=[0, 2, 3])
+
+
 class ToRGBLayer(torch.nn.Module):
     """1x1 modulated conv to RGB without demodulation + bias (networks.py:148-163).  With 3 output channels this is
     memory-bound; it runs as one batched [HW, C] x [C, 3] product per sample straight from the NHWC activations."""
@@ -55,9 +73,11 @@ class ToRGBLayer(torch.nn.Module):
             styles = self.affine(w)
         styles = styles * self.weight_gain
         N, C, H, W = x.shape
-        wmod = self.weight.reshape(1, -1, C) * styles.unsqueeze(1)                         # [N, 3, C]
-        xf = x.permute(0, 2, 3, 1).reshape(N, H * W, C)                                    # view of the NHWC storage
-        y = torch.baddbmm(self.bias.reshape(1, 1, -1), xf, wmod.transpose(1, 2))           # [N, HW, 3]
+        wmod = self.weight.reshape(1, -1, C) * styles.unsqueeze(1)                         # [N, 3, C]  (tiny, differentiable torch ops)
+        if wmod.shape[1] == 3 and x.is_cuda:
+            return _ToRGB.apply(x, wmod, self.bias)                                        # one pass over the NHWC activation
+        xf = x.permute(0, 2, 3, 1).reshape(N, H * W, C)
+        y = torch.baddbmm(self.bias.reshape(1, 1, -1), xf, wmod.transpose(1, 2))
         return y.reshape(N, H, W, -1).permute(0, 3, 1, 2).contiguous()                     # NCHW fp32 like the reference (networks.py:261)
 
 

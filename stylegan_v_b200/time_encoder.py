@@ -44,6 +44,26 @@ class EqualizedLinear(torch.nn.Module):
         return torch.addmm(b.unsqueeze(0), x, w.t())
 
 
+class _Conv1dFp32Fwd(torch.autograd.Function):
+    """conv1d whose FORWARD is true fp32 (see EqualizedConv1d.forward) while the backward may use TF32 tensor cores:
+    gradient noise of 1e-3 is harmless, and the fp32 cuDNN weight-gradient engine costs 1.1 ms per step here."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return F.conv1d(x, w, b)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=True):
+            gx, gw, gb = torch.ops.aten.convolution_backward(gy, x, w, [w.shape[0]], [1], [0], [1], False, [0], 1,
+                                                            [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]])
+        return gx, gw, gb
+
+
 class EqualizedConv1d(torch.nn.Module):
     """Conv1d with equalised learning rate + leaky ReLU (layers.py:331-373)."""
 
@@ -57,8 +77,7 @@ class EqualizedConv1d(torch.nn.Module):
     def forward(self, x):
         # true fp32: the embedding multiplies these features by phase scales up to 64 and takes sin/cos, so TF32 rounding
         # here (PyTorch's cuDNN default) would show up as ~1e-2 errors in motion_v; the reference trains with allow_tf32=False
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            y = F.conv1d(x, self.weight * self.weight_gain, self.bias * self.bias_gain)
+        y = _Conv1dFp32Fwd.apply(x, self.weight * self.weight_gain, self.bias * self.bias_gain)
         return F.leaky_relu(y, 0.2)
 
 

@@ -146,3 +146,30 @@ def test_network_vs_oracle_other_config():
     img = net(ws.cuda(), t.cuda(), motion_z=mz.cuda())
     e = rel_err(img, ref)
     assert e < 3e-3, e
+
+
+def test_layer_elementwise_kernels():
+    from stylegan_v_b200 import conv as C
+    gen = torch.Generator().manual_seed(3)
+    for (N, Cc, H) in ((3, 64, 9), (2, 512, 4), (2, 128, 16), (1, 1024, 4), (2, 16, 8)):
+        cl = lambda t: t.cuda().contiguous(memory_format=torch.channels_last)
+        dy = cl(torch.randn(N, Cc, H, H, generator=gen)); v = torch.randn(N, Cc, H, H, generator=gen)
+        bias = torch.randn(Cc, generator=gen).cuda(); gain = float(np.sqrt(2))
+        y = cl(torch.nn.functional.leaky_relu(v.cuda() + bias[None, :, None, None], 0.2) * gain)
+        dz, db, dd = C.act_bwd(dy, y, bias, 'lrelu', gain, True, True)
+        dz_ref = torch.where(y > 0, dy, dy * 0.2) * gain
+        assert rel_err(dz, dz_ref) < 1e-6 and rel_err(db, dz_ref.double().sum([0, 2, 3])) < 1e-5
+        assert rel_err(dd, (dz_ref.double() * v.cuda().double()).sum([2, 3])) < 1e-4
+        x = cl(torch.randn(N, Cc, H, H, generator=gen)); s = torch.randn(N, Cc, generator=gen).cuda()
+        dxs = cl(torch.randn(N, Cc, H, H, generator=gen)); keep = dxs.clone()
+        dx, ds = C.scale_reduce(dxs, x, s)
+        assert rel_err(dx, keep * s[:, :, None, None]) < 1e-6 and rel_err(ds, (keep.double() * x.double()).sum([2, 3])) < 1e-5
+        if Cc >= 16:
+            wmod = torch.randn(N, 3, Cc, generator=gen).cuda(); b3 = torch.randn(3, generator=gen).cuda()
+            yrgb = C.torgb_fwd(x, wmod, b3)
+            ref = torch.einsum('nchw,njc->njhw', x.double(), wmod.double()) + b3.double()[None, :, None, None]
+            assert yrgb.is_contiguous() and rel_err(yrgb, ref) < 1e-5
+            g3 = torch.randn(N, 3, H, H, generator=gen).cuda()
+            dxr, dwm = C.torgb_bwd(g3, x, wmod)
+            assert rel_err(dxr, torch.einsum('njhw,njc->nchw', g3.double(), wmod.double())) < 1e-5
+            assert rel_err(dwm, torch.einsum('njhw,nchw->njc', g3.double(), x.double())) < 1e-5
