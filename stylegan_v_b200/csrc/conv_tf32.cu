@@ -30,6 +30,7 @@ namespace sgv {
 using namespace ptx;
 
 int conv2d_tf32_v2(const sgv_conv_params* p, cudaStream_t stream);     // conv_tf32_v2.cu
+int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream);     // conv_tf32_v3.cu
 
 constexpr int kConvThreads = 192;
 constexpr int kBM = 128;
@@ -345,6 +346,12 @@ extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
 
     // v2 (halo patch + shifted descriptors, csrc/conv_tf32_v2.cu) covers stride-1 inputs on planes >= 12x12; SGV_CONV_V1=1 forces v1
     static const bool force_v1 = getenv("SGV_CONV_V1") != nullptr;
+    static const bool no_v3 = getenv("SGV_CONV_NO_V3") != nullptr;
+    if (!force_v1 && !no_v3)
+    {
+        rc = conv2d_tf32_v3(p, stream);      // persistent (csrc/conv_tf32_v3.cu)
+        if (rc != SGV_ERR_UNSUPPORTED) return rc;
+    }
     if (!force_v1)
     {
         rc = conv2d_tf32_v2(p, stream);

@@ -1,0 +1,354 @@
+// Implicit-GEMM convolution v3 for sm_100a: PERSISTENT version of v2 (haloed patch + shifted descriptors + 2 M-halves).
+//
+// v2 launches one CTA per 256-pixel tile.  For the high-resolution, few-channel layers a tile is only ~2.4 us of MMA work,
+// so the serial chain  TMA latency -> transform -> MMA -> TMEM read-out -> stores  (plus barrier init, TMEM alloc and
+// descriptor fetch per CTA) left the tensor pipe 24 % active (ncu: profiles/ncu_tc_r1l_summary.txt).  v3 keeps one CTA per
+// SM alive and walks tiles round-robin (tile = blockIdx.x + i * gridDim.x):
+//   * the TMA producer, the transform warps and the MMA issuer run ahead ACROSS tile boundaries through the same rings;
+//   * the accumulator is double-buffered in TMEM (when 2 * MH * BN <= 512 columns);
+//   * four dedicated epilogue warps drain tile i (TMEM -> regs -> dcoefs/bias/lrelu/gain -> NHWC stores) while tile i+1
+//     is being multiplied.
+// Operand staging is v2's: per 32-channel chunk ONE TMA box = output tile (16 rows x 16 cols) + halo; every tap's A matrix is
+// that patch through a shifted K-major SWIZZLE_128B descriptor (start row = (dy-dy_min)*PW + (dx-dx_min) + 8*half,
+// SBO = PW*128; legal because tcgen05 swizzles on absolute smem address bits — profiles/umma_probe_r1.txt).
+// Warps: 0 TMA producer, 1 MMA issuer + TMEM owner, 2-5 transform (styles * x, round to TF32), 6-9 epilogue.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+#include "../../include/sgv_b200_conv.h"
+
+namespace sgv {
+
+using namespace ptx;
+
+constexpr int kV3Threads = 64 + 128 + 128;
+constexpr int kV3TileH = 16;
+
+struct ConvV3Args
+{
+    float* y; const float* a_scale; const float* o_scale; const float* bias;
+    int n, cin, cout, out_h, out_w;
+    long long osn, osy, osx;
+    int ntaps;
+    int tap_row[SGV_CONV_MAX_TAPS];
+    int dy_min, dx_min, pw, ph;
+    int tiles_x, tiles_y, ntiles_n, total_tiles;
+    int act; float alpha, gain, clamp;
+};
+
+template <int BN, int MH, int SA, int SB>
+struct ConvV3Smem
+{
+    static constexpr int kPatch = (((16 + 2) * (8 * MH + 2) * 128) + 1023) & ~1023;
+    static constexpr int kBTile = BN * 128;
+    static constexpr int kBOffset = SA * kPatch;
+    static constexpr int kBarOffset = kBOffset + SB * kBTile;
+    static constexpr int kNumBars = 3 * SA + 2 * SB + 4;
+    static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024;
+    static constexpr int kAccBufs = (2 * MH * BN <= 512) ? 2 : 1;
+    static constexpr int kTmemCols = (kAccBufs * MH * BN) <= 32 ? 32 : (kAccBufs * MH * BN) <= 64 ? 64 : (kAccBufs * MH * BN) <= 128 ? 128
+                                     : (kAccBufs * MH * BN) <= 256 ? 256 : 512;
+};
+
+struct TileCoord { int n, ox0, oy0, nb0; };
+
+template <int BN, int MH>
+__device__ __forceinline__ TileCoord tile_coord(const ConvV3Args& p, int tile)
+{
+    // n-tile fastest: the CTAs working on the same pixels at the same time share the activation patch through L2
+    TileCoord c;
+    const int nt = tile % p.ntiles_n; tile /= p.ntiles_n;
+    const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+    const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+    c.n = tile; c.ox0 = tx * 8 * MH; c.oy0 = ty * kV3TileH; c.nb0 = nt * BN;
+    return c;
+}
+
+template <int BN, int MH, int SA, int SB>
+__global__ void __launch_bounds__(kV3Threads, 1)
+conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const ConvV3Args p)
+{
+    using L = ConvV3Smem<BN, MH, SA, SB>;
+    constexpr int NB = L::kAccBufs;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_a = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* ready_a = full_a + SA;
+    uint64_t* empty_a = ready_a + SA;
+    uint64_t* full_b = empty_a + SA;
+    uint64_t* empty_b = full_b + SB;
+    uint64_t* acc_full = empty_b + SB;       // [2]
+    uint64_t* acc_empty = acc_full + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kchunks = p.cin / 32;
+    const uint32_t patch_bytes = (uint32_t)(p.pw * p.ph * 128);
+
+    if (threadIdx.x == 0)
+    {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_w);
+        for (int s = 0; s < SA; s++) { mbar_init(full_a + s, 1); mbar_init(ready_a + s, 4); mbar_init(empty_a + s, 1); }
+        for (int s = 0; s < SB; s++) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, L::kTmemCols); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0)
+    {
+        // ===== TMA producer =====
+        if (elect_one())
+        {
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
+            {
+                const TileCoord tc = tile_coord<BN, MH>(p, tile);
+                for (int kc = 0; kc < kchunks; kc++)
+                {
+                    mbar_wait(empty_a + sa, pa ^ 1);
+                    mbar_expect_tx(full_a + sa, patch_bytes);
+                    tma_load_4d(smem + sa * L::kPatch, &tmap_x, full_a + sa, kc * 32, tc.ox0 + p.dx_min, tc.oy0 + p.dy_min, tc.n);
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
+                    for (int t = 0; t < p.ntaps; t++)
+                    {
+                        mbar_wait(empty_b + sb, pb ^ 1);
+                        mbar_expect_tx(full_b + sb, L::kBTile);
+                        tma_load_2d(smem + L::kBOffset + sb * L::kBTile, &tmap_w, full_b + sb, kc * 32, t * p.cout + tc.nb0);
+                        if (++sb == SB) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    }
+    else if (warp == 1)
+    {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
+        const uint64_t sbo_field = (uint64_t)((uint32_t)(p.pw * 128) >> 4) << 32;
+        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++)
+        {
+            const int buf = it % NB;
+            const uint32_t use = (uint32_t)(it / NB) & 1u;
+            mbar_wait(acc_empty + buf, use ^ 1);                     // epilogue has drained this accumulator buffer
+            tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t)(buf * MH * BN);
+            for (int kc = 0; kc < kchunks; kc++)
+            {
+                mbar_wait(ready_a + sa, pa);
+                tc_fence_after();
+                const uint32_t patch = smem_u32(smem + sa * L::kPatch);
+                for (int t = 0; t < p.ntaps; t++)
+                {
+                    mbar_wait(full_b + sb, pb);
+                    tc_fence_after();
+                    if (elect_one())
+                    {
+                        const uint64_t db = umma_desc_k_sw128(smem_u32(smem + L::kBOffset + sb * L::kBTile));
+#pragma unroll
+                        for (int h = 0; h < MH; h++)
+                        {
+                            uint64_t da = umma_desc_k_sw128(patch + (uint32_t)(p.tap_row[t] + 8 * h) * 128u);
+                            da = (da & ~((uint64_t)0x3FFF << 32)) | sbo_field;
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                mma_tf32(acc + (uint32_t)(h * BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc > 0 || t > 0 || k > 0) ? 1u : 0u);
+                        }
+                        mma_commit(empty_b + sb);
+                        if (t == p.ntaps - 1)
+                        {
+                            mma_commit(empty_a + sa);
+                            if (kc == kchunks - 1) mma_commit(acc_full + buf);
+                        }
+                    }
+                    __syncwarp();
+                    if (++sb == SB) { sb = 0; pb ^= 1; }
+                }
+                if (++sa == SA) { sa = 0; pa ^= 1; }
+            }
+        }
+    }
+    else if (warp < 6)
+    {
+        // ===== operand transform (4 warps) =====
+        const int tid = threadIdx.x - 64;
+        const int nrows = p.pw * p.ph;
+        int sa = 0; uint32_t pa = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
+        {
+            const TileCoord tc = tile_coord<BN, MH>(p, tile);
+            for (int kc = 0; kc < kchunks; kc++)
+            {
+                float sv[32];
+                if (p.a_scale)
+                {
+                    const float4* sp = reinterpret_cast<const float4*>(p.a_scale + (long long)tc.n * p.cin + kc * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { float4 v = __ldg(sp + j); sv[4 * j] = v.x; sv[4 * j + 1] = v.y; sv[4 * j + 2] = v.z; sv[4 * j + 3] = v.w; }
+                }
+                else
+                {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) sv[j] = 1.f;
+                }
+                mbar_wait(full_a + sa, pa);
+                uint8_t* patch = smem + sa * L::kPatch;
+                for (int row = tid; row < nrows; row += 128)
+                {
+                    uint8_t* arow = patch + row * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                    {
+                        float4* ptr = reinterpret_cast<float4*>(arow + ((j ^ (row & 7)) << 4));
+                        float4 v = *ptr;
+                        v.x = tf32_rn(v.x * sv[4 * j + 0]); v.y = tf32_rn(v.y * sv[4 * j + 1]);
+                        v.z = tf32_rn(v.z * sv[4 * j + 2]); v.w = tf32_rn(v.w * sv[4 * j + 3]);
+                        *ptr = v;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ready_a + sa);
+                if (++sa == SA) { sa = 0; pa ^= 1; }
+            }
+        }
+    }
+    else
+    {
+        // ===== epilogue (4 warps) =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++)
+        {
+            const TileCoord tc = tile_coord<BN, MH>(p, tile);
+            const int buf = it % NB;
+            const uint32_t use = (uint32_t)(it / NB) & 1u;
+            mbar_wait(acc_full + buf, use);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t)(buf * MH * BN);
+            const int oy = tc.oy0 + (row >> 3);
+            const float* osc = p.o_scale ? p.o_scale + (long long)tc.n * p.cout + tc.nb0 : nullptr;
+            const float* bia = p.bias ? p.bias + tc.nb0 : nullptr;
+#pragma unroll 1
+            for (int h = 0; h < MH; h++)
+            {
+                const int ox = tc.ox0 + 8 * h + (row & 7);
+                const bool valid = (oy < p.out_h) && (ox < p.out_w);
+                float* yrow = p.y + (long long)tc.n * p.osn + (long long)oy * p.osy + (long long)ox * p.osx + tc.nb0;
+#pragma unroll 1
+                for (int cc = 0; cc < BN / 32; cc++)
+                {
+                    uint32_t v[32];
+                    tmem_ld_32x32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN + cc * 32), v);
+                    tmem_ld_wait();
+                    if (valid)
+                    {
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                        {
+                            float o[4];
+#pragma unroll
+                            for (int e = 0; e < 4; e++)
+                            {
+                                const int col = cc * 32 + j * 4 + e;
+                                float f = __uint_as_float(v[j * 4 + e]);
+                                if (osc) f = __fmul_rn(f, __ldg(osc + col));
+                                if (bia) f = __fadd_rn(f, __ldg(bia + col));
+                                if (p.act == 3) f = (f > 0.f) ? f : f * p.alpha;
+                                f *= p.gain;
+                                if (p.clamp >= 0.f) f = (f > -p.clamp && f < p.clamp) ? f : (f >= 0.f ? p.clamp : -p.clamp);
+                                o[e] = f;
+                            }
+                            *reinterpret_cast<float4*>(yrow + cc * 32 + j * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + buf);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, L::kTmemCols);
+}
+
+template <int BN, int MH, int SA, int SB>
+static int launch_v3(const CUtensorMap& tx, const CUtensorMap& tw, const ConvV3Args& a, cudaStream_t stream)
+{
+    using L = ConvV3Smem<BN, MH, SA, SB>;
+    auto kern = conv_tf32_v3_kernel<BN, MH, SA, SB>;
+    static bool attr_set = false;
+    if (!attr_set)
+    {
+        SGV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        attr_set = true;
+    }
+    const int grid = a.total_tiles < num_sms() ? a.total_tiles : num_sms();
+    kern<<<grid, kV3Threads, L::kTotal, stream>>>(tx, tw, a);
+    SGV_LAUNCH_OK("conv_tf32_v3_kernel");
+    return SGV_OK;
+}
+
+// Returns SGV_ERR_UNSUPPORTED when the shape is outside the envelope (caller falls back to v2 / v1).
+int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
+{
+    if (p->in_stride != 1 || p->out_h < 12 || p->out_w < 12 || p->cout % 64 != 0) return SGV_ERR_UNSUPPORTED;
+    int dy_min = p->tap_dy[0], dy_max = p->tap_dy[0], dx_min = p->tap_dx[0], dx_max = p->tap_dx[0];
+    for (int t = 1; t < p->ntaps; t++)
+    {
+        dy_min = min(dy_min, p->tap_dy[t]); dy_max = max(dy_max, p->tap_dy[t]);
+        dx_min = min(dx_min, p->tap_dx[t]); dx_max = max(dx_max, p->tap_dx[t]);
+    }
+    if (dy_max - dy_min > 2 || dx_max - dx_min > 2) return SGV_ERR_UNSUPPORTED;
+    const int mh = 2;
+    ConvV3Args a;
+    a.y = p->y; a.a_scale = p->a_scale; a.o_scale = p->o_scale; a.bias = p->bias;
+    a.n = p->n; a.cin = p->cin; a.cout = p->cout; a.out_h = p->out_h; a.out_w = p->out_w;
+    a.osn = p->out_stride_n; a.osy = p->out_stride_y; a.osx = p->out_stride_x;
+    a.ntaps = p->ntaps;
+    a.dy_min = dy_min; a.dx_min = dx_min;
+    a.pw = 8 * mh + (dx_max - dx_min); a.ph = kV3TileH + (dy_max - dy_min);
+    for (int t = 0; t < SGV_CONV_MAX_TAPS; t++) a.tap_row[t] = t < p->ntaps ? (p->tap_dy[t] - dy_min) * a.pw + (p->tap_dx[t] - dx_min) : 0;
+    a.tiles_x = ceil_div(p->out_w, 8 * mh); a.tiles_y = ceil_div(p->out_h, kV3TileH);
+    a.act = p->act; a.alpha = p->alpha; a.gain = p->gain; a.clamp = p->clamp;
+    const int bn = (p->cout % 256 == 0) ? 256 : (p->cout % 128 == 0) ? 128 : 64;
+    a.ntiles_n = p->cout / bn;
+    a.total_tiles = a.tiles_x * a.tiles_y * p->n * a.ntiles_n;
+
+    CUtensorMap tmx, tmw;
+    {
+        const uint64_t dims[4] = {(uint64_t)p->cin, (uint64_t)p->w, (uint64_t)p->h, (uint64_t)p->n};
+        const uint64_t strides[3] = {(uint64_t)p->cin * 4, (uint64_t)p->w * p->cin * 4, (uint64_t)p->h * p->w * p->cin * 4};
+        const uint32_t box[4] = {32, (uint32_t)a.pw, (uint32_t)a.ph, 1};
+        const uint32_t es[4] = {1, 1, 1, 1};
+        int rc = make_tmap_f32(&tmx, p->x, 4, dims, strides, box, es);
+        if (rc != SGV_OK) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)p->cin, (uint64_t)p->ntaps * p->cout};
+        const uint64_t strides[1] = {(uint64_t)p->cin * 4};
+        const uint32_t box[2] = {32, (uint32_t)bn};
+        const uint32_t es[2] = {1, 1};
+        int rc = make_tmap_f32(&tmw, p->wp, 2, dims, strides, box, es);
+        if (rc != SGV_OK) return rc;
+    }
+    switch (bn)
+    {
+        case 256: return launch_v3<256, 2, 2, 3>(tmx, tmw, a, stream);     // 84 KB patches + 96 KB slabs, single accumulator buffer (512 cols)
+        case 128: return launch_v3<128, 2, 3, 5>(tmx, tmw, a, stream);     // 126 + 80 KB, double-buffered accumulators (512 cols)
+        default:  return launch_v3<64, 2, 3, 8>(tmx, tmw, a, stream);      // 126 + 64 KB, double-buffered accumulators (256 cols)
+    }
+}
+
+} // namespace sgv

@@ -479,13 +479,20 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
                         if (!act[s]) continue;
                         const int row = rr[s] < 128 ? rr[s] : rr[s] - 128;
                         uint8_t* rowp = sg + (rr[s] < 128 ? 0 : kW2GTile) + row * 128;
+                        // logical 16-byte chunk jj = j ^ bit2(row): the 8 rows a quarter-warp touches then hit 8 distinct physical
+                        // chunks of the 32-byte-atom swizzle (row & 3 only permutes 32 B pairs) -> no shared-memory bank conflicts
+                        const int flip = (row >> 2) & 1;
 #pragma unroll
                         for (int j = 0; j < 8; j++)
                         {
-                            float4* ptr = reinterpret_cast<float4*>(rowp + (((((j >> 1) ^ (row & 3)) << 1) | (j & 1)) << 4));
+                            const int jj = j ^ flip;
+                            float4* ptr = reinterpret_cast<float4*>(rowp + (((((jj >> 1) ^ (row & 3)) << 1) | (jj & 1)) << 4));
                             float4 v = *ptr;
-                            v.x = tf32_rn(v.x * sv[s][4 * j + 0]); v.y = tf32_rn(v.y * sv[s][4 * j + 1]);
-                            v.z = tf32_rn(v.z * sv[s][4 * j + 2]); v.w = tf32_rn(v.w * sv[s][4 * j + 3]);
+                            const float s0 = flip ? sv[s][4 * (j ^ 1) + 0] : sv[s][4 * j + 0];
+                            const float s1 = flip ? sv[s][4 * (j ^ 1) + 1] : sv[s][4 * j + 1];
+                            const float s2 = flip ? sv[s][4 * (j ^ 1) + 2] : sv[s][4 * j + 2];
+                            const float s3 = flip ? sv[s][4 * (j ^ 1) + 3] : sv[s][4 * j + 3];
+                            v.x = tf32_rn(v.x * s0); v.y = tf32_rn(v.y * s1); v.z = tf32_rn(v.z * s2); v.w = tf32_rn(v.w * s3);
                             *ptr = v;
                         }
                     }
@@ -574,9 +581,14 @@ int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, cudaStream_t stream)
     a.mtiles = ceil_div(p->cout, kWgM);
     const int nt = (p->cin % 128 == 0) ? 128 : (p->cin % 64 == 0) ? 64 : 32;
     const int base_ctas = a.mtiles * (p->cin / nt) * a.ngroups;
-    int ksplit = ceil_div(2 * num_sms(), base_ctas);
-    if (ksplit > a.ktiles) ksplit = a.ktiles;
+    // one CTA is resident per SM: size the split so that the grid is (just under) a whole number of waves, and keep >= 48
+    // k-steps per CTA so the prologue/epilogue (TMEM alloc, 3 x NT-column atomics) stays amortised
+    int waves = 1;
+    while (waves < 4 && a.ktiles / max(1, (waves * num_sms()) / base_ctas) > 1024) waves++;
+    int ksplit = (waves * num_sms()) / base_ctas;
     if (ksplit < 1) ksplit = 1;
+    while (ksplit > 1 && a.ktiles / ksplit < 48) ksplit--;
+    if (ksplit > a.ktiles) ksplit = a.ktiles;
     a.ksplit = ksplit;
 
     CUtensorMap tg, tx;
