@@ -52,6 +52,10 @@ typedef struct sgv_conv_params {
     const float* bias;         /* [cout] or NULL */
     int32_t act;               /* 1 = linear, 3 = lrelu (bias_act cuda_idx numbering) */
     float   alpha, gain, clamp;/* clamp < 0 disables */
+    /* optional: x is a strided VIEW [n, h, w, cin] of a larger NHWC tensor (element strides, channel stride 1); all zero = dense.
+     * Used to address one polyphase sub-lattice (pixel stride 2) of the transposed-conv gradient without a stride-2 gather. */
+    int64_t in_stride_n, in_stride_y, in_stride_x;
+    int32_t accumulate;        /* 1: y += result (no o_scale/bias/act allowed) — sums the four polyphase data-gradient launches */
 } sgv_conv_params;
 
 int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream);
@@ -78,6 +82,8 @@ typedef struct sgv_wgrad_params {
     int32_t x_dy[SGV_CONV_MAX_TAPS], x_dx[SGV_CONV_MAX_TAPS];
     const float* g_scale;      /* [n, cout] or NULL */
     const float* x_scale;      /* [n, cin]  or NULL */
+    /* optional: x is a strided VIEW [n, xh, xw, cin] of a larger NHWC tensor (element strides); all zero = dense */
+    int64_t x_stride_n, x_stride_y, x_stride_x;
 } sgv_wgrad_params;
 
 int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream);

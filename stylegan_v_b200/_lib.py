@@ -58,6 +58,7 @@ class ConvParams(ctypes.Structure):
         ('tap_dy', c_int * CONV_MAX_TAPS), ('tap_dx', c_int * CONV_MAX_TAPS),
         ('a_scale', c_vp), ('o_scale', c_vp), ('bias', c_vp),
         ('act', c_int), ('alpha', c_f32), ('gain', c_f32), ('clamp', c_f32),
+        ('in_stride_n', c_i64), ('in_stride_y', c_i64), ('in_stride_x', c_i64), ('accumulate', c_int),
     ]
 
 
@@ -69,6 +70,7 @@ class WgradParams(ctypes.Structure):
         ('out_h', c_int), ('out_w', c_int), ('g_stride', c_int), ('x_stride', c_int), ('ntaps', c_int),
         ('g_dy', c_int * CONV_MAX_TAPS), ('g_dx', c_int * CONV_MAX_TAPS), ('x_dy', c_int * CONV_MAX_TAPS), ('x_dx', c_int * CONV_MAX_TAPS),
         ('g_scale', c_vp), ('x_scale', c_vp),
+        ('x_stride_n', c_i64), ('x_stride_y', c_i64), ('x_stride_x', c_i64),
     ]
 
 

@@ -37,7 +37,7 @@ def prep_weights(w, taps, rows_dim=0, cols_dim=1):
 
 
 def igemm_conv(x, wp, tap_offsets, out=None, out_hw=None, out_view=None, in_stride=1,
-               a_scale=None, o_scale=None, bias=None, act='linear', alpha=0.2, gain=1.0, clamp=None):
+               a_scale=None, o_scale=None, bias=None, act='linear', alpha=0.2, gain=1.0, clamp=None, accumulate=False):
     """y[n,oy,ox,o] = epi(sum_{t,i} x[n, oy*in_stride+dy_t, ox*in_stride+dx_t, i] * a_scale[n,i] * wp[t,o,i]).
 
     x: [N, Cin, H, W] channels_last fp32.  wp: [ntaps, Cout, Cin] from prep_weights.  tap_offsets: [(dy, dx)].
@@ -45,7 +45,9 @@ def igemm_conv(x, wp, tap_offsets, out=None, out_hw=None, out_view=None, in_stri
     view [N, Cout, out_h, out_w] (channel stride 1) of a larger channels_last tensor."""
     _req(x.is_cuda and x.dtype == torch.float32 and x.ndim == 4, 'x must be a CUDA float32 [N,C,H,W] tensor')
     N, Cin, H, W = x.shape
-    _req(x.stride(1) == 1 and x.stride(3) == Cin and x.stride(2) == W * Cin and x.stride(0) == H * W * Cin, 'x must be dense channels_last (NHWC)')
+    dense = x.stride(1) == 1 and x.stride(3) == Cin and x.stride(2) == W * Cin and x.stride(0) == H * W * Cin
+    _req(dense or (x.stride(1) == 1 and all(st % 4 == 0 for st in (x.stride(0), x.stride(2), x.stride(3)))),
+         'x must be channels_last (NHWC), dense or a pixel-strided view with unit channel stride')
     nt, Cout, Cin2 = wp.shape
     _req(Cin2 == Cin and nt == len(tap_offsets) and wp.is_contiguous(), 'wp does not match x / taps')
     if out_view is not None:
@@ -76,6 +78,9 @@ def igemm_conv(x, wp, tap_offsets, out=None, out_hw=None, out_view=None, in_stri
     p.act = {'linear': 1, 'lrelu': 3}[act]
     p.alpha, p.gain = float(alpha), float(gain)
     p.clamp = float(clamp) if clamp is not None else -1.0
+    if not dense:
+        p.in_stride_n, p.in_stride_y, p.in_stride_x = x.stride(0), x.stride(2), x.stride(3)
+    p.accumulate = int(bool(accumulate))
     with torch.cuda.device(x.device):
         _lib.check(L.sgv_conv2d_tf32(ctypes.byref(p), _stream(x.device)), 'sgv_conv2d_tf32')
     return y
@@ -95,8 +100,10 @@ def igemm_wgrad(g, x, taps_g, taps_x, out_hw, g_stride=1, x_stride=1, g_scale=No
     g: [N, Cout, gh, gw], x: [N, Cin, xh, xw], both channels_last fp32; taps_*: per-tap (dy, dx) pixel offsets."""
     for name, t in (('g', g), ('x', x)):
         _req(t.is_cuda and t.dtype == torch.float32 and t.ndim == 4, f'{name} must be a CUDA float32 [N,C,H,W] tensor')
-        _req(t.stride(1) == 1 and t.stride(3) == t.shape[1] and t.stride(2) == t.shape[3] * t.shape[1] and t.stride(0) == t.shape[1] * t.shape[2] * t.shape[3],
-             f'{name} must be dense channels_last (NHWC)')
+    _req(_is_nhwc(g), 'g must be dense channels_last (NHWC)')
+    x_dense = _is_nhwc(x)
+    _req(x_dense or (x.stride(1) == 1 and all(st % 4 == 0 for st in (x.stride(0), x.stride(2), x.stride(3)))),
+         'x must be channels_last (NHWC), dense or a pixel-strided view with unit channel stride')
     N, Cout, gh, gw = g.shape
     N2, Cin, xh, xw = x.shape
     _req(N == N2 and len(taps_g) == len(taps_x), 'g / x / taps mismatch')
@@ -118,6 +125,8 @@ def igemm_wgrad(g, x, taps_g, taps_x, out_hw, g_stride=1, x_stride=1, g_scale=No
             _req(tuple(t.shape) == shape, f'{name} must be {shape}')
             keep.append(t)
             setattr(p, name, t.data_ptr())
+    if not x_dense:
+        p.x_stride_n, p.x_stride_y, p.x_stride_x = x.stride(0), x.stride(2), x.stride(3)
     with torch.cuda.device(x.device):
         _lib.check(L.sgv_conv2d_wgrad_tf32(ctypes.byref(p), _stream(x.device)), 'sgv_conv2d_wgrad_tf32')
     return dw

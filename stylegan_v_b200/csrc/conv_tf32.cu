@@ -47,6 +47,7 @@ struct ConvArgs
     int tw, th, tn;                   // activation box: tw*th*tn == 128
     int tiles_x, tiles_y, tiles_nb;
     int act; float alpha, gain, clamp;
+    int accumulate;
 };
 
 template <int BN, int STAGES>
@@ -225,7 +226,9 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         if (p.clamp >= 0.f) f = (f > -p.clamp && f < p.clamp) ? f : (f >= 0.f ? p.clamp : -p.clamp);
                         o[e] = f;
                     }
-                    *reinterpret_cast<float4*>(yrow + cc * 32 + j * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                    float4* dst = reinterpret_cast<float4*>(yrow + cc * 32 + j * 4);
+                    if (p.accumulate) { const float4 old = *dst; o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w; }
+                    *dst = make_float4(o[0], o[1], o[2], o[3]);
                 }
             }
         }
@@ -341,6 +344,11 @@ extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
                   (reinterpret_cast<uintptr_t>(p->y) & 15) == 0, "x, wp and y must be 16-byte aligned");
     SGV_CHECK_ARG(p->out_stride_n % 4 == 0 && p->out_stride_y % 4 == 0 && p->out_stride_x % 4 == 0, "output strides must be multiples of 4 elements");
     SGV_CHECK_ARG((long long)p->n * p->h * p->w * p->cin <= 0x7fffffffLL, "x is too large");
+    SGV_CHECK_ARG(!p->accumulate || (p->o_scale == nullptr && p->bias == nullptr && p->act == 1 && p->gain == 1.0f && p->clamp < 0.f),
+                  "accumulate=1 cannot be combined with o_scale / bias / activation / gain / clamp");
+    SGV_CHECK_ARG((p->in_stride_x == 0 && p->in_stride_y == 0 && p->in_stride_n == 0) ||
+                  (p->in_stride_x % 4 == 0 && p->in_stride_y % 4 == 0 && p->in_stride_n % 4 == 0 && p->in_stride_x > 0),
+                  "input view strides must be positive multiples of 4 elements (or all zero for a dense tensor)");
     int rc = sgv_device_check();
     if (rc != SGV_OK) return rc;
 
@@ -365,6 +373,7 @@ extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
     a.in_stride = p->in_stride; a.ntaps = p->ntaps;
     for (int t = 0; t < SGV_CONV_MAX_TAPS; t++) { a.tap_dy[t] = p->tap_dy[t]; a.tap_dx[t] = p->tap_dx[t]; }
     a.act = p->act; a.alpha = p->alpha; a.gain = p->gain; a.clamp = p->clamp;
+    a.accumulate = p->accumulate;
 
     // activation box of 128 output pixels: as square as the plane allows, spilling into the batch dimension for tiny planes
     int tw = pow2_floor(p->out_w < 16 ? p->out_w : 16);
@@ -380,7 +389,9 @@ extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
     CUtensorMap tmx, tmw;
     {
         const uint64_t dims[4] = {(uint64_t)p->cin, (uint64_t)p->w, (uint64_t)p->h, (uint64_t)p->n};
-        const uint64_t strides[3] = {(uint64_t)p->cin * 4, (uint64_t)p->w * p->cin * 4, (uint64_t)p->h * p->w * p->cin * 4};
+        const bool view = p->in_stride_x != 0;
+        const uint64_t strides[3] = {(uint64_t)(view ? p->in_stride_x : p->cin) * 4, (uint64_t)(view ? p->in_stride_y : (int64_t)p->w * p->cin) * 4,
+                                     (uint64_t)(view ? p->in_stride_n : (int64_t)p->h * p->w * p->cin) * 4};
         const uint32_t box[4] = {(uint32_t)kBK, (uint32_t)(tw * p->in_stride), (uint32_t)(th * p->in_stride), (uint32_t)tn};
         const uint32_t es[4] = {1, (uint32_t)p->in_stride, (uint32_t)p->in_stride, 1};
         SGV_CHECK_ARG(box[1] <= 256 && box[2] <= 256, "activation box too large");

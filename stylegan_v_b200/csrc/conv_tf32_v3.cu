@@ -34,6 +34,7 @@ struct ConvV3Args
     int dy_min, dx_min, pw, ph;
     int tiles_x, tiles_y, ntiles_n, total_tiles;
     int act; float alpha, gain, clamp;
+    int accumulate;
 };
 
 template <int BN, int MH, int SA, int SB>
@@ -267,7 +268,9 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                                 if (p.clamp >= 0.f) f = (f > -p.clamp && f < p.clamp) ? f : (f >= 0.f ? p.clamp : -p.clamp);
                                 o[e] = f;
                             }
-                            *reinterpret_cast<float4*>(yrow + cc * 32 + j * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                            float4* dst = reinterpret_cast<float4*>(yrow + cc * 32 + j * 4);
+                            if (p.accumulate) { const float4 old = *dst; o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w; }
+                            *dst = make_float4(o[0], o[1], o[2], o[3]);
                         }
                     }
                 }
@@ -322,6 +325,7 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
     for (int t = 0; t < SGV_CONV_MAX_TAPS; t++) a.tap_row[t] = t < p->ntaps ? (p->tap_dy[t] - dy_min) * a.pw + (p->tap_dx[t] - dx_min) : 0;
     a.tiles_x = ceil_div(p->out_w, 8 * mh); a.tiles_y = ceil_div(p->out_h, kV3TileH);
     a.act = p->act; a.alpha = p->alpha; a.gain = p->gain; a.clamp = p->clamp;
+    a.accumulate = p->accumulate;
     const int bn = (p->cout % 256 == 0) ? 256 : (p->cout % 128 == 0) ? 128 : 64;
     a.ntiles_n = p->cout / bn;
     a.total_tiles = a.tiles_x * a.tiles_y * p->n * a.ntiles_n;
@@ -329,7 +333,9 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
     CUtensorMap tmx, tmw;
     {
         const uint64_t dims[4] = {(uint64_t)p->cin, (uint64_t)p->w, (uint64_t)p->h, (uint64_t)p->n};
-        const uint64_t strides[3] = {(uint64_t)p->cin * 4, (uint64_t)p->w * p->cin * 4, (uint64_t)p->h * p->w * p->cin * 4};
+        const bool view = p->in_stride_x != 0;
+        const uint64_t strides[3] = {(uint64_t)(view ? p->in_stride_x : p->cin) * 4, (uint64_t)(view ? p->in_stride_y : (int64_t)p->w * p->cin) * 4,
+                                     (uint64_t)(view ? p->in_stride_n : (int64_t)p->h * p->w * p->cin) * 4};
         const uint32_t box[4] = {32, (uint32_t)a.pw, (uint32_t)a.ph, 1};
         const uint32_t es[4] = {1, 1, 1, 1};
         int rc = make_tmap_f32(&tmx, p->x, 4, dims, strides, box, es);

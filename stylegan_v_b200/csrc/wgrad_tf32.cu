@@ -263,6 +263,7 @@ extern "C" int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream_)
         rc = conv2d_wgrad_tf32_v2(p, stream);
         if (rc != SGV_ERR_UNSUPPORTED) return rc;
     }
+    if (p->x_stride_x != 0) return sgv::fail(SGV_ERR_UNSUPPORTED, "strided x views are only supported by the grouped-tap kernel (stride 1, out_w >= 8, out_h >= 4)");
 
     WgArgs a;
     a.dw = p->dw; a.g_scale = p->g_scale; a.x_scale = p->x_scale;
@@ -596,7 +597,9 @@ int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, cudaStream_t stream)
     if (rc != SGV_OK) return rc;
     {
         const uint64_t dims[5] = {32, (uint64_t)p->xw, (uint64_t)p->xh, (uint64_t)p->n, (uint64_t)(p->cin / 32)};
-        const uint64_t strides[4] = {(uint64_t)p->cin * 4, (uint64_t)p->xw * p->cin * 4, (uint64_t)p->xh * p->xw * p->cin * 4, 128};
+        const bool view = p->x_stride_x != 0;
+        const uint64_t strides[4] = {(uint64_t)(view ? p->x_stride_x : p->cin) * 4, (uint64_t)(view ? p->x_stride_y : (int64_t)p->xw * p->cin) * 4,
+                                     (uint64_t)(view ? p->x_stride_n : (int64_t)p->xh * p->xw * p->cin) * 4, 128};
         const uint32_t box[5] = {32, (uint32_t)a.pw, 4, 1, (uint32_t)(nt / 32)};
         const uint32_t es[5] = {1, 1, 1, 1, 1};
         rc = make_tmap_f32(&tx, p->x, 5, dims, strides, box, es, /*atom32=*/true);

@@ -65,6 +65,19 @@ def _wgrad_native(gout, x, styles, dscale, w_shape, up):
     if up == 1:
         taps_x = _OFFS3_FWD if kh == 3 else [(0, 0)]
         dw = _conv.igemm_wgrad(gout, x, [(0, 0)] * len(taps_x), taps_x, (H, W), g_scale=dscale, x_scale=styles)
+    elif H >= 8 and W >= 8:
+        # transposed (stride-2) conv: per polyphase sub-lattice (a, b) of the output gradient, a stride-1 correlation between the
+        # unshifted input (M side) and the pixel-strided VIEW gout[:, :, a::2, b::2] shifted by (ky//2, kx//2) (N side): the grouped-tap
+        # kernel applies; it returns dW^T [tap][I][O]
+        dw = torch.empty([O, I, kh, kw], dtype=torch.float32, device=x.device)
+        for a in (0, 1):
+            for b in (0, 1):
+                taps = [(ky, kx) for ky in range(a, 3, 2) for kx in range(b, 3, 2)]
+                offs = [(ky // 2, kx // 2) for ky, kx in taps]
+                dwt = _conv.igemm_wgrad(x, gout[:, :, a::2, b::2], [(0, 0)] * len(taps), offs, (H, W), g_scale=styles, x_scale=dscale)
+                for t, (ky, kx) in enumerate(taps):
+                    dw[:, :, ky, kx] = dwt[t].t()
+        return dw
     else:
         dw = _conv.igemm_wgrad(gout, x, _TAPS3, [(0, 0)] * 9, (H, W), g_stride=2, g_scale=dscale, x_scale=styles)
     return dw.reshape(kh, kw, O, I).permute(2, 3, 0, 1)
@@ -141,6 +154,9 @@ class _FusedModConv(torch.autograd.Function):
             wsrc_t = weight if not flip_weight else weight.flip([2, 3])
             # adjoint of the FIR pass (upfirdn2d.py:246-261): padding (fw - p - 1) = 2, flipped filter, same gain
             gout = _plugin.upfirdn2d(dz, _fir(x.device), 1, 1, 1, 1, 2, 2, 2, 2, True, 4.0)
+            # data gradient of the stride-2 transposed conv = stride-2 correlation: ONE launch with TMA element strides.
+            # (Measured alternative: 4 accumulate-launches over polyphase views of `gout` on the halo-patch kernel — 1.2 ms/step
+            #  slower at config 2 because dx is re-read/re-written 3 extra times; kept available through igemm_conv(accumulate=True).)
             wp = _conv.prep_weights(wsrc_t, _TAPS3, rows_dim=1, cols_dim=0)
             dxs = _conv.igemm_conv(gout, wp, _TAPS3, out_hw=(H, W), in_stride=2, a_scale=dscale)
         # dx = dxs * styles (in place) and dstyles = sum_hw dxs * x in ONE pass over (dxs, x)

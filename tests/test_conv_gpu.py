@@ -139,3 +139,24 @@ def test_argument_errors():
     x = torch.randn(1, 32, 8, 8).cuda()
     with pytest.raises(RuntimeError):
         C.igemm_conv(x, torch.zeros(1, 64, 32, device='cuda'), [(0, 0)])        # not channels_last
+
+
+def test_strided_view_input_and_accumulate():
+    """Polyphase views of a larger tensor as conv input (TMA strides) and y += accumulation across launches."""
+    g = torch.Generator().manual_seed(21)
+    N, Cin, Cout, h = 2, 64, 64, 16
+    du = _cl(torch.randn(N, Cin, 2 * h + 1, 2 * h + 1, generator=g).cuda())
+    w = torch.randn(Cout, Cin, 3, 3, generator=g).cuda()
+    out = None
+    for a in (0, 1):
+        for b in (0, 1):
+            taps = [(ky, kx) for ky in range(a, 3, 2) for kx in range(b, 3, 2)]
+            offs = [(ky // 2, kx // 2) for ky, kx in taps]
+            wp = C.prep_weights(w, taps)
+            view = du[:, :, a::2, b::2]
+            if out is None:
+                out = C.igemm_conv(view, wp, offs, out_hw=(h, h))
+            else:
+                C.igemm_conv(view, wp, offs, out_view=out, accumulate=True)
+    ref = F.conv2d(tf32_round(du).double(), tf32_round(w).double(), stride=2)
+    assert rel_err(out, ref) < 2e-5
