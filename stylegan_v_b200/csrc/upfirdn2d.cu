@@ -409,6 +409,83 @@ __global__ void __launch_bounds__(256) fir_nhwc_fast(FirArgs p, long long total)
     }
 }
 
+// Sliding-window channels_last kernel for the hot geometry (up = down = 1, 4x4 taps): a thread owns 4 channels of TWO output
+// rows and walks SEG output columns; the 5x4 input window lives in registers and only ONE new column (5 x 128-bit loads) is
+// fetched per step, i.e. 2.5 loads per output vector instead of 10.  Tap order per output is unchanged (rows, then columns, ascending) => same bits.
+template <bool EPI>
+__global__ void __launch_bounds__(256, 2) fir_nhwc_slide44(FirArgs p, long long total, int seg, int nseg)
+{
+    __shared__ float sf[16];
+    if (threadIdx.x < 16)
+    {
+        int fy = threadIdx.x >> 2, fx = threadIdx.x & 3;
+        int ffx = p.flip ? fx : 3 - fx;
+        int ffy = p.flip ? fy : 3 - fy;
+        sf[threadIdx.x] = p.f[ffx * p.fsx + ffy * p.fsy];
+    }
+    __syncthreads();
+    float fr[4][4];
+#pragma unroll
+    for (int i = 0; i < 16; i++) fr[i >> 2][i & 3] = sf[i];
+    const int cvecs = p.in_c >> 2;
+    const int rows2 = (p.out_h + 1) >> 1;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    {
+        long long r = idx;
+        const int cv = (int)(r % cvecs); r /= cvecs;
+        const int sg = (int)(r % nseg); r /= nseg;
+        const int oy2 = (int)(r % rows2);
+        const int n = (int)(r / rows2);
+        const int c0 = cv * 4;
+        const int outY0 = oy2 * 2;
+        const int x_begin = sg * seg;
+        const int x_end = min(x_begin + seg, p.out_w);
+        const int inY0 = outY0 - p.pad_y0;
+        const float* xb = (const float*)p.x + n * p.isn + c0;
+        const float* rowp[5]; bool rowok[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) { const int iy = inY0 + k; rowok[k] = iy >= 0 && iy < p.in_h; rowp[k] = xb + (long long)(rowok[k] ? iy : 0) * p.isy; }
+        auto load_col = [&](int inX, float4 (&col)[5]) {
+            const bool cok = inX >= 0 && inX < p.in_w;
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+                col[k] = (cok && rowok[k]) ? __ldg(reinterpret_cast<const float4*>(rowp[k] + (long long)inX * p.isx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        float4 win[4][5];                          // win[slot][row]: columns inX .. inX+3 of the current output, slots rotate
+        const int inX0 = x_begin - p.pad_x0;
+        load_col(inX0 + 0, win[0]); load_col(inX0 + 1, win[1]); load_col(inX0 + 2, win[2]);
+        for (int xo = x_begin; xo < x_end; xo += 4)
+        {
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+            {
+                const int outX = xo + u;
+                load_col(outX - p.pad_x0 + 3, win[(u + 3) & 3]);      // slot (u+3)%4 receives the newest column
+                if (outX < x_end)
+                {
+                    float4 a0, a1; vzero(a0); vzero(a1);
+#pragma unroll
+                    for (int ry = 0; ry < 4; ry++)
+#pragma unroll
+                        for (int cx = 0; cx < 4; cx++)
+                        {
+                            vfma(a0, win[(u + cx) & 3][ry], fr[ry][cx]);
+                        }
+#pragma unroll
+                    for (int ry = 0; ry < 4; ry++)
+#pragma unroll
+                        for (int cx = 0; cx < 4; cx++)
+                        {
+                            vfma(a1, win[(u + cx) & 3][ry + 1], fr[ry][cx]);
+                        }
+                    nhwc_store<4, EPI>(p, a0, n, c0, outY0, outX);
+                    if (outY0 + 1 < p.out_h) nhwc_store<4, EPI>(p, a1, n, c0, outY0 + 1, outX);
+                }
+            }
+        }
+    }
+}
+
 // General channels_last kernel (any up/down/filter), one output pixel x VEC channels per thread.
 template <int VEC>
 __global__ void __launch_bounds__(256) fir_nhwc_any(FirArgs p, long long total)
@@ -580,7 +657,15 @@ extern "C" int sgv_upfirdn2d(const sgv_upfirdn2d_params* p, void* stream_)
                 const bool epi = a.eact != 0;
 #define SGV_NHWC_FAST(V, D) do { if (epi) fir_nhwc_fast<V, D, 4, 4, true><<<grid, 256, 0, stream>>>(a, work); \
                                  else fir_nhwc_fast<V, D, 4, 4, false><<<grid, 256, 0, stream>>>(a, work); } while (0)
-                if (v4 && a.downx == 1) SGV_NHWC_FAST(4, 1);
+                if (v4 && a.downx == 1)
+                {
+                    const int seg = 32;
+                    const int nseg = ceil_div(ow, seg);
+                    const long long items = (long long)a.in_n * ((oh + 1) / 2) * nseg * cvecs;
+                    const unsigned g2 = (unsigned)min((long long)sms * 16, (items + 255) / 256);
+                    if (epi) fir_nhwc_slide44<true><<<g2, 256, 0, stream>>>(a, items, seg, nseg);
+                    else fir_nhwc_slide44<false><<<g2, 256, 0, stream>>>(a, items, seg, nseg);
+                }
                 else if (v4) SGV_NHWC_FAST(4, 2);
                 else if (a.downx == 1) SGV_NHWC_FAST(1, 1);
                 else SGV_NHWC_FAST(1, 2);
