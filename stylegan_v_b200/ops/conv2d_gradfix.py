@@ -9,14 +9,17 @@ into `aten::cudnn_convolution_backward_weight`; on newer torch it silently degra
 `no_weight_gradients()` stops having any effect.  Here the op is rebuilt on the stable
 `aten::convolution_backward` entry point so it works on current torch:
 
-  forward        dense contraction: the tcgen05 implicit-GEMM kernel of libsgv_b200 for the shapes it covers
-                 (see stylegan_v_b200/conv.py), the cuDNN library call otherwise — like the reference;
+  forward        dense contraction: the tcgen05 implicit-GEMM kernels of libsgv_b200 for the shapes they cover
+                 (stylegan_v_b200/native_conv.py: every conv the synthesis / discriminator blocks issue with channel
+                 counts % 32), the cuDNN library call otherwise — like the reference;
   grad input     the transposed op of the same class (arbitrary-order differentiable, conv2d_gradfix.py:125-128);
   grad weight    separate autograd node that is skipped entirely when `weight_gradients_disabled`
                  (conv2d_gradfix.py:130-132) and is itself differentiable (conv2d_gradfix.py:151-165).
 """
 import contextlib
 import torch
+
+from .. import native_conv as _native
 
 enabled = False                     # the reference's training loop sets this to True (training_loop.py:143)
 weight_gradients_disabled = False
@@ -58,6 +61,9 @@ def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_paddi
 
 
 def _forward_op(x, w, b, transpose, stride, padding, output_padding, dilation, groups):
+    y = _native.conv_forward(x, w, b, transpose, stride, padding, output_padding, dilation, groups)   # tcgen05 kernels when the shape allows
+    if y is not None:
+        return y
     F = torch.nn.functional
     if transpose:
         return F.conv_transpose2d(x, w, b, stride=stride, padding=padding, output_padding=output_padding, groups=groups, dilation=dilation)
@@ -96,6 +102,9 @@ class _ConvGradWeight(torch.autograd.Function):
     def forward(ctx, gy, x, w_shape, transpose, stride, padding, output_padding, dilation, groups):
         ctx.cfg = (w_shape, transpose, stride, padding, output_padding, dilation, groups)
         ctx.save_for_backward(gy, x)
+        gw = _native.conv_weight_grad(gy, x, w_shape, transpose, stride, padding, output_padding, dilation, groups)
+        if gw is not None:
+            return gw
         w_like = torch.empty(w_shape, dtype=x.dtype, device=x.device)
         _, gw, _ = torch.ops.aten.convolution_backward(gy, x, w_like, None, list(stride), list(padding), list(dilation),
                                                       transpose, list(output_padding), groups, [False, True, False])

@@ -1,0 +1,105 @@
+"""The drop-in `torch_utils.ops` package on the GPU: conv2d_gradfix routed to the tcgen05 kernels, conv2d_resample /
+modulated-conv style compositions vs the oracle, and a reference-structured Conv2dLayer-like block (D path)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, rel_err
+from oracle import ops_ref
+from stylegan_v_b200 import native_conv
+from stylegan_v_b200.ops import conv2d_gradfix as CG, conv2d_resample as CR, upfirdn2d as U, bias_act as B
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(autouse=True)
+def _enable():
+    old = CG.enabled
+    CG.enabled = True
+    yield
+    CG.enabled = old
+
+
+CASES = [
+    # transpose, Cin, Cout, k, stride, padding, H
+    (False, 64, 64, 3, 1, 1, 16), (False, 32, 128, 1, 1, 0, 12), (False, 64, 64, 3, 2, 0, 17), (False, 64, 128, 3, 2, 1, 16),
+    (True, 64, 64, 3, 2, 0, 8), (True, 64, 64, 3, 2, 0, 5), (True, 64, 32, 3, 1, 1, 12),
+]
+
+
+@pytest.mark.parametrize('transpose,ci,co,k,s,p,H', CASES)
+def test_conv2d_gradfix_native_matches_fp64(transpose, ci, co, k, s, p, H):
+    g = torch.Generator().manual_seed(ci + co + k + s)
+    x = torch.randn(2, ci, H, H, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(*((ci, co, k, k) if transpose else (co, ci, k, k)), generator=g) / np.sqrt(ci * k * k)).cuda().requires_grad_(True)
+    calls = {'n': 0}
+    orig = native_conv.conv_forward
+
+    def spy(*a, **kw):
+        r = orig(*a, **kw)
+        calls['n'] += r is not None
+        return r
+    native_conv.conv_forward = spy
+    try:
+        y = (CG.conv_transpose2d if transpose else CG.conv2d)(x, w, stride=s, padding=p)
+    finally:
+        native_conv.conv_forward = orig
+    assert calls['n'] == 1, 'expected the native tensor-core path'
+    xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    ref = (F.conv_transpose2d if transpose else F.conv2d)(xd, wd, stride=s, padding=p)
+    assert y.shape == ref.shape and rel_err(y, ref) < 1e-3
+    gy = torch.randn(y.shape, generator=g).cuda()
+    gx, gw = torch.autograd.grad(y, [x, w], gy)
+    rx, rw = torch.autograd.grad(ref, [xd, wd], gy.double())
+    assert rel_err(gx, rx) < 1e-3 and rel_err(gw, rw) < 1e-3
+
+
+def test_unsupported_shapes_fall_back_to_library():
+    x = torch.randn(2, 3, 16, 16).cuda()                 # fromrgb: 3 input channels
+    w = torch.randn(64, 3, 1, 1).cuda()
+    y = CG.conv2d(x, w)
+    assert rel_err(y, F.conv2d(x.double(), w.double())) < 1e-5
+
+
+def test_conv2d_resample_cuda_vs_goldens():
+    g, meta = load_golden('conv2d_resample_cases.npz')
+    f = _t(g['f']).cuda()
+    for i, m in enumerate(meta):
+        x = _t(g[f'c{i}_x']).cuda().requires_grad_(True); w = _t(g[f'c{i}_w']).cuda().requires_grad_(True)
+        y = CR.conv2d_resample(x=x, w=w, f=f, up=m['up'], down=m['down'], padding=m['k'] // 2, flip_weight=m['flip_weight'])
+        dx, dw = torch.autograd.grad(y, [x, w], _t(g[f'c{i}_dy']).cuda())
+        # 4->5 channel cases are outside the native envelope and take the library call, where PyTorch's cuDNN default
+        # (allow_tf32=True) applies: hold them to the same 1e-3 contract as the native TF32 kernels
+        assert rel_err(y, _t(g[f'c{i}_y'])) < 1e-3 and rel_err(dx, _t(g[f'c{i}_dx'])) < 1e-3 and rel_err(dw, _t(g[f'c{i}_dw'])) < 1e-3
+
+
+def test_discriminator_style_block_on_dropin_ops():
+    """DiscriminatorBlock arithmetic (networks.py:460-488: skip 1x1 down=2, conv0 3x3, conv1 3x3 down=2, residual add) with
+    64-channel tensors so every conv runs on the tensor-core kernels; compared with the oracle on CPU."""
+    gen = torch.Generator().manual_seed(9)
+    C_, H = 64, 32
+    x = torch.randn(2, C_, H, H, generator=gen)
+    f = U.setup_filter([1, 3, 3, 1])
+    ws = dict(skip=torch.randn(C_, C_, 1, 1, generator=gen) / 8, c0=torch.randn(C_, C_, 3, 3, generator=gen) / 24, c1=torch.randn(C_, C_, 3, 3, generator=gen) / 24)
+    bs = dict(c0=torch.randn(C_, generator=gen) * 0.1, c1=torch.randn(C_, generator=gen) * 0.1)
+
+    def block(x, conv, fir, act, dev):
+        mv = lambda t: t.to(dev)
+        y = conv(x=x, w=mv(ws['skip']), f=mv(f), down=2, padding=0, flip_weight=True)
+        y = act(y, None, act='linear', gain=np.sqrt(0.5))
+        h = conv(x=x, w=mv(ws['c0']), f=mv(f), padding=1, flip_weight=True)
+        h = act(h, mv(bs['c0']), act='lrelu')
+        h = conv(x=h, w=mv(ws['c1']), f=mv(f), down=2, padding=1, flip_weight=True)
+        h = act(h, mv(bs['c1']), act='lrelu', gain=np.sqrt(2) * np.sqrt(0.5))
+        return y + h
+    ref = block(x, lambda **kw: ops_ref.conv2d_resample_ref(**kw), None, lambda t, b, **kw: ops_ref.bias_act_ref_torch(t, b, **kw), 'cpu')
+    xg = x.cuda().requires_grad_(True)
+    out = block(xg, CR.conv2d_resample, None, B.bias_act, 'cuda')
+    assert rel_err(out, ref) < 2e-3
+    out.sum().backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad).all()
