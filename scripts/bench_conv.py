@@ -41,7 +41,10 @@ def main():
         fn = lambda: C.igemm_conv(x, wp, offs, a_scale=s, o_scale=d, bias=b, act='lrelu', gain=1.414)
         ms = timeit(fn)
         flops = 2.0 * N * res * res * cin * cout * 9
-        out = dict(kernel=name, cin=cin, cout=cout, res=res, ms=ms, tflops=flops / ms / 1e9)
+        g = torch.randn(N, cout, res, res, device='cuda').contiguous(memory_format=torch.channels_last)
+        ms_w = timeit(lambda: C.igemm_wgrad(g, x, [(0, 0)] * 9, offs, (res, res), g_scale=d, x_scale=s))
+        del g
+        out = dict(kernel=name, cin=cin, cout=cout, res=res, ms=ms, tflops=flops / ms / 1e9, wgrad_ms=ms_w, wgrad_tflops=flops / ms_w / 1e9)
         if not only:
             wcl = w.contiguous(memory_format=torch.channels_last)
             ms_cudnn = timeit(lambda: F.conv2d(x, wcl, padding=1))

@@ -200,18 +200,19 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     for (int j = 0; j < 32; j++) sv[j] = 1.f;
                 }
                 mbar_wait(full_a + sa, pa);
-                uint8_t* patch = smem + sa * L::kPatch;
+                const uint32_t patch = smem_u32(smem + sa * L::kPatch);
                 for (int row = tid; row < nrows; row += 128)
                 {
-                    uint8_t* arow = patch + row * 128;
+                    const uint32_t arow = patch + (uint32_t)row * 128u;
+                    float4 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v[j] = lds128(arow + (uint32_t)((j ^ (row & 7)) << 4));
 #pragma unroll
                     for (int j = 0; j < 8; j++)
                     {
-                        float4* ptr = reinterpret_cast<float4*>(arow + ((j ^ (row & 7)) << 4));
-                        float4 v = *ptr;
-                        v.x = tf32_rn(v.x * sv[4 * j + 0]); v.y = tf32_rn(v.y * sv[4 * j + 1]);
-                        v.z = tf32_rn(v.z * sv[4 * j + 2]); v.w = tf32_rn(v.w * sv[4 * j + 3]);
-                        *ptr = v;
+                        v[j].x = tf32_rn(v[j].x * sv[4 * j + 0]); v[j].y = tf32_rn(v[j].y * sv[4 * j + 1]);
+                        v[j].z = tf32_rn(v[j].z * sv[4 * j + 2]); v[j].w = tf32_rn(v[j].w * sv[4 * j + 3]);
+                        sts128(arow + (uint32_t)((j ^ (row & 7)) << 4), v[j]);
                     }
                 }
                 fence_proxy_async_smem();

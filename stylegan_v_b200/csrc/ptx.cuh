@@ -165,6 +165,19 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn = 
          | ((uint32_t)(M >> 4) << 24);
 }
 
+// explicit shared-space 128-bit accesses (the staging buffers are reached through integer-rounded pointers, which the compiler
+// would otherwise lower to generic LD.E / ST.E)
+__device__ __forceinline__ float4 lds128(uint32_t saddr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ float tf32_rn(float x)
 {
     uint32_t r;

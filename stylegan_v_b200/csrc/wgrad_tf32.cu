@@ -440,6 +440,7 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
             const int total_rows = 128 + xrows_blk * (NT / 32);
             float sv[2][32];
             int cur_n = -1;
+            const FastDiv div_plane((uint32_t)(p.tiles_x * p.tiles_y));
             int rr[2]; const float* sbase[2]; int sstride[2]; bool act[2];
 #pragma unroll
             for (int s = 0; s < 2; s++)
@@ -459,7 +460,7 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
                 int stage = 0; uint32_t phase = 0;
                 for (int kt = kt0; kt < kt1; kt++)
                 {
-                    const int n = min(kt / (p.tiles_x * p.tiles_y), p.n - 1);
+                    const int n = min((int)div_plane.div((uint32_t)kt), p.n - 1);
                     if (n != cur_n)
                     {
                         cur_n = n;
@@ -479,22 +480,27 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
                     {
                         if (!act[s]) continue;
                         const int row = rr[s] < 128 ? rr[s] : rr[s] - 128;
-                        uint8_t* rowp = sg + (rr[s] < 128 ? 0 : kW2GTile) + row * 128;
+                        const uint32_t rowp = smem_u32(sg) + (uint32_t)(rr[s] < 128 ? 0 : kW2GTile) + (uint32_t)row * 128u;
                         // logical 16-byte chunk jj = j ^ bit2(row): the 8 rows a quarter-warp touches then hit 8 distinct physical
                         // chunks of the 32-byte-atom swizzle (row & 3 only permutes 32 B pairs) -> no shared-memory bank conflicts
                         const int flip = (row >> 2) & 1;
+                        float4 v[8];
 #pragma unroll
                         for (int j = 0; j < 8; j++)
                         {
                             const int jj = j ^ flip;
-                            float4* ptr = reinterpret_cast<float4*>(rowp + (((((jj >> 1) ^ (row & 3)) << 1) | (jj & 1)) << 4));
-                            float4 v = *ptr;
+                            v[j] = lds128(rowp + (uint32_t)(((((jj >> 1) ^ (row & 3)) << 1) | (jj & 1)) << 4));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                        {
+                            const int jj = j ^ flip;
                             const float s0 = flip ? sv[s][4 * (j ^ 1) + 0] : sv[s][4 * j + 0];
                             const float s1 = flip ? sv[s][4 * (j ^ 1) + 1] : sv[s][4 * j + 1];
                             const float s2 = flip ? sv[s][4 * (j ^ 1) + 2] : sv[s][4 * j + 2];
                             const float s3 = flip ? sv[s][4 * (j ^ 1) + 3] : sv[s][4 * j + 3];
-                            v.x = tf32_rn(v.x * s0); v.y = tf32_rn(v.y * s1); v.z = tf32_rn(v.z * s2); v.w = tf32_rn(v.w * s3);
-                            *ptr = v;
+                            v[j].x = tf32_rn(v[j].x * s0); v[j].y = tf32_rn(v[j].y * s1); v[j].z = tf32_rn(v[j].z * s2); v[j].w = tf32_rn(v[j].w * s3);
+                            sts128(rowp + (uint32_t)(((((jj >> 1) ^ (row & 3)) << 1) | (jj & 1)) << 4), v[j]);
                         }
                     }
                     fence_proxy_async_smem();
