@@ -129,6 +129,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph of the step')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -166,12 +167,47 @@ def main():
     dimg = torch.randn(N, 3, RES, RES, device=dev)
     h_out = torch.zeros(1).pin_memory()
 
-    def step(ws, t, mz):
+    def step_compute(ws, t, mz):
         reducer.zero()
         ws = ws.requires_grad_(True)
         img = net(ws, t, motion_z=mz)
         loss = (img * dimg).sum()
         loss.backward()
+        return loss
+
+    # The step (about 1000 kernel launches: forward + backward of 20 fused layers) is captured ONCE into a CUDA graph and replayed:
+    # the GPU then never waits for the Python/ctypes launch path.  The gradient all-reduce (N > 1) is issued after each replay.
+    graph = None
+    graph_launches = 0
+    s_ws, s_t, s_mz = d_ws.clone(), d_t.clone(), d_mz.clone()      # static graph inputs
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step_compute(s_ws.detach(), s_t, s_mz)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                s_loss = step_compute(s_ws.detach(), s_t, s_mz)
+            graph_launches = _lib.launch_count() - l0
+        except Exception as e:      # capture is an optimisation, not a requirement
+            if rank == 0:
+                sys.stderr.write(f'[bench] CUDA graph capture failed ({type(e).__name__}: {e}); falling back to eager launches\n')
+            graph = None
+            torch.cuda.synchronize()
+
+    def step(ws, t, mz):
+        if graph is not None:
+            if ws.data_ptr() != s_ws.data_ptr():
+                s_ws.copy_(ws, non_blocking=True); s_t.copy_(t, non_blocking=True); s_mz.copy_(mz, non_blocking=True)
+            graph.replay()
+            loss = s_loss
+        else:
+            loss = step_compute(ws, t, mz)
         reducer.all_reduce()
         return loss
 
@@ -201,7 +237,10 @@ def main():
     if rank == 0:
         sampler.start()
     # (1) device-resident inputs
-    ms_total, launches = timed(lambda: step(d_ws.detach(), d_t, d_mz), args.steps, args.warmup)
+    ms_total, launches = timed(lambda: step(s_ws if graph is not None else d_ws.detach(), s_t if graph is not None else d_t, s_mz if graph is not None else d_mz),
+                               args.steps, args.warmup)
+    if graph is not None:
+        launches = graph_launches * args.steps      # launches recorded at capture time, replayed once per step
     clocks = sampler.stop() if rank == 0 else None
 
     # (2) end to end: H2D of the step's inputs from pinned memory, D2H of the loss, every step
@@ -273,7 +312,7 @@ def main():
                 ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='tf32 (fp32 storage, TF32 tensor-core products, fp32 accumulate)',
                 data='synthetic',
                 config=dict(workload='256x256 SynthesisNetwork forward+backward, 32 frames/GPU (32 latents x 1 frame), fmaps 0.5, random-init weights',
-                            frames_per_gpu=N, parallelism=f'dp{world}', l2='activation working set per step (>= 134 MB per layer at res >= 64, ~6 GB total) exceeds the 126 MB L2; no explicit flush',
+                            frames_per_gpu=N, parallelism=f'dp{world}', cuda_graph=graph is not None, l2='activation working set per step (>= 134 MB per layer at res >= 64, ~6 GB total) exceeds the 126 MB L2; no explicit flush',
                             conv_gflop_per_frame_fwd=conv_gflop_fwd),
                 e2e=dict(value=e2e_value, unit='frames/s', h2d_bytes_per_step=(h_ws.numel() + h_t.numel() + h_mz.numel()) * 4, d2h_bytes_per_step=4),
                 gpu_launches=launches, clocks=clocks, roofline=roofline, upfirdn2d=upfirdn, cpu_baseline=cpu_baseline,

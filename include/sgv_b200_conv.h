@@ -56,6 +56,11 @@ typedef struct sgv_conv_params {
      * Used to address one polyphase sub-lattice (pixel stride 2) of the transposed-conv gradient without a stride-2 gather. */
     int64_t in_stride_n, in_stride_y, in_stride_x;
     int32_t accumulate;        /* 1: y += result (no o_scale/bias/act allowed) — sums the four polyphase data-gradient launches */
+    /* optional fused reduction (gradient of the style modulation, networks.py:66): red_out[n, o] += sum_{oy,ox} raw[n,oy,ox,o] * red_x[n,oy,ox,o]
+     * where raw is the accumulator BEFORE o_scale/bias/act and red_x is a tensor addressed exactly like y (same strides).
+     * With o_scale = styles this turns the data-gradient launch into  dx = dxs * s  and  dstyles = sum_hw dxs * x  in one pass. */
+    const float* red_x;
+    float*       red_out;      /* [n, cout] float32, caller-zeroed */
 } sgv_conv_params;
 
 int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream);

@@ -37,7 +37,8 @@ def prep_weights(w, taps, rows_dim=0, cols_dim=1):
 
 
 def igemm_conv(x, wp, tap_offsets, out=None, out_hw=None, out_view=None, in_stride=1,
-               a_scale=None, o_scale=None, bias=None, act='linear', alpha=0.2, gain=1.0, clamp=None, accumulate=False):
+               a_scale=None, o_scale=None, bias=None, act='linear', alpha=0.2, gain=1.0, clamp=None, accumulate=False,
+               red_x=None, red_out=None):
     """y[n,oy,ox,o] = epi(sum_{t,i} x[n, oy*in_stride+dy_t, ox*in_stride+dx_t, i] * a_scale[n,i] * wp[t,o,i]).
 
     x: [N, Cin, H, W] channels_last fp32.  wp: [ntaps, Cout, Cin] from prep_weights.  tap_offsets: [(dy, dx)].
@@ -81,6 +82,11 @@ def igemm_conv(x, wp, tap_offsets, out=None, out_hw=None, out_view=None, in_stri
     if not dense:
         p.in_stride_n, p.in_stride_y, p.in_stride_x = x.stride(0), x.stride(2), x.stride(3)
     p.accumulate = int(bool(accumulate))
+    if red_out is not None:
+        _req(red_x is not None and red_x.shape == y.shape and red_x.stride() == y.stride() and red_x.dtype == torch.float32,
+             'red_x must have the shape and strides of the output')
+        _req(red_out.dtype == torch.float32 and red_out.is_contiguous() and tuple(red_out.shape) == (N, Cout), 'red_out must be a contiguous float32 [N, Cout] buffer')
+        p.red_x, p.red_out = red_x.data_ptr(), red_out.data_ptr()
     with torch.cuda.device(x.device):
         _lib.check(L.sgv_conv2d_tf32(ctypes.byref(p), _stream(x.device)), 'sgv_conv2d_tf32')
     return y

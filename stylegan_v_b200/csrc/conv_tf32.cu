@@ -48,6 +48,7 @@ struct ConvArgs
     int tiles_x, tiles_y, tiles_nb;
     int act; float alpha, gain, clamp;
     int accumulate;
+    const float* red_x; float* red_out;
 };
 
 template <int BN, int STAGES>
@@ -178,15 +179,16 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 for (int t = 0; t < p.ntaps; t++)
                 {
                     mbar_wait(full_bar + stage, phase);
-                    uint8_t* arow = smem + stage * L::kStageBytes + row * 128;
+                    const uint32_t arow = smem_u32(smem + stage * L::kStageBytes) + (uint32_t)row * 128u;
+                    float4 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v[j] = lds128(arow + (uint32_t)((j ^ (row & 7)) << 4));   // logical 16-byte chunk j
 #pragma unroll
                     for (int j = 0; j < 8; j++)
                     {
-                        float4* ptr = reinterpret_cast<float4*>(arow + ((j ^ (row & 7)) << 4));   // logical 16-byte chunk j
-                        float4 v = *ptr;
-                        v.x = tf32_rn(v.x * sv[4 * j + 0]); v.y = tf32_rn(v.y * sv[4 * j + 1]);
-                        v.z = tf32_rn(v.z * sv[4 * j + 2]); v.w = tf32_rn(v.w * sv[4 * j + 3]);
-                        *ptr = v;
+                        v[j].x = tf32_rn(v[j].x * sv[4 * j + 0]); v[j].y = tf32_rn(v[j].y * sv[4 * j + 1]);
+                        v[j].z = tf32_rn(v[j].z * sv[4 * j + 2]); v[j].w = tf32_rn(v[j].w * sv[4 * j + 3]);
+                        sts128(arow + (uint32_t)((j ^ (row & 7)) << 4), v[j]);
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
@@ -208,6 +210,31 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
             tmem_ld_wait();
+            if (p.red_out)
+            {
+                // fused style-gradient reduction (see conv_tf32_v3.cu); a warp's 32 rows may straddle samples when the box spills
+                // into the batch, so the sum is warp-reduced only when all rows share n, else accumulated per row
+                float prod[32];
+                const float* rx = p.red_x + (long long)nc * p.osn + (long long)oy * p.osy + (long long)ox * p.osx + nb0 + cc * 32;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                {
+                    const float4 xv = valid ? __ldg(reinterpret_cast<const float4*>(rx) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    prod[4 * j + 0] = __uint_as_float(v[4 * j + 0]) * xv.x; prod[4 * j + 1] = __uint_as_float(v[4 * j + 1]) * xv.y;
+                    prod[4 * j + 2] = __uint_as_float(v[4 * j + 2]) * xv.z; prod[4 * j + 3] = __uint_as_float(v[4 * j + 3]) * xv.w;
+                }
+                const int n_first = __shfl_sync(0xffffffffu, nc, 0);
+                if (__all_sync(0xffffffffu, nc == n_first))
+                {
+                    const float tot = warp_reduce_32x32(prod, lane);
+                    atomicAdd(p.red_out + (long long)n_first * p.cout + nb0 + cc * 32 + lane, tot);
+                }
+                else if (valid)
+                {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) atomicAdd(p.red_out + (long long)nc * p.cout + nb0 + cc * 32 + j, prod[j]);
+                }
+            }
             if (valid)
             {
 #pragma unroll
@@ -346,6 +373,7 @@ extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
     SGV_CHECK_ARG((long long)p->n * p->h * p->w * p->cin <= 0x7fffffffLL, "x is too large");
     SGV_CHECK_ARG(!p->accumulate || (p->o_scale == nullptr && p->bias == nullptr && p->act == 1 && p->gain == 1.0f && p->clamp < 0.f),
                   "accumulate=1 cannot be combined with o_scale / bias / activation / gain / clamp");
+    SGV_CHECK_ARG((p->red_out == nullptr) == (p->red_x == nullptr), "red_x and red_out must be given together");
     SGV_CHECK_ARG((p->in_stride_x == 0 && p->in_stride_y == 0 && p->in_stride_n == 0) ||
                   (p->in_stride_x % 4 == 0 && p->in_stride_y % 4 == 0 && p->in_stride_n % 4 == 0 && p->in_stride_x > 0),
                   "input view strides must be positive multiples of 4 elements (or all zero for a dense tensor)");
@@ -374,6 +402,7 @@ extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
     for (int t = 0; t < SGV_CONV_MAX_TAPS; t++) { a.tap_dy[t] = p->tap_dy[t]; a.tap_dx[t] = p->tap_dx[t]; }
     a.act = p->act; a.alpha = p->alpha; a.gain = p->gain; a.clamp = p->clamp;
     a.accumulate = p->accumulate;
+    a.red_x = p->red_x; a.red_out = p->red_out;
 
     // activation box of 128 output pixels: as square as the plane allows, spilling into the batch dimension for tiny planes
     int tw = pow2_floor(p->out_w < 16 ? p->out_w : 16);
@@ -384,7 +413,11 @@ extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
     a.tw = tw; a.th = th; a.tn = tn;
     a.tiles_x = ceil_div(p->out_w, tw); a.tiles_y = ceil_div(p->out_h, th); a.tiles_nb = ceil_div(p->n, tn);
 
-    const int bn = (p->cout % 256 == 0) ? 256 : (p->cout % 128 == 0) ? 128 : (p->cout % 64 == 0) ? 64 : p->cout;
+    // widest N tile that still gives the grid about one CTA per SM: the 4x4 / 8x8 layers have only 4-16 pixel tiles, and a
+    // 256-wide tile would leave them on 8-32 CTAs walking K = 9216 serially (b4.conv1: 198 us on 8 CTAs)
+    const int mtiles_total = a.tiles_x * a.tiles_y * a.tiles_nb;
+    int bn = (p->cout % 256 == 0) ? 256 : (p->cout % 128 == 0) ? 128 : (p->cout % 64 == 0) ? 64 : p->cout;
+    while (bn > 64 && p->cout % (bn / 2) == 0 && mtiles_total * (p->cout / bn) < num_sms()) bn /= 2;
 
     CUtensorMap tmx, tmw;
     {

@@ -261,7 +261,7 @@ static int launch_v2(const CUtensorMap& tx, const CUtensorMap& tw, const ConvV2A
 int conv2d_tf32_v2(const sgv_conv_params* p, cudaStream_t stream)
 {
     if (p->in_stride != 1 || p->out_h < 12 || p->out_w < 12 || p->cout % 64 != 0) return SGV_ERR_UNSUPPORTED;
-    if (p->in_stride_x != 0 || p->accumulate) return SGV_ERR_UNSUPPORTED;
+    if (p->in_stride_x != 0 || p->accumulate || p->red_out) return SGV_ERR_UNSUPPORTED;
     int dy_min = p->tap_dy[0], dy_max = p->tap_dy[0], dx_min = p->tap_dx[0], dx_max = p->tap_dx[0];
     for (int t = 1; t < p->ntaps; t++)
     {

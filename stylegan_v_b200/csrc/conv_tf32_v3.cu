@@ -35,6 +35,7 @@ struct ConvV3Args
     int tiles_x, tiles_y, ntiles_n, total_tiles;
     int act; float alpha, gain, clamp;
     int accumulate;
+    const float* red_x; float* red_out;
 };
 
 template <int BN, int MH, int SA, int SB>
@@ -251,6 +252,21 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     uint32_t v[32];
                     tmem_ld_32x32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN + cc * 32), v);
                     tmem_ld_wait();
+                    if (p.red_out)
+                    {
+                        // fused style-gradient reduction: sum over this warp's 32 pixels of raw * red_x, one channel per lane
+                        float prod[32];
+                        const float* rx = p.red_x + (long long)tc.n * p.osn + (long long)oy * p.osy + (long long)ox * p.osx + tc.nb0 + cc * 32;
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                        {
+                            const float4 xv = valid ? __ldg(reinterpret_cast<const float4*>(rx) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            prod[4 * j + 0] = __uint_as_float(v[4 * j + 0]) * xv.x; prod[4 * j + 1] = __uint_as_float(v[4 * j + 1]) * xv.y;
+                            prod[4 * j + 2] = __uint_as_float(v[4 * j + 2]) * xv.z; prod[4 * j + 3] = __uint_as_float(v[4 * j + 3]) * xv.w;
+                        }
+                        const float tot = warp_reduce_32x32(prod, lane);
+                        atomicAdd(p.red_out + (long long)tc.n * p.cout + tc.nb0 + cc * 32 + lane, tot);
+                    }
                     if (valid)
                     {
 #pragma unroll
@@ -327,6 +343,7 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
     a.tiles_x = ceil_div(p->out_w, 8 * mh); a.tiles_y = ceil_div(p->out_h, kV3TileH);
     a.act = p->act; a.alpha = p->alpha; a.gain = p->gain; a.clamp = p->clamp;
     a.accumulate = p->accumulate;
+    a.red_x = p->red_x; a.red_out = p->red_out;
     const int bn = (p->cout % 256 == 0) ? 256 : (p->cout % 128 == 0) ? 128 : 64;
     a.ntiles_n = p->cout / bn;
     a.total_tiles = a.tiles_x * a.tiles_y * p->n * a.ntiles_n;

@@ -178,6 +178,25 @@ __device__ __forceinline__ void sts128(uint32_t saddr, float4 v)
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Warp "transpose-reduce": every lane contributes v[0..31]; afterwards lane l holds sum over lanes of v[l] (31 shuffles
+// instead of 32 x 5).  All 32 lanes must call.
+__device__ __forceinline__ float warp_reduce_32x32(float (&v)[32], int lane)
+{
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1)
+    {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; i++)
+        {
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
 __device__ __forceinline__ float tf32_rn(float x)
 {
     uint32_t r;

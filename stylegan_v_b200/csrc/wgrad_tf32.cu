@@ -51,17 +51,25 @@ struct WgSmem
 };
 
 // scales one staged 128-byte row (32 channels of one pixel) by sc[0..31] and rounds to TF32, in place
-__device__ __forceinline__ void wg_transform_row(uint8_t* rowp, int row, const float* __restrict__ sc)
+__device__ __forceinline__ void wg_transform_row(uint8_t* rowp_generic, int row, const float* __restrict__ sc)
 {
+    const uint32_t rowp = smem_u32(rowp_generic);
+    const int flip = (row >> 2) & 1;          // chunk order that keeps a quarter-warp's 8 rows on 8 distinct bank groups
+    float4 v[8];
 #pragma unroll
     for (int j = 0; j < 8; j++)
     {
-        // SWIZZLE_128B_ATOM_32B: logical 32-byte chunk (j >> 1) lives at physical chunk (j >> 1) ^ (row & 3)
-        float4* ptr = reinterpret_cast<float4*>(rowp + (((((j >> 1) ^ (row & 3)) << 1) | (j & 1)) << 4));
-        float4 v = *ptr;
-        float4 s = sc ? __ldg(reinterpret_cast<const float4*>(sc) + j) : make_float4(1.f, 1.f, 1.f, 1.f);
-        v.x = tf32_rn(v.x * s.x); v.y = tf32_rn(v.y * s.y); v.z = tf32_rn(v.z * s.z); v.w = tf32_rn(v.w * s.w);
-        *ptr = v;
+        const int jj = j ^ flip;
+        // SWIZZLE_128B_ATOM_32B: logical 32-byte chunk (jj >> 1) lives at physical chunk (jj >> 1) ^ (row & 3)
+        v[j] = lds128(rowp + (uint32_t)(((((jj >> 1) ^ (row & 3)) << 1) | (jj & 1)) << 4));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+    {
+        const int jj = j ^ flip;
+        const float4 s = sc ? __ldg(reinterpret_cast<const float4*>(sc) + jj) : make_float4(1.f, 1.f, 1.f, 1.f);
+        v[j].x = tf32_rn(v[j].x * s.x); v[j].y = tf32_rn(v[j].y * s.y); v[j].z = tf32_rn(v[j].z * s.z); v[j].w = tf32_rn(v[j].w * s.w);
+        sts128(rowp + (uint32_t)(((((jj >> 1) ^ (row & 3)) << 1) | (jj & 1)) << 4), v[j]);
     }
 }
 

@@ -141,26 +141,24 @@ class _FusedModConv(torch.autograd.Function):
         ddcoefs = dd / dcoefs if want_dd else None
         dscale = dcoefs if has_d else None
         wsrc_same = weight if flip_weight else weight.flip([2, 3])
-        # ---- data gradient (w.r.t. the modulated input x*s), then ds and dx ----
+        # ---- data gradient: ONE launch gives dx = dxs * styles (epilogue scale) and dstyles = sum_hw dxs * x (fused reduction) ----
+        want_ds = ctx.needs_input_grad[2]
+        ds = torch.zeros([N, I], dtype=torch.float32, device=x.device) if want_ds else None
+        red = dict(red_x=x, red_out=ds) if want_ds else {}
         if up == 1:
             gout = dz
-            if kh == 3:
-                wp = _conv.prep_weights(wsrc_same, _TAPS3, rows_dim=1, cols_dim=0)
-                dxs = _conv.igemm_conv(dz, wp, _OFFS3_DGRAD, a_scale=dscale)
-            else:
-                wp = _conv.prep_weights(wsrc_same, [(0, 0)], rows_dim=1, cols_dim=0)
-                dxs = _conv.igemm_conv(dz, wp, [(0, 0)], a_scale=dscale)
+            taps, offs = (_TAPS3, _OFFS3_DGRAD) if kh == 3 else ([(0, 0)], [(0, 0)])
+            wp = _conv.prep_weights(wsrc_same, taps, rows_dim=1, cols_dim=0)
+            dx = _conv.igemm_conv(dz, wp, offs, a_scale=dscale, o_scale=styles, **red)
         else:
             wsrc_t = weight if not flip_weight else weight.flip([2, 3])
             # adjoint of the FIR pass (upfirdn2d.py:246-261): padding (fw - p - 1) = 2, flipped filter, same gain
             gout = _plugin.upfirdn2d(dz, _fir(x.device), 1, 1, 1, 1, 2, 2, 2, 2, True, 4.0)
             # data gradient of the stride-2 transposed conv = stride-2 correlation: ONE launch with TMA element strides.
             # (Measured alternative: 4 accumulate-launches over polyphase views of `gout` on the halo-patch kernel — 1.2 ms/step
-            #  slower at config 2 because dx is re-read/re-written 3 extra times; kept available through igemm_conv(accumulate=True).)
+            #  slower at config 2; kept available through igemm_conv(accumulate=True).)
             wp = _conv.prep_weights(wsrc_t, _TAPS3, rows_dim=1, cols_dim=0)
-            dxs = _conv.igemm_conv(gout, wp, _TAPS3, out_hw=(H, W), in_stride=2, a_scale=dscale)
-        # dx = dxs * styles (in place) and dstyles = sum_hw dxs * x in ONE pass over (dxs, x)
-        dx, ds = _conv.scale_reduce(dxs, x, styles, want_dx=ctx.needs_input_grad[0], want_ds=ctx.needs_input_grad[2])
+            dx = _conv.igemm_conv(gout, wp, _TAPS3, out_hw=(H, W), in_stride=2, a_scale=dscale, o_scale=styles, **red)
         # ---- weight gradient ----
         dw = None
         if ctx.needs_input_grad[1]:
