@@ -61,6 +61,9 @@ SHAPES = [
     (1, 3, 33, 47, 2, 2, [3, 1, 0, 2], False, 2),        # up and down together, ragged
     (1, 2, 40, 40, 3, 1, [2, 2, 2, 2], False, 9),        # factor not covered by the tiled kernel -> generic
     (1, 2, 31, 29, [1, 2], [2, 1], [0, 1, 2, 0], True, 1),
+    (2, 8, 128, 128, 1, 1, [2, 2, 2, 2], True, 4),       # backward of the b128 FIR: 128 -> 129 (ragged last tile), pipelined kernel
+    (1, 3, 200, 150, 1, 1, [1, 1, 1, 1], False, 4),      # wide, not a multiple of the tile
+    (1, 2, 100, 517, 1, 1, [2, 1, 1, 2], False, 1),      # 5 tiles across, asymmetric padding
 ]
 
 
