@@ -12,6 +12,7 @@
 // that patch through a shifted K-major SWIZZLE_128B descriptor (start row = (dy-dy_min)*PW + (dx-dx_min) + 8*half,
 // SBO = PW*128; legal because tcgen05 swizzles on absolute smem address bits — profiles/umma_probe_r1.txt).
 // Warps: 0 TMA producer, 1 MMA issuer + TMEM owner, 2-5 transform (styles * x, round to TF32), 6-9 epilogue.
+#include <stdlib.h>
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -32,7 +33,7 @@ struct ConvV3Args
     int ntaps;
     int tap_row[SGV_CONV_MAX_TAPS];
     int dy_min, dx_min, pw, ph;
-    int tiles_x, tiles_y, ntiles_n, total_tiles;
+    int tiles_x, tiles_y, ntiles_n, total_groups;      // group = CL pixel tiles x one n-tile, one tile per CTA of a cluster
     int act; float alpha, gain, clamp;
     int accumulate;
     const float* red_x; float* red_out;
@@ -54,19 +55,21 @@ struct ConvV3Smem
 
 struct TileCoord { int n, ox0, oy0, nb0; };
 
-template <int BN, int MH>
-__device__ __forceinline__ TileCoord tile_coord(const ConvV3Args& p, int tile)
+template <int BN, int MH, int CL>
+__device__ __forceinline__ TileCoord tile_coord(const ConvV3Args& p, int group, int crank)
 {
-    // n-tile fastest: the CTAs working on the same pixels at the same time share the activation patch through L2
+    // n-tile fastest: the CTAs working on the same pixels at the same time share the activation patch through L2;
+    // the CL CTAs of a cluster take CL consecutive pixel tiles of the SAME n-tile (they share every weight slab)
     TileCoord c;
-    const int nt = tile % p.ntiles_n; tile /= p.ntiles_n;
+    const int nt = group % p.ntiles_n;
+    int tile = (group / p.ntiles_n) * CL + crank;
     const int tx = tile % p.tiles_x; tile /= p.tiles_x;
     const int ty = tile % p.tiles_y; tile /= p.tiles_y;
     c.n = tile; c.ox0 = tx * 8 * MH; c.oy0 = ty * kV3TileH; c.nb0 = nt * BN;
     return c;
 }
 
-template <int BN, int MH, int SA, int SB>
+template <int BN, int MH, int SA, int SB, int CL>
 __global__ void __launch_bounds__(kV3Threads, 1)
 conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const ConvV3Args p)
 {
@@ -84,6 +87,9 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
     const int kchunks = p.cin / 32;
     const uint32_t patch_bytes = (uint32_t)(p.pw * p.ph * 128);
 
@@ -92,13 +98,13 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         prefetch_tmap(&tmap_x);
         prefetch_tmap(&tmap_w);
         for (int s = 0; s < SA; s++) { mbar_init(full_a + s, 1); mbar_init(ready_a + s, 4); mbar_init(empty_a + s, 1); }
-        for (int s = 0; s < SB; s++) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, 1); }
+        for (int s = 0; s < SB; s++) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, CL); }   // a slab slot is freed by the MMAs of all CL CTAs
         for (int s = 0; s < 2; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
         fence_mbar_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, L::kTmemCols); tmem_relinquish(); }
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers are initialised before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -108,9 +114,9 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         if (elect_one())
         {
             int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
+            for (int g = cid; g < p.total_groups; g += ncl)
             {
-                const TileCoord tc = tile_coord<BN, MH>(p, tile);
+                const TileCoord tc = tile_coord<BN, MH, CL>(p, g, crank);
                 for (int kc = 0; kc < kchunks; kc++)
                 {
                     mbar_wait(empty_a + sa, pa ^ 1);
@@ -121,7 +127,11 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     {
                         mbar_wait(empty_b + sb, pb ^ 1);
                         mbar_expect_tx(full_b + sb, L::kBTile);
-                        tma_load_2d(smem + L::kBOffset + sb * L::kBTile, &tmap_w, full_b + sb, kc * 32, t * p.cout + tc.nb0);
+                        if (CL == 1)
+                            tma_load_2d(smem + L::kBOffset + sb * L::kBTile, &tmap_w, full_b + sb, kc * 32, t * p.cout + tc.nb0);
+                        else    // this CTA fetches rows [crank * BN/CL, +BN/CL) of the slab once and multicasts them to the whole cluster
+                            tma_load_2d_mc(smem + L::kBOffset + sb * L::kBTile + crank * (BN / CL) * 128, &tmap_w, full_b + sb, kc * 32,
+                                           t * p.cout + tc.nb0 + crank * (BN / CL), kMask);
                         if (++sb == SB) { sb = 0; pb ^= 1; }
                     }
                 }
@@ -135,7 +145,7 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const uint64_t sbo_field = (uint64_t)((uint32_t)(p.pw * 128) >> 4) << 32;
         int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++)
+        for (int g = cid; g < p.total_groups; g += ncl, it++)
         {
             const int buf = it % NB;
             const uint32_t use = (uint32_t)(it / NB) & 1u;
@@ -163,7 +173,7 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                             for (int k = 0; k < 4; k++)
                                 mma_tf32(acc + (uint32_t)(h * BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc > 0 || t > 0 || k > 0) ? 1u : 0u);
                         }
-                        mma_commit(empty_b + sb);
+                        if (CL == 1) mma_commit(empty_b + sb); else mma_commit_mc(empty_b + sb, kMask);
                         if (t == p.ntaps - 1)
                         {
                             mma_commit(empty_a + sa);
@@ -183,9 +193,9 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int tid = threadIdx.x - 64;
         const int nrows = p.pw * p.ph;
         int sa = 0; uint32_t pa = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
+        for (int g = cid; g < p.total_groups; g += ncl)
         {
-            const TileCoord tc = tile_coord<BN, MH>(p, tile);
+            const TileCoord tc = tile_coord<BN, MH, CL>(p, g, crank);
             for (int kc = 0; kc < kchunks; kc++)
             {
                 float sv[32];
@@ -229,9 +239,9 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int q = warp & 3;
         const int row = q * 32 + lane;
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++)
+        for (int g = cid; g < p.total_groups; g += ncl, it++)
         {
-            const TileCoord tc = tile_coord<BN, MH>(p, tile);
+            const TileCoord tc = tile_coord<BN, MH, CL>(p, g, crank);
             const int buf = it % NB;
             const uint32_t use = (uint32_t)(it / NB) & 1u;
             mbar_wait(acc_full + buf, use);
@@ -299,25 +309,64 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();      // no CTA leaves while a peer may still multicast into it
     if (warp == 1) tmem_dealloc(tmem_base, L::kTmemCols);
 }
 
-template <int BN, int MH, int SA, int SB>
+template <int BN, int MH, int SA, int SB, int CL>
 static int launch_v3(const CUtensorMap& tx, const CUtensorMap& tw, const ConvV3Args& a, cudaStream_t stream)
 {
     using L = ConvV3Smem<BN, MH, SA, SB>;
-    auto kern = conv_tf32_v3_kernel<BN, MH, SA, SB>;
-    static bool attr_set = false;
-    if (!attr_set)
+    auto kern = conv_tf32_v3_kernel<BN, MH, SA, SB, CL>;
+    static int max_clusters = 0;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(kV3Threads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = stream;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (max_clusters == 0)
     {
         SGV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-        attr_set = true;
+        int nc = num_sms() / CL;
+        if (CL > 1)
+        {
+            cfg.gridDim = dim3((unsigned)(nc * CL));
+            SGV_CUDA_OK(cudaOccupancyMaxActiveClusters(&nc, kern, &cfg));     // GPC granularity can leave fewer than num_sms / CL co-resident
+        }
+        SGV_CHECK_ARG(nc >= 1, "conv_tf32_v3: no co-resident cluster of this size");
+        max_clusters = nc;
     }
-    const int grid = a.total_tiles < num_sms() ? a.total_tiles : num_sms();
-    kern<<<grid, kV3Threads, L::kTotal, stream>>>(tx, tw, a);
+    const int clusters = a.total_groups < max_clusters ? a.total_groups : max_clusters;
+    cfg.gridDim = dim3((unsigned)(clusters * CL));
+    ConvV3Args args = a;
+    SGV_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tx, tw, args));
     SGV_LAUNCH_OK("conv_tf32_v3_kernel");
     return SGV_OK;
+}
+
+template <int CL>
+static int launch_v3_bn(int bn, const CUtensorMap& tx, const CUtensorMap& tw, const ConvV3Args& a, cudaStream_t stream)
+{
+    switch (bn)
+    {
+        case 256: return launch_v3<256, 2, 2, 3, CL>(tx, tw, a, stream);     // 84 KB patches + 96 KB slabs, single accumulator buffer (512 cols)
+        case 128: return launch_v3<128, 2, 3, 5, CL>(tx, tw, a, stream);     // 126 + 80 KB, double-buffered accumulators (512 cols)
+        default:  return launch_v3<64, 2, 3, 8, CL>(tx, tw, a, stream);      // 126 + 64 KB, double-buffered accumulators (256 cols)
+    }
+}
+
+// thread-block cluster size (CTAs sharing each weight slab through TMA multicast); SGV_CONV_CLUSTER=1|2|4 overrides
+static int v3_cluster_pref()
+{
+    static int pref = -1;
+    if (pref < 0)
+    {
+        const char* e = getenv("SGV_CONV_CLUSTER");
+        pref = e ? atoi(e) : 2;
+        if (pref != 1 && pref != 2 && pref != 4) pref = 2;
+    }
+    return pref;
 }
 
 // Returns SGV_ERR_UNSUPPORTED when the shape is outside the envelope (caller falls back to v2 / v1).
@@ -346,7 +395,10 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
     a.red_x = p->red_x; a.red_out = p->red_out;
     const int bn = (p->cout % 256 == 0) ? 256 : (p->cout % 128 == 0) ? 128 : 64;
     a.ntiles_n = p->cout / bn;
-    a.total_tiles = a.tiles_x * a.tiles_y * p->n * a.ntiles_n;
+    const int pixel_tiles = a.tiles_x * a.tiles_y * p->n;
+    int cl = v3_cluster_pref();
+    while (cl > 1 && (pixel_tiles % cl != 0 || pixel_tiles / cl * a.ntiles_n < num_sms() / cl)) cl >>= 1;   // small problems: fill the SMs first
+    a.total_groups = pixel_tiles / cl * a.ntiles_n;
 
     CUtensorMap tmx, tmw;
     {
@@ -362,17 +414,14 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
     {
         const uint64_t dims[2] = {(uint64_t)p->cin, (uint64_t)p->ntaps * p->cout};
         const uint64_t strides[1] = {(uint64_t)p->cin * 4};
-        const uint32_t box[2] = {32, (uint32_t)bn};
+        const uint32_t box[2] = {32, (uint32_t)(bn / cl)};
         const uint32_t es[2] = {1, 1};
         int rc = make_tmap_f32(&tmw, p->wp, 2, dims, strides, box, es);
         if (rc != SGV_OK) return rc;
     }
-    switch (bn)
-    {
-        case 256: return launch_v3<256, 2, 2, 3>(tmx, tmw, a, stream);     // 84 KB patches + 96 KB slabs, single accumulator buffer (512 cols)
-        case 128: return launch_v3<128, 2, 3, 5>(tmx, tmw, a, stream);     // 126 + 80 KB, double-buffered accumulators (512 cols)
-        default:  return launch_v3<64, 2, 3, 8>(tmx, tmw, a, stream);      // 126 + 64 KB, double-buffered accumulators (256 cols)
-    }
+    if (cl == 4) return launch_v3_bn<4>(bn, tmx, tmw, a, stream);
+    if (cl == 2) return launch_v3_bn<2>(bn, tmx, tmw, a, stream);
+    return launch_v3_bn<1>(bn, tmx, tmw, a, stream);
 }
 
 } // namespace sgv

@@ -86,6 +86,22 @@ def _wgrad_native(gout, x, styles, dscale, w_shape, up):
 USE_NATIVE_WGRAD = True      # False -> cuDNN library call (kept for A/B measurements)
 
 
+def prepare_weights(weight, up, flip_weight):
+    """Tap-major TF32 weight slabs of one layer for the forward and the data-gradient launches (non-differentiable; the weight
+    gradient is produced directly by the wgrad kernel).  Depends on the weight only, so a caller may build it ahead of the layer
+    (SynthesisNetwork does, on its parameter stream) and hand it to fused_modulated_conv(prep=...)."""
+    O, I, kh, kw = weight.shape
+    if up == 1:
+        wsrc = weight if flip_weight else weight.flip([2, 3])      # conv2d_resample.py:35-36
+        taps = _TAPS3 if kh == 3 else [(0, 0)]
+        return dict(fwd=[_conv.prep_weights(wsrc, taps)], dgrad=_conv.prep_weights(wsrc, taps, rows_dim=1, cols_dim=0))
+    # conv2d_resample passes flip_weight = not flip_weight to the transposed conv (conv2d_resample.py:138);
+    # the synthesis layers call with flip_weight=False for up=2 (networks.py:136) => no flip is executed.
+    wsrc = weight if not flip_weight else weight.flip([2, 3])
+    fwd = [_conv.prep_weights(wsrc, _phase_taps(a, b)[0]) for a in (0, 1) for b in (0, 1)]
+    return dict(fwd=fwd, dgrad=_conv.prep_weights(wsrc, _TAPS3, rows_dim=1, cols_dim=0))
+
+
 def _wgrad_library(gout, xin, w_shape, transposed, stride):
     """Weight gradient through the library call the reference uses (cuDNN), TF32 allowed to match the native kernels."""
     w_like = torch.empty(w_shape, dtype=xin.dtype, device=xin.device)
@@ -97,33 +113,27 @@ def _wgrad_library(gout, xin, w_shape, transposed, stride):
 
 class _FusedModConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, styles, dcoefs, bias, up, act, gain, flip_weight):
+    def forward(ctx, x, weight, styles, dcoefs, bias, up, act, gain, flip_weight, prep):
         assert x.is_cuda and x.dtype == torch.float32, 'the fused layer op is CUDA / float32 only (no CPU path)'
         x = _nhwc(x)
         O, I, kh, kw = weight.shape
         N, _, H, W = x.shape
         assert kh == kw and kh in (1, 3)
-        wsrc = weight if flip_weight else weight.flip([2, 3])      # conv2d_resample.py:35-36
+        if prep is None:
+            prep = prepare_weights(weight, up, flip_weight)
         if up == 1:
-            taps = _TAPS3 if kh == 3 else [(0, 0)]
             offs = _OFFS3_FWD if kh == 3 else [(0, 0)]
-            wp = _conv.prep_weights(wsrc, taps)
-            y = _conv.igemm_conv(x, wp, offs, a_scale=styles, o_scale=dcoefs, bias=bias, act=act, gain=gain)
-            u = None
+            y = _conv.igemm_conv(x, prep['fwd'][0], offs, a_scale=styles, o_scale=dcoefs, bias=bias, act=act, gain=gain)
         else:
             assert up == 2 and kh == 3
-            # conv2d_resample passes flip_weight = not flip_weight to the transposed conv (conv2d_resample.py:138);
-            # the synthesis layers call with flip_weight=False for up=2 (networks.py:136) => no flip is executed.
-            wsrc = weight if not flip_weight else weight.flip([2, 3])
             u = torch.empty([N, O, 2 * H + 1, 2 * W + 1], dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
-            for a in (0, 1):
-                for b in (0, 1):
-                    taps, offs = _phase_taps(a, b)
-                    _conv.igemm_conv(x, _conv.prep_weights(wsrc, taps), offs, a_scale=styles, out_view=u[:, :, a::2, b::2])
+            for j, (a, b) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+                _conv.igemm_conv(x, prep['fwd'][j], _phase_taps(a, b)[1], a_scale=styles, out_view=u[:, :, a::2, b::2])
             y = _plugin.upfirdn2d(u, _fir(x.device), 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0,
                                   epilogue=dict(scale=dcoefs, bias=bias, act=act, alpha=0.2, gain=gain, clamp=None))
         ctx.save_for_backward(x, weight, styles, dcoefs if dcoefs is not None else x.new_empty(0), bias if bias is not None else x.new_empty(0), y)
         ctx.cfg = (up, act, gain, flip_weight, dcoefs is not None, bias is not None)
+        ctx.wp_dgrad = prep['dgrad']
         return y
 
     @staticmethod
@@ -140,24 +150,21 @@ class _FusedModConv(torch.autograd.Function):
         dz, db, dd = _conv.act_bwd(dy, y, bias if has_b else None, act, gain, want_db, want_dd)
         ddcoefs = dd / dcoefs if want_dd else None
         dscale = dcoefs if has_d else None
-        wsrc_same = weight if flip_weight else weight.flip([2, 3])
+        wp = ctx.wp_dgrad
         # ---- data gradient: ONE launch gives dx = dxs * styles (epilogue scale) and dstyles = sum_hw dxs * x (fused reduction) ----
         want_ds = ctx.needs_input_grad[2]
         ds = torch.zeros([N, I], dtype=torch.float32, device=x.device) if want_ds else None
         red = dict(red_x=x, red_out=ds) if want_ds else {}
         if up == 1:
             gout = dz
-            taps, offs = (_TAPS3, _OFFS3_DGRAD) if kh == 3 else ([(0, 0)], [(0, 0)])
-            wp = _conv.prep_weights(wsrc_same, taps, rows_dim=1, cols_dim=0)
+            offs = _OFFS3_DGRAD if kh == 3 else [(0, 0)]
             dx = _conv.igemm_conv(dz, wp, offs, a_scale=dscale, o_scale=styles, **red)
         else:
-            wsrc_t = weight if not flip_weight else weight.flip([2, 3])
             # adjoint of the FIR pass (upfirdn2d.py:246-261): padding (fw - p - 1) = 2, flipped filter, same gain
             gout = _plugin.upfirdn2d(dz, _fir(x.device), 1, 1, 1, 1, 2, 2, 2, 2, True, 4.0)
             # data gradient of the stride-2 transposed conv = stride-2 correlation: ONE launch with TMA element strides.
             # (Measured alternative: 4 accumulate-launches over polyphase views of `gout` on the halo-patch kernel — 1.2 ms/step
             #  slower at config 2; kept available through igemm_conv(accumulate=True).)
-            wp = _conv.prep_weights(wsrc_t, _TAPS3, rows_dim=1, cols_dim=0)
             dx = _conv.igemm_conv(gout, wp, _TAPS3, out_hw=(H, W), in_stride=2, a_scale=dscale, o_scale=styles, **red)
         # ---- weight gradient ----
         dw = None
@@ -175,15 +182,16 @@ class _FusedModConv(torch.autograd.Function):
                 dw = dw.flip([2, 3])
             if up == 2 and flip_weight:
                 dw = dw.flip([2, 3])
-        return dx, dw, ds, ddcoefs, db, None, None, None, None
+        return dx, dw, ds, ddcoefs, db, None, None, None, None, None
 
 
-def fused_modulated_conv(x, weight, styles, bias=None, up=1, demodulate=True, act='lrelu', gain=None, flip_weight=True):
+def fused_modulated_conv(x, weight, styles, bias=None, up=1, demodulate=True, act='lrelu', gain=None, flip_weight=True, dcoefs=None, prep=None):
     """y = clamp-free bias_act(modulated_conv2d(x, weight, styles, up, demodulate), bias, act, gain) on NHWC fp32 tensors.
 
     Equivalent (up to TF32 rounding of the contraction operands) to the reference's training-mode sequence
     modulated_conv2d(..., fused_modconv=False) + bias_act (networks.py:30-86,141-143)."""
     if gain is None:
         gain = float(np.sqrt(2)) if act == 'lrelu' else 1.0
-    dcoefs = demod_coefs(weight, styles) if demodulate else None
-    return _FusedModConv.apply(x, weight, styles, dcoefs, bias, up, act, float(gain), flip_weight)
+    if dcoefs is None and demodulate:
+        dcoefs = demod_coefs(weight, styles)
+    return _FusedModConv.apply(x, weight, styles, dcoefs, bias, up, act, float(gain), flip_weight, prep)

@@ -11,11 +11,14 @@ What differs from the reference is how a layer is executed (see stylegan_v_b200/
 implicit-GEMM launch (plus one FIR launch for up=2) instead of x*styles, cuDNN conv, upfirdn2d, *dcoefs, bias_act;
 all style affines of a forward pass are evaluated as ONE stacked GEMM up front.
 """
+import contextlib
+import os
+
 import numpy as np
 import torch
 
 from . import conv as _conv
-from .modconv import fused_modulated_conv
+from .modconv import fused_modulated_conv, demod_coefs, prepare_weights
 from .ops import upfirdn2d as _upfirdn2d
 from .time_encoder import EqualizedLinear, MotionMappingNetwork
 
@@ -33,11 +36,16 @@ class SynthesisLayer(torch.nn.Module):
         self.weight = torch.nn.Parameter(torch.randn(out_channels, in_channels, kernel_size, kernel_size))
         self.bias = torch.nn.Parameter(torch.zeros(out_channels))
 
-    def forward(self, x, w=None, styles=None, gain=1.0):
-        if styles is None:
-            styles = self.affine(w)
-        return fused_modulated_conv(x, self.weight, styles, self.bias, up=self.up, demodulate=True, act='lrelu',
-                                    gain=float(np.sqrt(2)) * gain, flip_weight=(self.up == 1))
+    def plan(self, styles):
+        """Everything of this layer that depends on parameters and styles only (not on activations): demodulation coefficients
+        and the TF32 weight slabs.  SynthesisNetwork evaluates the plans of all layers on its parameter stream."""
+        return dict(styles=styles, dcoefs=demod_coefs(self.weight, styles), prep=prepare_weights(self.weight, self.up, self.up == 1))
+
+    def forward(self, x, w=None, styles=None, gain=1.0, plan=None):
+        if plan is None:
+            plan = dict(styles=styles if styles is not None else self.affine(w), dcoefs=None, prep=None)
+        return fused_modulated_conv(x, self.weight, plan['styles'], self.bias, up=self.up, demodulate=True, act='lrelu',
+                                    gain=float(np.sqrt(2)) * gain, flip_weight=(self.up == 1), dcoefs=plan['dcoefs'], prep=plan['prep'])
 
 
 class _ToRGB(torch.autograd.Function):
@@ -68,12 +76,15 @@ class ToRGBLayer(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.zeros(out_channels))
         self.weight_gain = 1 / np.sqrt(in_channels)
 
-    def forward(self, x, w=None, styles=None):
-        if styles is None:
-            styles = self.affine(w)
-        styles = styles * self.weight_gain
+    def plan(self, styles):
+        C = self.weight.shape[1]
+        return dict(wmod=self.weight.reshape(1, -1, C) * (styles * self.weight_gain).unsqueeze(1))   # [N, 3, C]  (tiny, differentiable torch ops)
+
+    def forward(self, x, w=None, styles=None, plan=None):
+        if plan is None:
+            plan = self.plan(styles if styles is not None else self.affine(w))
+        wmod = plan['wmod']
         N, C, H, W = x.shape
-        wmod = self.weight.reshape(1, -1, C) * styles.unsqueeze(1)                         # [N, 3, C]  (tiny, differentiable torch ops)
         if wmod.shape[1] == 3 and x.is_cuda:
             return _ToRGB.apply(x, wmod, self.bias)                                        # one pass over the NHWC activation
         xf = x.permute(0, 2, 3, 1).reshape(N, H * W, C)
@@ -127,17 +138,18 @@ class SynthesisBlock(torch.nn.Module):
     def layers(self):
         return ([] if self.in_channels == 0 else [self.conv0]) + [self.conv1, self.torgb]
 
-    def forward(self, x, img, styles, motion_v=None):
-        """styles: list of per-layer style tensors in layer order (conv0?, conv1, torgb)."""
-        it = iter(styles)
+    def forward(self, x, img, plans, motion_v=None):
+        """plans: list of per-layer plans in layer order (conv0?, conv1, torgb); each is a callable returning the plan dict
+        (it makes the compute stream wait for the parameter stream first)."""
+        it = iter(plans)
         if self.in_channels == 0:
             x = self.input(motion_v)
         else:
-            x = self.conv0(x, styles=next(it))
-        x = self.conv1(x, styles=next(it))
+            x = self.conv0(x, plan=next(it)())
+        x = self.conv1(x, plan=next(it)())
         if img is not None:
             img = _upfirdn2d.upsample2d(img, self.resample_filter)
-        y = self.torgb(x, styles=next(it))
+        y = self.torgb(x, plan=next(it)())
         img = img.add_(y) if img is not None else y
         return x, img
 
@@ -199,9 +211,60 @@ class SynthesisNetwork(torch.nn.Module):
         if motion_v is None:
             motion_v = self.motion_encoder(t, motion_z=motion_z, t_max=t_max)['motion_v']
         ws = ws.to(torch.float32).repeat_interleave(t.shape[1], dim=0)
-        styles = self._all_styles(ws)
+        plans = self._plan_layers(ws)
         x = img = None
         for res in self.block_resolutions:
             block = getattr(self, f'b{res}')
-            x, img = block(x, img, [styles[id(l)] for l in block.layers()], motion_v=motion_v)
+            x, img = block(x, img, [plans[id(l)] for l in block.layers()], motion_v=motion_v)
         return img
+
+    # evaluate the per-layer plans on a second CUDA stream (SGV_PARAM_STREAM=0 or False: same stream, for A/B measurements)
+    param_stream = os.environ.get('SGV_PARAM_STREAM', '1') != '0'
+
+    def _plan_layers(self, ws):
+        """Style affines, demodulation coefficients, ToRGB modulated weights and TF32 weight slabs of EVERY layer depend on
+        (parameters, ws) only.  They are ~25 tiny launches per layer; evaluated here on a second stream they overlap the
+        activation-sized kernels of the compute stream instead of sitting between them, and autograd replays their backward on
+        that same stream.  Returns {id(layer): thunk}; the thunk makes the current stream wait for that layer's plan."""
+        main = torch.cuda.current_stream(ws.device)
+        use_side = self.param_stream and ws.is_cuda
+        if use_side:
+            if getattr(self, '_pstream', None) is None or self._pstream.device != ws.device:
+                self._pstream = torch.cuda.Stream(ws.device)
+            side = self._pstream
+            side.wait_stream(main)
+        out = {}
+        with torch.cuda.stream(side) if use_side else contextlib.nullcontext():
+            styles = self._all_styles(ws)
+            for res in self.block_resolutions:
+                for layer in getattr(self, f'b{res}').layers():
+                    plan = layer.plan(styles[id(layer)])
+                    ev = None
+                    if use_side:
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                    out[id(layer)] = _PlanThunk(plan, ev, main if use_side else None)
+        return out
+
+
+def _plan_tensors(obj):
+    if isinstance(obj, torch.Tensor):
+        yield obj
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            yield from _plan_tensors(v)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            yield from _plan_tensors(v)
+
+
+class _PlanThunk:
+    def __init__(self, plan, event, consumer_stream):
+        self.plan, self.event, self.consumer = plan, event, consumer_stream
+
+    def __call__(self):
+        if self.event is not None:
+            self.consumer.wait_event(self.event)
+            for t in _plan_tensors(self.plan):
+                t.record_stream(self.consumer)      # allocated on the parameter stream, consumed on the compute stream
+        return self.plan

@@ -100,7 +100,7 @@ def test_fused_layer_backward_with_matched_forward(up):
     d = (torch.rand(N, O, generator=gen) + 0.5).cuda().requires_grad_(True)
     b = (0.3 * torch.randn(O, generator=gen)).cuda().requires_grad_(True)
     gain = float(np.sqrt(2))
-    y = modconv._FusedModConv.apply(x, w, s, d, b, up, 'lrelu', gain, up == 1)
+    y = modconv._FusedModConv.apply(x, w, s, d, b, up, 'lrelu', gain, up == 1, None)
     dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).cuda()
     got = torch.autograd.grad(y, [x, w, s, d, b], dy)
     # reference: same rounded operands, fp64 arithmetic, autograd
