@@ -11,7 +11,10 @@
 // Operand staging is v2's: per 32-channel chunk ONE TMA box = output tile (16 rows x 16 cols) + halo; every tap's A matrix is
 // that patch through a shifted K-major SWIZZLE_128B descriptor (start row = (dy-dy_min)*PW + (dx-dx_min) + 8*half,
 // SBO = PW*128; legal because tcgen05 swizzles on absolute smem address bits — profiles/umma_probe_r1.txt).
-// Warps: 0 TMA producer, 1 MMA issuer + TMEM owner, 2-5 transform (styles * x, round to TF32), 6-9 epilogue.
+// Warps: 0 activation-patch TMA producer, 1 MMA issuer + TMEM owner, 2-5 transform (styles * x, round to TF32), 6-9 epilogue,
+// 10 weight-slab TMA producer.  The two producers are separate threads on purpose: with one thread issuing "patch, then its
+// ntaps slabs" the next patch could not be requested until the MMAs had freed slab slots, and the transform warps spent 2/3 of
+// their time waiting for patches (ncu source view, profiles/ncu_v3_r1y_summary.txt).
 #include <stdlib.h>
 #include "common.cuh"
 #include "ptx.cuh"
@@ -22,7 +25,7 @@ namespace sgv {
 
 using namespace ptx;
 
-constexpr int kV3Threads = 64 + 128 + 128;
+constexpr int kV3Threads = 64 + 128 + 128 + 32;
 constexpr int kV3TileH = 16;
 
 struct ConvV3Args
@@ -37,6 +40,7 @@ struct ConvV3Args
     int act; float alpha, gain, clamp;
     int accumulate;
     const float* red_x; float* red_out;
+    int debug;      // TEMP experiment switches (SGV_V3_DEBUG): 1 skip transform, 2 skip epilogue, 4 skip MMAs
 };
 
 template <int BN, int MH, int SA, int SB>
@@ -45,7 +49,8 @@ struct ConvV3Smem
     static constexpr int kPatch = (((16 + 2) * (8 * MH + 2) * 128) + 1023) & ~1023;
     static constexpr int kBTile = BN * 128;
     static constexpr int kBOffset = SA * kPatch;
-    static constexpr int kBarOffset = kBOffset + SB * kBTile;
+    static constexpr int kStageOffset = kBOffset + SB * kBTile;      // 2 x 16 KB output staging (128 pixels x 32 channels, 128B-swizzled)
+    static constexpr int kBarOffset = kStageOffset + 2 * 16384;
     static constexpr int kNumBars = 3 * SA + 2 * SB + 4;
     static constexpr int kTotal = kBarOffset + kNumBars * 8 + 16 + 1024;
     static constexpr int kAccBufs = (2 * MH * BN <= 512) ? 2 : 1;
@@ -71,7 +76,8 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvV3Args& p, int group, 
 
 template <int BN, int MH, int SA, int SB, int CL>
 __global__ void __launch_bounds__(kV3Threads, 1)
-conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const ConvV3Args p)
+conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_y, const ConvV3Args p)
 {
     using L = ConvV3Smem<BN, MH, SA, SB>;
     constexpr int NB = L::kAccBufs;
@@ -97,6 +103,7 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     {
         prefetch_tmap(&tmap_x);
         prefetch_tmap(&tmap_w);
+        prefetch_tmap(&tmap_y);
         for (int s = 0; s < SA; s++) { mbar_init(full_a + s, 1); mbar_init(ready_a + s, 4); mbar_init(empty_a + s, 1); }
         for (int s = 0; s < SB; s++) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, CL); }   // a slab slot is freed by the MMAs of all CL CTAs
         for (int s = 0; s < 2; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
@@ -110,10 +117,10 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 
     if (warp == 0)
     {
-        // ===== TMA producer =====
+        // ===== activation-patch producer =====
         if (elect_one())
         {
-            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            int sa = 0; uint32_t pa = 0;
             for (int g = cid; g < p.total_groups; g += ncl)
             {
                 const TileCoord tc = tile_coord<BN, MH, CL>(p, g, crank);
@@ -123,15 +130,30 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     mbar_expect_tx(full_a + sa, patch_bytes);
                     tma_load_4d(smem + sa * L::kPatch, &tmap_x, full_a + sa, kc * 32, tc.ox0 + p.dx_min, tc.oy0 + p.dy_min, tc.n);
                     if (++sa == SA) { sa = 0; pa ^= 1; }
+                }
+            }
+        }
+    }
+    else if (warp == 10)
+    {
+        // ===== weight-slab producer =====
+        if (elect_one())
+        {
+            int sb = 0; uint32_t pb = 0;
+            for (int g = cid; g < p.total_groups; g += ncl)
+            {
+                const int nb0 = (g % p.ntiles_n) * BN;
+                for (int kc = 0; kc < kchunks; kc++)
+                {
                     for (int t = 0; t < p.ntaps; t++)
                     {
                         mbar_wait(empty_b + sb, pb ^ 1);
                         mbar_expect_tx(full_b + sb, L::kBTile);
                         if (CL == 1)
-                            tma_load_2d(smem + L::kBOffset + sb * L::kBTile, &tmap_w, full_b + sb, kc * 32, t * p.cout + tc.nb0);
+                            tma_load_2d(smem + L::kBOffset + sb * L::kBTile, &tmap_w, full_b + sb, kc * 32, t * p.cout + nb0);
                         else    // this CTA fetches rows [crank * BN/CL, +BN/CL) of the slab once and multicasts them to the whole cluster
                             tma_load_2d_mc(smem + L::kBOffset + sb * L::kBTile + crank * (BN / CL) * 128, &tmap_w, full_b + sb, kc * 32,
-                                           t * p.cout + tc.nb0 + crank * (BN / CL), kMask);
+                                           t * p.cout + nb0 + crank * (BN / CL), kMask);
                         if (++sb == SB) { sb = 0; pb ^= 1; }
                     }
                 }
@@ -170,7 +192,7 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                             uint64_t da = umma_desc_k_sw128(patch + (uint32_t)(p.tap_row[t] + 8 * h) * 128u);
                             da = (da & ~((uint64_t)0x3FFF << 32)) | sbo_field;
 #pragma unroll
-                            for (int k = 0; k < 4; k++)
+                            for (int k = 0; k < ((p.debug & 4) ? 0 : 4); k++)
                                 mma_tf32(acc + (uint32_t)(h * BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc > 0 || t > 0 || k > 0) ? 1u : 0u);
                         }
                         if (CL == 1) mma_commit(empty_b + sb); else mma_commit_mc(empty_b + sb, kMask);
@@ -212,7 +234,7 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 }
                 mbar_wait(full_a + sa, pa);
                 const uint32_t patch = smem_u32(smem + sa * L::kPatch);
-                for (int row = tid; row < nrows; row += 128)
+                for (int row = tid; row < ((p.debug & 1) ? 0 : nrows); row += 128)
                 {
                     const uint32_t arow = patch + (uint32_t)row * 128u;
                     float4 v[8];
@@ -235,9 +257,16 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
     else
     {
-        // ===== epilogue (4 warps) =====
+        // ===== epilogue (4 warps): TMEM -> registers -> dcoefs/bias/lrelu/gain -> swizzled staging -> TMA store =====
+        // Thread `row` owns one output pixel of the 16 x 8 half tile and 32 consecutive channels per unit.  Writing those straight to
+        // global memory made every STG.128 touch 32 different lines (16 B partial writes): the drain took 2-4x the MMA time of a tile
+        // (ablation: profiles/conv_v3_ablation_r1.txt).  Instead the unit is staged as 128 rows x 128 B in the TMA 128B-swizzle
+        // (conflict-free STS.128) and written by ONE bulk tensor store, which also clips the ragged right / bottom edge.
         const int q = warp & 3;
         const int row = q * 32 + lane;
+        const bool issuer = (threadIdx.x == 192);
+        const uint32_t stage0 = smem_u32(smem + L::kStageOffset);
+        uint32_t unit = 0;
         int it = 0;
         for (int g = cid; g < p.total_groups; g += ncl, it++)
         {
@@ -248,20 +277,24 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)(buf * MH * BN);
             const int oy = tc.oy0 + (row >> 3);
-            const float* osc = p.o_scale ? p.o_scale + (long long)tc.n * p.cout + tc.nb0 : nullptr;
-            const float* bia = p.bias ? p.bias + tc.nb0 : nullptr;
 #pragma unroll 1
-            for (int h = 0; h < MH; h++)
+            for (int h = 0; h < ((p.debug & 2) ? 0 : MH); h++)
             {
                 const int ox = tc.ox0 + 8 * h + (row & 7);
                 const bool valid = (oy < p.out_h) && (ox < p.out_w);
-                float* yrow = p.y + (long long)tc.n * p.osn + (long long)oy * p.osy + (long long)ox * p.osx + tc.nb0;
 #pragma unroll 1
-                for (int cc = 0; cc < BN / 32; cc++)
+                for (int cc = 0; cc < BN / 32; cc++, unit++)
                 {
                     uint32_t v[32];
                     tmem_ld_32x32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN + cc * 32), v);
                     tmem_ld_wait();
+                    if (h == MH - 1 && cc == BN / 32 - 1)
+                    {
+                        // the accumulator buffer is in registers now: hand it back to the MMA issuer before the stores
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty + buf);
+                    }
                     if (p.red_out)
                     {
                         // fused style-gradient reduction: sum over this warp's 32 pixels of raw * red_x, one channel per lane
@@ -277,35 +310,41 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         const float tot = warp_reduce_32x32(prod, lane);
                         atomicAdd(p.red_out + (long long)tc.n * p.cout + tc.nb0 + cc * 32 + lane, tot);
                     }
-                    if (valid)
+                    const float4* osc = p.o_scale ? reinterpret_cast<const float4*>(p.o_scale + (long long)tc.n * p.cout + tc.nb0 + cc * 32) : nullptr;
+                    const float4* bia = p.bias ? reinterpret_cast<const float4*>(p.bias + tc.nb0 + cc * 32) : nullptr;
+                    const uint32_t stage = stage0 + (unit & 1u) * 16384u;
+                    if (issuer) bulk_wait_read<1>();                 // the store issued two units ago has finished reading this buffer
+                    named_bar_sync(1, 128);
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
                     {
+                        float o[4] = {__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])};
+                        if (osc) { const float4 sv = __ldg(osc + j); o[0] = __fmul_rn(o[0], sv.x); o[1] = __fmul_rn(o[1], sv.y); o[2] = __fmul_rn(o[2], sv.z); o[3] = __fmul_rn(o[3], sv.w); }
+                        if (bia) { const float4 bv = __ldg(bia + j); o[0] = __fadd_rn(o[0], bv.x); o[1] = __fadd_rn(o[1], bv.y); o[2] = __fadd_rn(o[2], bv.z); o[3] = __fadd_rn(o[3], bv.w); }
 #pragma unroll
-                        for (int j = 0; j < 8; j++)
+                        for (int e = 0; e < 4; e++)
                         {
-                            float o[4];
-#pragma unroll
-                            for (int e = 0; e < 4; e++)
-                            {
-                                const int col = cc * 32 + j * 4 + e;
-                                float f = __uint_as_float(v[j * 4 + e]);
-                                if (osc) f = __fmul_rn(f, __ldg(osc + col));
-                                if (bia) f = __fadd_rn(f, __ldg(bia + col));
-                                if (p.act == 3) f = (f > 0.f) ? f : f * p.alpha;
-                                f *= p.gain;
-                                if (p.clamp >= 0.f) f = (f > -p.clamp && f < p.clamp) ? f : (f >= 0.f ? p.clamp : -p.clamp);
-                                o[e] = f;
-                            }
-                            float4* dst = reinterpret_cast<float4*>(yrow + cc * 32 + j * 4);
-                            if (p.accumulate) { const float4 old = *dst; o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w; }
-                            *dst = make_float4(o[0], o[1], o[2], o[3]);
+                            float f = o[e];
+                            if (p.act == 3) f = (f > 0.f) ? f : f * p.alpha;
+                            f *= p.gain;
+                            if (p.clamp >= 0.f) f = (f > -p.clamp && f < p.clamp) ? f : (f >= 0.f ? p.clamp : -p.clamp);
+                            o[e] = f;
                         }
+                        sts128(stage + (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4), make_float4(o[0], o[1], o[2], o[3]));
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 128);
+                    if (issuer)
+                    {
+                        if (p.accumulate) tma_reduce_add_4d(&tmap_y, stage, tc.nb0 + cc * 32, tc.ox0 + 8 * h, tc.oy0, tc.n);
+                        else tma_store_4d(&tmap_y, stage, tc.nb0 + cc * 32, tc.ox0 + 8 * h, tc.oy0, tc.n);
+                        bulk_commit();
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + buf);
+            if (p.debug & 2) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(acc_empty + buf); }
         }
+        if (issuer) bulk_wait_all();
     }
 
     tc_fence_before();
@@ -314,7 +353,7 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 }
 
 template <int BN, int MH, int SA, int SB, int CL>
-static int launch_v3(const CUtensorMap& tx, const CUtensorMap& tw, const ConvV3Args& a, cudaStream_t stream)
+static int launch_v3(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvV3Args& a, cudaStream_t stream)
 {
     using L = ConvV3Smem<BN, MH, SA, SB>;
     auto kern = conv_tf32_v3_kernel<BN, MH, SA, SB, CL>;
@@ -340,19 +379,19 @@ static int launch_v3(const CUtensorMap& tx, const CUtensorMap& tw, const ConvV3A
     const int clusters = a.total_groups < max_clusters ? a.total_groups : max_clusters;
     cfg.gridDim = dim3((unsigned)(clusters * CL));
     ConvV3Args args = a;
-    SGV_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tx, tw, args));
+    SGV_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tx, tw, ty, args));
     SGV_LAUNCH_OK("conv_tf32_v3_kernel");
     return SGV_OK;
 }
 
 template <int CL>
-static int launch_v3_bn(int bn, const CUtensorMap& tx, const CUtensorMap& tw, const ConvV3Args& a, cudaStream_t stream)
+static int launch_v3_bn(int bn, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvV3Args& a, cudaStream_t stream)
 {
     switch (bn)
     {
-        case 256: return launch_v3<256, 2, 2, 3, CL>(tx, tw, a, stream);     // 84 KB patches + 96 KB slabs, single accumulator buffer (512 cols)
-        case 128: return launch_v3<128, 2, 3, 5, CL>(tx, tw, a, stream);     // 126 + 80 KB, double-buffered accumulators (512 cols)
-        default:  return launch_v3<64, 2, 3, 8, CL>(tx, tw, a, stream);      // 126 + 64 KB, double-buffered accumulators (256 cols)
+        case 256: return launch_v3<256, 2, 2, 3, CL>(tx, tw, ty, a, stream);     // 84 KB patches + 96 KB slabs, single accumulator buffer (512 cols)
+        case 128: return launch_v3<128, 2, 3, 4, CL>(tx, tw, ty, a, stream);     // 126 + 64 KB, double-buffered accumulators (512 cols)
+        default:  return launch_v3<64, 2, 3, 8, CL>(tx, tw, ty, a, stream);      // 126 + 64 KB, double-buffered accumulators (256 cols)
     }
 }
 
@@ -393,6 +432,7 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
     a.act = p->act; a.alpha = p->alpha; a.gain = p->gain; a.clamp = p->clamp;
     a.accumulate = p->accumulate;
     a.red_x = p->red_x; a.red_out = p->red_out;
+    { const char* e = getenv("SGV_V3_DEBUG"); a.debug = e ? atoi(e) : 0; }
     const int bn = (p->cout % 256 == 0) ? 256 : (p->cout % 128 == 0) ? 128 : 64;
     a.ntiles_n = p->cout / bn;
     const int pixel_tiles = a.tiles_x * a.tiles_y * p->n;
@@ -400,7 +440,7 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
     while (cl > 1 && (pixel_tiles % cl != 0 || pixel_tiles / cl * a.ntiles_n < num_sms() / cl)) cl >>= 1;   // small problems: fill the SMs first
     a.total_groups = pixel_tiles / cl * a.ntiles_n;
 
-    CUtensorMap tmx, tmw;
+    CUtensorMap tmx, tmw, tmy;
     {
         const uint64_t dims[4] = {(uint64_t)p->cin, (uint64_t)p->w, (uint64_t)p->h, (uint64_t)p->n};
         const bool view = p->in_stride_x != 0;
@@ -419,9 +459,18 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
         int rc = make_tmap_f32(&tmw, p->wp, 2, dims, strides, box, es);
         if (rc != SGV_OK) return rc;
     }
-    if (cl == 4) return launch_v3_bn<4>(bn, tmx, tmw, a, stream);
-    if (cl == 2) return launch_v3_bn<2>(bn, tmx, tmw, a, stream);
-    return launch_v3_bn<1>(bn, tmx, tmw, a, stream);
+    {
+        // output (possibly a pixel-strided view): box = 32 channels x 8 columns x 16 rows, the unit one epilogue pass stages
+        const uint64_t dims[4] = {(uint64_t)p->cout, (uint64_t)p->out_w, (uint64_t)p->out_h, (uint64_t)p->n};
+        const uint64_t strides[3] = {(uint64_t)p->out_stride_x * 4, (uint64_t)p->out_stride_y * 4, (uint64_t)p->out_stride_n * 4};
+        const uint32_t box[4] = {32, 8, (uint32_t)kV3TileH, 1};
+        const uint32_t es[4] = {1, 1, 1, 1};
+        int rc = make_tmap_f32(&tmy, p->y, 4, dims, strides, box, es);
+        if (rc != SGV_OK) return rc;
+    }
+    if (cl == 4) return launch_v3_bn<4>(bn, tmx, tmw, tmy, a, stream);
+    if (cl == 2) return launch_v3_bn<2>(bn, tmx, tmw, tmy, a, stream);
+    return launch_v3_bn<1>(bn, tmx, tmw, tmy, a, stream);
 }
 
 } // namespace sgv
