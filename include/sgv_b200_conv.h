@@ -101,12 +101,19 @@ int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream);
  *   act = linear(1) / lrelu(3)):  dz = act'(.) * dy * gain;  db[c] += sum_{n,hw} dz;  dd[n,c] += sum_hw dz * (v)   where
  *   v = act^-1(y / gain) - bias is recovered from y (so the un-activated conv output never needs to be stored).
  *   Replaces BiasActCudaGrad + dx.sum() (bias_act.py:161-186) and the reduction in the autograd of x*dcoefs (networks.py:68-71).
+ * sgv_modconv_act_bwd_rgb: the same with the ToRGB branch that reads the same activation folded in (networks.py:262-265: the block
+ *   output x feeds both the next block and torgb): the incoming gradient is dy (may be NULL: last block) + sum_j dyimg[n,j,hw] *
+ *   wmod[n,j,c], and dwmod[n,j,c] += sum_hw dyimg[n,j,hw] * y[n,hw,c]  (dyimg: [n,3,hw] NCHW, wmod / dwmod: [n,3,c]).  One pass
+ *   instead of sgv_torgb_bwd + the autograd sum of the two gradients + sgv_modconv_act_bwd.  dyimg == NULL: plain sgv_modconv_act_bwd.
  * sgv_modconv_scale_reduce:  dx = dxs * s[n,c] (dx may be NULL or alias dxs);  ds[n,c] += sum_hw dxs * x    (networks.py:66 autograd)
  * sgv_torgb_fwd:  y[n,j,hw] = sum_c x[n,hw,c] * wmod[n,j,c] + bias[j],  j < 3, y in NCHW            (networks.py:159-163)
  * sgv_torgb_bwd:  dx[n,hw,c] = sum_j dy[n,j,hw] * wmod[n,j,c];  dwmod[n,j,c] += sum_hw dy[n,j,hw] * x[n,hw,c]
  */
 int sgv_modconv_act_bwd(const float* dy, const float* y, const float* bias, float* dz, float* db, float* dd,
                         int32_t n, int32_t hw, int32_t c, int32_t act, float alpha, float gain, void* stream);
+int sgv_modconv_act_bwd_rgb(const float* dy, const float* y, const float* bias, float* dz, float* db, float* dd,
+                            const float* dyimg, const float* wmod, float* dwmod,
+                            int32_t n, int32_t hw, int32_t c, int32_t act, float alpha, float gain, void* stream);
 int sgv_modconv_scale_reduce(const float* dxs, const float* x, const float* s, float* dx, float* ds,
                              int32_t n, int32_t hw, int32_t c, void* stream);
 int sgv_torgb_fwd(const float* x, const float* wmod, const float* bias, float* y, int32_t n, int32_t hw, int32_t c, void* stream);

@@ -92,6 +92,7 @@ SYMBOLS = [
     ('sgv_conv2d_tf32', c_int, [ctypes.POINTER(ConvParams), c_vp]),
     ('sgv_conv2d_wgrad_tf32', c_int, [ctypes.POINTER(WgradParams), c_vp]),
     ('sgv_modconv_act_bwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),
+    ('sgv_modconv_act_bwd_rgb', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),
     ('sgv_modconv_scale_reduce', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     ('sgv_torgb_fwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     ('sgv_torgb_bwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),

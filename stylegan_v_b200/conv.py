@@ -149,19 +149,33 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
-def act_bwd(dy, y, bias, act, gain, want_db, want_dd, alpha=0.2):
-    """dz, db[C], dd[N,C] (see sgv_modconv_act_bwd).  dy, y: [N,C,H,W] channels_last."""
-    _req(dy.is_cuda and dy.dtype == torch.float32 and _is_nhwc(dy) and _is_nhwc(y) and dy.shape == y.shape, 'dy / y must be matching NHWC float32 CUDA tensors')
-    N, C, H, W = dy.shape
-    dz = torch.empty_like(dy)
-    db = torch.zeros([C], dtype=torch.float32, device=dy.device) if want_db else None
-    dd = torch.zeros([N, C], dtype=torch.float32, device=dy.device) if want_dd else None
+def act_bwd(dy, y, bias, act, gain, want_db, want_dd, alpha=0.2, dyimg=None, wmod=None):
+    """dz, db[C], dd[N,C] (see sgv_modconv_act_bwd).  dy, y: [N,C,H,W] channels_last.
+
+    With dyimg [N,3,H,W] (contiguous) and wmod [N,3,C] the ToRGB branch reading the same activation is folded in
+    (sgv_modconv_act_bwd_rgb): dy may then be None, and a fourth result dwmod [N,3,C] is returned."""
+    _req(y.is_cuda and y.dtype == torch.float32 and _is_nhwc(y), 'y must be an NHWC float32 CUDA tensor')
+    _req(dy is None or (dy.dtype == torch.float32 and _is_nhwc(dy) and dy.shape == y.shape), 'dy must match y (NHWC float32)')
+    N, C, H, W = y.shape
+    rgb = dyimg is not None
+    _req(rgb or dy is not None, 'dy is required without a ToRGB branch')
+    dz = torch.empty_like(y)
+    db = torch.zeros([C], dtype=torch.float32, device=y.device) if want_db else None
+    dd = torch.zeros([N, C], dtype=torch.float32, device=y.device) if want_dd else None
     b = bias.to(torch.float32).contiguous() if bias is not None else None
     L = _lib.lib()
-    with torch.cuda.device(dy.device):
-        _lib.check(L.sgv_modconv_act_bwd(dy.data_ptr(), y.data_ptr(), _ptr(b), dz.data_ptr(), _ptr(db), _ptr(dd), N, H * W, C,
-                                         {'linear': 1, 'lrelu': 3}[act], float(alpha), float(gain), _stream(dy.device)), 'sgv_modconv_act_bwd')
-    return dz, db, dd
+    args = (_ptr(dy), y.data_ptr(), _ptr(b), dz.data_ptr(), _ptr(db), _ptr(dd))
+    tail = (N, H * W, C, {'linear': 1, 'lrelu': 3}[act], float(alpha), float(gain), _stream(y.device))
+    with torch.cuda.device(y.device):
+        if not rgb:
+            _lib.check(L.sgv_modconv_act_bwd(*args, *tail), 'sgv_modconv_act_bwd')
+            return dz, db, dd
+        dyimg = dyimg.to(torch.float32).contiguous()
+        wmod = wmod.to(torch.float32).contiguous()
+        _req(tuple(dyimg.shape) == (N, 3, H, W) and tuple(wmod.shape) == (N, 3, C), 'dyimg must be [N,3,H,W] and wmod [N,3,C]')
+        dwmod = torch.zeros([N, 3, C], dtype=torch.float32, device=y.device)
+        _lib.check(L.sgv_modconv_act_bwd_rgb(*args, dyimg.data_ptr(), wmod.data_ptr(), dwmod.data_ptr(), *tail), 'sgv_modconv_act_bwd_rgb')
+    return dz, db, dd, dwmod
 
 
 def scale_reduce(dxs, x, s, want_dx=True, want_ds=True):

@@ -40,14 +40,18 @@ struct ActBwdArgs
 {
     const float* dy; const float* y; const float* bias; float* dz; float* db; float* dd;
     int act; float alpha, gain;
+    // optional ToRGB branch hanging off the same activation (RGB = true): dy_total = dy (may be NULL) + sum_j dyimg[n,j,hw] * wmod[n,j,c];
+    // dwmod[n,j,c] += sum_hw dyimg[n,j,hw] * y[n,hw,c]
+    const float* dyimg; const float* wmod; float* dwmod;
     EwGeom g;
 };
 
+template <bool RGB>
 __global__ void __launch_bounds__(kEwThreads) modconv_act_bwd_kernel(ActBwdArgs p)
 {
-    extern __shared__ float sacc[];            // [2][c]: db partials, dd partials
+    extern __shared__ float sacc[];            // [2 (+3)][c]: db, dd (, dwmod[0..2]) partials
     const EwGeom g = p.g;
-    for (int i = threadIdx.x; i < 2 * g.c; i += kEwThreads) sacc[i] = 0.f;
+    for (int i = threadIdx.x; i < (RGB ? 5 : 2) * g.c; i += kEwThreads) sacc[i] = 0.f;
     __syncthreads();
     const int n = blockIdx.x / g.chunks, chunk = blockIdx.x % g.chunks;
     const int cv = threadIdx.x % g.cvecs, lane = threadIdx.x / g.cvecs;
@@ -58,10 +62,19 @@ __global__ void __launch_bounds__(kEwThreads) modconv_act_bwd_kernel(ActBwdArgs 
     {
         const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias) + cv) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 sdb = make_float4(0.f, 0.f, 0.f, 0.f), sdd = sdb;
+        float4 wm[3], sdw[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+        {
+            sdw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            wm[j] = RGB ? __ldg(reinterpret_cast<const float4*>(p.wmod + ((long long)n * 3 + j) * g.c) + cv) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float* gimg = RGB ? p.dyimg + (long long)n * 3 * g.hw : nullptr;
         const int stride = g.lanes * g.chunks;
         for (int p0 = chunk * g.lanes + lane; p0 < g.hw; p0 += stride * kEwUnroll)
         {
             float4 vdy[kEwUnroll], vy[kEwUnroll];
+            float gi[kEwUnroll][3];
 #pragma unroll
             for (int u = 0; u < kEwUnroll; u++)
             {
@@ -69,8 +82,13 @@ __global__ void __launch_bounds__(kEwThreads) modconv_act_bwd_kernel(ActBwdArgs 
                 if (px < g.hw)
                 {
                     const long long off = base + (long long)px * g.c + cv * 4;
-                    vdy[u] = __ldcs(reinterpret_cast<const float4*>(p.dy + off));
+                    vdy[u] = (!RGB || p.dy) ? __ldcs(reinterpret_cast<const float4*>(p.dy + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     vy[u] = __ldcs(reinterpret_cast<const float4*>(p.y + off));
+                    if (RGB)
+                    {
+#pragma unroll
+                        for (int j = 0; j < 3; j++) gi[u][j] = __ldg(gimg + (long long)j * g.hw + px);
+                    }
                 }
             }
 #pragma unroll
@@ -78,6 +96,17 @@ __global__ void __launch_bounds__(kEwThreads) modconv_act_bwd_kernel(ActBwdArgs 
             {
                 const int px = p0 + u * stride;
                 if (px >= g.hw) continue;
+                if (RGB)
+                {
+#pragma unroll
+                    for (int j = 0; j < 3; j++)
+                    {
+                        vdy[u].x = fmaf(gi[u][j], wm[j].x, vdy[u].x); vdy[u].y = fmaf(gi[u][j], wm[j].y, vdy[u].y);
+                        vdy[u].z = fmaf(gi[u][j], wm[j].z, vdy[u].z); vdy[u].w = fmaf(gi[u][j], wm[j].w, vdy[u].w);
+                        sdw[j].x = fmaf(gi[u][j], vy[u].x, sdw[j].x); sdw[j].y = fmaf(gi[u][j], vy[u].y, sdw[j].y);
+                        sdw[j].z = fmaf(gi[u][j], vy[u].z, sdw[j].z); sdw[j].w = fmaf(gi[u][j], vy[u].w, sdw[j].w);
+                    }
+                }
                 float d[4] = {vdy[u].x, vdy[u].y, vdy[u].z, vdy[u].w};
                 float yv[4] = {vy[u].x, vy[u].y, vy[u].z, vy[u].w};
                 float bb[4] = {b4.x, b4.y, b4.z, b4.w};
@@ -100,12 +129,22 @@ __global__ void __launch_bounds__(kEwThreads) modconv_act_bwd_kernel(ActBwdArgs 
         }
         if (p.db) smem_acc4(sacc, cv * 4, sdb);
         if (p.dd) smem_acc4(sacc + g.c, cv * 4, sdd);
+        if (RGB)
+        {
+#pragma unroll
+            for (int j = 0; j < 3; j++) smem_acc4(sacc + (2 + j) * g.c, cv * 4, sdw[j]);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < g.c; i += kEwThreads)
     {
         if (p.db) atomicAdd(p.db + i, sacc[i]);
         if (p.dd) atomicAdd(p.dd + (long long)n * g.c + i, sacc[g.c + i]);
+        if (RGB)
+        {
+#pragma unroll
+            for (int j = 0; j < 3; j++) atomicAdd(p.dwmod + ((long long)n * 3 + j) * g.c + i, sacc[(2 + j) * g.c + i]);
+        }
     }
 }
 
@@ -305,22 +344,35 @@ static int make_geom(EwGeom* g, int n, int hw, int c)
 
 } // namespace sgv
 
-extern "C" int sgv_modconv_act_bwd(const float* dy, const float* y, const float* bias, float* dz, float* db, float* dd,
-                                   int32_t n, int32_t hw, int32_t c, int32_t act, float alpha, float gain, void* stream_)
+extern "C" int sgv_modconv_act_bwd_rgb(const float* dy, const float* y, const float* bias, float* dz, float* db, float* dd,
+                                       const float* dyimg, const float* wmod, float* dwmod,
+                                       int32_t n, int32_t hw, int32_t c, int32_t act, float alpha, float gain, void* stream_)
 {
     using namespace sgv;
-    SGV_CHECK_ARG(dy && y && dz, "sgv_modconv_act_bwd: dy, y, dz must be non-NULL");
+    const bool rgb = dyimg != nullptr;
+    SGV_CHECK_ARG(y && dz && (dy || rgb), "sgv_modconv_act_bwd: y, dz and at least one of dy / dyimg must be non-NULL");
+    SGV_CHECK_ARG(!rgb || (wmod && dwmod), "sgv_modconv_act_bwd_rgb: dyimg needs wmod and dwmod");
     SGV_CHECK_ARG(act == 1 || act == 3, "act must be 1 (linear) or 3 (lrelu)");
     SGV_CHECK_ARG(gain != 0.f && (act != 3 || alpha != 0.f), "gain (and alpha for lrelu) must be non-zero");
     int rc = sgv_device_check();
     if (rc != SGV_OK) return rc;
     ActBwdArgs a;
     a.dy = dy; a.y = y; a.bias = bias; a.dz = dz; a.db = db; a.dd = dd; a.act = act; a.alpha = alpha; a.gain = gain;
+    a.dyimg = dyimg; a.wmod = wmod; a.dwmod = dwmod;
     rc = make_geom(&a.g, n, hw, c);
     if (rc != SGV_OK) return rc;
-    modconv_act_bwd_kernel<<<(unsigned)(n * a.g.chunks), kEwThreads, 2 * c * sizeof(float), (cudaStream_t)stream_>>>(a);
+    const unsigned grid = (unsigned)(n * a.g.chunks);
+    if (rgb) modconv_act_bwd_kernel<true><<<grid, kEwThreads, 5 * c * sizeof(float), (cudaStream_t)stream_>>>(a);
+    else modconv_act_bwd_kernel<false><<<grid, kEwThreads, 2 * c * sizeof(float), (cudaStream_t)stream_>>>(a);
     SGV_LAUNCH_OK("modconv_act_bwd_kernel");
     return SGV_OK;
+}
+
+extern "C" int sgv_modconv_act_bwd(const float* dy, const float* y, const float* bias, float* dz, float* db, float* dd,
+                                   int32_t n, int32_t hw, int32_t c, int32_t act, float alpha, float gain, void* stream_)
+{
+    SGV_CHECK_ARG(dy != nullptr, "sgv_modconv_act_bwd: dy must be non-NULL");
+    return sgv_modconv_act_bwd_rgb(dy, y, bias, dz, db, dd, nullptr, nullptr, nullptr, n, hw, c, act, alpha, gain, stream_);
 }
 
 extern "C" int sgv_modconv_scale_reduce(const float* dxs, const float* x, const float* s, float* dx, float* ds,

@@ -451,6 +451,31 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_slide44(FirArgs p, long long 
             for (int k = 0; k < 5; k++)
                 col[k] = (cok && rowok[k]) ? __ldg(reinterpret_cast<const float4*>(rowp[k] + (long long)inX * p.isx)) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
+        // fused epilogue constants of this item (n and the 4 channels are fixed): loaded once instead of per output
+        float4 esc = make_float4(1.f, 1.f, 1.f, 1.f), ebi = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EPI && p.eact != 0)
+        {
+            if (p.escale) esc = __ldg(reinterpret_cast<const float4*>(p.escale + (long long)n * p.in_c + c0));
+            if (p.ebias) ebi = __ldg(reinterpret_cast<const float4*>(p.ebias + c0));
+        }
+        auto store = [&](float4 a, int outY, int outX) {
+            float4 o = make_float4(a.x * p.gain, a.y * p.gain, a.z * p.gain, a.w * p.gain);
+            if (EPI && p.eact != 0)
+            {
+                // separate roundings (no FMA contraction): bit-identical to the unfused op sequence, like fir_epilogue
+                if (p.escale) { o.x = __fmul_rn(o.x, esc.x); o.y = __fmul_rn(o.y, esc.y); o.z = __fmul_rn(o.z, esc.z); o.w = __fmul_rn(o.w, esc.w); }
+                if (p.ebias) { o.x = __fadd_rn(o.x, ebi.x); o.y = __fadd_rn(o.y, ebi.y); o.z = __fadd_rn(o.z, ebi.z); o.w = __fadd_rn(o.w, ebi.w); }
+                if (p.eact == 3) { o.x = o.x > 0.f ? o.x : o.x * p.ealpha; o.y = o.y > 0.f ? o.y : o.y * p.ealpha; o.z = o.z > 0.f ? o.z : o.z * p.ealpha; o.w = o.w > 0.f ? o.w : o.w * p.ealpha; }
+                o.x *= p.egain; o.y *= p.egain; o.z *= p.egain; o.w *= p.egain;
+                if (p.eclamp >= 0.f)
+                {
+                    const float cl = p.eclamp;
+                    o.x = (o.x > -cl && o.x < cl) ? o.x : (o.x >= 0.f ? cl : -cl); o.y = (o.y > -cl && o.y < cl) ? o.y : (o.y >= 0.f ? cl : -cl);
+                    o.z = (o.z > -cl && o.z < cl) ? o.z : (o.z >= 0.f ? cl : -cl); o.w = (o.w > -cl && o.w < cl) ? o.w : (o.w >= 0.f ? cl : -cl);
+                }
+            }
+            __stcs(reinterpret_cast<float4*>((float*)p.y + n * p.osn + outY * p.osy + outX * p.osx + c0), o);
+        };
         float4 win[4][5];                          // win[slot][row]: columns inX .. inX+3 of the current output, slots rotate
         const int inX0 = x_begin - p.pad_x0;
         load_col(inX0 + 0, win[0]); load_col(inX0 + 1, win[1]); load_col(inX0 + 2, win[2]);
@@ -478,8 +503,8 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_slide44(FirArgs p, long long 
                         {
                             vfma(a1, win[(u + cx) & 3][ry + 1], fr[ry][cx]);
                         }
-                    nhwc_store<4, EPI>(p, a0, n, c0, outY0, outX);
-                    if (outY0 + 1 < p.out_h) nhwc_store<4, EPI>(p, a1, n, c0, outY0 + 1, outX);
+                    store(a0, outY0, outX);
+                    if (outY0 + 1 < p.out_h) store(a1, outY0 + 1, outX);
                 }
             }
         }

@@ -113,7 +113,7 @@ def _wgrad_library(gout, xin, w_shape, transposed, stride):
 
 class _FusedModConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, styles, dcoefs, bias, up, act, gain, flip_weight, prep):
+    def forward(ctx, x, weight, styles, dcoefs, bias, up, act, gain, flip_weight, prep, wmod=None, rgb_bias=None):
         assert x.is_cuda and x.dtype == torch.float32, 'the fused layer op is CUDA / float32 only (no CPU path)'
         x = _nhwc(x)
         O, I, kh, kw = weight.shape
@@ -134,20 +134,34 @@ class _FusedModConv(torch.autograd.Function):
         ctx.save_for_backward(x, weight, styles, dcoefs if dcoefs is not None else x.new_empty(0), bias if bias is not None else x.new_empty(0), y)
         ctx.cfg = (up, act, gain, flip_weight, dcoefs is not None, bias is not None)
         ctx.wp_dgrad = prep['dgrad']
-        return y
+        if wmod is None:
+            ctx.wmod = None
+            return y
+        # ToRGB branch on the same activation (networks.py:262-265): second output, its backward is folded into this node's
+        ctx.wmod = wmod.detach()
+        ctx.set_materialize_grads(False)
+        return y, _conv.torgb_fwd(y, wmod, rgb_bias)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, dy):
+    def backward(ctx, dy, drgb=None):
         x, weight, styles, dcoefs, bias, y = ctx.saved_tensors
         up, act, gain, flip_weight, has_d, has_b = ctx.cfg
         O, I, kh, kw = weight.shape
         N, _, H, W = x.shape
-        dy = _nhwc(dy)
-        # ---- activation (+ bias) gradient dz, bias gradient and the dcoefs reduction in ONE pass over (dy, y) ----
+        dy = _nhwc(dy) if dy is not None else None
+        # ---- activation (+ bias) gradient dz, bias gradient and the dcoefs reduction in ONE pass over (dy, y); with a ToRGB
+        #      branch also its data gradient (added to dy on the fly) and d(wmod) ----
         want_db = has_b and ctx.needs_input_grad[4]
         want_dd = has_d and ctx.needs_input_grad[3]
-        dz, db, dd = _conv.act_bwd(dy, y, bias if has_b else None, act, gain, want_db, want_dd)
+        dwmod = drgb_bias = None
+        if ctx.wmod is not None and drgb is not None:
+            dz, db, dd, dwmod = _conv.act_bwd(dy, y, bias if has_b else None, act, gain, want_db, want_dd, dyimg=drgb, wmod=ctx.wmod)
+            drgb_bias = drgb.sum(dim=[0, 2, 3])
+        else:
+            if dy is None:
+                return (None,) * 12
+            dz, db, dd = _conv.act_bwd(dy, y, bias if has_b else None, act, gain, want_db, want_dd)
         ddcoefs = dd / dcoefs if want_dd else None
         dscale = dcoefs if has_d else None
         wp = ctx.wp_dgrad
@@ -182,10 +196,11 @@ class _FusedModConv(torch.autograd.Function):
                 dw = dw.flip([2, 3])
             if up == 2 and flip_weight:
                 dw = dw.flip([2, 3])
-        return dx, dw, ds, ddcoefs, db, None, None, None, None, None
+        return dx, dw, ds, ddcoefs, db, None, None, None, None, None, dwmod, drgb_bias
 
 
-def fused_modulated_conv(x, weight, styles, bias=None, up=1, demodulate=True, act='lrelu', gain=None, flip_weight=True, dcoefs=None, prep=None):
+def fused_modulated_conv(x, weight, styles, bias=None, up=1, demodulate=True, act='lrelu', gain=None, flip_weight=True, dcoefs=None, prep=None,
+                         torgb_wmod=None, torgb_bias=None):
     """y = clamp-free bias_act(modulated_conv2d(x, weight, styles, up, demodulate), bias, act, gain) on NHWC fp32 tensors.
 
     Equivalent (up to TF32 rounding of the contraction operands) to the reference's training-mode sequence
@@ -194,4 +209,7 @@ def fused_modulated_conv(x, weight, styles, bias=None, up=1, demodulate=True, ac
         gain = float(np.sqrt(2)) if act == 'lrelu' else 1.0
     if dcoefs is None and demodulate:
         dcoefs = demod_coefs(weight, styles)
-    return _FusedModConv.apply(x, weight, styles, dcoefs, bias, up, act, float(gain), flip_weight, prep)
+    if torgb_wmod is not None:
+        # -> (y, rgb): rgb[n,j,hw] = sum_c y[n,hw,c] * torgb_wmod[n,j,c] + torgb_bias[j]  (ToRGBLayer arithmetic, one autograd node)
+        return _FusedModConv.apply(x, weight, styles, dcoefs, bias, up, act, float(gain), flip_weight, prep, torgb_wmod, torgb_bias)
+    return _FusedModConv.apply(x, weight, styles, dcoefs, bias, up, act, float(gain), flip_weight, prep, None, None)

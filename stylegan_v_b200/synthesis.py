@@ -41,11 +41,13 @@ class SynthesisLayer(torch.nn.Module):
         and the TF32 weight slabs.  SynthesisNetwork evaluates the plans of all layers on its parameter stream."""
         return dict(styles=styles, dcoefs=demod_coefs(self.weight, styles), prep=prepare_weights(self.weight, self.up, self.up == 1))
 
-    def forward(self, x, w=None, styles=None, gain=1.0, plan=None):
+    def forward(self, x, w=None, styles=None, gain=1.0, plan=None, torgb_wmod=None, torgb_bias=None):
+        """With torgb_wmod [N,3,C] / torgb_bias [3] the block's ToRGB layer is evaluated in the same autograd node: returns (x, rgb)."""
         if plan is None:
             plan = dict(styles=styles if styles is not None else self.affine(w), dcoefs=None, prep=None)
         return fused_modulated_conv(x, self.weight, plan['styles'], self.bias, up=self.up, demodulate=True, act='lrelu',
-                                    gain=float(np.sqrt(2)) * gain, flip_weight=(self.up == 1), dcoefs=plan['dcoefs'], prep=plan['prep'])
+                                    gain=float(np.sqrt(2)) * gain, flip_weight=(self.up == 1), dcoefs=plan['dcoefs'], prep=plan['prep'],
+                                    torgb_wmod=torgb_wmod, torgb_bias=torgb_bias)
 
 
 class _ToRGB(torch.autograd.Function):
@@ -146,10 +148,14 @@ class SynthesisBlock(torch.nn.Module):
             x = self.input(motion_v)
         else:
             x = self.conv0(x, plan=next(it)())
-        x = self.conv1(x, plan=next(it)())
+        conv1_plan, rgb_plan = next(it)(), next(it)()
+        if rgb_plan['wmod'].shape[1] == 3:
+            x, y = self.conv1(x, plan=conv1_plan, torgb_wmod=rgb_plan['wmod'], torgb_bias=self.torgb.bias)    # conv1 + ToRGB: one node
+        else:
+            x = self.conv1(x, plan=conv1_plan)
+            y = self.torgb(x, plan=rgb_plan)
         if img is not None:
             img = _upfirdn2d.upsample2d(img, self.resample_filter)
-        y = self.torgb(x, plan=next(it)())
         img = img.add_(y) if img is not None else y
         return x, img
 

@@ -100,7 +100,7 @@ def test_fused_layer_backward_with_matched_forward(up):
     d = (torch.rand(N, O, generator=gen) + 0.5).cuda().requires_grad_(True)
     b = (0.3 * torch.randn(O, generator=gen)).cuda().requires_grad_(True)
     gain = float(np.sqrt(2))
-    y = modconv._FusedModConv.apply(x, w, s, d, b, up, 'lrelu', gain, up == 1, None)
+    y = modconv._FusedModConv.apply(x, w, s, d, b, up, 'lrelu', gain, up == 1, None, None, None)
     dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).cuda()
     got = torch.autograd.grad(y, [x, w, s, d, b], dy)
     # reference: same rounded operands, fp64 arithmetic, autograd
@@ -173,3 +173,11 @@ def test_layer_elementwise_kernels():
             dxr, dwm = C.torgb_bwd(g3, x, wmod)
             assert rel_err(dxr, torch.einsum('njhw,njc->nchw', g3.double(), wmod.double())) < 1e-5
             assert rel_err(dwm, torch.einsum('njhw,nchw->njc', g3.double(), x.double())) < 1e-5
+            # the same ToRGB gradient folded into act_bwd (sgv_modconv_act_bwd_rgb): dy + torgb data gradient, and d(wmod) from y
+            for with_dy in (True, False):
+                dz2, db2, dd2, dwm2 = C.act_bwd(dy if with_dy else None, y, bias, 'lrelu', gain, True, True, dyimg=g3, wmod=wmod)
+                dtot = torch.einsum('njhw,njc->nchw', g3.double(), wmod.double()) + (dy.double() if with_dy else 0)
+                dz2_ref = torch.where(y > 0, dtot, dtot * 0.2) * gain
+                assert rel_err(dz2, dz2_ref) < 1e-6 and rel_err(db2, dz2_ref.sum([0, 2, 3])) < 1e-5
+                assert rel_err(dd2, (dz2_ref * v.cuda().double()).sum([2, 3])) < 1e-4
+                assert rel_err(dwm2, torch.einsum('njhw,nchw->njc', g3.double(), y.double())) < 1e-5
