@@ -1,0 +1,11 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/ -m gpu -x -q 2>&1 | tail -3
+cd scripts
+timeout 200 python bench_conv.py main4 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    try: d = json.loads(l); print(d['kernel'], 'conv', round(d['ms'],3), round(d['tflops']), 'wgrad', round(d['wgrad_ms'],3), round(d['wgrad_tflops']))
+    except Exception: print(l.rstrip()[:200])"
+timeout 120 python bench_dgrad_up.py
+cd ..
+timeout 300 python bench.py --no-cpu-baseline 2>gpurun_out/bench_r1ai.err | tee gpurun_out/bench_r1ai.json | cut -c1-330

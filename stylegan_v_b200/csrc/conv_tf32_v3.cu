@@ -16,6 +16,7 @@
 // ntaps slabs" the next patch could not be requested until the MMAs had freed slab slots, and the transform warps spent 2/3 of
 // their time waiting for patches (ncu source view, profiles/ncu_v3_r1y_summary.txt).
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -34,8 +35,14 @@ struct ConvV3Args
     int n, cin, cout, out_h, out_w;
     long long osn, osy, osx;
     int ntaps;
-    int tap_row[SGV_CONV_MAX_TAPS];
-    int dy_min, dx_min, pw, ph;
+    // Taps are grouped into patch CLASSES: all taps of a class read the same TMA box (origin cls_ox/oy relative to the tile's first
+    // input pixel, sampled with the input stride) through shifted descriptors.  Stride 1: one class.  Stride 2 (data gradient of the
+    // stride-2 transposed conv): one class per (dy, dx) parity, i.e. 4 boxes of every-other pixel per 32-channel chunk.
+    int in_stride, ncls;
+    int cls_ntaps[4], cls_ox[4], cls_oy[4];
+    int tap_row[SGV_CONV_MAX_TAPS];        // class-ordered: start row of the tap's A matrix inside its class patch
+    int tap_slab[SGV_CONV_MAX_TAPS];       // class-ordered: index of the tap's weight slab in wp
+    int pw, ph;
     int tiles_x, tiles_y, ntiles_n, total_groups;      // group = CL pixel tiles x one n-tile, one tile per CTA of a cluster
     int act; float alpha, gain, clamp;
     int accumulate;
@@ -125,12 +132,14 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             {
                 const TileCoord tc = tile_coord<BN, MH, CL>(p, g, crank);
                 for (int kc = 0; kc < kchunks; kc++)
-                {
-                    mbar_wait(empty_a + sa, pa ^ 1);
-                    mbar_expect_tx(full_a + sa, patch_bytes);
-                    tma_load_4d(smem + sa * L::kPatch, &tmap_x, full_a + sa, kc * 32, tc.ox0 + p.dx_min, tc.oy0 + p.dy_min, tc.n);
-                    if (++sa == SA) { sa = 0; pa ^= 1; }
-                }
+                    for (int c = 0; c < p.ncls; c++)
+                    {
+                        mbar_wait(empty_a + sa, pa ^ 1);
+                        mbar_expect_tx(full_a + sa, patch_bytes);
+                        tma_load_4d(smem + sa * L::kPatch, &tmap_x, full_a + sa, kc * 32, tc.ox0 * p.in_stride + p.cls_ox[c],
+                                    tc.oy0 * p.in_stride + p.cls_oy[c], tc.n);
+                        if (++sa == SA) { sa = 0; pa ^= 1; }
+                    }
             }
         }
     }
@@ -150,10 +159,10 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         mbar_wait(empty_b + sb, pb ^ 1);
                         mbar_expect_tx(full_b + sb, L::kBTile);
                         if (CL == 1)
-                            tma_load_2d(smem + L::kBOffset + sb * L::kBTile, &tmap_w, full_b + sb, kc * 32, t * p.cout + nb0);
+                            tma_load_2d(smem + L::kBOffset + sb * L::kBTile, &tmap_w, full_b + sb, kc * 32, p.tap_slab[t] * p.cout + nb0);
                         else    // this CTA fetches rows [crank * BN/CL, +BN/CL) of the slab once and multicasts them to the whole cluster
                             tma_load_2d_mc(smem + L::kBOffset + sb * L::kBTile + crank * (BN / CL) * 128, &tmap_w, full_b + sb, kc * 32,
-                                           t * p.cout + nb0 + crank * (BN / CL), kMask);
+                                           p.tap_slab[t] * p.cout + nb0 + crank * (BN / CL), kMask);
                         if (++sb == SB) { sb = 0; pb ^= 1; }
                     }
                 }
@@ -176,36 +185,41 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             const uint32_t acc = tmem_base + (uint32_t)(buf * MH * BN);
             for (int kc = 0; kc < kchunks; kc++)
             {
-                mbar_wait(ready_a + sa, pa);
-                tc_fence_after();
-                const uint32_t patch = smem_u32(smem + sa * L::kPatch);
-                for (int t = 0; t < p.ntaps; t++)
+                int t = 0;
+                for (int c = 0; c < p.ncls; c++)
                 {
-                    mbar_wait(full_b + sb, pb);
+                    mbar_wait(ready_a + sa, pa);
                     tc_fence_after();
-                    if (elect_one())
+                    const uint32_t patch = smem_u32(smem + sa * L::kPatch);
+                    const int t_end = t + p.cls_ntaps[c];
+                    for (; t < t_end; t++)
                     {
-                        const uint64_t db = umma_desc_k_sw128(smem_u32(smem + L::kBOffset + sb * L::kBTile));
-#pragma unroll
-                        for (int h = 0; h < MH; h++)
+                        mbar_wait(full_b + sb, pb);
+                        tc_fence_after();
+                        if (elect_one())
                         {
-                            uint64_t da = umma_desc_k_sw128(patch + (uint32_t)(p.tap_row[t] + 8 * h) * 128u);
-                            da = (da & ~((uint64_t)0x3FFF << 32)) | sbo_field;
+                            const uint64_t db = umma_desc_k_sw128(smem_u32(smem + L::kBOffset + sb * L::kBTile));
 #pragma unroll
-                            for (int k = 0; k < ((p.debug & 4) ? 0 : 4); k++)
-                                mma_tf32(acc + (uint32_t)(h * BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc > 0 || t > 0 || k > 0) ? 1u : 0u);
+                            for (int h = 0; h < MH; h++)
+                            {
+                                uint64_t da = umma_desc_k_sw128(patch + (uint32_t)(p.tap_row[t] + 8 * h) * 128u);
+                                da = (da & ~((uint64_t)0x3FFF << 32)) | sbo_field;
+#pragma unroll
+                                for (int k = 0; k < ((p.debug & 4) ? 0 : 4); k++)
+                                    mma_tf32(acc + (uint32_t)(h * BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc > 0 || t > 0 || k > 0) ? 1u : 0u);
+                            }
+                            if (CL == 1) mma_commit(empty_b + sb); else mma_commit_mc(empty_b + sb, kMask);
+                            if (t == t_end - 1)
+                            {
+                                mma_commit(empty_a + sa);
+                                if (kc == kchunks - 1 && c == p.ncls - 1) mma_commit(acc_full + buf);
+                            }
                         }
-                        if (CL == 1) mma_commit(empty_b + sb); else mma_commit_mc(empty_b + sb, kMask);
-                        if (t == p.ntaps - 1)
-                        {
-                            mma_commit(empty_a + sa);
-                            if (kc == kchunks - 1) mma_commit(acc_full + buf);
-                        }
+                        __syncwarp();
+                        if (++sb == SB) { sb = 0; pb ^= 1; }
                     }
-                    __syncwarp();
-                    if (++sb == SB) { sb = 0; pb ^= 1; }
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
                 }
-                if (++sa == SA) { sa = 0; pa ^= 1; }
             }
         }
     }
@@ -232,26 +246,29 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 #pragma unroll
                     for (int j = 0; j < 32; j++) sv[j] = 1.f;
                 }
-                mbar_wait(full_a + sa, pa);
-                const uint32_t patch = smem_u32(smem + sa * L::kPatch);
-                for (int row = tid; row < ((p.debug & 1) ? 0 : nrows); row += 128)
+                for (int c = 0; c < p.ncls; c++)
                 {
-                    const uint32_t arow = patch + (uint32_t)row * 128u;
-                    float4 v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) v[j] = lds128(arow + (uint32_t)((j ^ (row & 7)) << 4));
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
+                    mbar_wait(full_a + sa, pa);
+                    const uint32_t patch = smem_u32(smem + sa * L::kPatch);
+                    for (int row = tid; row < ((p.debug & 1) ? 0 : nrows); row += 128)
                     {
-                        v[j].x = tf32_rn(v[j].x * sv[4 * j + 0]); v[j].y = tf32_rn(v[j].y * sv[4 * j + 1]);
-                        v[j].z = tf32_rn(v[j].z * sv[4 * j + 2]); v[j].w = tf32_rn(v[j].w * sv[4 * j + 3]);
-                        sts128(arow + (uint32_t)((j ^ (row & 7)) << 4), v[j]);
+                        const uint32_t arow = patch + (uint32_t)row * 128u;
+                        float4 v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) v[j] = lds128(arow + (uint32_t)((j ^ (row & 7)) << 4));
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                        {
+                            v[j].x = tf32_rn(v[j].x * sv[4 * j + 0]); v[j].y = tf32_rn(v[j].y * sv[4 * j + 1]);
+                            v[j].z = tf32_rn(v[j].z * sv[4 * j + 2]); v[j].w = tf32_rn(v[j].w * sv[4 * j + 3]);
+                            sts128(arow + (uint32_t)((j ^ (row & 7)) << 4), v[j]);
+                        }
                     }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(ready_a + sa);
+                    if (++sa == SA) { sa = 0; pa ^= 1; }
                 }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(ready_a + sa);
-                if (++sa == SA) { sa = 0; pa ^= 1; }
             }
         }
     }
@@ -411,31 +428,65 @@ static int v3_cluster_pref()
 // Returns SGV_ERR_UNSUPPORTED when the shape is outside the envelope (caller falls back to v2 / v1).
 int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
 {
-    if (p->in_stride != 1 || p->out_h < 12 || p->out_w < 12 || p->cout % 64 != 0) return SGV_ERR_UNSUPPORTED;
-    int dy_min = p->tap_dy[0], dy_max = p->tap_dy[0], dx_min = p->tap_dx[0], dx_max = p->tap_dx[0];
-    for (int t = 1; t < p->ntaps; t++)
-    {
-        dy_min = min(dy_min, p->tap_dy[t]); dy_max = max(dy_max, p->tap_dy[t]);
-        dx_min = min(dx_min, p->tap_dx[t]); dx_max = max(dx_max, p->tap_dx[t]);
-    }
-    if (dy_max - dy_min > 2 || dx_max - dx_min > 2) return SGV_ERR_UNSUPPORTED;
-    const int mh = 2;
+    if ((p->in_stride != 1 && p->in_stride != 2) || p->out_h < 12 || p->out_w < 12 || p->cout % 64 != 0) return SGV_ERR_UNSUPPORTED;
+    if (p->in_stride == 2 && p->in_stride_x != 0) return SGV_ERR_UNSUPPORTED;      // strided sampling of a strided view: not needed by any caller
+    const int mh = 2, st = p->in_stride;
     ConvV3Args a;
+    memset(&a, 0, sizeof(a));
+    // group the taps into patch classes by the parity of (dy, dx) modulo the input stride
+    int cls_of[SGV_CONV_MAX_TAPS], cmin_x[4], cmin_y[4], cmax_x[4], cmax_y[4], ckey[4];
+    a.ncls = 0;
+    for (int t = 0; t < p->ntaps; t++)
+    {
+        const int key = (((p->tap_dy[t] % st) + st) % st) * st + (((p->tap_dx[t] % st) + st) % st);
+        int c = -1;
+        for (int j = 0; j < a.ncls; j++) if (ckey[j] == key) c = j;
+        if (c < 0)
+        {
+            c = a.ncls++;
+            ckey[c] = key; cmin_x[c] = cmax_x[c] = p->tap_dx[t]; cmin_y[c] = cmax_y[c] = p->tap_dy[t];
+        }
+        cmin_x[c] = min(cmin_x[c], p->tap_dx[t]); cmax_x[c] = max(cmax_x[c], p->tap_dx[t]);
+        cmin_y[c] = min(cmin_y[c], p->tap_dy[t]); cmax_y[c] = max(cmax_y[c], p->tap_dy[t]);
+        cls_of[t] = c;
+    }
+    int ext_x = 0, ext_y = 0;
+    for (int c = 0; c < a.ncls; c++) { ext_x = max(ext_x, (cmax_x[c] - cmin_x[c]) / st); ext_y = max(ext_y, (cmax_y[c] - cmin_y[c]) / st); }
+    if (ext_x > 2 || ext_y > 2) return SGV_ERR_UNSUPPORTED;
     a.y = p->y; a.a_scale = p->a_scale; a.o_scale = p->o_scale; a.bias = p->bias;
     a.n = p->n; a.cin = p->cin; a.cout = p->cout; a.out_h = p->out_h; a.out_w = p->out_w;
     a.osn = p->out_stride_n; a.osy = p->out_stride_y; a.osx = p->out_stride_x;
-    a.ntaps = p->ntaps;
-    a.dy_min = dy_min; a.dx_min = dx_min;
-    a.pw = 8 * mh + (dx_max - dx_min); a.ph = kV3TileH + (dy_max - dy_min);
-    for (int t = 0; t < SGV_CONV_MAX_TAPS; t++) a.tap_row[t] = t < p->ntaps ? (p->tap_dy[t] - dy_min) * a.pw + (p->tap_dx[t] - dx_min) : 0;
+    a.ntaps = p->ntaps; a.in_stride = st;
+    a.pw = 8 * mh + ext_x; a.ph = kV3TileH + ext_y;
+    {
+        int j = 0;
+        for (int c = 0; c < a.ncls; c++)
+        {
+            a.cls_ox[c] = cmin_x[c]; a.cls_oy[c] = cmin_y[c]; a.cls_ntaps[c] = 0;
+            for (int t = 0; t < p->ntaps; t++)
+                if (cls_of[t] == c)
+                {
+                    a.tap_row[j] = (p->tap_dy[t] - cmin_y[c]) / st * a.pw + (p->tap_dx[t] - cmin_x[c]) / st;
+                    a.tap_slab[j] = t;
+                    a.cls_ntaps[c]++; j++;
+                }
+        }
+    }
     a.tiles_x = ceil_div(p->out_w, 8 * mh); a.tiles_y = ceil_div(p->out_h, kV3TileH);
     a.act = p->act; a.alpha = p->alpha; a.gain = p->gain; a.clamp = p->clamp;
     a.accumulate = p->accumulate;
     a.red_x = p->red_x; a.red_out = p->red_out;
     { const char* e = getenv("SGV_V3_DEBUG"); a.debug = e ? atoi(e) : 0; }
-    const int bn = (p->cout % 256 == 0) ? 256 : (p->cout % 128 == 0) ? 128 : 64;
-    a.ntiles_n = p->cout / bn;
     const int pixel_tiles = a.tiles_x * a.tiles_y * p->n;
+    // N tile: 256 columns leave no room to double-buffer the accumulator (2 halves x 256 = all 512 TMEM columns), so the drain of a
+    // tile is exposed; that only pays off when K is long (cin >= 512) and there are enough tiles to fill the SMs.  Measured
+    // (profiles/conv_v3_ablation_r1.txt): 256->256 ch 0.263 vs 0.242 ms, 512->512 ch 0.230 vs 0.267 ms for BN = 256 vs 128.
+    static int max_bn = 0;
+    if (max_bn == 0) { const char* e = getenv("SGV_V3_MAXBN"); max_bn = e ? atoi(e) : 256; }
+    const bool wide = p->cout % 256 == 0 && max_bn >= 256 && p->cin >= 512 && pixel_tiles * (p->cout / 256) >= num_sms();
+    const int bn = wide ? 256 : (p->cout % 128 == 0 && max_bn >= 128) ? 128 : 64;
+    a.ntiles_n = p->cout / bn;
+    if (st == 2 && pixel_tiles * a.ntiles_n < (3 * num_sms()) / 4) return SGV_ERR_UNSUPPORTED;     // too few tiles for one CTA per SM: the per-tap kernel's finer grid wins
     int cl = v3_cluster_pref();
     while (cl > 1 && (pixel_tiles % cl != 0 || pixel_tiles / cl * a.ntiles_n < num_sms() / cl)) cl >>= 1;   // small problems: fill the SMs first
     a.total_groups = pixel_tiles / cl * a.ntiles_n;
@@ -446,8 +497,8 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
         const bool view = p->in_stride_x != 0;
         const uint64_t strides[3] = {(uint64_t)(view ? p->in_stride_x : p->cin) * 4, (uint64_t)(view ? p->in_stride_y : (int64_t)p->w * p->cin) * 4,
                                      (uint64_t)(view ? p->in_stride_n : (int64_t)p->h * p->w * p->cin) * 4};
-        const uint32_t box[4] = {32, (uint32_t)a.pw, (uint32_t)a.ph, 1};
-        const uint32_t es[4] = {1, 1, 1, 1};
+        const uint32_t box[4] = {32, (uint32_t)(a.pw * st), (uint32_t)(a.ph * st), 1};      // ceil(box / elementStride) samples per dim
+        const uint32_t es[4] = {1, (uint32_t)st, (uint32_t)st, 1};
         int rc = make_tmap_f32(&tmx, p->x, 4, dims, strides, box, es);
         if (rc != SGV_OK) return rc;
     }

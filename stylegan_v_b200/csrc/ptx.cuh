@@ -241,11 +241,12 @@ __device__ __forceinline__ float warp_reduce_32x32(float (&v)[32], int lane)
     return v[0];
 }
 
+// Round fp32 to TF32 (10-bit mantissa), nearest with ties away from zero — the result cvt.rna.tf32.f32 gives — with two
+// full-rate integer ops: add half an ulp to the magnitude bits, clear the 13 dropped bits.  cvt.rna issues at a quarter of the
+// ALU rate, which made the operand-staging warps of the weight-gradient kernel the bottleneck (profiles/wgrad_ablation_r1.txt).
 __device__ __forceinline__ float tf32_rn(float x)
 {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 }} // namespace sgv::ptx

@@ -335,6 +335,7 @@ struct Wg2Args
     int grp_col[SGV_CONV_MAX_TAPS][kW2MaxGroupTaps];        // dx_t - dx_min: column offset inside the patch
     int dx_min, pw;
     int tiles_x, tiles_y, mtiles, ktiles, ksplit;
+    int debug;      // TEMP experiment switches (SGV_WG_DEBUG): 1 skip transform, 2 skip epilogue, 4 skip MMAs
 };
 
 template <int NT, int STAGES>
@@ -424,7 +425,7 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
                     for (int t = 0; t < gtaps; t++)
                     {
 #pragma unroll
-                        for (int k = 0; k < 4; k++)        // image row k of the 8x4 tile = 8 consecutive pixel rows
+                        for (int k = 0; k < ((p.debug & 4) ? 0 : 4); k++)        // image row k of the 8x4 tile = 8 consecutive pixel rows
                         {
                             const uint64_t da = umma_desc_mn_sw128_32b(sg + k * 1024, 32 * 128, 512);
                             const uint64_t db = umma_desc_mn_sw128_32b(sx + (uint32_t)(p.grp_col[grp][t] + k * p.pw) * 128u, (uint32_t)xblock, 512);
@@ -486,7 +487,7 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
 #pragma unroll
                     for (int s = 0; s < 2; s++)
                     {
-                        if (!act[s]) continue;
+                        if (!act[s] || (p.debug & 1)) continue;
                         const int row = rr[s] < 128 ? rr[s] : rr[s] - 128;
                         const uint32_t rowp = smem_u32(sg) + (uint32_t)(rr[s] < 128 ? 0 : kW2GTile) + (uint32_t)row * 128u;
                         // logical 16-byte chunk jj = j ^ bit2(row): the 8 rows a quarter-warp touches then hit 8 distinct physical
@@ -532,7 +533,7 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NT + cc * 32), v);
                     tmem_ld_wait();
-                    if (o < p.cout && c0 + cc * 32 < p.cin)
+                    if (o < p.cout && c0 + cc * 32 < p.cin && !(p.debug & 2))
                     {
 #pragma unroll
                         for (int j = 0; j < 8; j++)
@@ -605,6 +606,7 @@ int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, cudaStream_t stream)
     while (ksplit > 1 && a.ktiles / ksplit < 48) ksplit--;
     if (ksplit > a.ktiles) ksplit = a.ktiles;
     a.ksplit = ksplit;
+    { const char* e = getenv("SGV_WG_DEBUG"); a.debug = e ? atoi(e) : 0; }
 
     CUtensorMap tg, tx;
     int rc = make_blocked_tmap(&tg, p->g, p->cout, p->gw, p->gh, p->n, 8, 4, 1, 1, kWgM / 32);

@@ -87,10 +87,11 @@ def test_transposed_conv_as_four_phases():
     assert rel_err(u, ref) < 2e-5
 
 
-def test_stride2_input():
-    """data gradient of the transposed conv = stride-2 correlation (TMA element strides)."""
+@pytest.mark.parametrize('N,Cin,Cout,h', [(2, 64, 64, 10), (3, 64, 128, 16), (2, 128, 64, 21), (5, 32, 256, 32)])
+def test_stride2_input(N, Cin, Cout, h):
+    """data gradient of the transposed conv = stride-2 correlation (TMA element strides); h >= 12 runs on the persistent
+    kernel with one every-other-pixel patch per (dy, dx) parity class, smaller outputs on the per-tap kernel."""
     g = torch.Generator().manual_seed(5)
-    N, Cin, Cout, h = 2, 64, 64, 10
     du = torch.randn(N, Cin, 2 * h + 1, 2 * h + 1, generator=g).cuda()
     w = torch.randn(Cout, Cin, 3, 3, generator=g).cuda()
     taps = C.TAPS_3x3

@@ -29,6 +29,7 @@ CASES = [
     # transpose, Cin, Cout, k, stride, padding, H
     (False, 64, 64, 3, 1, 1, 16), (False, 32, 128, 1, 1, 0, 12), (False, 64, 64, 3, 2, 0, 17), (False, 64, 128, 3, 2, 1, 16),
     (True, 64, 64, 3, 2, 0, 8), (True, 64, 64, 3, 2, 0, 5), (True, 64, 32, 3, 1, 1, 12),
+    (False, 64, 64, 3, 2, 1, 40), (True, 64, 128, 3, 2, 0, 16),
 ]
 
 
