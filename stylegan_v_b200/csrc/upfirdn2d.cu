@@ -16,7 +16,10 @@
 //   fir_generic      any dtype / stride / factor: one gather per output (same math as upfirdn2d_kernel_large).
 //
 // All three optionally apply the fused epilogue of sgv_upfirdn2d_params (scale[n,c], bias[c], lrelu, gain, clamp).
+#include <stdlib.h>
 #include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
 
 namespace sgv {
 
@@ -511,6 +514,127 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_slide44(FirArgs p, long long 
     }
 }
 
+// channels_last, up = down = 1, 4x4 filter, C % 32 == 0: TMA-fed persistent kernel.
+// A CTA walks tiles of 8 x 32 output pixels x 32 channels.  The (8+3) x (32+3) pixel x 128 B input box of tile i+1 (and i+2) is in
+// flight (cp.async.bulk.tensor, out-of-range pixels = the zero padding) while tile i is filtered out of shared memory, so ~100 KB
+// of reads per SM are always outstanding — the LDG sliding-window kernel above issues its loads right before it needs them and
+// reaches about half of the HBM rate (profiles/launches_r1ac summary: 2.1-3.3 TB/s).  Thread = 4 channels x one output column,
+// walking down the 8 rows with a 4 x 4 register window (4 LDS.128 per output); tap order = fir_nhwc_slide44's, results identical.
+constexpr int kFtTW = 32, kFtTH = 8;
+constexpr int kFtBoxW = kFtTW + 3, kFtBoxH = kFtTH + 3;
+constexpr int kFtStage = ((kFtBoxW * kFtBoxH * 128) + 1023) & ~1023;
+constexpr int kFtSmem = 2 * kFtStage + 2 * 8 + 1024;
+
+template <bool EPI>
+__global__ void __launch_bounds__(256, 2) fir_nhwc_tma44(const __grid_constant__ CUtensorMap tmap_x, FirArgs p, int tiles_x, int tiles_y, int cblocks, int total_tiles)
+{
+    using namespace ptx;
+    extern __shared__ uint8_t fsmem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fsmem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * kFtStage);
+    __shared__ float sf[16];
+    if (threadIdx.x < 16)
+    {
+        int fy = threadIdx.x >> 2, fx = threadIdx.x & 3;
+        int ffx = p.flip ? fx : 3 - fx;
+        int ffy = p.flip ? fy : 3 - fy;
+        sf[threadIdx.x] = p.f[ffx * p.fsx + ffy * p.fsy];
+    }
+    if (threadIdx.x == 0)
+    {
+        prefetch_tmap(&tmap_x);
+        mbar_init(full + 0, 1); mbar_init(full + 1, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    float fr[4][4];
+#pragma unroll
+    for (int i = 0; i < 16; i++) fr[i >> 2][i & 3] = sf[i];
+
+    auto decode = [&](int t, int& n, int& oy0, int& ox0, int& cb) {
+        cb = t % cblocks; t /= cblocks;
+        ox0 = (t % tiles_x) * kFtTW; t /= tiles_x;
+        oy0 = (t % tiles_y) * kFtTH;
+        n = t / tiles_y;
+    };
+    auto issue = [&](int t, int s) {
+        int n, oy0, ox0, cb;
+        decode(t, n, oy0, ox0, cb);
+        mbar_expect_tx(full + s, (uint32_t)(kFtBoxW * kFtBoxH * 128));
+        tma_load_4d(smem + s * kFtStage, &tmap_x, full + s, cb * 32, ox0 - p.pad_x0, oy0 - p.pad_y0, n);
+    };
+    if (threadIdx.x == 0)
+    {
+        if ((int)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+        if ((int)(blockIdx.x + gridDim.x) < total_tiles) issue(blockIdx.x + gridDim.x, 1);
+    }
+    const int cv = threadIdx.x & 7, col = threadIdx.x >> 3;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++)
+    {
+        const int s = it & 1;
+        int n, oy0, ox0, cb;
+        decode(t, n, oy0, ox0, cb);
+        const int c0 = cb * 32 + cv * 4;
+        float4 esc = make_float4(1.f, 1.f, 1.f, 1.f), ebi = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EPI && p.eact != 0)
+        {
+            if (p.escale) esc = __ldg(reinterpret_cast<const float4*>(p.escale + (long long)n * p.in_c + c0));
+            if (p.ebias) ebi = __ldg(reinterpret_cast<const float4*>(p.ebias + c0));
+        }
+        mbar_wait(full + s, (uint32_t)(it >> 1) & 1u);
+        const uint32_t base = smem_u32(smem + s * kFtStage);
+        auto load_row = [&](int r, float4 (&w)[4]) {
+#pragma unroll
+            for (int cx = 0; cx < 4; cx++)
+            {
+                const uint32_t line = (uint32_t)(r * kFtBoxW + col + cx);
+                w[cx] = lds128(base + line * 128u + (uint32_t)((cv ^ (line & 7u)) << 4));
+            }
+        };
+        float4 win[4][4];                              // win[slot][cx]: input row (slot rotates), columns col .. col+3
+        load_row(0, win[0]); load_row(1, win[1]); load_row(2, win[2]);
+        const int ox = ox0 + col;
+        float* ycol = (float*)p.y + n * p.osn + ox * p.osx + c0;
+#pragma unroll
+        for (int r = 0; r < kFtTH; r++)
+        {
+            load_row(r + 3, win[(r + 3) & 3]);
+            float4 a; vzero(a);
+#pragma unroll
+            for (int ry = 0; ry < 4; ry++)
+#pragma unroll
+                for (int cx = 0; cx < 4; cx++) vfma(a, win[(r + ry) & 3][cx], fr[ry][cx]);
+            const int oy = oy0 + r;
+            if (oy < p.out_h && ox < p.out_w)
+            {
+                float4 o = make_float4(a.x * p.gain, a.y * p.gain, a.z * p.gain, a.w * p.gain);
+                if (EPI && p.eact != 0)
+                {
+                    // separate roundings (no FMA contraction): bit-identical to the unfused op sequence, like fir_epilogue
+                    if (p.escale) { o.x = __fmul_rn(o.x, esc.x); o.y = __fmul_rn(o.y, esc.y); o.z = __fmul_rn(o.z, esc.z); o.w = __fmul_rn(o.w, esc.w); }
+                    if (p.ebias) { o.x = __fadd_rn(o.x, ebi.x); o.y = __fadd_rn(o.y, ebi.y); o.z = __fadd_rn(o.z, ebi.z); o.w = __fadd_rn(o.w, ebi.w); }
+                    if (p.eact == 3) { o.x = o.x > 0.f ? o.x : o.x * p.ealpha; o.y = o.y > 0.f ? o.y : o.y * p.ealpha; o.z = o.z > 0.f ? o.z : o.z * p.ealpha; o.w = o.w > 0.f ? o.w : o.w * p.ealpha; }
+                    o.x *= p.egain; o.y *= p.egain; o.z *= p.egain; o.w *= p.egain;
+                    if (p.eclamp >= 0.f)
+                    {
+                        const float cl = p.eclamp;
+                        o.x = (o.x > -cl && o.x < cl) ? o.x : (o.x >= 0.f ? cl : -cl); o.y = (o.y > -cl && o.y < cl) ? o.y : (o.y >= 0.f ? cl : -cl);
+                        o.z = (o.z > -cl && o.z < cl) ? o.z : (o.z >= 0.f ? cl : -cl); o.w = (o.w > -cl && o.w < cl) ? o.w : (o.w >= 0.f ? cl : -cl);
+                    }
+                }
+                __stcs(reinterpret_cast<float4*>(ycol + oy * p.osy), o);
+            }
+        }
+        __syncthreads();                               // every thread is done reading stage s
+        if (threadIdx.x == 0)
+        {
+            const long long nxt = (long long)t + 2LL * gridDim.x;
+            if (nxt < total_tiles) issue((int)nxt, s);
+        }
+    }
+}
+
 // General channels_last kernel (any up/down/filter), one output pixel x VEC channels per thread.
 template <int VEC>
 __global__ void __launch_bounds__(256) fir_nhwc_any(FirArgs p, long long total)
@@ -682,7 +806,32 @@ extern "C" int sgv_upfirdn2d(const sgv_upfirdn2d_params* p, void* stream_)
                 const bool epi = a.eact != 0;
 #define SGV_NHWC_FAST(V, D) do { if (epi) fir_nhwc_fast<V, D, 4, 4, true><<<grid, 256, 0, stream>>>(a, work); \
                                  else fir_nhwc_fast<V, D, 4, 4, false><<<grid, 256, 0, stream>>>(a, work); } while (0)
-                if (v4 && a.downx == 1)
+                static int use_tma = -1;
+                if (use_tma < 0) { const char* e = getenv("SGV_FIR_NO_TMA"); use_tma = (e && atoi(e)) ? 0 : 1; }
+                if (v4 && a.downx == 1 && use_tma && a.in_c % 32 == 0 && ow >= kFtTW && oh >= kFtTH)
+                {
+                    CUtensorMap tm;
+                    const uint64_t dims[4] = {(uint64_t)a.in_c, (uint64_t)a.in_w, (uint64_t)a.in_h, (uint64_t)a.in_n};
+                    const uint64_t strides[3] = {(uint64_t)a.isx * 4, (uint64_t)a.isy * 4, (uint64_t)a.isn * 4};
+                    const uint32_t box[4] = {32, (uint32_t)kFtBoxW, (uint32_t)kFtBoxH, 1};
+                    const uint32_t es[4] = {1, 1, 1, 1};
+                    rc = make_tmap_f32(&tm, a.x, 4, dims, strides, box, es);
+                    if (rc != SGV_OK) return rc;
+                    const int tiles_x = ceil_div(ow, kFtTW), tiles_y = ceil_div(oh, kFtTH), cblocks = a.in_c / 32;
+                    const long long tiles = (long long)tiles_x * tiles_y * cblocks * a.in_n;
+                    SGV_CHECK_ARG(tiles <= 0x7fffffffLL, "too many tiles");
+                    const unsigned g3 = (unsigned)min((long long)sms * 2, tiles);
+                    static bool attr_set = false;
+                    if (!attr_set)
+                    {
+                        SGV_CUDA_OK(cudaFuncSetAttribute(fir_nhwc_tma44<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmem));
+                        SGV_CUDA_OK(cudaFuncSetAttribute(fir_nhwc_tma44<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmem));
+                        attr_set = true;
+                    }
+                    if (epi) fir_nhwc_tma44<true><<<g3, 256, kFtSmem, stream>>>(tm, a, tiles_x, tiles_y, cblocks, (int)tiles);
+                    else fir_nhwc_tma44<false><<<g3, 256, kFtSmem, stream>>>(tm, a, tiles_x, tiles_y, cblocks, (int)tiles);
+                }
+                else if (v4 && a.downx == 1)
                 {
                     const int seg = 32;
                     const int nseg = ceil_div(ow, seg);

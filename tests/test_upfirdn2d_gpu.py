@@ -64,6 +64,9 @@ SHAPES = [
     (2, 8, 128, 128, 1, 1, [2, 2, 2, 2], True, 4),       # backward of the b128 FIR: 128 -> 129 (ragged last tile), pipelined kernel
     (1, 3, 200, 150, 1, 1, [1, 1, 1, 1], False, 4),      # wide, not a multiple of the tile
     (1, 2, 100, 517, 1, 1, [2, 1, 1, 2], False, 1),      # 5 tiles across, asymmetric padding
+    (2, 64, 65, 65, 1, 1, [1, 1, 1, 1], False, 4),       # channels_last + C % 32 == 0: the TMA-fed persistent kernel, 2 channel blocks
+    (3, 32, 40, 52, 1, 1, [2, 2, 2, 2], True, 4),        # its backward geometry, ragged tiles in both directions
+    (1, 96, 33, 100, 1, 1, [2, 1, 1, 2], False, 1),      # 3 channel blocks, asymmetric padding
 ]
 
 
@@ -140,12 +143,12 @@ def test_fused_epilogue_matches_unfused_sequence():
     dev = torch.device('cuda')
     f = U.setup_filter([1, 3, 3, 1], device=dev)
     from stylegan_v_b200.ops import bias_act as B
-    for cl in (False, True):
-        x = torch.randn(3, 8, 33, 33, device=dev)
+    for cl, C, H in ((False, 8, 33), (True, 8, 33), (True, 64, 47)):     # the last one runs on the TMA-fed channels_last kernel
+        x = torch.randn(3, C, H, H, device=dev)
         if cl:
             x = x.contiguous(memory_format=torch.channels_last)
-        scale = torch.rand(3, 8, device=dev) + 0.5
-        bias = torch.randn(8, device=dev)
+        scale = torch.rand(3, C, device=dev) + 0.5
+        bias = torch.randn(C, device=dev)
         y = plugin.upfirdn2d(x, f, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0,
                              epilogue=dict(scale=scale, bias=bias, act='lrelu', alpha=0.2, gain=np.sqrt(2), clamp=None))
         ref = U.upfirdn2d(x, f, padding=1, gain=4) * scale[:, :, None, None]
