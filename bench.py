@@ -285,15 +285,26 @@ def main():
         per_layer.append(dict(layer=name, ms=ms, tflops=fl / ms / 1e9, flops=fl))
         del x, wp
     dom = max(per_layer, key=lambda z: z['ms'])
-    roofline = dict(bound='tensor', kernel=f"conv_tf32_kernel @ {dom['layer']} (N={N})", achieved=dom['tflops'], peak=peaks['bf16_tflops'],
-                    unit='TFLOP/s', frac=dom['tflops'] / peaks['bf16_tflops'], traffic=None, peak_source=peaks['source'] + ' (dense bf16 cuBLAS; the kernel runs kind::tf32 = half that rate)',
+    # DRAM bytes per launch of these kernels from the committed `ncu --set full` capture (profiles/ncu_v3_r1y_summary.txt):
+    # dram__bytes_read.sum + dram__bytes_write.sum; the algorithmic minimum is x once + y once
+    ncu_traffic = {'b256.conv1': 537123584 + 484198656, 'b128.conv1': 269219328 + 214358272, 'b64.conv1': 137792768 + 81528320}
+    roofline = dict(bound='tensor', kernel=f"conv_tf32_v3_kernel @ {dom['layer']} (N={N})", achieved=dom['tflops'], peak=peaks['bf16_tflops'],
+                    unit='TFLOP/s', frac=dom['tflops'] / peaks['bf16_tflops'], traffic=ncu_traffic.get(dom['layer']), traffic_unit='bytes/launch (ncu, profiles/ncu_v3_r1y_summary.txt)',
+                    peak_source=peaks['source'] + ' (dense bf16 cuBLAS; the kernel runs kind::tf32, whose measured issue-rate ceiling is 1164 TFLOP/s for N >= 128 and '
+                                                  '776 TFLOP/s for N = 64 output channels — profiles/mma_rate_probe_r1.txt)',
+                    tf32_issue_rate_ceiling_tflops=776.0 if dom['layer'] == 'b256.conv1' else 1164.0,
                     algorithmic_flops_per_launch=dom['flops'], per_layer=per_layer)
+    # the FIR pass of the up layers as the network runs it (channels_last, TMA-fed kernel) and the NCHW kernel the drop-in op uses
     f = U.setup_filter([1, 3, 3, 1], device=dev)
     xf = torch.randn(N, 64, 257, 257, device=dev)
-    fir_ms = kernel_ms(lambda: plugin.upfirdn2d(xf, f, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0))
     fir_bytes = (xf.numel() + N * 64 * 256 * 256) * 4
-    upfirdn = dict(bound='hbm', kernel='fir_nchw_tiled [32,64,257,257]->[32,64,256,256]', achieved=fir_bytes / fir_ms / 1e6, peak=peaks['hbm_gbs'], unit='GB/s',
-                   frac=fir_bytes / fir_ms / 1e6 / peaks['hbm_gbs'], traffic=None, algorithmic_bytes_per_launch=fir_bytes, peak_source=peaks['source'])
+    fir_nchw_ms = kernel_ms(lambda: plugin.upfirdn2d(xf, f, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0))
+    xf = xf.contiguous(memory_format=torch.channels_last)
+    fir_ms = kernel_ms(lambda: plugin.upfirdn2d(xf, f, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0))
+    upfirdn = dict(bound='hbm', kernel='fir_nhwc_tma44 [32,257,257,64]->[32,256,256,64] (channels_last, as the synthesis path runs it)', achieved=fir_bytes / fir_ms / 1e6,
+                   peak=peaks['hbm_gbs'], unit='GB/s', frac=fir_bytes / fir_ms / 1e6 / peaks['hbm_gbs'], traffic=None, algorithmic_bytes_per_launch=fir_bytes,
+                   peak_source=peaks['source'], nchw=dict(kernel='fir_nchw_tiled, same extents in NCHW (odd row pitch: not TMA-addressable)', achieved=fir_bytes / fir_nchw_ms / 1e6,
+                                                          frac=fir_bytes / fir_nchw_ms / 1e6 / peaks['hbm_gbs']))
     del xf
 
     cfg = sr.SynthesisConfig(img_resolution=RES)

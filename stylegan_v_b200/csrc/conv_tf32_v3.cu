@@ -47,7 +47,7 @@ struct ConvV3Args
     int act; float alpha, gain, clamp;
     int accumulate;
     const float* red_x; float* red_out;
-    int debug;      // TEMP experiment switches (SGV_V3_DEBUG): 1 skip transform, 2 skip epilogue, 4 skip MMAs
+    int debug;      // ablation switches, env SGV_V3_DEBUG (measurement only; profiles/conv_v3_ablation_r1.txt): 1 skip transform, 2 skip epilogue, 4 skip MMAs
 };
 
 template <int BN, int MH, int SA, int SB>

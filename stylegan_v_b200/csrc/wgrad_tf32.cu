@@ -335,7 +335,7 @@ struct Wg2Args
     int grp_col[SGV_CONV_MAX_TAPS][kW2MaxGroupTaps];        // dx_t - dx_min: column offset inside the patch
     int dx_min, pw;
     int tiles_x, tiles_y, mtiles, ktiles, ksplit;
-    int debug;      // TEMP experiment switches (SGV_WG_DEBUG): 1 skip transform, 2 skip epilogue, 4 skip MMAs
+    int debug;      // ablation switches, env SGV_WG_DEBUG (measurement only; profiles/wgrad_ablation_r1.txt): 1 skip transform, 2 skip epilogue, 4 skip MMAs
 };
 
 template <int NT, int STAGES>
