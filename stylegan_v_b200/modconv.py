@@ -111,9 +111,49 @@ def _wgrad_library(gout, xin, w_shape, transposed, stride):
     return gw
 
 
+class WeightGradBox:
+    """Mailbox between a fused layer node and the WeightGradNode of its weight (see WeightGradNode)."""
+    __slots__ = ('job', 'stream')
+
+    def __init__(self, stream):
+        self.job, self.stream = None, stream
+
+
+class WeightGradNode(torch.autograd.Function):
+    """Identity on a layer weight, applied on the stream that should run the layer's weight-gradient contraction.
+
+    Autograd runs a node's backward on the stream its forward ran on and orders it after the producers of its incoming gradients.
+    Routing `weight` through this node on the network's parameter stream therefore moves the (tensor-core bound) weight-gradient
+    kernels off the activation-gradient stream: the fused layer's backward posts the contraction as a job in the box and hands a
+    shape-only placeholder down; this node executes the job and returns the real gradient.  Results are identical; only the
+    stream the kernels are issued on changes."""
+
+    @staticmethod
+    def forward(ctx, weight, box):
+        ctx.box = box
+        return weight.view_as(weight)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        job, ctx.box.job = ctx.box.job, None
+        return (job() if job is not None else grad), None
+
+
+_PLACEHOLDERS = {}
+
+
+def _placeholder(like):
+    """A zero-stride tensor of `like`'s shape (no memory traffic): stands in for a gradient that a later node fills in."""
+    key = (like.device, like.dtype)
+    if key not in _PLACEHOLDERS:
+        _PLACEHOLDERS[key] = torch.zeros(1, dtype=like.dtype, device=like.device)
+    return _PLACEHOLDERS[key].expand(like.shape)
+
+
 class _FusedModConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, styles, dcoefs, bias, up, act, gain, flip_weight, prep, wmod=None, rgb_bias=None):
+    def forward(ctx, x, weight, styles, dcoefs, bias, up, act, gain, flip_weight, prep, wmod=None, rgb_bias=None, wbox=None):
         assert x.is_cuda and x.dtype == torch.float32, 'the fused layer op is CUDA / float32 only (no CPU path)'
         x = _nhwc(x)
         O, I, kh, kw = weight.shape
@@ -134,6 +174,7 @@ class _FusedModConv(torch.autograd.Function):
         ctx.save_for_backward(x, weight, styles, dcoefs if dcoefs is not None else x.new_empty(0), bias if bias is not None else x.new_empty(0), y)
         ctx.cfg = (up, act, gain, flip_weight, dcoefs is not None, bias is not None)
         ctx.wp_dgrad = prep['dgrad']
+        ctx.wbox = wbox
         if wmod is None:
             ctx.wmod = None
             return y
@@ -160,7 +201,7 @@ class _FusedModConv(torch.autograd.Function):
             drgb_bias = drgb.sum(dim=[0, 2, 3])
         else:
             if dy is None:
-                return (None,) * 12
+                return (None,) * 13
             dz, db, dd = _conv.act_bwd(dy, y, bias if has_b else None, act, gain, want_db, want_dd)
         ddcoefs = dd / dcoefs if want_dd else None
         dscale = dcoefs if has_d else None
@@ -181,8 +222,7 @@ class _FusedModConv(torch.autograd.Function):
             #  slower at config 2; kept available through igemm_conv(accumulate=True).)
             dx = _conv.igemm_conv(gout, wp, _TAPS3, out_hw=(H, W), in_stride=2, a_scale=dscale, o_scale=styles, **red)
         # ---- weight gradient ----
-        dw = None
-        if ctx.needs_input_grad[1]:
+        def weight_grad():
             if USE_NATIVE_WGRAD and I % 32 == 0 and O % 32 == 0:
                 dw = _wgrad_native(gout, x, styles, dscale, (O, I, kh, kw), up)
             else:
@@ -192,15 +232,28 @@ class _FusedModConv(torch.autograd.Function):
                     dw = _wgrad_library(g, xs, (O, I, kh, kw), False, 1)
                 else:
                     dw = _wgrad_library(g, xs, (I, O, kh, kw), True, 2).transpose(0, 1)
-            if up == 1 and not flip_weight:
+            if (up == 1 and not flip_weight) or (up == 2 and flip_weight):
                 dw = dw.flip([2, 3])
-            if up == 2 and flip_weight:
-                dw = dw.flip([2, 3])
-        return dx, dw, ds, ddcoefs, db, None, None, None, None, None, dwmod, drgb_bias
+            return dw
+        dw = None
+        if ctx.needs_input_grad[1]:
+            box = ctx.wbox
+            if box is None:
+                dw = weight_grad()
+            else:
+                # deferred: the WeightGradNode that fed `weight` into this op runs the contraction when the engine reaches it, on the
+                # stream IT was created on (the parameter stream) — i.e. concurrently with the next layers' HBM-bound gradient kernels
+                # on this stream.  The node receives a shape-only placeholder and substitutes the real gradient.
+                for t in (gout, x, styles, dscale):
+                    if t is not None and box.stream is not None:
+                        t.record_stream(box.stream)
+                box.job = weight_grad
+                dw = _placeholder(weight)
+        return dx, dw, ds, ddcoefs, db, None, None, None, None, None, dwmod, drgb_bias, None
 
 
 def fused_modulated_conv(x, weight, styles, bias=None, up=1, demodulate=True, act='lrelu', gain=None, flip_weight=True, dcoefs=None, prep=None,
-                         torgb_wmod=None, torgb_bias=None):
+                         torgb_wmod=None, torgb_bias=None, wbox=None):
     """y = clamp-free bias_act(modulated_conv2d(x, weight, styles, up, demodulate), bias, act, gain) on NHWC fp32 tensors.
 
     Equivalent (up to TF32 rounding of the contraction operands) to the reference's training-mode sequence
@@ -211,5 +264,5 @@ def fused_modulated_conv(x, weight, styles, bias=None, up=1, demodulate=True, ac
         dcoefs = demod_coefs(weight, styles)
     if torgb_wmod is not None:
         # -> (y, rgb): rgb[n,j,hw] = sum_c y[n,hw,c] * torgb_wmod[n,j,c] + torgb_bias[j]  (ToRGBLayer arithmetic, one autograd node)
-        return _FusedModConv.apply(x, weight, styles, dcoefs, bias, up, act, float(gain), flip_weight, prep, torgb_wmod, torgb_bias)
-    return _FusedModConv.apply(x, weight, styles, dcoefs, bias, up, act, float(gain), flip_weight, prep, None, None)
+        return _FusedModConv.apply(x, weight, styles, dcoefs, bias, up, act, float(gain), flip_weight, prep, torgb_wmod, torgb_bias, wbox)
+    return _FusedModConv.apply(x, weight, styles, dcoefs, bias, up, act, float(gain), flip_weight, prep, None, None, wbox)

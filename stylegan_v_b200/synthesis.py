@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import conv as _conv
-from .modconv import fused_modulated_conv, demod_coefs, prepare_weights
+from .modconv import fused_modulated_conv, demod_coefs, prepare_weights, WeightGradBox, WeightGradNode
 from .ops import upfirdn2d as _upfirdn2d
 from .time_encoder import EqualizedLinear, MotionMappingNetwork
 
@@ -36,18 +36,24 @@ class SynthesisLayer(torch.nn.Module):
         self.weight = torch.nn.Parameter(torch.randn(out_channels, in_channels, kernel_size, kernel_size))
         self.bias = torch.nn.Parameter(torch.zeros(out_channels))
 
-    def plan(self, styles):
+    def plan(self, styles, async_wgrad_stream=None):
         """Everything of this layer that depends on parameters and styles only (not on activations): demodulation coefficients
         and the TF32 weight slabs.  SynthesisNetwork evaluates the plans of all layers on its parameter stream."""
-        return dict(styles=styles, dcoefs=demod_coefs(self.weight, styles), prep=prepare_weights(self.weight, self.up, self.up == 1))
+        plan = dict(styles=styles, dcoefs=demod_coefs(self.weight, styles), prep=prepare_weights(self.weight, self.up, self.up == 1),
+                    weight=self.weight, wbox=None)
+        if async_wgrad_stream is not None and self.weight.requires_grad and torch.is_grad_enabled():
+            # the weight-gradient contraction of this layer will be issued on the parameter stream (see modconv.WeightGradNode)
+            plan['wbox'] = WeightGradBox(async_wgrad_stream)
+            plan['weight'] = WeightGradNode.apply(self.weight, plan['wbox'])
+        return plan
 
     def forward(self, x, w=None, styles=None, gain=1.0, plan=None, torgb_wmod=None, torgb_bias=None):
         """With torgb_wmod [N,3,C] / torgb_bias [3] the block's ToRGB layer is evaluated in the same autograd node: returns (x, rgb)."""
         if plan is None:
-            plan = dict(styles=styles if styles is not None else self.affine(w), dcoefs=None, prep=None)
-        return fused_modulated_conv(x, self.weight, plan['styles'], self.bias, up=self.up, demodulate=True, act='lrelu',
+            plan = dict(styles=styles if styles is not None else self.affine(w), dcoefs=None, prep=None, weight=self.weight, wbox=None)
+        return fused_modulated_conv(x, plan['weight'], plan['styles'], self.bias, up=self.up, demodulate=True, act='lrelu',
                                     gain=float(np.sqrt(2)) * gain, flip_weight=(self.up == 1), dcoefs=plan['dcoefs'], prep=plan['prep'],
-                                    torgb_wmod=torgb_wmod, torgb_bias=torgb_bias)
+                                    torgb_wmod=torgb_wmod, torgb_bias=torgb_bias, wbox=plan['wbox'])
 
 
 class _ToRGB(torch.autograd.Function):
@@ -226,6 +232,8 @@ class SynthesisNetwork(torch.nn.Module):
 
     # evaluate the per-layer plans on a second CUDA stream (SGV_PARAM_STREAM=0 or False: same stream, for A/B measurements)
     param_stream = os.environ.get('SGV_PARAM_STREAM', '1') != '0'
+    # issue the weight-gradient contractions on the parameter stream too (SGV_ASYNC_WGRAD=0: on the compute stream, inside the layer node)
+    async_wgrad = os.environ.get('SGV_ASYNC_WGRAD', '1') != '0'
 
     def _plan_layers(self, ws):
         """Style affines, demodulation coefficients, ToRGB modulated weights and TF32 weight slabs of EVERY layer depend on
@@ -244,7 +252,10 @@ class SynthesisNetwork(torch.nn.Module):
             styles = self._all_styles(ws)
             for res in self.block_resolutions:
                 for layer in getattr(self, f'b{res}').layers():
-                    plan = layer.plan(styles[id(layer)])
+                    if isinstance(layer, SynthesisLayer):
+                        plan = layer.plan(styles[id(layer)], async_wgrad_stream=side if (use_side and self.async_wgrad) else None)
+                    else:
+                        plan = layer.plan(styles[id(layer)])
                     ev = None
                     if use_side:
                         ev = torch.cuda.Event()
