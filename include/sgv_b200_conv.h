@@ -30,6 +30,13 @@ int sgv_conv_prep_weights(const float* w, int64_t stride_row, int64_t stride_col
                           int32_t rows, int32_t cols, int32_t ntaps, const int32_t* tap_ky, const int32_t* tap_kx,
                           float* wp, void* stream);
 
+/* Both slab sets of a layer from one read of a DENSE weight w[out_ch][in_ch][kh][kw] (1x1 or 3x3, channel counts % 32 == 0):
+ *   wp_a[t][o][i] = tf32_rn(w[o][i][a_ky[t]][a_kx[t]])   (forward contraction: rows = out_ch)          — skipped when wp_a is NULL
+ *   wp_b[t][i][o] = tf32_rn(w[o][i][b_ky[t]][b_kx[t]])   (data-gradient contraction: rows = in_ch)     — skipped when wp_b is NULL */
+int sgv_conv_prep_weights_pair(const float* w, int32_t out_ch, int32_t in_ch, int32_t kh, int32_t kw,
+                               int32_t ntaps_a, const int32_t* a_ky, const int32_t* a_kx, float* wp_a,
+                               int32_t ntaps_b, const int32_t* b_ky, const int32_t* b_kx, float* wp_b, void* stream);
+
 /* y[n, oy, ox, o] = epilogue( sum_{t, i}  x[n, oy*in_stride + tap_dy[t], ox*in_stride + tap_dx[t], i] * a_scale[n, i] * wp[t][o][i] )
  *   epilogue(v) = clamp( act( v * o_scale[n, o] + bias[o] ) * gain )        (each piece optional)
  * Out-of-range input pixels read as zero.  Output element (n, oy, ox, o) lives at
@@ -89,6 +96,10 @@ typedef struct sgv_wgrad_params {
     const float* x_scale;      /* [n, cin]  or NULL */
     /* optional: x is a strided VIEW [n, xh, xw, cin] of a larger NHWC tensor (element strides); all zero = dense */
     int64_t x_stride_n, x_stride_y, x_stride_x;
+    /* optional: tap t accumulates into dw + dw_slot[t] * cout * cin instead of dw + t * cout * cin (use_dw_slot != 0) — lets the four
+     * polyphase calls of a stride-2 transposed conv fill ONE [9][..][..] gradient buffer */
+    int32_t use_dw_slot;
+    int32_t dw_slot[SGV_CONV_MAX_TAPS];
 } sgv_wgrad_params;
 
 int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream);

@@ -72,6 +72,7 @@ class WgradParams(ctypes.Structure):
         ('g_dy', c_int * CONV_MAX_TAPS), ('g_dx', c_int * CONV_MAX_TAPS), ('x_dy', c_int * CONV_MAX_TAPS), ('x_dx', c_int * CONV_MAX_TAPS),
         ('g_scale', c_vp), ('x_scale', c_vp),
         ('x_stride_n', c_i64), ('x_stride_y', c_i64), ('x_stride_x', c_i64),
+        ('use_dw_slot', c_int), ('dw_slot', c_int * CONV_MAX_TAPS),
     ]
 
 
@@ -89,6 +90,8 @@ SYMBOLS = [
     ('sgv_bias_act', c_int, [ctypes.POINTER(BiasActParams), c_vp]),
     ('sgv_conv_prep_weights', c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int,
                                       ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_vp, c_vp]),
+    ('sgv_conv_prep_weights_pair', c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_vp,
+                                           c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_vp, c_vp]),
     ('sgv_conv2d_tf32', c_int, [ctypes.POINTER(ConvParams), c_vp]),
     ('sgv_conv2d_wgrad_tf32', c_int, [ctypes.POINTER(WgradParams), c_vp]),
     ('sgv_modconv_act_bwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),

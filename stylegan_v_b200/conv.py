@@ -36,6 +36,22 @@ def prep_weights(w, taps, rows_dim=0, cols_dim=1):
     return wp
 
 
+def prep_weights_pair(w, taps_fwd, taps_dgrad):
+    """Dense [O, I, kh, kw] weight -> (wp_fwd [len(taps_fwd), O, I], wp_dgrad [len(taps_dgrad), I, O]), TF32-rounded, ONE launch
+    (sgv_conv_prep_weights_pair).  Equivalent to prep_weights(w, taps_fwd) and prep_weights(w, taps_dgrad, rows_dim=1, cols_dim=0)."""
+    _req(w.is_cuda and w.dtype == torch.float32 and w.ndim == 4 and w.is_contiguous(), 'weight must be a dense CUDA float32 [O, I, kh, kw] tensor')
+    O, I, kh, kw = w.shape
+    na, nb = len(taps_fwd), len(taps_dgrad)
+    wa = torch.empty([na, O, I], dtype=torch.float32, device=w.device)
+    wb = torch.empty([nb, I, O], dtype=torch.float32, device=w.device)
+    arr = lambda taps, j: (ctypes.c_int32 * max(len(taps), 1))(*[int(t[j]) for t in taps])
+    L = _lib.lib()
+    with torch.cuda.device(w.device):
+        _lib.check(L.sgv_conv_prep_weights_pair(w.data_ptr(), O, I, kh, kw, na, arr(taps_fwd, 0), arr(taps_fwd, 1), wa.data_ptr(),
+                                                nb, arr(taps_dgrad, 0), arr(taps_dgrad, 1), wb.data_ptr(), _stream(w.device)), 'sgv_conv_prep_weights_pair')
+    return wa, wb
+
+
 def igemm_conv(x, wp, tap_offsets, out=None, out_hw=None, out_view=None, in_stride=1,
                a_scale=None, o_scale=None, bias=None, act='linear', alpha=0.2, gain=1.0, clamp=None, accumulate=False,
                red_x=None, red_out=None):
@@ -100,10 +116,11 @@ def conv3x3_taps():
     return TAPS_3x3, [(ky - 1, kx - 1) for ky, kx in TAPS_3x3]
 
 
-def igemm_wgrad(g, x, taps_g, taps_x, out_hw, g_stride=1, x_stride=1, g_scale=None, x_scale=None):
+def igemm_wgrad(g, x, taps_g, taps_x, out_hw, g_stride=1, x_stride=1, g_scale=None, x_scale=None, out=None, slots=None):
     """dw[t,o,i] = sum_{n,p} g[n, p*gs + dg_t, o] * g_scale[n,o] * x[n, p*xs + dx_t, i] * x_scale[n,i]  ->  [ntaps, Cout, Cin].
 
-    g: [N, Cout, gh, gw], x: [N, Cin, xh, xw], both channels_last fp32; taps_*: per-tap (dy, dx) pixel offsets."""
+    g: [N, Cout, gh, gw], x: [N, Cin, xh, xw], both channels_last fp32; taps_*: per-tap (dy, dx) pixel offsets.
+    out / slots: accumulate tap t into out[slots[t]] of a caller-provided (zeroed) [S, Cout, Cin] buffer instead of a fresh result."""
     for name, t in (('g', g), ('x', x)):
         _req(t.is_cuda and t.dtype == torch.float32 and t.ndim == 4, f'{name} must be a CUDA float32 [N,C,H,W] tensor')
     _req(_is_nhwc(g), 'g must be dense channels_last (NHWC)')
@@ -114,7 +131,12 @@ def igemm_wgrad(g, x, taps_g, taps_x, out_hw, g_stride=1, x_stride=1, g_scale=No
     N2, Cin, xh, xw = x.shape
     _req(N == N2 and len(taps_g) == len(taps_x), 'g / x / taps mismatch')
     nt = len(taps_g)
-    dw = torch.zeros([nt, Cout, Cin], dtype=torch.float32, device=x.device)
+    if out is None:
+        dw = torch.zeros([nt, Cout, Cin], dtype=torch.float32, device=x.device)
+    else:
+        dw = out
+        _req(slots is not None and len(slots) == nt and dw.is_contiguous() and dw.dtype == torch.float32 and tuple(dw.shape[1:]) == (Cout, Cin)
+             and all(0 <= int(sl) < dw.shape[0] for sl in slots), 'out must be a contiguous float32 [S, Cout, Cin] buffer and slots index its first dim')
     L = _lib.lib()
     p = _lib.WgradParams()
     p.g, p.x, p.dw = g.data_ptr(), x.data_ptr(), dw.data_ptr()
@@ -133,6 +155,10 @@ def igemm_wgrad(g, x, taps_g, taps_x, out_hw, g_stride=1, x_stride=1, g_scale=No
             setattr(p, name, t.data_ptr())
     if not x_dense:
         p.x_stride_n, p.x_stride_y, p.x_stride_x = x.stride(0), x.stride(2), x.stride(3)
+    if out is not None:
+        p.use_dw_slot = 1
+        for i, sl in enumerate(slots):
+            p.dw_slot[i] = int(sl)
     with torch.cuda.device(x.device):
         _lib.check(L.sgv_conv2d_wgrad_tf32(ctypes.byref(p), _stream(x.device)), 'sgv_conv2d_wgrad_tf32')
     return dw

@@ -282,6 +282,35 @@ __global__ void __launch_bounds__(256) conv_prep_weights_kernel(const float* __r
     }
 }
 
+
+// Both slab sets of one layer from ONE coalesced read of a dense [O][I][kh][kw] weight: wp_a[t][o][i] (forward: rows = O) and
+// wp_b[t][i][o] (data gradient: rows = I), each with its own tap order.  A CTA stages a 32 (o) x 32 (i) x KK block — 32 runs of
+// 32*KK contiguous floats — in shared memory and writes every slab row as 128 contiguous bytes.  (The gather kernel above reads
+// with a 4*KK-byte stride: 16 us per call on a 512x512x3x3 weight, 44 calls per step.)
+struct TapPair { int na, nb; int a[SGV_CONV_MAX_TAPS]; int b[SGV_CONV_MAX_TAPS]; };      // tap = ky * kw + kx
+
+template <int KK>
+__global__ void __launch_bounds__(256) conv_prep_pair_kernel(const float* __restrict__ w, int O, int I, TapPair taps, float* __restrict__ wa, float* __restrict__ wb)
+{
+    __shared__ float tile[32][32 * KK + 1];
+    const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+    for (int idx = threadIdx.x; idx < 32 * 32 * KK; idx += 256)
+    {
+        const int ol = idx / (32 * KK), rem = idx - ol * (32 * KK);
+        tile[ol][rem] = ptx::tf32_rn(w[((long long)(o0 + ol) * I + i0) * KK + rem]);
+    }
+    __syncthreads();
+    const int lo = threadIdx.x & 31, hi = threadIdx.x >> 5;      // 8 row groups
+    if (wa)
+        for (int t = 0; t < taps.na; t++)
+            for (int ol = hi; ol < 32; ol += 8)
+                wa[((long long)t * O + o0 + ol) * I + i0 + lo] = tile[ol][lo * KK + taps.a[t]];
+    if (wb)
+        for (int t = 0; t < taps.nb; t++)
+            for (int il = hi; il < 32; il += 8)
+                wb[((long long)t * I + i0 + il) * O + o0 + lo] = tile[lo][il * KK + taps.b[t]];
+}
+
 // ---- host ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -331,6 +360,29 @@ static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvA
 }
 
 } // namespace sgv
+
+extern "C" int sgv_conv_prep_weights_pair(const float* w, int32_t out_ch, int32_t in_ch, int32_t kh, int32_t kw,
+                                          int32_t ntaps_a, const int32_t* a_ky, const int32_t* a_kx, float* wp_a,
+                                          int32_t ntaps_b, const int32_t* b_ky, const int32_t* b_kx, float* wp_b, void* stream_)
+{
+    using namespace sgv;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SGV_CHECK_ARG(w && (wp_a || wp_b), "sgv_conv_prep_weights_pair: NULL argument");
+    SGV_CHECK_ARG((kh == 3 && kw == 3) || (kh == 1 && kw == 1), "kernel must be 1x1 or 3x3");
+    SGV_CHECK_ARG(out_ch % 32 == 0 && in_ch % 32 == 0 && out_ch > 0 && in_ch > 0, "channel counts must be positive multiples of 32");
+    SGV_CHECK_ARG(ntaps_a >= 0 && ntaps_a <= SGV_CONV_MAX_TAPS && ntaps_b >= 0 && ntaps_b <= SGV_CONV_MAX_TAPS, "ntaps must be in [0, %d]", SGV_CONV_MAX_TAPS);
+    int rc = sgv_device_check();
+    if (rc != SGV_OK) return rc;
+    TapPair tp;
+    tp.na = wp_a ? ntaps_a : 0; tp.nb = wp_b ? ntaps_b : 0;
+    for (int t = 0; t < tp.na; t++) { SGV_CHECK_ARG(a_ky[t] >= 0 && a_ky[t] < kh && a_kx[t] >= 0 && a_kx[t] < kw, "tap out of range"); tp.a[t] = a_ky[t] * kw + a_kx[t]; }
+    for (int t = 0; t < tp.nb; t++) { SGV_CHECK_ARG(b_ky[t] >= 0 && b_ky[t] < kh && b_kx[t] >= 0 && b_kx[t] < kw, "tap out of range"); tp.b[t] = b_ky[t] * kw + b_kx[t]; }
+    dim3 grid((unsigned)(in_ch / 32), (unsigned)(out_ch / 32));
+    if (kh == 3) conv_prep_pair_kernel<9><<<grid, 256, 0, stream>>>(w, out_ch, in_ch, tp, wp_a, wp_b);
+    else conv_prep_pair_kernel<1><<<grid, 256, 0, stream>>>(w, out_ch, in_ch, tp, wp_a, wp_b);
+    SGV_LAUNCH_OK("conv_prep_pair_kernel");
+    return SGV_OK;
+}
 
 extern "C" int sgv_conv_prep_weights(const float* w, int64_t stride_row, int64_t stride_col, int64_t stride_ky, int64_t stride_kx,
                                      int32_t rows, int32_t cols, int32_t ntaps, const int32_t* tap_ky, const int32_t* tap_kx,

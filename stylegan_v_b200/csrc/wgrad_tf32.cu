@@ -39,6 +39,7 @@ struct WgArgs
     int tw, th, tn;                   // pixel box: tw*th*tn == 32
     int tiles_x, tiles_y, tiles_nb;
     int mtiles, ktiles, ksplit;
+    int dw_slot[SGV_CONV_MAX_TAPS];   // dw block each tap accumulates into
 };
 
 template <int BN, int STAGES>
@@ -200,7 +201,7 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
             tc_fence_after();
             const int q = warp & 3;
             const int o = m0 + q * 32 + lane;
-            float* drow = p.dw + ((long long)tap * p.cout + o) * p.cin + c0;
+            float* drow = p.dw + ((long long)p.dw_slot[tap] * p.cout + o) * p.cin + c0;
 #pragma unroll 1
             for (int cc = 0; cc < BN / 32; cc++)
             {
@@ -277,7 +278,7 @@ extern "C" int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream_)
     a.dw = p->dw; a.g_scale = p->g_scale; a.x_scale = p->x_scale;
     a.n = p->n; a.cin = p->cin; a.cout = p->cout; a.out_h = p->out_h; a.out_w = p->out_w;
     a.g_stride = p->g_stride; a.x_stride = p->x_stride; a.ntaps = p->ntaps;
-    for (int t = 0; t < SGV_CONV_MAX_TAPS; t++) { a.g_dy[t] = p->g_dy[t]; a.g_dx[t] = p->g_dx[t]; a.x_dy[t] = p->x_dy[t]; a.x_dx[t] = p->x_dx[t]; }
+    for (int t = 0; t < SGV_CONV_MAX_TAPS; t++) { a.g_dy[t] = p->g_dy[t]; a.g_dx[t] = p->g_dx[t]; a.x_dy[t] = p->x_dy[t]; a.x_dx[t] = p->x_dx[t]; a.dw_slot[t] = p->use_dw_slot ? p->dw_slot[t] : t; }
     // 32-pixel box, spilling into the batch dimension for tiny planes
     int tw = 1; while (tw * 2 <= p->out_w && tw < 8) tw *= 2;
     int th = 32 / tw; { int ph = 1; while (ph < p->out_h) ph *= 2; if (th > ph) th = ph; }
@@ -588,7 +589,7 @@ int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, cudaStream_t stream)
         int g = -1;
         for (int j = 0; j < a.ngroups; j++) if (a.grp_dy[j] == p->x_dy[t] && a.grp_ntaps[j] < kW2MaxGroupTaps) { g = j; break; }
         if (g < 0) { g = a.ngroups++; a.grp_dy[g] = p->x_dy[t]; a.grp_ntaps[g] = 0; }
-        a.grp_tap[g][a.grp_ntaps[g]] = t;
+        a.grp_tap[g][a.grp_ntaps[g]] = p->use_dw_slot ? p->dw_slot[t] : t;
         a.grp_col[g][a.grp_ntaps[g]] = p->x_dx[t] - dx_min;
         a.grp_ntaps[g]++;
     }

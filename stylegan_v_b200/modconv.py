@@ -69,15 +69,14 @@ def _wgrad_native(gout, x, styles, dscale, w_shape, up):
         # transposed (stride-2) conv: per polyphase sub-lattice (a, b) of the output gradient, a stride-1 correlation between the
         # unshifted input (M side) and the pixel-strided VIEW gout[:, :, a::2, b::2] shifted by (ky//2, kx//2) (N side): the grouped-tap
         # kernel applies; it returns dW^T [tap][I][O]
-        dw = torch.empty([O, I, kh, kw], dtype=torch.float32, device=x.device)
+        dwt = torch.zeros([kh * kw, I, O], dtype=torch.float32, device=x.device)       # all four calls accumulate into their tap slots
         for a in (0, 1):
             for b in (0, 1):
                 taps = [(ky, kx) for ky in range(a, 3, 2) for kx in range(b, 3, 2)]
                 offs = [(ky // 2, kx // 2) for ky, kx in taps]
-                dwt = _conv.igemm_wgrad(x, gout[:, :, a::2, b::2], [(0, 0)] * len(taps), offs, (H, W), g_scale=styles, x_scale=dscale)
-                for t, (ky, kx) in enumerate(taps):
-                    dw[:, :, ky, kx] = dwt[t].t()
-        return dw
+                _conv.igemm_wgrad(x, gout[:, :, a::2, b::2], [(0, 0)] * len(taps), offs, (H, W), g_scale=styles, x_scale=dscale,
+                                  out=dwt, slots=[ky * kw + kx for ky, kx in taps])
+        return dwt.reshape(kh, kw, I, O).permute(3, 2, 0, 1)
     else:
         dw = _conv.igemm_wgrad(gout, x, _TAPS3, [(0, 0)] * 9, (H, W), g_stride=2, g_scale=dscale, x_scale=styles)
     return dw.reshape(kh, kw, O, I).permute(2, 3, 0, 1)
@@ -91,24 +90,27 @@ def prepare_weights(weight, up, flip_weight):
     gradient is produced directly by the wgrad kernel).  Depends on the weight only, so a caller may build it ahead of the layer
     (SynthesisNetwork does, on its parameter stream) and hand it to fused_modulated_conv(prep=...)."""
     O, I, kh, kw = weight.shape
+    # a flipped kernel is the same weight read with mirrored tap indices: no flip kernel
+    flipped = (not flip_weight) if up == 1 else flip_weight      # conv2d_resample.py:35-36 (up = 1) / :138 (transposed conv: flag inverted)
+    mirror = (lambda t: (kh - 1 - t[0], kw - 1 - t[1])) if flipped else (lambda t: t)
+    base = _TAPS3 if kh == 3 else [(0, 0)]
     if up == 1:
-        wsrc = weight if flip_weight else weight.flip([2, 3])      # conv2d_resample.py:35-36
-        taps = _TAPS3 if kh == 3 else [(0, 0)]
-        return dict(fwd=[_conv.prep_weights(wsrc, taps)], dgrad=_conv.prep_weights(wsrc, taps, rows_dim=1, cols_dim=0))
-    # conv2d_resample passes flip_weight = not flip_weight to the transposed conv (conv2d_resample.py:138);
-    # the synthesis layers call with flip_weight=False for up=2 (networks.py:136) => no flip is executed.
-    wsrc = weight if not flip_weight else weight.flip([2, 3])
-    fwd = [_conv.prep_weights(wsrc, _phase_taps(a, b)[0]) for a in (0, 1) for b in (0, 1)]
-    return dict(fwd=fwd, dgrad=_conv.prep_weights(wsrc, _TAPS3, rows_dim=1, cols_dim=0))
-
-
-def _wgrad_library(gout, xin, w_shape, transposed, stride):
-    """Weight gradient through the library call the reference uses (cuDNN), TF32 allowed to match the native kernels."""
-    w_like = torch.empty(w_shape, dtype=xin.dtype, device=xin.device)
-    with torch.backends.cudnn.flags(enabled=True, allow_tf32=True):
-        _, gw, _ = torch.ops.aten.convolution_backward(gout, xin, w_like, None, [stride, stride], [0, 0] if transposed else [w_shape[2] // 2] * 2,
-                                                      [1, 1], transposed, [0, 0], 1, [False, True, False])
-    return gw
+        groups = [base]
+    else:
+        groups = [_phase_taps(a, b)[0] for a in (0, 1) for b in (0, 1)]
+    order = [t for g in groups for t in g]
+    pair_ok = weight.is_contiguous() and O % 32 == 0 and I % 32 == 0
+    if pair_ok:
+        wf, wd = _conv.prep_weights_pair(weight, [mirror(t) for t in order], [mirror(t) for t in base])
+    else:
+        wsrc = weight.flip([2, 3]) if flipped else weight
+        wf = _conv.prep_weights(wsrc, order)
+        wd = _conv.prep_weights(wsrc, base, rows_dim=1, cols_dim=0)
+    fwd, start = [], 0
+    for g in groups:
+        fwd.append(wf[start:start + len(g)])
+        start += len(g)
+    return dict(fwd=fwd, dgrad=wd)
 
 
 class WeightGradBox:

@@ -115,15 +115,14 @@ def conv_weight_grad(gy, x, w_shape, transpose, stride, padding, output_padding,
         g = _nhwc(gy)
         xn = _nhwc(x)
         if H >= 8 and W >= 8:
-            dw = torch.empty([I, O, 3, 3], dtype=torch.float32, device=x.device)
+            dwt = torch.zeros([9, I, O], dtype=torch.float32, device=x.device)      # the four polyphase calls accumulate into their tap slots
             for a in (0, 1):
                 for c in (0, 1):
                     ph_taps = [(ky, kx) for ky in range(a, 3, 2) for kx in range(c, 3, 2)]
                     offs = [(ky // 2, kx // 2) for ky, kx in ph_taps]
-                    dwt = _conv.igemm_wgrad(xn, g[:, :, a:2 * H + 1:2, c:2 * W + 1:2], [(0, 0)] * len(ph_taps), offs, (H, W))
-                    for t, (ky, kx) in enumerate(ph_taps):
-                        dw[:, :, ky, kx] = dwt[t]
-            return dw
+                    _conv.igemm_wgrad(xn, g[:, :, a:2 * H + 1:2, c:2 * W + 1:2], [(0, 0)] * len(ph_taps), offs, (H, W),
+                                      out=dwt, slots=[ky * 3 + kx for ky, kx in ph_taps])
+            return dwt.reshape(3, 3, I, O).permute(2, 3, 0, 1)
         dw = _conv.igemm_wgrad(g, xn, taps, [(0, 0)] * 9, (H, W), g_stride=2)
         return dw.reshape(3, 3, O, I).permute(3, 2, 0, 1)
     return None

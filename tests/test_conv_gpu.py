@@ -161,3 +161,28 @@ def test_strided_view_input_and_accumulate():
                 C.igemm_conv(view, wp, offs, out_view=out, accumulate=True)
     ref = F.conv2d(tf32_round(du).double(), tf32_round(w).double(), stride=2)
     assert rel_err(out, ref) < 2e-5
+
+
+def test_prep_weights_pair_equals_gather():
+    """sgv_conv_prep_weights_pair (one coalesced pass) == two sgv_conv_prep_weights gathers, bit for bit, incl. mirrored taps."""
+    g = torch.Generator().manual_seed(21)
+    for O, I, k in ((64, 96, 3), (128, 32, 3), (32, 64, 1)):
+        w = torch.randn(O, I, k, k, generator=g).cuda()
+        base = [(ky, kx) for ky in range(k) for kx in range(k)]
+        fwd = base[::-1] if k == 3 else base                                     # an arbitrary (here: mirrored) order
+        a, b = C.prep_weights_pair(w, fwd, base)
+        assert torch.equal(a, C.prep_weights(w, fwd)) and torch.equal(b, C.prep_weights(w, base, rows_dim=1, cols_dim=0))
+
+
+def test_wgrad_into_slots():
+    g = torch.Generator().manual_seed(22)
+    N, Ci, Co, H = 2, 64, 32, 12
+    x = _cl(torch.randn(N, Ci, H, H, generator=g).cuda()); gy = _cl(torch.randn(N, Co, H, H, generator=g).cuda())
+    taps, offs = C.conv3x3_taps()
+    ref = C.igemm_wgrad(gy, x, [(0, 0)] * 9, offs, (H, W) if (W := H) else None)
+    out = torch.zeros(9, Co, Ci, device='cuda')
+    perm = [8, 0, 3, 1, 2, 7, 6, 4, 5]
+    C.igemm_wgrad(gy, x, [(0, 0)] * 4, offs[:4], (H, H), out=out, slots=perm[:4])
+    C.igemm_wgrad(gy, x, [(0, 0)] * 5, offs[4:], (H, H), out=out, slots=perm[4:])
+    for t in range(9):
+        assert rel_err(out[perm[t]], ref[t]) < 1e-6
