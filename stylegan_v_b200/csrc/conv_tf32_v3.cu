@@ -171,57 +171,62 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
     else if (warp == 1)
     {
-        // ===== MMA issuer =====
-        constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
-        const uint64_t sbo_field = (uint64_t)((uint32_t)(p.pw * 128) >> 4) << 32;
-        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-        int it = 0;
-        for (int g = cid; g < p.total_groups; g += ncl, it++)
+        // ===== MMA issuer: ONE elected thread runs the whole role (no per-tap election / reconvergence), descriptors are built
+        //       from a constant high word and a 32-bit low word that only needs integer adds per tap / half / k-step =====
+        if (elect_one())
         {
-            const int buf = it % NB;
-            const uint32_t use = (uint32_t)(it / NB) & 1u;
-            mbar_wait(acc_empty + buf, use ^ 1);                     // epilogue has drained this accumulator buffer
-            tc_fence_after();
-            const uint32_t acc = tmem_base + (uint32_t)(buf * MH * BN);
-            for (int kc = 0; kc < kchunks; kc++)
+            constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
+            const uint64_t proto = umma_desc_k_sw128(0);
+            const uint32_t b_hi = (uint32_t)(proto >> 32);
+            const uint32_t a_hi = (b_hi & ~0x3FFFu) | (((uint32_t)(p.pw * 128) >> 4) & 0x3FFFu);      // SBO = patch row pitch
+            const uint32_t lo_flags = (uint32_t)proto;                                                   // LBO field (start address bits are 0)
+            const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFFu) >> 4;
+            auto desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
+            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            int it = 0;
+            for (int g = cid; g < p.total_groups; g += ncl, it++)
             {
-                int t = 0;
-                for (int c = 0; c < p.ncls; c++)
+                const int buf = it % NB;
+                const uint32_t use = (uint32_t)(it / NB) & 1u;
+                mbar_wait(acc_empty + buf, use ^ 1);                     // epilogue has drained this accumulator buffer
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(buf * MH * BN);
+                for (int kc = 0; kc < kchunks; kc++)
                 {
-                    mbar_wait(ready_a + sa, pa);
-                    tc_fence_after();
-                    const uint32_t patch = smem_u32(smem + sa * L::kPatch);
-                    const int t_end = t + p.cls_ntaps[c];
-                    for (; t < t_end; t++)
+                    int t = 0;
+                    for (int c = 0; c < p.ncls; c++)
                     {
-                        mbar_wait(full_b + sb, pb);
+                        mbar_wait(ready_a + sa, pa);
                         tc_fence_after();
-                        if (elect_one())
+                        const uint32_t patch_lo = (smem_lo + (uint32_t)(sa * (L::kPatch >> 4))) | lo_flags;
+                        const int t_end = t + p.cls_ntaps[c];
+                        for (; t < t_end; t++)
                         {
-                            const uint64_t db = umma_desc_k_sw128(smem_u32(smem + L::kBOffset + sb * L::kBTile));
+                            const uint32_t a_lo = patch_lo + (uint32_t)p.tap_row[t] * 8u;                     // 128-byte rows -> 16-byte units
+                            const uint32_t b_lo = (smem_lo + (uint32_t)((L::kBOffset + sb * L::kBTile) >> 4)) | lo_flags;
+                            mbar_wait(full_b + sb, pb);
+                            tc_fence_after();
 #pragma unroll
                             for (int h = 0; h < MH; h++)
-                            {
-                                uint64_t da = umma_desc_k_sw128(patch + (uint32_t)(p.tap_row[t] + 8 * h) * 128u);
-                                da = (da & ~((uint64_t)0x3FFF << 32)) | sbo_field;
 #pragma unroll
-                                for (int k = 0; k < ((p.debug & 4) ? 0 : 4); k++)
-                                    mma_tf32(acc + (uint32_t)(h * BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kc > 0 || t > 0 || k > 0) ? 1u : 0u);
-                            }
+                                for (int k = 0; k < 4; k++)
+                                    if (!(p.debug & 4))
+                                        mma_tf32(acc + (uint32_t)(h * BN), desc(a_lo + (uint32_t)(h * 64 + k * 2), a_hi), desc(b_lo + (uint32_t)(k * 2), b_hi), idesc,
+                                                 (kc > 0 || t > 0 || k > 0) ? 1u : 0u);
                             if (CL == 1) mma_commit(empty_b + sb); else mma_commit_mc(empty_b + sb, kMask);
                             if (t == t_end - 1)
                             {
                                 mma_commit(empty_a + sa);
                                 if (kc == kchunks - 1 && c == p.ncls - 1) mma_commit(acc_full + buf);
                             }
+                            if (++sb == SB) { sb = 0; pb ^= 1; }
                         }
-                        __syncwarp();
-                        if (++sb == SB) { sb = 0; pb ^= 1; }
+                        if (++sa == SA) { sa = 0; pa ^= 1; }
                     }
-                    if (++sa == SA) { sa = 0; pa ^= 1; }
                 }
             }
         }
+        __syncwarp();
     }
     else if (warp < 6)
     {
@@ -402,13 +407,15 @@ static int launch_v3(const CUtensorMap& tx, const CUtensorMap& tw, const CUtenso
 }
 
 template <int CL>
-static int launch_v3_bn(int bn, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvV3Args& a, cudaStream_t stream)
+static int launch_v3_bn(int bn, int mh, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvV3Args& a, cudaStream_t stream)
 {
     switch (bn)
     {
         case 256: return launch_v3<256, 2, 2, 3, CL>(tx, tw, ty, a, stream);     // 84 KB patches + 96 KB slabs, single accumulator buffer (512 cols)
         case 128: return launch_v3<128, 2, 3, 4, CL>(tx, tw, ty, a, stream);     // 126 + 64 KB, double-buffered accumulators (512 cols)
-        default:  return launch_v3<64, 2, 3, 8, CL>(tx, tw, ty, a, stream);      // 126 + 64 KB, double-buffered accumulators (256 cols)
+        default:
+            if (mh == 4) return launch_v3<64, 4, 2, 4, CL>(tx, tw, ty, a, stream);   // 154 KB patches + 32 KB slabs, double-buffered accumulators (512 cols)
+            return launch_v3<64, 2, 3, 8, CL>(tx, tw, ty, a, stream);                // 126 + 64 KB, double-buffered accumulators (256 cols)
     }
 }
 
@@ -430,7 +437,12 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
 {
     if ((p->in_stride != 1 && p->in_stride != 2) || p->out_h < 12 || p->out_w < 12 || p->cout % 64 != 0) return SGV_ERR_UNSUPPORTED;
     if (p->in_stride == 2 && p->in_stride_x != 0) return SGV_ERR_UNSUPPORTED;      // strided sampling of a strided view: not needed by any caller
-    const int mh = 2, st = p->in_stride;
+    const int st = p->in_stride;
+    // 64 output channels: each weight slab feeds only 128 x 64 MMAs, so slabs re-streamed per tile saturate the ~40 B/clk L2 -> SM path
+    // (profiles/conv_v3_ablation_r1.txt); tiles of 4 halves (16 x 32 pixels) halve that traffic and still fit two accumulator buffers.
+    static int mh4 = -1;
+    if (mh4 < 0) { const char* e = getenv("SGV_V3_MH4"); mh4 = (e && !atoi(e)) ? 0 : 1; }
+    const int mh = (mh4 && p->cout % 128 != 0 && p->out_w >= 32) ? 4 : 2;
     ConvV3Args a;
     memset(&a, 0, sizeof(a));
     // group the taps into patch classes by the parity of (dy, dx) modulo the input stride
@@ -519,9 +531,9 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
         int rc = make_tmap_f32(&tmy, p->y, 4, dims, strides, box, es);
         if (rc != SGV_OK) return rc;
     }
-    if (cl == 4) return launch_v3_bn<4>(bn, tmx, tmw, tmy, a, stream);
-    if (cl == 2) return launch_v3_bn<2>(bn, tmx, tmw, tmy, a, stream);
-    return launch_v3_bn<1>(bn, tmx, tmw, tmy, a, stream);
+    if (cl == 4) return launch_v3_bn<4>(bn, mh, tmx, tmw, tmy, a, stream);
+    if (cl == 2) return launch_v3_bn<2>(bn, mh, tmx, tmw, tmy, a, stream);
+    return launch_v3_bn<1>(bn, mh, tmx, tmw, tmy, a, stream);
 }
 
 } // namespace sgv

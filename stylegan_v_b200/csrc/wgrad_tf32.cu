@@ -414,20 +414,21 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
         else if (warp == 1)
         {
             constexpr uint32_t idesc = umma_idesc_tf32(kWgM, NT, 1, 1);
-            int stage = 0; uint32_t phase = 0;
-            for (int ks = 0; ks < ksteps; ks++)
+            if (elect_one())      // one thread runs the whole issue loop (no per-step election / reconvergence)
             {
-                mbar_wait(ready_bar + stage, phase);
-                tc_fence_after();
-                if (elect_one())
+                int stage = 0; uint32_t phase = 0;
+                for (int ks = 0; ks < ksteps; ks++)
                 {
+                    mbar_wait(ready_bar + stage, phase);
+                    tc_fence_after();
                     const uint32_t sg = smem_u32(smem + stage * L::kStage);
                     const uint32_t sx = sg + kW2GTile;
                     for (int t = 0; t < gtaps; t++)
                     {
 #pragma unroll
-                        for (int k = 0; k < ((p.debug & 4) ? 0 : 4); k++)        // image row k of the 8x4 tile = 8 consecutive pixel rows
+                        for (int k = 0; k < 4; k++)        // image row k of the 8x4 tile = 8 consecutive pixel rows
                         {
+                            if (p.debug & 4) continue;
                             const uint64_t da = umma_desc_mn_sw128_32b(sg + k * 1024, 32 * 128, 512);
                             const uint64_t db = umma_desc_mn_sw128_32b(sx + (uint32_t)(p.grp_col[grp][t] + k * p.pw) * 128u, (uint32_t)xblock, 512);
                             mma_tf32(tmem_base + (uint32_t)(t * NT), da, db, idesc, (ks > 0 || k > 0) ? 1u : 0u);
@@ -435,10 +436,10 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
                     }
                     mma_commit(empty_bar + stage);
                     if (ks == ksteps - 1) mma_commit(accum_bar);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
         }
         else
         {
