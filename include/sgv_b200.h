@@ -76,6 +76,8 @@ typedef struct sgv_upfirdn2d_params {
     const float* epi_bias;     /* [c] or NULL */
     int32_t epi_act;           /* 0 = none, 1 = linear, 3 = lrelu (bias_act cuda_idx numbering) */
     float   epi_alpha, epi_gain, epi_clamp;   /* clamp < 0 disables */
+    int32_t epi_round_tf32;                   /* != 0 (needs epi_act != 0): round the result to TF32 (nearest, ties away) — lets a tensor-core
+                                                 consumer skip its operand-rounding pass; channels_last 4x4 up=down=1 kernels only */
 } sgv_upfirdn2d_params;
 
 int sgv_upfirdn2d_out_size(int in_size, int up, int pad0, int pad1, int fsize, int down);

@@ -100,6 +100,9 @@ typedef struct sgv_wgrad_params {
      * polyphase calls of a stride-2 transposed conv fill ONE [9][..][..] gradient buffer */
     int32_t use_dw_slot;
     int32_t dw_slot[SGV_CONV_MAX_TAPS];
+    /* optional: the operand already holds TF32-representable values with its scale applied (g_scale / x_scale must then be NULL): the
+     * kernel skips that operand's staging pass (scale + round in shared memory), which is its bottleneck (profiles/wgrad_ablation_r1.txt) */
+    int32_t g_ready, x_ready;
 } sgv_wgrad_params;
 
 int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream);
@@ -125,6 +128,12 @@ int sgv_modconv_act_bwd(const float* dy, const float* y, const float* bias, floa
 int sgv_modconv_act_bwd_rgb(const float* dy, const float* y, const float* bias, float* dz, float* db, float* dd,
                             const float* dyimg, const float* wmod, float* dwmod,
                             int32_t n, int32_t hw, int32_t c, int32_t act, float alpha, float gain, void* stream);
+/* sgv_modconv_act_bwd_ex: sgv_modconv_act_bwd_rgb plus an optional output scale: when oscale [n,c] is given dz is STORED as
+ * tf32_rn(dz * oscale[n,c]) (db / dd are still reduced from the unscaled dz) — the demodulation factor of the layer folded into the
+ * gradient once, so that the data-gradient and weight-gradient contractions that read dz need no operand scaling or rounding. */
+int sgv_modconv_act_bwd_ex(const float* dy, const float* y, const float* bias, float* dz, float* db, float* dd,
+                           const float* dyimg, const float* wmod, float* dwmod, const float* oscale,
+                           int32_t n, int32_t hw, int32_t c, int32_t act, float alpha, float gain, void* stream);
 int sgv_modconv_scale_reduce(const float* dxs, const float* x, const float* s, float* dx, float* ds,
                              int32_t n, int32_t hw, int32_t c, void* stream);
 int sgv_torgb_fwd(const float* x, const float* wmod, const float* bias, float* y, int32_t n, int32_t hw, int32_t c, void* stream);

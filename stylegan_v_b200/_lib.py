@@ -29,7 +29,7 @@ class UpfirdnParams(ctypes.Structure):
         ('out_w', c_int), ('out_h', c_int),
         ('out_stride_x', c_i64), ('out_stride_y', c_i64), ('out_stride_c', c_i64), ('out_stride_n', c_i64),
         ('epi_scale', c_vp), ('epi_bias', c_vp), ('epi_act', c_int),
-        ('epi_alpha', c_f32), ('epi_gain', c_f32), ('epi_clamp', c_f32),
+        ('epi_alpha', c_f32), ('epi_gain', c_f32), ('epi_clamp', c_f32), ('epi_round_tf32', c_int),
     ]
 
 
@@ -73,6 +73,7 @@ class WgradParams(ctypes.Structure):
         ('g_scale', c_vp), ('x_scale', c_vp),
         ('x_stride_n', c_i64), ('x_stride_y', c_i64), ('x_stride_x', c_i64),
         ('use_dw_slot', c_int), ('dw_slot', c_int * CONV_MAX_TAPS),
+        ('g_ready', c_int), ('x_ready', c_int),
     ]
 
 
@@ -96,6 +97,7 @@ SYMBOLS = [
     ('sgv_conv2d_wgrad_tf32', c_int, [ctypes.POINTER(WgradParams), c_vp]),
     ('sgv_modconv_act_bwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),
     ('sgv_modconv_act_bwd_rgb', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),
+    ('sgv_modconv_act_bwd_ex', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),
     ('sgv_modconv_scale_reduce', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     ('sgv_torgb_fwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     ('sgv_torgb_bwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),

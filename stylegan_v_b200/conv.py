@@ -116,10 +116,11 @@ def conv3x3_taps():
     return TAPS_3x3, [(ky - 1, kx - 1) for ky, kx in TAPS_3x3]
 
 
-def igemm_wgrad(g, x, taps_g, taps_x, out_hw, g_stride=1, x_stride=1, g_scale=None, x_scale=None, out=None, slots=None):
+def igemm_wgrad(g, x, taps_g, taps_x, out_hw, g_stride=1, x_stride=1, g_scale=None, x_scale=None, out=None, slots=None, g_ready=False, x_ready=False):
     """dw[t,o,i] = sum_{n,p} g[n, p*gs + dg_t, o] * g_scale[n,o] * x[n, p*xs + dx_t, i] * x_scale[n,i]  ->  [ntaps, Cout, Cin].
 
     g: [N, Cout, gh, gw], x: [N, Cin, xh, xw], both channels_last fp32; taps_*: per-tap (dy, dx) pixel offsets.
+    g_ready / x_ready: that operand already holds TF32-representable, fully scaled values (its scale must be None): no staging pass.
     out / slots: accumulate tap t into out[slots[t]] of a caller-provided (zeroed) [S, Cout, Cin] buffer instead of a fresh result."""
     for name, t in (('g', g), ('x', x)):
         _req(t.is_cuda and t.dtype == torch.float32 and t.ndim == 4, f'{name} must be a CUDA float32 [N,C,H,W] tensor')
@@ -155,6 +156,7 @@ def igemm_wgrad(g, x, taps_g, taps_x, out_hw, g_stride=1, x_stride=1, g_scale=No
             setattr(p, name, t.data_ptr())
     if not x_dense:
         p.x_stride_n, p.x_stride_y, p.x_stride_x = x.stride(0), x.stride(2), x.stride(3)
+    p.g_ready, p.x_ready = int(bool(g_ready and g_scale is None)), int(bool(x_ready and x_scale is None))
     if out is not None:
         p.use_dw_slot = 1
         for i, sl in enumerate(slots):
@@ -175,11 +177,12 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
-def act_bwd(dy, y, bias, act, gain, want_db, want_dd, alpha=0.2, dyimg=None, wmod=None):
+def act_bwd(dy, y, bias, act, gain, want_db, want_dd, alpha=0.2, dyimg=None, wmod=None, oscale=None):
     """dz, db[C], dd[N,C] (see sgv_modconv_act_bwd).  dy, y: [N,C,H,W] channels_last.
 
     With dyimg [N,3,H,W] (contiguous) and wmod [N,3,C] the ToRGB branch reading the same activation is folded in
-    (sgv_modconv_act_bwd_rgb): dy may then be None, and a fourth result dwmod [N,3,C] is returned."""
+    (sgv_modconv_act_bwd_rgb): dy may then be None, and a fourth result dwmod [N,3,C] is returned.
+    oscale [N,C]: dz is returned as tf32_rn(dz * oscale) (db / dd are reduced from the unscaled dz) — sgv_modconv_act_bwd_ex."""
     _req(y.is_cuda and y.dtype == torch.float32 and _is_nhwc(y), 'y must be an NHWC float32 CUDA tensor')
     _req(dy is None or (dy.dtype == torch.float32 and _is_nhwc(dy) and dy.shape == y.shape), 'dy must match y (NHWC float32)')
     N, C, H, W = y.shape
@@ -190,18 +193,20 @@ def act_bwd(dy, y, bias, act, gain, want_db, want_dd, alpha=0.2, dyimg=None, wmo
     dd = torch.zeros([N, C], dtype=torch.float32, device=y.device) if want_dd else None
     b = bias.to(torch.float32).contiguous() if bias is not None else None
     L = _lib.lib()
-    args = (_ptr(dy), y.data_ptr(), _ptr(b), dz.data_ptr(), _ptr(db), _ptr(dd))
     tail = (N, H * W, C, {'linear': 1, 'lrelu': 3}[act], float(alpha), float(gain), _stream(y.device))
-    with torch.cuda.device(y.device):
-        if not rgb:
-            _lib.check(L.sgv_modconv_act_bwd(*args, *tail), 'sgv_modconv_act_bwd')
-            return dz, db, dd
+    dwmod = None
+    if rgb:
         dyimg = dyimg.to(torch.float32).contiguous()
         wmod = wmod.to(torch.float32).contiguous()
         _req(tuple(dyimg.shape) == (N, 3, H, W) and tuple(wmod.shape) == (N, 3, C), 'dyimg must be [N,3,H,W] and wmod [N,3,C]')
         dwmod = torch.zeros([N, 3, C], dtype=torch.float32, device=y.device)
-        _lib.check(L.sgv_modconv_act_bwd_rgb(*args, dyimg.data_ptr(), wmod.data_ptr(), dwmod.data_ptr(), *tail), 'sgv_modconv_act_bwd_rgb')
-    return dz, db, dd, dwmod
+    if oscale is not None:
+        oscale = oscale.to(torch.float32).contiguous()
+        _req(tuple(oscale.shape) == (N, C), 'oscale must be [N, C]')
+    with torch.cuda.device(y.device):
+        _lib.check(L.sgv_modconv_act_bwd_ex(_ptr(dy), y.data_ptr(), _ptr(b), dz.data_ptr(), _ptr(db), _ptr(dd), _ptr(dyimg), _ptr(wmod), _ptr(dwmod),
+                                            _ptr(oscale), *tail), 'sgv_modconv_act_bwd_ex')
+    return (dz, db, dd, dwmod) if rgb else (dz, db, dd)
 
 
 def scale_reduce(dxs, x, s, want_dx=True, want_ds=True):

@@ -12,6 +12,7 @@
 // stride, keeping per-channel partial sums in registers; partials are merged through shared-memory atomics, then one
 // global atomicAdd per channel per CTA.
 #include "common.cuh"
+#include "ptx.cuh"
 #include "../../include/sgv_b200_conv.h"
 
 namespace sgv {
@@ -43,6 +44,7 @@ struct ActBwdArgs
     // optional ToRGB branch hanging off the same activation (RGB = true): dy_total = dy (may be NULL) + sum_j dyimg[n,j,hw] * wmod[n,j,c];
     // dwmod[n,j,c] += sum_hw dyimg[n,j,hw] * y[n,hw,c]
     const float* dyimg; const float* wmod; float* dwmod;
+    const float* oscale;      // optional [n, c]: dz is stored as tf32_rn(dz * oscale) (reductions use the unscaled dz)
     EwGeom g;
 };
 
@@ -61,6 +63,7 @@ __global__ void __launch_bounds__(kEwThreads) modconv_act_bwd_kernel(ActBwdArgs 
     if (active)
     {
         const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias) + cv) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 os4 = p.oscale ? __ldg(reinterpret_cast<const float4*>(p.oscale + (long long)n * g.c) + cv) : make_float4(1.f, 1.f, 1.f, 1.f);
         float4 sdb = make_float4(0.f, 0.f, 0.f, 0.f), sdd = sdb;
         float4 wm[3], sdw[3];
 #pragma unroll
@@ -122,7 +125,9 @@ __global__ void __launch_bounds__(kEwThreads) modconv_act_bwd_kernel(ActBwdArgs 
                     pr[e] = pre - bb[e];
                 }
                 const float4 z4 = make_float4(z[0], z[1], z[2], z[3]);
-                __stcs(reinterpret_cast<float4*>(p.dz + base + (long long)px * g.c + cv * 4), z4);
+                float4 zo = z4;
+                if (p.oscale) zo = make_float4(ptx::tf32_rn(z[0] * os4.x), ptx::tf32_rn(z[1] * os4.y), ptx::tf32_rn(z[2] * os4.z), ptx::tf32_rn(z[3] * os4.w));
+                __stcs(reinterpret_cast<float4*>(p.dz + base + (long long)px * g.c + cv * 4), zo);
                 f4_acc(sdb, z4);
                 f4_acc(sdd, make_float4(z[0] * pr[0], z[1] * pr[1], z[2] * pr[2], z[3] * pr[3]));
             }
@@ -344,9 +349,9 @@ static int make_geom(EwGeom* g, int n, int hw, int c)
 
 } // namespace sgv
 
-extern "C" int sgv_modconv_act_bwd_rgb(const float* dy, const float* y, const float* bias, float* dz, float* db, float* dd,
-                                       const float* dyimg, const float* wmod, float* dwmod,
-                                       int32_t n, int32_t hw, int32_t c, int32_t act, float alpha, float gain, void* stream_)
+extern "C" int sgv_modconv_act_bwd_ex(const float* dy, const float* y, const float* bias, float* dz, float* db, float* dd,
+                                      const float* dyimg, const float* wmod, float* dwmod, const float* oscale,
+                                      int32_t n, int32_t hw, int32_t c, int32_t act, float alpha, float gain, void* stream_)
 {
     using namespace sgv;
     const bool rgb = dyimg != nullptr;
@@ -358,7 +363,7 @@ extern "C" int sgv_modconv_act_bwd_rgb(const float* dy, const float* y, const fl
     if (rc != SGV_OK) return rc;
     ActBwdArgs a;
     a.dy = dy; a.y = y; a.bias = bias; a.dz = dz; a.db = db; a.dd = dd; a.act = act; a.alpha = alpha; a.gain = gain;
-    a.dyimg = dyimg; a.wmod = wmod; a.dwmod = dwmod;
+    a.dyimg = dyimg; a.wmod = wmod; a.dwmod = dwmod; a.oscale = oscale;
     rc = make_geom(&a.g, n, hw, c);
     if (rc != SGV_OK) return rc;
     const unsigned grid = (unsigned)(n * a.g.chunks);
@@ -368,11 +373,18 @@ extern "C" int sgv_modconv_act_bwd_rgb(const float* dy, const float* y, const fl
     return SGV_OK;
 }
 
+extern "C" int sgv_modconv_act_bwd_rgb(const float* dy, const float* y, const float* bias, float* dz, float* db, float* dd,
+                                       const float* dyimg, const float* wmod, float* dwmod,
+                                       int32_t n, int32_t hw, int32_t c, int32_t act, float alpha, float gain, void* stream_)
+{
+    return sgv_modconv_act_bwd_ex(dy, y, bias, dz, db, dd, dyimg, wmod, dwmod, nullptr, n, hw, c, act, alpha, gain, stream_);
+}
+
 extern "C" int sgv_modconv_act_bwd(const float* dy, const float* y, const float* bias, float* dz, float* db, float* dd,
                                    int32_t n, int32_t hw, int32_t c, int32_t act, float alpha, float gain, void* stream_)
 {
     SGV_CHECK_ARG(dy != nullptr, "sgv_modconv_act_bwd: dy must be non-NULL");
-    return sgv_modconv_act_bwd_rgb(dy, y, bias, dz, db, dd, nullptr, nullptr, nullptr, n, hw, c, act, alpha, gain, stream_);
+    return sgv_modconv_act_bwd_ex(dy, y, bias, dz, db, dd, nullptr, nullptr, nullptr, nullptr, n, hw, c, act, alpha, gain, stream_);
 }
 
 extern "C" int sgv_modconv_scale_reduce(const float* dxs, const float* x, const float* s, float* dx, float* ds,

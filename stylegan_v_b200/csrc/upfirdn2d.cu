@@ -30,7 +30,7 @@ struct FirArgs
     int in_w, in_h, in_c, in_n; long long isx, isy, isc, isn;
     int f_w, f_h; long long fsx, fsy;
     int out_w, out_h; long long osx, osy, osc, osn;
-    const float* escale; const float* ebias; int eact; float ealpha, egain, eclamp;
+    const float* escale; const float* ebias; int eact; float ealpha, egain, eclamp; int eround;
 };
 
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
@@ -476,6 +476,7 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_slide44(FirArgs p, long long 
                     o.x = (o.x > -cl && o.x < cl) ? o.x : (o.x >= 0.f ? cl : -cl); o.y = (o.y > -cl && o.y < cl) ? o.y : (o.y >= 0.f ? cl : -cl);
                     o.z = (o.z > -cl && o.z < cl) ? o.z : (o.z >= 0.f ? cl : -cl); o.w = (o.w > -cl && o.w < cl) ? o.w : (o.w >= 0.f ? cl : -cl);
                 }
+                if (p.eround) { o.x = ptx::tf32_rn(o.x); o.y = ptx::tf32_rn(o.y); o.z = ptx::tf32_rn(o.z); o.w = ptx::tf32_rn(o.w); }
             }
             __stcs(reinterpret_cast<float4*>((float*)p.y + n * p.osn + outY * p.osy + outX * p.osx + c0), o);
         };
@@ -622,6 +623,7 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_tma44(const __grid_constant__
                         o.x = (o.x > -cl && o.x < cl) ? o.x : (o.x >= 0.f ? cl : -cl); o.y = (o.y > -cl && o.y < cl) ? o.y : (o.y >= 0.f ? cl : -cl);
                         o.z = (o.z > -cl && o.z < cl) ? o.z : (o.z >= 0.f ? cl : -cl); o.w = (o.w > -cl && o.w < cl) ? o.w : (o.w >= 0.f ? cl : -cl);
                     }
+                    if (p.eround) { o.x = ptx::tf32_rn(o.x); o.y = ptx::tf32_rn(o.y); o.z = ptx::tf32_rn(o.z); o.w = ptx::tf32_rn(o.w); }
                 }
                 __stcs(reinterpret_cast<float4*>(ycol + oy * p.osy), o);
             }
@@ -781,7 +783,13 @@ extern "C" int sgv_upfirdn2d(const sgv_upfirdn2d_params* p, void* stream_)
     a.out_w = ow; a.out_h = oh;
     a.osx = p->out_stride_x; a.osy = p->out_stride_y; a.osc = p->out_stride_c; a.osn = p->out_stride_n;
     a.escale = p->epi_scale; a.ebias = p->epi_bias; a.eact = p->epi_act;
-    a.ealpha = p->epi_alpha; a.egain = p->epi_gain; a.eclamp = p->epi_clamp;
+    a.ealpha = p->epi_alpha; a.egain = p->epi_gain; a.eclamp = p->epi_clamp; a.eround = p->epi_round_tf32;
+    SGV_CHECK_ARG(!a.eround || a.eact != 0, "epi_round_tf32 needs a fused epilogue (epi_act != 0)");
+    // the rounding flag is honoured by the two channels_last 4x4 kernels below; any other route rejects it rather than ignore it
+    const bool round_ok = p->dtype == SGV_F32 && a.upx == 1 && a.upy == 1 && a.downx == 1 && a.downy == 1 && a.f_w == 4 && a.f_h == 4 && a.in_c % 4 == 0 && a.in_c > 1
+                          && dense_nhwc(a.in_w, a.in_h, a.in_c, a.isx, a.isy, a.isc, a.isn) && dense_nhwc(ow, oh, a.in_c, a.osx, a.osy, a.osc, a.osn)
+                          && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->y) & 15) == 0;
+    SGV_CHECK_ARG(!a.eround || round_ok, "epi_round_tf32: only for float32 channels_last tensors, up = down = 1, 4x4 filter, C %% 4 == 0");
 
     const long long total = (long long)ow * oh * p->in_c * p->in_n;
     const int sms = num_sms();

@@ -336,6 +336,7 @@ struct Wg2Args
     int grp_col[SGV_CONV_MAX_TAPS][kW2MaxGroupTaps];        // dx_t - dx_min: column offset inside the patch
     int dx_min, pw;
     int tiles_x, tiles_y, mtiles, ktiles, ksplit;
+    int g_ready, x_ready;     // operand needs no staging pass
     int debug;      // ablation switches, env SGV_WG_DEBUG (measurement only; profiles/wgrad_ablation_r1.txt): 1 skip transform, 2 skip epilogue, 4 skip MMAs
 };
 
@@ -461,8 +462,8 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
                 sbase[s] = nullptr; sstride[s] = 0;
                 if (act[s])
                 {
-                    if (rr[s] < 128) { const int ch = m0 + (rr[s] >> 5) * 32; act[s] = ch < p.cout; if (p.g_scale) { sbase[s] = p.g_scale + ch; sstride[s] = p.cout; } }
-                    else { const int ch = c0 + ((rr[s] - 128) / xrows_blk) * 32; act[s] = ch < p.cin; if (p.x_scale) { sbase[s] = p.x_scale + ch; sstride[s] = p.cin; } }
+                    if (rr[s] < 128) { const int ch = m0 + (rr[s] >> 5) * 32; act[s] = ch < p.cout && !p.g_ready; if (p.g_scale) { sbase[s] = p.g_scale + ch; sstride[s] = p.cout; } }
+                    else { const int ch = c0 + ((rr[s] - 128) / xrows_blk) * 32; act[s] = ch < p.cin && !p.x_ready; if (p.x_scale) { sbase[s] = p.x_scale + ch; sstride[s] = p.cin; } }
                 }
 #pragma unroll
                 for (int j = 0; j < 32; j++) sv[s][j] = 1.f;
@@ -609,6 +610,7 @@ int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, cudaStream_t stream)
     if (ksplit > a.ktiles) ksplit = a.ktiles;
     a.ksplit = ksplit;
     { const char* e = getenv("SGV_WG_DEBUG"); a.debug = e ? atoi(e) : 0; }
+    a.g_ready = p->g_ready && !p->g_scale; a.x_ready = p->x_ready && !p->x_scale;
 
     CUtensorMap tg, tx;
     int rc = make_blocked_tmap(&tg, p->g, p->cout, p->gw, p->gh, p->n, 8, 4, 1, 1, kWgM / 32);

@@ -20,6 +20,8 @@ Backward (first order; second order is served by the unfused drop-in ops in styl
                                         outside this Function (see demod_coefs), so their dependence on styles / weight
                                         is handled by autograd on [N,C]-sized tensors.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -58,13 +60,13 @@ def _fir(device):
     return _FIR_1331
 
 
-def _wgrad_native(gout, x, styles, dscale, w_shape, up):
+def _wgrad_native(gout, x, styles, dscale, w_shape, up, g_ready=False):
     """Weight gradient on the tcgen05 split-K kernel (csrc/wgrad_tf32.cu) with styles / dcoefs folded into operand staging."""
     O, I, kh, kw = w_shape
     N, _, H, W = x.shape
     if up == 1:
         taps_x = _OFFS3_FWD if kh == 3 else [(0, 0)]
-        dw = _conv.igemm_wgrad(gout, x, [(0, 0)] * len(taps_x), taps_x, (H, W), g_scale=dscale, x_scale=styles)
+        dw = _conv.igemm_wgrad(gout, x, [(0, 0)] * len(taps_x), taps_x, (H, W), g_scale=dscale, x_scale=styles, g_ready=g_ready)
     elif H >= 8 and W >= 8:
         # transposed (stride-2) conv: per polyphase sub-lattice (a, b) of the output gradient, a stride-1 correlation between the
         # unshifted input (M side) and the pixel-strided VIEW gout[:, :, a::2, b::2] shifted by (ky//2, kx//2) (N side): the grouped-tap
@@ -75,7 +77,7 @@ def _wgrad_native(gout, x, styles, dscale, w_shape, up):
                 taps = [(ky, kx) for ky in range(a, 3, 2) for kx in range(b, 3, 2)]
                 offs = [(ky // 2, kx // 2) for ky, kx in taps]
                 _conv.igemm_wgrad(x, gout[:, :, a::2, b::2], [(0, 0)] * len(taps), offs, (H, W), g_scale=styles, x_scale=dscale,
-                                  out=dwt, slots=[ky * kw + kx for ky, kx in taps])
+                                  out=dwt, slots=[ky * kw + kx for ky, kx in taps], x_ready=g_ready)
         return dwt.reshape(kh, kw, I, O).permute(3, 2, 0, 1)
     else:
         dw = _conv.igemm_wgrad(gout, x, _TAPS3, [(0, 0)] * 9, (H, W), g_stride=2, g_scale=dscale, x_scale=styles)
@@ -83,6 +85,7 @@ def _wgrad_native(gout, x, styles, dscale, w_shape, up):
 
 
 USE_NATIVE_WGRAD = True      # False -> cuDNN library call (kept for A/B measurements)
+PRESCALE_GRADIENT = os.environ.get('SGV_PRESCALE', '1') != '0'     # fold dcoefs + TF32 rounding into the activation-gradient pass (see backward)
 
 
 def prepare_weights(weight, up, flip_weight):
@@ -198,15 +201,21 @@ class _FusedModConv(torch.autograd.Function):
         want_db = has_b and ctx.needs_input_grad[4]
         want_dd = has_d and ctx.needs_input_grad[3]
         dwmod = drgb_bias = None
+        # PRESCALE: dz leaves the kernel as tf32_rn(dz * dcoefs) (the FIR adjoint of the up layers re-rounds its result), i.e. exactly the
+        # operand both contractions below need — they then skip scaling, and the weight-gradient kernel skips the staging pass of
+        # that operand altogether (`ready`).  db / dd are reduced from the unscaled gradient inside the same kernel.
+        native_w = USE_NATIVE_WGRAD and I % 32 == 0 and O % 32 == 0
+        prescale = PRESCALE_GRADIENT and has_d and native_w
+        osc = dcoefs if prescale else None
         if ctx.wmod is not None and drgb is not None:
-            dz, db, dd, dwmod = _conv.act_bwd(dy, y, bias if has_b else None, act, gain, want_db, want_dd, dyimg=drgb, wmod=ctx.wmod)
+            dz, db, dd, dwmod = _conv.act_bwd(dy, y, bias if has_b else None, act, gain, want_db, want_dd, dyimg=drgb, wmod=ctx.wmod, oscale=osc)
             drgb_bias = drgb.sum(dim=[0, 2, 3])
         else:
             if dy is None:
                 return (None,) * 13
-            dz, db, dd = _conv.act_bwd(dy, y, bias if has_b else None, act, gain, want_db, want_dd)
+            dz, db, dd = _conv.act_bwd(dy, y, bias if has_b else None, act, gain, want_db, want_dd, oscale=osc)
         ddcoefs = dd / dcoefs if want_dd else None
-        dscale = dcoefs if has_d else None
+        dscale = dcoefs if (has_d and not prescale) else None
         wp = ctx.wp_dgrad
         # ---- data gradient: ONE launch gives dx = dxs * styles (epilogue scale) and dstyles = sum_hw dxs * x (fused reduction) ----
         want_ds = ctx.needs_input_grad[2]
@@ -218,15 +227,16 @@ class _FusedModConv(torch.autograd.Function):
             dx = _conv.igemm_conv(dz, wp, offs, a_scale=dscale, o_scale=styles, **red)
         else:
             # adjoint of the FIR pass (upfirdn2d.py:246-261): padding (fw - p - 1) = 2, flipped filter, same gain
-            gout = _plugin.upfirdn2d(dz, _fir(x.device), 1, 1, 1, 1, 2, 2, 2, 2, True, 4.0)
+            gout = _plugin.upfirdn2d(dz, _fir(x.device), 1, 1, 1, 1, 2, 2, 2, 2, True, 4.0,
+                                     epilogue=dict(act='linear', round_tf32=True) if prescale else None)
             # data gradient of the stride-2 transposed conv = stride-2 correlation: ONE launch with TMA element strides.
             # (Measured alternative: 4 accumulate-launches over polyphase views of `gout` on the halo-patch kernel — 1.2 ms/step
             #  slower at config 2; kept available through igemm_conv(accumulate=True).)
             dx = _conv.igemm_conv(gout, wp, _TAPS3, out_hw=(H, W), in_stride=2, a_scale=dscale, o_scale=styles, **red)
         # ---- weight gradient ----
         def weight_grad():
-            if USE_NATIVE_WGRAD and I % 32 == 0 and O % 32 == 0:
-                dw = _wgrad_native(gout, x, styles, dscale, (O, I, kh, kw), up)
+            if native_w:
+                dw = _wgrad_native(gout, x, styles, dscale, (O, I, kh, kw), up, g_ready=prescale)
             else:
                 xs = x * styles.reshape(N, I, 1, 1)
                 g = gout * dscale.reshape(N, O, 1, 1) if has_d else gout

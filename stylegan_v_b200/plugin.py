@@ -84,6 +84,7 @@ def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, ga
         p.epi_gain = float(epilogue.get('gain', 1.0))
         cl = epilogue.get('clamp')
         p.epi_clamp = float(cl) if cl is not None else -1.0
+        p.epi_round_tf32 = int(bool(epilogue.get('round_tf32', False)))
     with torch.cuda.device(x.device):
         _lib.check(L.sgv_upfirdn2d(ctypes.byref(p), _stream_ptr(x.device)), 'sgv_upfirdn2d')
     return y
