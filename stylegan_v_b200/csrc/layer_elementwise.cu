@@ -230,7 +230,50 @@ __global__ void __launch_bounds__(kEwThreads) torgb_fwd_kernel(ToRgbArgs p)
     const float b0 = p.bias ? p.bias[0] : 0.f, b1 = p.bias ? p.bias[1] : 0.f, b2 = p.bias ? p.bias[2] : 0.f;
     const int stride = g.lanes * g.chunks;
     const int iters = (g.hw + stride - 1) / stride;               // uniform trip count: shuffles / barriers below need every thread
-    for (int it = 0; it < iters; it++)
+    int it0 = 0;
+    if (g.cvecs <= 32)
+    {
+        // fast path (C <= 128, the high-resolution blocks): 4 pixels per trip so that four 128-bit loads are in flight per thread
+        for (; it0 + 4 <= iters; it0 += 4)
+        {
+            float r[4][3];
+            float4 v[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+            {
+                const int px = chunk * g.lanes + lane + (it0 + u) * stride;
+                ok[u] = px < g.hw && lane < g.lanes;
+                v[u] = ok[u] ? __ldcs(reinterpret_cast<const float4*>(p.x + base + (long long)px * g.c + cv * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+            {
+                r[u][0] = v[u].x * w0.x + v[u].y * w0.y + v[u].z * w0.z + v[u].w * w0.w;
+                r[u][1] = v[u].x * w1.x + v[u].y * w1.y + v[u].z * w1.z + v[u].w * w1.w;
+                r[u][2] = v[u].x * w2.x + v[u].y * w2.y + v[u].z * w2.z + v[u].w * w2.w;
+            }
+            for (int o = g.cvecs >> 1; o > 0; o >>= 1)
+            {
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                {
+                    r[u][0] += __shfl_down_sync(0xffffffffu, r[u][0], o, 32);
+                    r[u][1] += __shfl_down_sync(0xffffffffu, r[u][1], o, 32);
+                    r[u][2] += __shfl_down_sync(0xffffffffu, r[u][2], o, 32);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (cv == 0 && ok[u])
+                {
+                    const int px = chunk * g.lanes + lane + (it0 + u) * stride;
+                    float* yo = p.y + (long long)n * 3 * g.hw + px;
+                    yo[0] = r[u][0] + b0; yo[g.hw] = r[u][1] + b1; yo[2 * g.hw] = r[u][2] + b2;
+                }
+        }
+    }
+    for (int it = it0; it < iters; it++)
     {
         const int px = chunk * g.lanes + lane + it * stride;
         float r0 = 0.f, r1 = 0.f, r2 = 0.f;

@@ -148,6 +148,44 @@ def test_network_vs_oracle_other_config():
     assert e < 3e-3, e
 
 
+def test_network_vs_oracle_32_channel_ladder():
+    """The channel ladder of config 5 (1024x1024, fmaps 1) ends in 64 -> 32 -> 32 channels; the same ladder at 128x128 against the
+    CPU oracle: exercises the 32-column conv tiles, the 32-channel weight-gradient tiles and the 32-channel FIR / ToRGB paths."""
+    cfg = sr.SynthesisConfig(img_resolution=128, w_dim=128, channel_base=4096, channel_max=128, motion_z_dim=64, motion_v_dim=64, time_enc_dim=32)
+    assert [cfg.channels(r) for r in (32, 64, 128)] == [128, 64, 32]
+    P = sr.init_params(cfg, seed=4)
+    net = SynthesisNetwork.from_config(cfg)
+    sd = net.state_dict()
+    for k in sd:
+        if k in P:
+            sd[k] = P[k]
+    net.load_state_dict(sd)
+    net = net.cuda()
+    gen = torch.Generator().manual_seed(6)
+    ws = torch.randn(2, cfg.num_ws, cfg.w_dim, generator=gen)
+    t = torch.tensor([[1.0], [250.5]])
+    mz = torch.randn(2, sr.max_traj_len(cfg, 1023.0), cfg.motion_z_dim, generator=gen)
+    ref = sr.synthesis_forward(P, cfg, ws, t, motion_z=mz, fused_modconv=False)
+    wsg = ws.cuda().requires_grad_(True)
+    img = net(wsg, t.cuda(), motion_z=mz.cuda())
+    assert rel_err(img, ref) < 3e-3
+    img.square().mean().backward()
+    assert torch.isfinite(wsg.grad).all() and all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters() if p.requires_grad)
+
+
+def test_config5_1024_forward_runs():
+    """BASELINE config 5 geometry (1024x1024, channel_base 32768: ... 512:64, 1024:32) at batch 1: shape, finiteness, determinism."""
+    net = SynthesisNetwork(img_resolution=1024, channel_base=32768).cuda().eval()
+    gen = torch.Generator().manual_seed(7)
+    ws = torch.randn(1, net.num_ws, net.w_dim, generator=gen).cuda()
+    t = torch.zeros(1, 1).cuda()
+    mz = torch.randn(1, net.motion_encoder.traj_len(), 512, generator=gen).cuda()
+    with torch.no_grad():
+        a = net(ws, t, motion_z=mz)
+        b = net(ws, t, motion_z=mz)
+    assert a.shape == (1, 3, 1024, 1024) and torch.isfinite(a).all() and torch.equal(a, b)
+
+
 def test_layer_elementwise_kernels():
     from stylegan_v_b200 import conv as C
     gen = torch.Generator().manual_seed(3)
