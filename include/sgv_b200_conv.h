@@ -68,6 +68,9 @@ typedef struct sgv_conv_params {
      * With o_scale = styles this turns the data-gradient launch into  dx = dxs * s  and  dstyles = sum_hw dxs * x  in one pass. */
     const float* red_x;
     float*       red_out;      /* [n, cout] float32, caller-zeroed */
+    /* optional: x already holds TF32-representable values and needs no scaling (a_scale must be NULL): the persistent kernel skips its
+     * operand-staging pass over the activation patches (they go TMA -> MMA directly) */
+    int32_t      a_ready;
 } sgv_conv_params;
 
 int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream);

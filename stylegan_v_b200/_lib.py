@@ -59,7 +59,7 @@ class ConvParams(ctypes.Structure):
         ('a_scale', c_vp), ('o_scale', c_vp), ('bias', c_vp),
         ('act', c_int), ('alpha', c_f32), ('gain', c_f32), ('clamp', c_f32),
         ('in_stride_n', c_i64), ('in_stride_y', c_i64), ('in_stride_x', c_i64), ('accumulate', c_int),
-        ('red_x', c_vp), ('red_out', c_vp),
+        ('red_x', c_vp), ('red_out', c_vp), ('a_ready', c_int),
     ]
 
 

@@ -54,7 +54,7 @@ def prep_weights_pair(w, taps_fwd, taps_dgrad):
 
 def igemm_conv(x, wp, tap_offsets, out=None, out_hw=None, out_view=None, in_stride=1,
                a_scale=None, o_scale=None, bias=None, act='linear', alpha=0.2, gain=1.0, clamp=None, accumulate=False,
-               red_x=None, red_out=None):
+               red_x=None, red_out=None, a_ready=False):
     """y[n,oy,ox,o] = epi(sum_{t,i} x[n, oy*in_stride+dy_t, ox*in_stride+dx_t, i] * a_scale[n,i] * wp[t,o,i]).
 
     x: [N, Cin, H, W] channels_last fp32.  wp: [ntaps, Cout, Cin] from prep_weights.  tap_offsets: [(dy, dx)].
@@ -98,6 +98,7 @@ def igemm_conv(x, wp, tap_offsets, out=None, out_hw=None, out_view=None, in_stri
     if not dense:
         p.in_stride_n, p.in_stride_y, p.in_stride_x = x.stride(0), x.stride(2), x.stride(3)
     p.accumulate = int(bool(accumulate))
+    p.a_ready = int(bool(a_ready and a_scale is None))      # x is already TF32-exact: no staging pass (persistent kernel)
     if red_out is not None:
         _req(red_x is not None and red_x.shape == y.shape and red_x.stride() == y.stride() and red_x.dtype == torch.float32,
              'red_x must have the shape and strides of the output')

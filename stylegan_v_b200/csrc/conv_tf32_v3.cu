@@ -47,6 +47,7 @@ struct ConvV3Args
     int act; float alpha, gain, clamp;
     int accumulate;
     const float* red_x; float* red_out;
+    int a_ready;    // activation patches need no staging pass
     int debug;      // ablation switches, env SGV_V3_DEBUG (measurement only; profiles/conv_v3_ablation_r1.txt): 1 skip transform, 2 skip epilogue, 4 skip MMAs
 };
 
@@ -255,7 +256,7 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 {
                     mbar_wait(full_a + sa, pa);
                     const uint32_t patch = smem_u32(smem + sa * L::kPatch);
-                    for (int row = tid; row < ((p.debug & 1) ? 0 : nrows); row += 128)
+                    for (int row = tid; row < (((p.debug & 1) || p.a_ready) ? 0 : nrows); row += 128)
                     {
                         const uint32_t arow = patch + (uint32_t)row * 128u;
                         float4 v[8];
@@ -488,6 +489,7 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
     a.act = p->act; a.alpha = p->alpha; a.gain = p->gain; a.clamp = p->clamp;
     a.accumulate = p->accumulate;
     a.red_x = p->red_x; a.red_out = p->red_out;
+    a.a_ready = p->a_ready && !p->a_scale;
     { const char* e = getenv("SGV_V3_DEBUG"); a.debug = e ? atoi(e) : 0; }
     const int pixel_tiles = a.tiles_x * a.tiles_y * p->n;
     // N tile: 256 columns leave no room to double-buffer the accumulator (2 halves x 256 = all 512 TMEM columns), so the drain of a

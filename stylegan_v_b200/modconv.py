@@ -224,7 +224,7 @@ class _FusedModConv(torch.autograd.Function):
         if up == 1:
             gout = dz
             offs = _OFFS3_DGRAD if kh == 3 else [(0, 0)]
-            dx = _conv.igemm_conv(dz, wp, offs, a_scale=dscale, o_scale=styles, **red)
+            dx = _conv.igemm_conv(dz, wp, offs, a_scale=dscale, o_scale=styles, a_ready=prescale, **red)
         else:
             # adjoint of the FIR pass (upfirdn2d.py:246-261): padding (fw - p - 1) = 2, flipped filter, same gain
             gout = _plugin.upfirdn2d(dz, _fir(x.device), 1, 1, 1, 1, 2, 2, 2, 2, True, 4.0,
@@ -232,7 +232,7 @@ class _FusedModConv(torch.autograd.Function):
             # data gradient of the stride-2 transposed conv = stride-2 correlation: ONE launch with TMA element strides.
             # (Measured alternative: 4 accumulate-launches over polyphase views of `gout` on the halo-patch kernel — 1.2 ms/step
             #  slower at config 2; kept available through igemm_conv(accumulate=True).)
-            dx = _conv.igemm_conv(gout, wp, _TAPS3, out_hw=(H, W), in_stride=2, a_scale=dscale, o_scale=styles, **red)
+            dx = _conv.igemm_conv(gout, wp, _TAPS3, out_hw=(H, W), in_stride=2, a_scale=dscale, o_scale=styles, a_ready=prescale, **red)
         # ---- weight gradient ----
         def weight_grad():
             if native_w:
