@@ -11,8 +11,8 @@
 // Operand staging is v2's: per 32-channel chunk ONE TMA box = output tile (16 rows x 16 cols) + halo; every tap's A matrix is
 // that patch through a shifted K-major SWIZZLE_128B descriptor (start row = (dy-dy_min)*PW + (dx-dx_min) + 8*half,
 // SBO = PW*128; legal because tcgen05 swizzles on absolute smem address bits — profiles/umma_probe_r1.txt).
-// Warps: 0 activation-patch TMA producer, 1 MMA issuer + TMEM owner, 2-5 transform (styles * x, round to TF32), 6-9 epilogue,
-// 10 weight-slab TMA producer.  The two producers are separate threads on purpose: with one thread issuing "patch, then its
+// Warps: 0 activation-patch TMA producer, 1 MMA issuer + TMEM owner, 2-5 transform (styles * x, round to TF32), 6-13 epilogue
+// (two groups of four warps = one per TMEM lane quarter; the groups take alternate 32-column units of a tile), 14 weight-slab TMA producer.  The two producers are separate threads on purpose: with one thread issuing "patch, then its
 // ntaps slabs" the next patch could not be requested until the MMAs had freed slab slots, and the transform warps spent 2/3 of
 // their time waiting for patches (ncu source view, profiles/ncu_v3_r1y_summary.txt).
 #include <stdlib.h>
@@ -26,7 +26,7 @@ namespace sgv {
 
 using namespace ptx;
 
-constexpr int kV3Threads = 64 + 128 + 128 + 32;
+constexpr int kV3Threads = 64 + 128 + 256 + 32;
 constexpr int kV3TileH = 16;
 
 struct ConvV3Args
@@ -114,7 +114,7 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         prefetch_tmap(&tmap_y);
         for (int s = 0; s < SA; s++) { mbar_init(full_a + s, 1); mbar_init(ready_a + s, 4); mbar_init(empty_a + s, 1); }
         for (int s = 0; s < SB; s++) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, CL); }   // a slab slot is freed by the MMAs of all CL CTAs
-        for (int s = 0; s < 2; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }
+        for (int s = 0; s < 2; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 8); }
         fence_mbar_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, L::kTmemCols); tmem_relinquish(); }
@@ -144,7 +144,7 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             }
         }
     }
-    else if (warp == 10)
+    else if (warp == 14)
     {
         // ===== weight-slab producer =====
         if (elect_one())
@@ -280,16 +280,16 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
     else
     {
-        // ===== epilogue (4 warps): TMEM -> registers -> dcoefs/bias/lrelu/gain -> swizzled staging -> TMA store =====
+        // ===== epilogue (8 warps in two groups): TMEM -> registers -> dcoefs/bias/lrelu/gain -> swizzled staging -> TMA store =====
         // Thread `row` owns one output pixel of the 16 x 8 half tile and 32 consecutive channels per unit.  Writing those straight to
         // global memory made every STG.128 touch 32 different lines (16 B partial writes): the drain took 2-4x the MMA time of a tile
         // (ablation: profiles/conv_v3_ablation_r1.txt).  Instead the unit is staged as 128 rows x 128 B in the TMA 128B-swizzle
         // (conflict-free STS.128) and written by ONE bulk tensor store, which also clips the ragged right / bottom edge.
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const bool issuer = (threadIdx.x == 192);
-        const uint32_t stage0 = smem_u32(smem + L::kStageOffset);
-        uint32_t unit = 0;
+        const int grp = (warp - 6) >> 2;                          // epilogue group 0 / 1: units with cc % 2 == grp, own staging buffer + named barrier
+        const bool issuer = (threadIdx.x == 192 + grp * 128);
+        const uint32_t stage = smem_u32(smem + L::kStageOffset) + (uint32_t)grp * 16384u;
         int it = 0;
         for (int g = cid; g < p.total_groups; g += ncl, it++)
         {
@@ -306,12 +306,12 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 const int ox = tc.ox0 + 8 * h + (row & 7);
                 const bool valid = (oy < p.out_h) && (ox < p.out_w);
 #pragma unroll 1
-                for (int cc = 0; cc < BN / 32; cc++, unit++)
+                for (int cc = grp; cc < BN / 32; cc += 2)
                 {
                     uint32_t v[32];
                     tmem_ld_32x32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN + cc * 32), v);
                     tmem_ld_wait();
-                    if (h == MH - 1 && cc == BN / 32 - 1)
+                    if (h == MH - 1 && cc == BN / 32 - 2 + grp)
                     {
                         // the accumulator buffer is in registers now: hand it back to the MMA issuer before the stores
                         tc_fence_before();
@@ -335,9 +335,8 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     }
                     const float4* osc = p.o_scale ? reinterpret_cast<const float4*>(p.o_scale + (long long)tc.n * p.cout + tc.nb0 + cc * 32) : nullptr;
                     const float4* bia = p.bias ? reinterpret_cast<const float4*>(p.bias + tc.nb0 + cc * 32) : nullptr;
-                    const uint32_t stage = stage0 + (unit & 1u) * 16384u;
-                    if (issuer) bulk_wait_read<1>();                 // the store issued two units ago has finished reading this buffer
-                    named_bar_sync(1, 128);
+                    if (issuer) bulk_wait_read<0>();                 // this group's previous store has finished reading the staging buffer
+                    named_bar_sync(1 + grp, 128);
 #pragma unroll
                     for (int j = 0; j < 8; j++)
                     {
@@ -356,7 +355,7 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         sts128(stage + (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4), make_float4(o[0], o[1], o[2], o[3]));
                     }
                     fence_proxy_async_smem();
-                    named_bar_sync(1, 128);
+                    named_bar_sync(1 + grp, 128);
                     if (issuer)
                     {
                         if (p.accumulate) tma_reduce_add_4d(&tmap_y, stage, tc.nb0 + cc * 32, tc.ox0 + 8 * h, tc.oy0, tc.n);
