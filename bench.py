@@ -285,11 +285,11 @@ def main():
         per_layer.append(dict(layer=name, ms=ms, tflops=fl / ms / 1e9, flops=fl))
         del x, wp
     dom = max(per_layer, key=lambda z: z['ms'])
-    # DRAM bytes per launch of these kernels from the committed `ncu --set full` capture (profiles/ncu_v3_r1y_summary.txt):
-    # dram__bytes_read.sum + dram__bytes_write.sum; the algorithmic minimum is x once + y once
-    ncu_traffic = {'b256.conv1': 537123584 + 484198656, 'b128.conv1': 269219328 + 214358272, 'b64.conv1': 137792768 + 81528320}
+    # DRAM bytes per launch of these kernels from the committed `ncu --set full` captures (profiles/ncu_final_r1aw_summary.txt, b64 from
+    # profiles/ncu_v3_r1y_summary.txt): dram__bytes_read.sum + dram__bytes_write.sum; the algorithmic minimum is x once + y once
+    ncu_traffic = {'b256.conv1': 537104000 + 483684352, 'b128.conv1': 269128704 + 215464960, 'b64.conv1': 137792768 + 81528320, 'b32.conv1': 81619000 + 19873792}
     roofline = dict(bound='tensor', kernel=f"conv_tf32_v3_kernel @ {dom['layer']} (N={N})", achieved=dom['tflops'], peak=peaks['bf16_tflops'],
-                    unit='TFLOP/s', frac=dom['tflops'] / peaks['bf16_tflops'], traffic=ncu_traffic.get(dom['layer']), traffic_unit='bytes/launch (ncu, profiles/ncu_v3_r1y_summary.txt)',
+                    unit='TFLOP/s', frac=dom['tflops'] / peaks['bf16_tflops'], traffic=ncu_traffic.get(dom['layer']), traffic_unit='bytes/launch (ncu, profiles/ncu_final_r1aw_summary.txt)',
                     peak_source=peaks['source'] + ' (dense bf16 cuBLAS; the kernel runs kind::tf32, whose measured issue-rate ceiling is 1164 TFLOP/s for N >= 128 and '
                                                   '776 TFLOP/s for N = 64 output channels — profiles/mma_rate_probe_r1.txt)',
                     tf32_issue_rate_ceiling_tflops=776.0 if dom['layer'] == 'b256.conv1' else 1164.0,

@@ -496,7 +496,9 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
     // (profiles/conv_v3_ablation_r1.txt): 256->256 ch 0.263 vs 0.242 ms, 512->512 ch 0.230 vs 0.267 ms for BN = 256 vs 128.
     static int max_bn = 0;
     if (max_bn == 0) { const char* e = getenv("SGV_V3_MAXBN"); max_bn = e ? atoi(e) : 256; }
-    const bool wide = p->cout % 256 == 0 && max_bn >= 256 && p->cin >= 512 && pixel_tiles * (p->cout / 256) >= num_sms();
+    static int wide_cin = 0;
+    if (wide_cin == 0) { const char* e = getenv("SGV_V3_WIDE_CIN"); wide_cin = e ? atoi(e) : 512; }
+    const bool wide = p->cout % 256 == 0 && max_bn >= 256 && p->cin >= wide_cin && pixel_tiles * (p->cout / 256) >= num_sms();
     const int bn = wide ? 256 : (p->cout % 128 == 0 && max_bn >= 128) ? 128 : 64;
     a.ntiles_n = p->cout / bn;
     if (st == 2 && pixel_tiles * a.ntiles_n < (3 * num_sms()) / 4) return SGV_ERR_UNSUPPORTED;     // too few tiles for one CTA per SM: the per-tap kernel's finer grid wins
