@@ -1,0 +1,79 @@
+/*
+ * sgv_b200_aux.h — C ABI of the two small pieces either side of the contraction stack (same contract as sgv_b200.h:
+ * caller-owned buffers, explicit stream, no allocation / synchronisation, int status + sgv_last_error()).
+ *
+ *   1. the elementwise tail of the continuous Fourier time-encoder (AlignedTimeEncoder.forward,
+ *      src/training/motion.py:185-214) and its gradient;
+ *   2. the parameter update that follows every backward pass: nan_to_num on the gradients, Adam, and the
+ *      G_ema lerp (src/training/training_loop.py:381-386,392-400) as ONE pass over flat fp32 buffers.
+ */
+#ifndef SGV_B200_AUX_H
+#define SGV_B200_AUX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Fourier time-encoder tail --------------------------------------------------------------------
+ * Replaces ~25 PyTorch kernels of AlignedTimeEncoder.forward (motion.py:198-212).  With F = num_freqs and, per row m,
+ *   heads_left[m]     = [P u_L | Phi u_L | A u_L]  (F + F + 2F columns: the three bias-free predictors of motion.py:174-180
+ *                       applied to the left neighbour code u_L as one stacked GEMM by the caller)
+ *   aligners_right[m] = A u_R                       (2F columns)
+ *   r = t mod d (python remainder), t_L = t - r, t_R = t_L + d, a = r / d          (motion.py:105-115)
+ *   raw(tau)[f] = freqs[f] * (tanh(P u_L)[f] + 1) * tau + (Phi u_L)[f] * phase_scales[f]          (motion.py:201-203)
+ *   out[m, f]     = sin raw(t) - lerp(sin raw(t_L), sin raw(t_R), a) + lerp(A u_L, A u_R, a)[f]
+ *   out[m, F + f] = cos ...                                                    + lerp(...)[F + f]  (motion.py:205-212)
+ * Arithmetic: every product / sum is rounded separately (no FMA contraction) in the reference's operation order, so
+ * `raw` is bit-identical to the PyTorch expression; sin/cos/tanh are the accurate libdevice functions (arguments reach
+ * hundreds of radians — no fast-math intrinsics).
+ * The gradient entry point recomputes sin/cos and returns d(heads_left) [m, 4F] and d(aligners_right) [m, 2F]; t is not
+ * differentiated (the reference never asks for it).
+ */
+int sgv_time_encoder_fwd(const float* heads_left, const float* aligners_right, const float* t,
+                         const float* freqs, const float* phase_scales, float* out,
+                         int32_t m, int32_t num_freqs, float motion_z_distance, void* stream);
+int sgv_time_encoder_bwd(const float* dout, const float* heads_left, const float* t,
+                         const float* freqs, const float* phase_scales, float* d_heads_left, float* d_aligners_right,
+                         int32_t m, int32_t num_freqs, float motion_z_distance, void* stream);
+
+/* ---- fused optimiser step ---------------------------------------------------------------------------
+ * One pass over flat fp32 buffers of `numel` elements (all parameters of a module laid out back to back, gradients
+ * in the matching flat buffer that the NCCL all-reduce ran on):
+ *   g      = clamp(nan->0 (grad * grad_scale), -grad_clamp, +grad_clamp)         misc.nan_to_num(nan=0, posinf=1e5, neginf=-1e5)
+ *                                                                                 = clamp(nansum) (torch_utils/misc.py:49-56)
+ *   m      = m + (g - m) * (1 - beta1)                                           torch.optim.Adam (training_loop.py:386,
+ *   v      = v * beta2 + (1 - beta2) * g * g                                      opt_kwargs train.py:192-193: betas (0, 0.99), eps 1e-8)
+ *   p      = p - step_size * m / (sqrt(v) / bias_correction2_sqrt + eps)
+ *   p_ema  = lerp(p, p_ema, ema_beta)   (optional; torch.lerp's two-sided formula)  training_loop.py:392-400
+ *   grad   = 0                          (optional; replaces zero_grad)
+ * with step_size = lr / (1 - beta1^t) and bias_correction2_sqrt = sqrt(1 - beta2^t) evaluated in double like torch does.
+ * The step number t comes either by value (`step`, host-side counter) or — for launches that sit inside a replayed CUDA
+ * graph — from the DEVICE counter `step_count`: with `advance_step` != 0 a one-thread kernel increments it first, so each
+ * replay is the next optimiser step without any host involvement.
+ * Buffers must be 16-byte aligned.  HBM traffic per parameter: 5 loads + 4 stores of 4 B with EMA and gradient zeroing.
+ */
+typedef struct sgv_adam_params {
+    float*       param;
+    float*       grad;
+    float*       exp_avg;
+    float*       exp_avg_sq;
+    float*       param_ema;              /* NULL = no EMA update */
+    int64_t      numel;
+    float        lr, beta1, beta2, eps;
+    float        ema_beta;
+    float        grad_scale;             /* 1 = none; e.g. 1/world_size after a sum all-reduce */
+    float        grad_clamp;             /* <= 0 disables the nan_to_num + clamp */
+    int32_t      step;                   /* t >= 1, used when step_count == NULL */
+    int32_t*     step_count;             /* optional device counter holding t (see above) */
+    int32_t      advance_step;           /* != 0: ++*step_count before the update */
+    int32_t      zero_grad;              /* != 0: store zeros to grad */
+} sgv_adam_params;
+
+int sgv_adam_ema_step(const sgv_adam_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGV_B200_AUX_H */

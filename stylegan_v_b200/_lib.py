@@ -77,8 +77,19 @@ class WgradParams(ctypes.Structure):
     ]
 
 
+class AdamParams(ctypes.Structure):
+    """struct sgv_adam_params (include/sgv_b200_aux.h)"""
+    _fields_ = [
+        ('param', c_vp), ('grad', c_vp), ('exp_avg', c_vp), ('exp_avg_sq', c_vp), ('param_ema', c_vp),
+        ('numel', c_i64),
+        ('lr', c_f32), ('beta1', c_f32), ('beta2', c_f32), ('eps', c_f32),
+        ('ema_beta', c_f32), ('grad_scale', c_f32), ('grad_clamp', c_f32),
+        ('step', c_int), ('step_count', c_vp), ('advance_step', c_int), ('zero_grad', c_int),
+    ]
+
+
 STRUCTS = {'sgv_upfirdn2d_params': UpfirdnParams, 'sgv_bias_act_params': BiasActParams, 'sgv_conv_params': ConvParams,
-           'sgv_wgrad_params': WgradParams}
+           'sgv_wgrad_params': WgradParams, 'sgv_adam_params': AdamParams}
 
 # every symbol include/sgv_b200*.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -101,6 +112,9 @@ SYMBOLS = [
     ('sgv_modconv_scale_reduce', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     ('sgv_torgb_fwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     ('sgv_torgb_bwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
+    ('sgv_time_encoder_fwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_vp]),
+    ('sgv_time_encoder_bwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_vp]),
+    ('sgv_adam_ema_step', c_int, [ctypes.POINTER(AdamParams), c_vp]),
 ]
 
 _lib = None

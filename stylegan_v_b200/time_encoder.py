@@ -10,12 +10,53 @@ Computation (same maths, reorganised):
   embedding      emb(tau) = [sin, cos](freqs * (tanh(P u_L) + 1) * tau + (Phi u_L) * phase_scales)
                  v = emb(t) - lerp(emb(t_L), emb(t_R), alpha) + lerp(A u_L, A u_R, alpha)         (motion.py:198-212)
 The three predictors on u_L share one stacked GEMM ([P; Phi; A]).  Arguments of sin/cos reach ~800 rad, so accurate
-(not fast-math) sin/cos are required for parity; the elementwise tail currently runs as PyTorch ops (it is <0.1% of a
-forward pass: [B*F, 512] elements).
+(not fast-math) sin/cos are required for parity.  On CUDA the whole elementwise tail (remainder / neighbour positions,
+tanh, three phase arguments, sin/cos, both lerps) is ONE kernel forward and ONE backward (csrc/time_encoder.cu,
+`sgv_time_encoder_fwd/_bwd`) instead of ~25 + ~60 PyTorch launches; CPU tensors evaluate the same expression with
+PyTorch ops like the reference does.
 """
+import ctypes
+
 import numpy as np
 import torch
 import torch.nn.functional as F
+
+from . import _lib
+
+
+class _TimeEncoderTail(torch.autograd.Function):
+    """out = emb(t) - lerp(emb(t_L), emb(t_R), a) + lerp(A u_L, A u_R, a) from the stacked predictor outputs (CUDA, fp32)."""
+
+    @staticmethod
+    def forward(ctx, heads_left, aligners_right, t, freqs, phase_scales, d):
+        heads_left, aligners_right = heads_left.contiguous(), aligners_right.contiguous()
+        t = t.to(torch.float32).contiguous()
+        freqs, phase_scales = freqs.reshape(-1).contiguous(), phase_scales.reshape(-1).contiguous()
+        m, nf = t.numel(), freqs.numel()
+        assert heads_left.shape == (m, 4 * nf) and aligners_right.shape == (m, 2 * nf)
+        assert heads_left.dtype == aligners_right.dtype == freqs.dtype == phase_scales.dtype == torch.float32
+        out = torch.empty([m, 2 * nf], dtype=torch.float32, device=t.device)
+        with torch.cuda.device(t.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+            _lib.check(_lib.lib().sgv_time_encoder_fwd(heads_left.data_ptr(), aligners_right.data_ptr(), t.data_ptr(), freqs.data_ptr(),
+                                                       phase_scales.data_ptr(), out.data_ptr(), m, nf, float(d), stream), 'sgv_time_encoder_fwd')
+        ctx.save_for_backward(heads_left, t, freqs, phase_scales)
+        ctx.d = float(d)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        heads_left, t, freqs, phase_scales = ctx.saved_tensors
+        m, nf = t.numel(), freqs.numel()
+        dout = dout.to(torch.float32).contiguous()
+        dhl = torch.empty_like(heads_left)
+        dar = torch.empty([m, 2 * nf], dtype=torch.float32, device=t.device)
+        with torch.cuda.device(t.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+            _lib.check(_lib.lib().sgv_time_encoder_bwd(dout.data_ptr(), heads_left.data_ptr(), t.data_ptr(), freqs.data_ptr(), phase_scales.data_ptr(),
+                                                       dhl.data_ptr(), dar.data_ptr(), m, nf, ctx.d, stream), 'sgv_time_encoder_bwd')
+        return dhl, dar, None, None, None, None
 
 
 def linspaced_frequencies(num_freqs, min_period_len, max_period_len):
@@ -94,13 +135,17 @@ class AlignedTimeEncoder(torch.nn.Module):
     def get_dim(self):
         return self.freqs.shape[1] * 2
 
-    def forward(self, t, u_left, u_right, alpha, t_left, t_right):
-        """t, t_left, t_right [M]; u_left, u_right [M, latent]; alpha [M, 1] -> [M, 2*num_freqs]."""
+    def forward(self, t, u_left, u_right, alpha, t_left, t_right, motion_z_distance=None):
+        """t, t_left, t_right [M]; u_left, u_right [M, latent]; alpha [M, 1] -> [M, 2*num_freqs].
+        With `motion_z_distance` (d) given, CUDA inputs run the fused tail kernel, which derives t_left / t_right / alpha from
+        (t, d) itself exactly as MotionMappingNetwork does (motion.py:111-115)."""
         nf = self.freqs.shape[1]
         # one stacked GEMM for the three heads on u_left, one for the aligners on u_right
         heads = torch.cat([self.periods_predictor.weight, self.phase_predictor.weight, self.aligners_predictor.weight], dim=0)
         gain = self.periods_predictor.weight_gain
         hl = u_left.matmul((heads * gain).t())
+        if motion_z_distance is not None and t.is_cuda and hl.dtype == torch.float32:
+            return _TimeEncoderTail.apply(hl, self.aligners_predictor(u_right), t.reshape(-1), self.freqs, self.phase_scales, motion_z_distance)
         periods = hl[:, :nf].tanh() + 1
         phases = hl[:, nf:2 * nf]
         al_left = hl[:, 2 * nf:]
@@ -149,7 +194,11 @@ class MotionMappingNetwork(torch.nn.Module):
         rows = torch.arange(B, device=t.device).unsqueeze(1).expand(B, Fr)
         u_left = trajs[rows, left].reshape(B * Fr, -1)
         u_right = trajs[rows, left + 1].reshape(B * Fr, -1)
-        t_left = t - t % d
-        alpha = ((t % d) / d).reshape(-1, 1).to(torch.float32)
-        v = self.time_encoder(t.reshape(-1), u_left, u_right, alpha, t_left.reshape(-1), (t_left + d).reshape(-1))
+        if t.is_cuda and (t.dtype == torch.float32 or not t.dtype.is_floating_point):
+            # fused tail: remainder / neighbour positions / alpha are derived from (t, d) inside the kernel (exact for integer frame indices too)
+            v = self.time_encoder(t.reshape(-1).to(torch.float32), u_left, u_right, None, None, None, motion_z_distance=d)
+        else:
+            t_left = t - t % d
+            alpha = ((t % d) / d).reshape(-1, 1).to(torch.float32)
+            v = self.time_encoder(t.reshape(-1), u_left, u_right, alpha, t_left.reshape(-1), (t_left + d).reshape(-1))
         return dict(motion_v=v, motion_z=motion_z)
