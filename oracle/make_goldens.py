@@ -207,6 +207,100 @@ def gen_synthesis(ref):
     np.savez_compressed(os.path.join(OUT, 'synthesis_tiny.npz'), **out)
 
 
+TINY_D = dict(img_resolution=32, channel_base=1024, channel_max=32, num_frames_per_video=3, max_num_frames=1024, concat_res=16,
+              num_frames_div_factor=2, mbstd_group_size=2, mapping_layers=2)
+
+
+def gen_discriminator(ref):
+    """Reference Discriminator (networks.py:580-673) on a tiny config: logits, first-order parameter gradients of the Dmain loss terms
+    and the R1 double-backward (loss.py:151-160), plus the 2-layer Generator mapping network."""
+    d = TINY_D
+    dcfg = ref_loader.to_cfg(dict(sampling=dict(num_frames_per_video=d['num_frames_per_video'], max_num_frames=d['max_num_frames'], type='random'),
+                                  concat_res=d['concat_res'], num_frames_div_factor=d['num_frames_div_factor'], dummy_c=False))
+    torch.manual_seed(3)
+    D = ref.networks.Discriminator(c_dim=0, img_resolution=d['img_resolution'], img_channels=3, channel_base=d['channel_base'],
+                                   channel_max=d['channel_max'], cfg=dcfg, mapping_kwargs=dict(num_layers=d['mapping_layers']),
+                                   epilogue_kwargs=dict(mbstd_group_size=d['mbstd_group_size']))
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for n, p in D.named_parameters():
+            if n.endswith('.bias'):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    B, Fr, R = 2, d['num_frames_per_video'], d['img_resolution']
+    img = torch.randn(B * Fr, 3, R, R, generator=g).requires_grad_(True)
+    t = torch.tensor([[0.0, 5.0, 9.0], [100.0, 101.0, 131.0]])
+    c = torch.zeros(B, 0)
+    D.train()
+    logits = D(img, c, t)['image_logits']
+    params = dict(D.named_parameters())
+    names = sorted(params.keys())
+    loss = torch.nn.functional.softplus(-logits).mean()                                 # loss.py:146 (Dreal term)
+    grads = torch.autograd.grad(loss, [params[n] for n in names], retain_graph=True, allow_unused=True)
+    # R1: gradient of the logits w.r.t. the images, differentiated again w.r.t. the parameters (loss.py:151-160; gamma = 1)
+    with ref.conv2d_gradfix.no_weight_gradients():
+        r1_grads, = torch.autograd.grad(logits.sum(), [img], create_graph=True)
+    r1_penalty = r1_grads.square().sum([1, 2, 3])
+    loss_r1 = (r1_penalty * 0.5).view(-1, Fr).mean(dim=1).mean()
+    grads_r1 = torch.autograd.grad(loss_r1, [params[n] for n in names], allow_unused=True)
+    out = {}
+    for k, v in D.state_dict().items():
+        out['p:' + k] = v.detach().numpy()
+    out.update(img=img.detach().numpy(), t=t.numpy(), logits=logits.detach().numpy(), r1_grads=r1_grads.detach().numpy(),
+               r1_penalty=r1_penalty.detach().numpy())
+    for n, a, b in zip(names, grads, grads_r1):
+        if a is not None:
+            out['g:' + n] = a.numpy()
+        if b is not None:
+            out['r1:' + n] = b.numpy()
+    # Generator mapping network (layers.py:22-104): z -> ws, train mode updates w_avg
+    torch.manual_seed(5)
+    M = ref.layers.MappingNetwork(z_dim=16, c_dim=0, w_dim=24, num_ws=5, num_layers=2)
+    z = torch.randn(4, 16, generator=g)
+    M.train()
+    ws = M(z, torch.zeros(4, 0))
+    for k, v in M.state_dict().items():
+        out['m:' + k] = v.detach().numpy()
+    out.update(map_z=z.numpy(), map_ws=ws.detach().numpy())
+    M.eval()
+    out['map_ws_trunc'] = M(z, torch.zeros(4, 0), truncation_psi=0.7, truncation_cutoff=3).detach().numpy()
+    out['meta'] = np.frombuffer(json.dumps(TINY_D).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, 'discriminator_tiny.npz'), **out)
+
+
+def gen_path_length(ref):
+    """Path-length regularisation through the reference synthesis network (loss.py:101-119): pl_grads = d(img * noise).sum() / d ws with
+    create_graph, penalty gradient w.r.t. parameters — a second-order quantity of the hot path."""
+    cfg = sr.SynthesisConfig(**TINY)
+    rcfg = ref_loader.to_cfg(cfg.reference_generator_cfg())
+    torch.manual_seed(0)
+    S = ref.networks.SynthesisNetwork(w_dim=cfg.w_dim, img_resolution=cfg.img_resolution, img_channels=3,
+                                      channel_base=cfg.channel_base, channel_max=cfg.channel_max, cfg=rcfg)
+    g = torch.Generator().manual_seed(11)
+    B = 2
+    ws = torch.randn(B, S.num_ws, cfg.w_dim, generator=g).requires_grad_(True)
+    t = torch.tensor([[3.0, 20.5, 40.0], [7.25, 8.0, 500.0]])
+    c = torch.zeros(B, 0)
+    mz = torch.randn(B, sr.max_traj_len(cfg, float(t.max())), cfg.motion_z_dim, generator=g)
+    S.train()
+    img = S(ws, t=t, c=c, motion_z=mz)
+    noise = torch.randn(img.shape, generator=g) / np.sqrt(img.shape[2] * img.shape[3])
+    with ref.conv2d_gradfix.no_weight_gradients():
+        pl_grads, = torch.autograd.grad([(img * noise).sum()], [ws], create_graph=True)
+    pl_lengths = pl_grads.square().sum(2).mean(1).sqrt()
+    pl_penalty = (pl_lengths - 0.5).square()
+    params = dict(S.named_parameters())
+    names = sorted(n for n in params if not n.startswith('motion_encoder'))
+    grads = torch.autograd.grad((img[:, 0, 0, 0] * 0 + (pl_penalty * 2.0).repeat_interleave(t.shape[1])).mean(), [params[n] for n in names], allow_unused=True)
+    out = {'p:' + k: v.detach().numpy() for k, v in S.state_dict().items()}
+    out.update(ws=ws.detach().numpy(), t=t.numpy(), motion_z=mz.numpy(), noise=noise.numpy(), pl_grads=pl_grads.detach().numpy(),
+               pl_lengths=pl_lengths.detach().numpy())
+    for n, a in zip(names, grads):
+        if a is not None:
+            out['g:' + n] = a.numpy()
+    out['meta'] = np.frombuffer(json.dumps(TINY).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, 'path_length_tiny.npz'), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
@@ -216,6 +310,8 @@ def main():
     gen_modconv(ref)
     gen_conv2d_resample(ref)
     gen_synthesis(ref)
+    gen_discriminator(ref)
+    gen_path_length(ref)
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
 

@@ -1,0 +1,331 @@
+"""Generator / Discriminator of StyleGAN-V around the native synthesis network — the callers either side of the hot path
+(SURVEY.md §8 rows a14-a16 and §8f rank 4), state-dict compatible with the reference so its checkpoints load:
+
+    Generator        mapping (MappingNetwork) + synthesis (stylegan_v_b200.synthesis.SynthesisNetwork)   networks.py:370-404
+    Discriminator    b{256..8} DiscriminatorBlock ('resnet'), frame concat at `concat_res`, time-difference
+                     conditioning (TemporalDifferenceEncoder -> MappingNetwork -> projection), b4 epilogue       networks.py:407-673
+
+Every convolution layer is `Conv2dLayer` = conv2d_resample + bias_act on the drop-in ops (layers.py:141-197): on CUDA the FIR
+and bias/activation kernels of libsgv_b200 and, through conv2d_gradfix, the tcgen05 implicit-GEMM kernels for every shape with
+channel counts % 32 (the 3-channel fromrgb and the 513-channel epilogue conv use the library call like the reference).  These
+ops are differentiable to any order, which the R1 penalty needs (loss.py:151-160).  fp16 blocks (`num_fp16_res`) are not built:
+the fp32 contract of BASELINE.json applies.
+"""
+import numpy as np
+import torch
+
+from .ops import bias_act, conv2d_resample, upfirdn2d
+from .synthesis import SynthesisNetwork
+
+
+def normalize_2nd_moment(x, dim=1, eps=1e-8):
+    return x * (x.square().mean(dim=dim, keepdim=True) + eps).rsqrt()
+
+
+class FullyConnectedLayer(torch.nn.Module):
+    """Equalised-lr dense layer with optional activation (layers.py:108-138)."""
+
+    def __init__(self, in_features, out_features, bias=True, activation='linear', lr_multiplier=1.0, bias_init=0.0):
+        super().__init__()
+        self.activation = activation
+        self.weight = torch.nn.Parameter(torch.randn(out_features, in_features) / lr_multiplier)
+        self.bias = torch.nn.Parameter(torch.full([out_features], float(bias_init))) if bias else None
+        self.weight_gain = lr_multiplier / np.sqrt(in_features)
+        self.bias_gain = lr_multiplier
+
+    def forward(self, x):
+        w = self.weight.to(x.dtype) * self.weight_gain
+        b = self.bias
+        if b is not None:
+            b = b.to(x.dtype)
+            if self.bias_gain != 1:
+                b = b * self.bias_gain
+        if self.activation == 'linear' and b is not None:
+            return torch.addmm(b.unsqueeze(0), x, w.t())
+        return bias_act.bias_act(x.matmul(w.t()), b, act=self.activation)
+
+
+class MappingNetwork(torch.nn.Module):
+    """z (and / or an embedded condition c) -> w, broadcast to num_ws rows, with the running w_avg (layers.py:22-104)."""
+
+    def __init__(self, z_dim, c_dim, w_dim, num_ws, num_layers=8, embed_features=None, layer_features=None, activation='lrelu',
+                 lr_multiplier=0.01, w_avg_beta=0.995):
+        super().__init__()
+        self.z_dim, self.c_dim, self.w_dim, self.num_ws, self.num_layers, self.w_avg_beta = z_dim, c_dim, w_dim, num_ws, num_layers, w_avg_beta
+        embed_features = 0 if c_dim == 0 else (w_dim if embed_features is None else embed_features)
+        layer_features = w_dim if layer_features is None else layer_features
+        widths = [z_dim + embed_features] + [layer_features] * (num_layers - 1) + [w_dim]
+        if c_dim > 0:
+            self.embed = FullyConnectedLayer(c_dim, embed_features)
+        for i in range(num_layers):
+            setattr(self, f'fc{i}', FullyConnectedLayer(widths[i], widths[i + 1], activation=activation, lr_multiplier=lr_multiplier))
+        if num_ws is not None and w_avg_beta is not None:
+            self.register_buffer('w_avg', torch.zeros([w_dim]))
+
+    def forward(self, z, c, truncation_psi=1, truncation_cutoff=None, skip_w_avg_update=False):
+        parts = []
+        if self.z_dim > 0:
+            assert z.shape[1] == self.z_dim
+            parts.append(normalize_2nd_moment(z.to(torch.float32)))
+        if self.c_dim > 0:
+            assert c.shape[1] == self.c_dim
+            parts.append(normalize_2nd_moment(self.embed(c.to(torch.float32))))
+        x = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+        for i in range(self.num_layers):
+            x = getattr(self, f'fc{i}')(x)
+        if self.w_avg_beta is not None and self.training and not skip_w_avg_update:
+            self.w_avg.copy_(x.detach().mean(dim=0).lerp(self.w_avg, self.w_avg_beta))
+        if self.num_ws is not None:
+            x = x.unsqueeze(1).repeat([1, self.num_ws, 1])
+        if truncation_psi != 1:
+            assert self.w_avg_beta is not None
+            if self.num_ws is None or truncation_cutoff is None:
+                x = self.w_avg.lerp(x, truncation_psi)
+            else:
+                x[:, :truncation_cutoff] = self.w_avg.lerp(x[:, :truncation_cutoff], truncation_psi)
+        return x
+
+
+class Conv2dLayer(torch.nn.Module):
+    """Equalised-lr convolution with optional 2x resampling, bias, activation, gain, clamp (layers.py:141-197)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, bias=True, activation='linear', up=1, down=1, resample_filter=(1, 3, 3, 1),
+                 conv_clamp=None, trainable=True):
+        super().__init__()
+        self.activation, self.up, self.down, self.conv_clamp = activation, up, down, conv_clamp
+        self.register_buffer('resample_filter', upfirdn2d.setup_filter(list(resample_filter)))
+        self.padding = kernel_size // 2
+        self.weight_gain = 1 / np.sqrt(in_channels * kernel_size ** 2)
+        self.act_gain = bias_act.activation_funcs[activation].def_gain
+        weight = torch.randn(out_channels, in_channels, kernel_size, kernel_size)
+        b = torch.zeros(out_channels) if bias else None
+        if trainable:
+            self.weight = torch.nn.Parameter(weight)
+            self.bias = torch.nn.Parameter(b) if b is not None else None
+        else:                                                      # Freeze-D (networks.py:441-447)
+            self.register_buffer('weight', weight)
+            if b is not None:
+                self.register_buffer('bias', b)
+            else:
+                self.bias = None
+
+    def forward(self, x, gain=1):
+        w = self.weight * self.weight_gain
+        b = self.bias.to(x.dtype) if self.bias is not None else None
+        x = conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down, padding=self.padding,
+                                            flip_weight=(self.up == 1))
+        clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        return bias_act.bias_act(x, b, act=self.activation, gain=self.act_gain * gain, clamp=clamp)
+
+
+class DiscriminatorBlock(torch.nn.Module):
+    """One resolution of the discriminator (networks.py:407-488): fromrgb (first block / 'skip'), conv0, conv1 (down 2) and, for
+    'resnet', the 1x1 down-2 skip branch; both branches scaled by sqrt(1/2)."""
+
+    def __init__(self, in_channels, tmp_channels, out_channels, resolution, img_channels, first_layer_idx, architecture='resnet',
+                 activation='lrelu', resample_filter=(1, 3, 3, 1), conv_clamp=None, freeze_layers=0):
+        assert architecture in ('orig', 'skip', 'resnet')
+        super().__init__()
+        self.in_channels, self.resolution, self.img_channels, self.architecture = in_channels, resolution, img_channels, architecture
+        self.register_buffer('resample_filter', upfirdn2d.setup_filter(list(resample_filter)))
+        self.num_layers = 0
+
+        def trainable():
+            flag = (first_layer_idx + self.num_layers) >= freeze_layers
+            self.num_layers += 1
+            return flag
+        conv0_in = in_channels if in_channels > 0 else tmp_channels
+        if in_channels == 0 or architecture == 'skip':
+            self.fromrgb = Conv2dLayer(img_channels, tmp_channels, 1, activation=activation, trainable=trainable(), conv_clamp=conv_clamp)
+        self.conv0 = Conv2dLayer(conv0_in, tmp_channels, 3, activation=activation, trainable=trainable(), conv_clamp=conv_clamp)
+        self.conv1 = Conv2dLayer(tmp_channels, out_channels, 3, activation=activation, down=2, trainable=trainable(),
+                                 resample_filter=resample_filter, conv_clamp=conv_clamp)
+        if architecture == 'resnet':
+            self.skip = Conv2dLayer(conv0_in, out_channels, 1, bias=False, down=2, trainable=trainable(), resample_filter=resample_filter)
+
+    def forward(self, x, img):
+        if x is not None:
+            assert x.shape[1] == self.in_channels and x.shape[2] == x.shape[3] == self.resolution
+            x = x.to(torch.float32)
+        if self.in_channels == 0 or self.architecture == 'skip':
+            assert img.shape[1] == self.img_channels and img.shape[2] == img.shape[3] == self.resolution
+            img = img.to(torch.float32)
+            y = self.fromrgb(img)
+            x = x + y if x is not None else y
+            img = upfirdn2d.downsample2d(img, self.resample_filter) if self.architecture == 'skip' else None
+        if self.architecture == 'resnet':
+            y = self.skip(x, gain=np.sqrt(0.5))
+            x = self.conv1(self.conv0(x), gain=np.sqrt(0.5))
+            x = y.add_(x)
+        else:
+            x = self.conv1(self.conv0(x))
+        return x, img
+
+
+class MinibatchStdLayer(torch.nn.Module):
+    """Appends the per-group standard deviation, averaged over channels and pixels, as extra feature maps (networks.py:492-516)."""
+
+    def __init__(self, group_size, num_channels=1):
+        super().__init__()
+        self.group_size, self.num_channels = group_size, num_channels
+
+    def forward(self, x):
+        N, C, H, W = x.shape
+        G = min(self.group_size, N) if self.group_size is not None else N
+        F = self.num_channels
+        y = x.reshape(G, -1, F, C // F, H, W)
+        y = y - y.mean(dim=0)
+        y = (y.square().mean(dim=0) + 1e-8).sqrt()
+        y = y.mean(dim=[2, 3, 4]).reshape(-1, F, 1, 1).repeat(G, 1, H, W)
+        return torch.cat([x, y], dim=1)
+
+
+class DiscriminatorEpilogue(torch.nn.Module):
+    """4x4 tail: minibatch-std, 3x3 conv, two dense layers, projection onto the mapped condition (networks.py:520-576)."""
+
+    def __init__(self, in_channels, cmap_dim, resolution, img_channels, architecture='resnet', mbstd_group_size=4, mbstd_num_channels=1,
+                 activation='lrelu', conv_clamp=None):
+        assert architecture in ('orig', 'skip', 'resnet')
+        super().__init__()
+        self.in_channels, self.cmap_dim, self.resolution, self.img_channels, self.architecture = in_channels, cmap_dim, resolution, img_channels, architecture
+        if architecture == 'skip':
+            self.fromrgb = Conv2dLayer(img_channels, in_channels, 1, activation=activation)
+        self.mbstd = MinibatchStdLayer(mbstd_group_size, mbstd_num_channels) if mbstd_num_channels > 0 else None
+        self.conv = Conv2dLayer(in_channels + mbstd_num_channels, in_channels, 3, activation=activation, conv_clamp=conv_clamp)
+        self.fc = FullyConnectedLayer(in_channels * resolution ** 2, in_channels, activation=activation)
+        self.out = FullyConnectedLayer(in_channels, 1 if cmap_dim == 0 else cmap_dim)
+
+    def forward(self, x, img, cmap):
+        assert x.shape[1] == self.in_channels and x.shape[2] == x.shape[3] == self.resolution
+        x = x.to(dtype=torch.float32, memory_format=torch.contiguous_format)
+        if self.architecture == 'skip':
+            x = x + self.fromrgb(img.to(dtype=torch.float32, memory_format=torch.contiguous_format))
+        if self.mbstd is not None:
+            x = self.mbstd(x)
+        x = self.conv(x)
+        # flatten in (C, H, W) order like the reference, whatever memory format the conv returned
+        x = self.out(self.fc(x.contiguous().flatten(1)))
+        if self.cmap_dim > 0:
+            assert cmap.shape[1] == self.cmap_dim
+            x = (x * cmap).sum(dim=1, keepdim=True) * (1 / np.sqrt(self.cmap_dim))
+        return x
+
+
+def log_spaced_frequencies(max_num_frames, skip_small_t_freqs=0):
+    """pi * 2^k / T for k < log2 T, T = max_num_frames rounded up to a power of two (layers.py:439-446)."""
+    resolution = 2 ** int(np.ceil(np.log2(max_num_frames)))
+    count = int(np.ceil(np.log2(resolution)))
+    powers = (2 ** torch.arange(count))[:count - skip_small_t_freqs]
+    return powers.unsqueeze(0).float() * np.pi / resolution
+
+
+class FixedTimeEncoder(torch.nn.Module):
+    """[sin, cos](coefs * t) with fixed log-spaced coefficients (layers.py:300-327)."""
+
+    def __init__(self, max_num_frames, skip_small_t_freqs=0):
+        super().__init__()
+        assert max_num_frames >= 1
+        self.register_buffer('fourier_coefs', log_spaced_frequencies(max_num_frames, skip_small_t_freqs))
+
+    def get_dim(self):
+        return self.fourier_coefs.shape[1] * 2
+
+    def forward(self, t):
+        assert t.ndim == 2
+        raw = self.fourier_coefs * t.reshape(-1).float().unsqueeze(1)
+        return torch.cat([raw.sin(), raw.cos()], dim=1)
+
+
+class TemporalDifferenceEncoder(torch.nn.Module):
+    """Condition of the discriminator: learned + Fourier embedding of the frame distances of a clip (layers.py:255-296)."""
+
+    def __init__(self, num_frames_per_video, max_num_frames, sampling_type='random', skip_small_t_freqs=0):
+        super().__init__()
+        self.num_frames_per_video, self.sampling_type = num_frames_per_video, sampling_type
+        if num_frames_per_video > 1:
+            self.d = 256
+            self.const_embed = torch.nn.Embedding(max_num_frames, self.d)
+            self.time_encoder = FixedTimeEncoder(max_num_frames, skip_small_t_freqs=skip_small_t_freqs)
+
+    def get_dim(self):
+        if self.num_frames_per_video == 1:
+            return 1
+        per_diff = self.d + self.time_encoder.get_dim()
+        return per_diff if self.sampling_type == 'uniform' else per_diff * (self.num_frames_per_video - 1)
+
+    def forward(self, t):
+        assert t.ndim == 2 and t.shape[1] == self.num_frames_per_video
+        B = t.shape[0]
+        if self.num_frames_per_video == 1:
+            return torch.zeros(B, 1, device=t.device)
+        diffs = (t[:, 1] - t[:, 0]) if self.sampling_type == 'uniform' else (t[:, 1:] - t[:, :-1]).reshape(-1)
+        emb = torch.cat([self.const_embed(diffs.float().round().long()), self.time_encoder(diffs.unsqueeze(1))], dim=1)
+        return emb.reshape(B, -1)
+
+
+class Discriminator(torch.nn.Module):
+    """StyleGAN-V discriminator (networks.py:580-673).  Frames of a clip are processed independently down to `concat_res`, where the
+    channel dimension of the F frames is concatenated; logits are conditioned on the frame time differences."""
+
+    def __init__(self, c_dim=0, img_resolution=256, img_channels=3, architecture='resnet', channel_base=16384, channel_max=512,
+                 conv_clamp=None, cmap_dim=None, num_frames_per_video=3, max_num_frames=1024, sampling_type='random', concat_res=16,
+                 num_frames_div_factor=2, dummy_c=False, mbstd_group_size=4, mbstd_num_channels=1, mapping_layers=2, freeze_layers=0,
+                 resample_filter=(1, 3, 3, 1)):
+        super().__init__()
+        self.c_dim, self.img_resolution, self.img_channels = c_dim, img_resolution, img_channels
+        self.num_frames_per_video, self.concat_res, self.dummy_c = num_frames_per_video, concat_res, dummy_c
+        log2 = int(np.log2(img_resolution))
+        self.block_resolutions = [2 ** i for i in range(log2, 2, -1)]
+        ch = {res: min(channel_base // res, channel_max) for res in self.block_resolutions + [4]}
+        if cmap_dim is None:
+            cmap_dim = ch[4]
+        self.time_encoder = TemporalDifferenceEncoder(num_frames_per_video, max_num_frames, sampling_type) if num_frames_per_video > 1 else None
+        if c_dim == 0 and self.time_encoder is None:
+            cmap_dim = 0
+        total_c_dim = c_dim + (0 if self.time_encoder is None else self.time_encoder.get_dim())
+        layer_idx = 0
+        for res in self.block_resolutions:
+            cin = ch[res] if res < img_resolution else 0
+            cout = ch[res // 2]
+            if res // 2 == concat_res:
+                cout = cout // num_frames_div_factor
+            if res == concat_res:
+                cin = (cin // num_frames_div_factor) * num_frames_per_video
+            block = DiscriminatorBlock(cin, ch[res], cout, res, img_channels, layer_idx, architecture=architecture, conv_clamp=conv_clamp,
+                                       freeze_layers=freeze_layers, resample_filter=resample_filter)
+            setattr(self, f'b{res}', block)
+            layer_idx += block.num_layers
+        if c_dim > 0 or self.time_encoder is not None:
+            self.mapping = MappingNetwork(z_dim=0, c_dim=total_c_dim, w_dim=cmap_dim, num_ws=None, w_avg_beta=None, num_layers=mapping_layers)
+        self.b4 = DiscriminatorEpilogue(ch[4], cmap_dim, 4, img_channels, architecture=architecture, mbstd_group_size=mbstd_group_size,
+                                        mbstd_num_channels=mbstd_num_channels, conv_clamp=conv_clamp)
+
+    def forward(self, img, c, t):
+        assert t.ndim == 2 and len(img) == t.shape[0] * t.shape[1]
+        if self.time_encoder is not None:
+            c = torch.cat([c, self.time_encoder(t.reshape(-1, self.num_frames_per_video))], dim=1)
+            if self.dummy_c:
+                c = c * 0.0
+        x = None
+        for res in self.block_resolutions:
+            if res == self.concat_res:
+                x = x.contiguous().reshape(-1, self.num_frames_per_video * x.shape[1], *x.shape[2:])     # [B, F*C, h, w] in (frame, channel) order
+            x, img = getattr(self, f'b{res}')(x, img)
+        cmap = self.mapping(None, c) if c.shape[1] > 0 else None
+        return {'image_logits': self.b4(x, img, cmap).squeeze(1)}
+
+
+class Generator(torch.nn.Module):
+    """z, c, t -> frames: mapping network + native synthesis network (networks.py:370-404)."""
+
+    def __init__(self, z_dim=512, c_dim=0, w_dim=512, img_resolution=256, img_channels=3, mapping_layers=2, **synthesis_kwargs):
+        super().__init__()
+        self.z_dim, self.c_dim, self.w_dim, self.img_resolution, self.img_channels = z_dim, c_dim, w_dim, img_resolution, img_channels
+        self.synthesis = SynthesisNetwork(w_dim=w_dim, img_resolution=img_resolution, img_channels=img_channels, **synthesis_kwargs)
+        self.num_ws = self.synthesis.num_ws
+        self.mapping = MappingNetwork(z_dim=z_dim, c_dim=c_dim, w_dim=w_dim, num_ws=self.num_ws, num_layers=mapping_layers)
+
+    def forward(self, z, c, t, truncation_psi=1, truncation_cutoff=None, **synthesis_kwargs):
+        assert len(z) == len(c) == len(t) and t.ndim == 2
+        ws = self.mapping(z, c, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff)
+        return self.synthesis(ws, t=t, c=c, **synthesis_kwargs)

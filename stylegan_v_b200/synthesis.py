@@ -20,6 +20,8 @@ import torch
 from . import conv as _conv
 from .modconv import fused_modulated_conv, demod_coefs, prepare_weights, WeightGradBox, WeightGradNode
 from .ops import upfirdn2d as _upfirdn2d
+from .ops import bias_act as _bias_act
+from .ops.modulated_conv import modulated_conv2d as _modulated_conv2d
 from .time_encoder import EqualizedLinear, MotionMappingNetwork
 
 
@@ -54,6 +56,21 @@ class SynthesisLayer(torch.nn.Module):
         return fused_modulated_conv(x, plan['weight'], plan['styles'], self.bias, up=self.up, demodulate=True, act='lrelu',
                                     gain=float(np.sqrt(2)) * gain, flip_weight=(self.up == 1), dcoefs=plan['dcoefs'], prep=plan['prep'],
                                     torgb_wmod=torgb_wmod, torgb_bias=torgb_bias, wbox=plan['wbox'])
+
+
+def _layer_unfused(layer, x, w, fused_modconv, gain=1.0):
+    """SynthesisLayer.forward of the reference (networks.py:124-144, use_noise = false) on the drop-in ops."""
+    styles = layer.affine(w)
+    x = _modulated_conv2d(x=x, weight=layer.weight, styles=styles, up=layer.up, padding=1, resample_filter=layer.resample_filter,
+                          flip_weight=(layer.up == 1), fused_modconv=fused_modconv)
+    return _bias_act.bias_act(x, layer.bias.to(x.dtype), act='lrelu', gain=float(np.sqrt(2)) * gain)
+
+
+def _torgb_unfused(layer, x, w, fused_modconv):
+    """ToRGBLayer.forward of the reference (networks.py:159-163) on the drop-in ops."""
+    styles = layer.affine(w) * layer.weight_gain
+    x = _modulated_conv2d(x=x, weight=layer.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
+    return _bias_act.bias_act(x, layer.bias.to(x.dtype))
 
 
 class _ToRGB(torch.autograd.Function):
@@ -165,6 +182,21 @@ class SynthesisBlock(torch.nn.Module):
         img = img.add_(y) if img is not None else y
         return x, img
 
+    def forward_unfused(self, x, img, ws, motion_v=None, fused_modconv=False):
+        """SynthesisBlock.forward of the reference (networks.py:224-266, 'skip' architecture, fp32) layer by layer on the drop-in ops:
+        differentiable to any order and runnable on CPU tensors.  ws [N, num_conv + num_torgb, w_dim]."""
+        w_iter = iter(ws.unbind(dim=1))
+        if self.in_channels == 0:
+            x = self.input(motion_v).contiguous()
+        else:
+            x = _layer_unfused(self.conv0, x, next(w_iter), fused_modconv)
+        x = _layer_unfused(self.conv1, x, next(w_iter), fused_modconv)
+        if img is not None:
+            img = _upfirdn2d.upsample2d(img, self.resample_filter)
+        y = _torgb_unfused(self.torgb, x, next(w_iter), fused_modconv).to(dtype=torch.float32, memory_format=torch.contiguous_format)
+        img = img.add_(y) if img is not None else y
+        return x, img
+
 
 class SynthesisNetwork(torch.nn.Module):
     def __init__(self, w_dim=512, img_resolution=256, img_channels=3, channel_base=16384, channel_max=512,
@@ -216,13 +248,31 @@ class SynthesisNetwork(torch.nn.Module):
                 out[id(l)] = piece
         return out
 
-    def forward(self, ws, t, c=None, motion_z=None, motion_v=None, t_max=None):
-        """ws [B, num_ws, w_dim], t [B, F] -> img [B*F, 3, R, R] (fp32, NCHW) — networks.py:324-366 semantics."""
+    def forward(self, ws, t, c=None, motion_z=None, motion_v=None, t_max=None, unfused=None, fused_modconv=None):
+        """ws [B, num_ws, w_dim], t [B, F] -> img [B*F, 3, R, R] (fp32, NCHW) — networks.py:324-366 semantics.
+
+        unfused=None (default): CUDA inputs run the fused NHWC layers (first-order differentiable); CPU inputs, or unfused=True,
+        run the layer-by-layer formulation on the drop-in ops (any-order differentiable: path-length regularisation).
+        fused_modconv only applies to the unfused formulation: None = the reference's rule (grouped per-sample-weight conv in eval
+        mode, shared-weight conv in training mode, networks.py:232)."""
         assert t.ndim == 2 and len(ws) == len(t)
         assert ws.shape[1] == self.num_ws and ws.shape[2] == self.w_dim
         if motion_v is None:
             motion_v = self.motion_encoder(t, motion_z=motion_z, t_max=t_max)['motion_v']
         ws = ws.to(torch.float32).repeat_interleave(t.shape[1], dim=0)
+        if unfused is None:
+            unfused = not ws.is_cuda
+        if unfused:
+            if fused_modconv is None:
+                fused_modconv = not self.training
+            x = img = None
+            w_idx = 0
+            for res in self.block_resolutions:
+                block = getattr(self, f'b{res}')
+                x, img = block.forward_unfused(x, img, ws.narrow(1, w_idx, block.num_conv + block.num_torgb), motion_v=motion_v,
+                                               fused_modconv=fused_modconv)
+                w_idx += block.num_conv
+            return img
         plans = self._plan_layers(ws)
         x = img = None
         for res in self.block_resolutions:
