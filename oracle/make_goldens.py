@@ -256,11 +256,11 @@ def gen_discriminator(ref):
     torch.manual_seed(5)
     M = ref.layers.MappingNetwork(z_dim=16, c_dim=0, w_dim=24, num_ws=5, num_layers=2)
     z = torch.randn(4, 16, generator=g)
+    for k, v in M.state_dict().items():
+        out['m:' + k] = v.detach().numpy().copy()
     M.train()
     ws = M(z, torch.zeros(4, 0))
-    for k, v in M.state_dict().items():
-        out['m:' + k] = v.detach().numpy()
-    out.update(map_z=z.numpy(), map_ws=ws.detach().numpy())
+    out.update(map_z=z.numpy(), map_ws=ws.detach().numpy(), map_w_avg_after=M.w_avg.numpy().copy())
     M.eval()
     out['map_ws_trunc'] = M(z, torch.zeros(4, 0), truncation_psi=0.7, truncation_cutoff=3).detach().numpy()
     out['meta'] = np.frombuffer(json.dumps(TINY_D).encode(), dtype=np.uint8)
@@ -301,6 +301,53 @@ def gen_path_length(ref):
     np.savez_compressed(os.path.join(OUT, 'path_length_tiny.npz'), **out)
 
 
+def gen_loss_phases(ref):
+    """The reference's StyleGAN2Loss.accumulate_gradients (loss.py:73-173) on tiny reference G and D, one call per phase with fixed RNG
+    state: per-parameter gradient sums and norms (+ a few full tensors) for Gmain, Dmain and Dreg (R1)."""
+    cfg = sr.SynthesisConfig(**TINY)
+    gcfg = ref_loader.to_cfg(cfg.reference_generator_cfg())
+    d = TINY_D
+    dcfg = ref_loader.to_cfg(dict(sampling=dict(num_frames_per_video=3, max_num_frames=d['max_num_frames'], type='random'),
+                                  concat_res=d['concat_res'], num_frames_div_factor=d['num_frames_div_factor'], dummy_c=False))
+    torch.manual_seed(21)
+    G = ref.networks.Generator(c_dim=0, w_dim=cfg.w_dim, img_resolution=cfg.img_resolution, img_channels=3, cfg=gcfg,
+                               mapping_kwargs=dict(num_layers=2),
+                               synthesis_kwargs=dict(channel_base=cfg.channel_base, channel_max=cfg.channel_max))
+    D = ref.networks.Discriminator(c_dim=0, img_resolution=d['img_resolution'], img_channels=3, channel_base=d['channel_base'],
+                                   channel_max=d['channel_max'], cfg=dcfg, mapping_kwargs=dict(num_layers=d['mapping_layers']),
+                                   epilogue_kwargs=dict(mbstd_group_size=d['mbstd_group_size']))
+    loss = ref.loss.StyleGAN2Loss(cfg=None, device=torch.device('cpu'), G_mapping=G.mapping, G_synthesis=G.synthesis, D=D,
+                                  style_mixing_prob=0.0, r1_gamma=0.5, pl_weight=0.0)
+    g = torch.Generator().manual_seed(22)
+    B, Fr, R = 2, 3, cfg.img_resolution
+    real = torch.randn(B, Fr, 3, R, R, generator=g).clamp(-1, 1)
+    real_t = torch.tensor([[0.0, 4.0, 20.0], [30.0, 31.0, 33.0]])
+    gen_t = torch.tensor([[2.0, 10.0, 11.0], [500.0, 516.0, 530.0]])
+    z = torch.randn(B, cfg.w_dim, generator=g)
+    c = torch.zeros(B, 0)
+    out = {'g:' + k: v.detach().numpy().copy() for k, v in G.state_dict().items()}     # copies: w_avg is updated in place below
+    out.update({'d:' + k: v.detach().numpy().copy() for k, v in D.state_dict().items()})
+    out.update(real=real.numpy(), real_t=real_t.numpy(), gen_t=gen_t.numpy(), z=z.numpy())
+    G.train(); D.train()
+    for phase, module, gain in [('Gmain', G, 1), ('Dmain', D, 1), ('Dreg', D, 16)]:
+        G.requires_grad_(module is G); D.requires_grad_(module is D)
+        for p in module.parameters():
+            p.grad = None
+        torch.manual_seed(100)                                   # motion noise z ~ randn inside G.synthesis (motion.py:83)
+        loss.accumulate_gradients(phase=phase, real_img=real, real_c=c, real_t=real_t, gen_z=z, gen_c=c, gen_t=gen_t, sync=True, gain=gain)
+        stats = {}
+        for n, p in module.named_parameters():
+            if p.grad is not None:
+                stats[n] = [float(p.grad.double().sum()), float(p.grad.double().norm())]
+        out['stats:' + phase] = np.frombuffer(json.dumps(stats).encode(), dtype=np.uint8)
+        keep = ['synthesis.b16.conv0.weight', 'mapping.fc1.weight', 'synthesis.b32.torgb.bias'] if module is G else ['b32.conv1.weight', 'b4.out.weight', 'b16.skip.weight']
+        for n in keep:
+            out[f'grad:{phase}:{n}'] = dict(module.named_parameters())[n].grad.numpy().copy()
+    out['w_avg_after'] = G.mapping.w_avg.numpy().copy()
+    out['meta'] = np.frombuffer(json.dumps(dict(G=TINY, D=TINY_D, r1_gamma=0.5)).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, 'loss_phases_tiny.npz'), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
@@ -312,6 +359,7 @@ def main():
     gen_synthesis(ref)
     gen_discriminator(ref)
     gen_path_length(ref)
+    gen_loss_phases(ref)
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
 

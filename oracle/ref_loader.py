@@ -79,5 +79,6 @@ def load():
     ns.networks = importlib.import_module('training.networks')
     ns.layers = importlib.import_module('training.layers')
     ns.motion = importlib.import_module('training.motion')
+    ns.loss = importlib.import_module('training.loss')
     _loaded = ns
     return ns

@@ -1,0 +1,150 @@
+"""The training phases around the hot path (BASELINE configs 3 and 4): loss terms, gradient exchange and parameter update.
+
+Follows the reference's StyleGAN2Loss.accumulate_gradients (src/training/loss.py:73-173) and the phase loop of
+training_loop.py:236-262,340-400, restricted to what StyleGAN-V's own config uses (c_dim = 0, no ADA pipe, style mixing off):
+
+    Gmain   softplus(-D(G(z, t)))                           gradients into G                 loss.py:84-99
+    Greg    path-length penalty (second order through G)    every G_reg_interval steps        loss.py:101-119
+    Dmain   softplus(D(G(z, t).detach())) + softplus(-D(real))                                loss.py:121-147
+    Dreg    R1 penalty gamma/2 * |d logits / d real|^2      every D_reg_interval steps        loss.py:149-160
+
+What is B200-specific is the plumbing: parameters, gradients, Adam moments and the EMA copy of each network live in flat fp32
+buffers (optim.FlatModuleState); a phase ends with ONE NCCL all-reduce of the flat gradient buffer and ONE fused
+nan_to_num + Adam (+ EMA) launch (csrc/optim_step.cu) that also re-zeroes the gradients.  Gmain / Dmain run the fused NHWC
+synthesis layers; Greg needs gradients of gradients and runs the synthesis network's `unfused` formulation on the drop-in ops.
+"""
+import copy
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .ops import conv2d_gradfix
+from .optim import FlatModuleState, FusedAdamEMA
+
+
+def generator_main_loss(G, D, z, c, t, **synthesis_kwargs):
+    img = G(z, c, t, **synthesis_kwargs)
+    return F.softplus(-D(img, c, t)['image_logits']).mean()
+
+
+def discriminator_main_loss(G, D, real_img, real_c, real_t, z, c, t, **synthesis_kwargs):
+    """Returns (loss on generated frames, loss on real frames); the reference backpropagates them separately (loss.py:139,173)."""
+    with torch.no_grad():
+        fake = G(z, c, t, **synthesis_kwargs)
+    loss_gen = F.softplus(D(fake, c, t)['image_logits']).mean()
+    loss_real = F.softplus(-D(real_img, real_c, real_t)['image_logits']).mean()
+    return loss_gen, loss_real
+
+
+def discriminator_r1_loss(D, real_img, real_c, real_t, r1_gamma):
+    img = real_img.detach().requires_grad_(True)
+    logits = D(img, real_c, real_t)['image_logits']
+    with conv2d_gradfix.no_weight_gradients():
+        grads, = torch.autograd.grad([logits.sum()], [img], create_graph=True, only_inputs=True)
+    penalty = grads.square().sum([1, 2, 3]) * (r1_gamma / 2)                      # per frame
+    per_clip = penalty.view(-1, len(img) // len(logits)).mean(dim=1)              # loss.py:158
+    return (logits * 0 + per_clip).mean()
+
+
+def generator_path_length_loss(G, z, c, t, pl_mean, pl_weight=2.0, pl_decay=0.01, pl_batch_shrink=2, **synthesis_kwargs):
+    """Path-length regularisation (loss.py:101-119).  pl_mean: 0-dim tensor, updated in place.  The reference's last line adds a [B]
+    penalty to a [B * F] dummy, which only broadcasts for F = 1 (its stylegan-v config disables the term); here the per-latent penalty
+    is averaged over latents, which is the same value for every F."""
+    n = max(z.shape[0] // pl_batch_shrink, 1)
+    ws = G.mapping(z[:n], c[:n])
+    img = G.synthesis(ws, t=t[:n], c=c[:n], unfused=True, **synthesis_kwargs)
+    noise = torch.randn_like(img) / np.sqrt(img.shape[2] * img.shape[3])
+    with conv2d_gradfix.no_weight_gradients():
+        grads, = torch.autograd.grad([(img * noise).sum()], [ws], create_graph=True, only_inputs=True)
+    lengths = grads.square().sum(2).mean(1).sqrt()
+    mean = pl_mean.lerp(lengths.mean(), pl_decay)
+    pl_mean.copy_(mean.detach())
+    return (img[:, 0, 0, 0].sum() * 0 + (lengths - mean).square() * pl_weight).mean()
+
+
+class TrainingPhases:
+    """G and D with flat state, lazily-regularised Adam (training_loop.py:243-250) and the EMA generator.
+
+    step(...) runs the phases due at this iteration in the reference's order (Gmain, [Greg], Dmain, [Dreg]) and returns their loss
+    values (tensors; no host sync)."""
+
+    def __init__(self, G, D, lr=0.0025, betas=(0.0, 0.99), eps=1e-8, r1_gamma=0.2048, pl_weight=0.0, G_reg_interval=4, D_reg_interval=16,
+                 ema_kimg=20.0, ema_rampup=None, batch_size=64, process_group=None, device_step=False):
+        assert next(G.parameters()).is_cuda, 'TrainingPhases drives the CUDA path only'
+        conv2d_gradfix.enabled = True                                               # training_loop.py:143
+        self.G, self.D = G, D
+        if getattr(G.synthesis, '_pstream', None) is not None:
+            G.synthesis._pstream = None                                             # a CUDA stream handle is not deep-copyable; it is re-created lazily
+        self.G_ema = copy.deepcopy(G).eval().requires_grad_(False)
+        self.r1_gamma, self.pl_weight = r1_gamma, pl_weight
+        self.G_reg_interval = G_reg_interval if pl_weight != 0 else None
+        self.D_reg_interval = D_reg_interval if r1_gamma != 0 else None
+        self.ema_kimg, self.ema_rampup, self.batch_size = ema_kimg, ema_rampup, batch_size
+        self.pl_mean = torch.zeros([], device=next(G.parameters()).device)
+        self.G_state = FlatModuleState(list(G.parameters()), list(self.G_ema.parameters()), process_group)
+        self.D_state = FlatModuleState(list(D.parameters()), None, process_group)
+
+        def make_opt(state, interval):
+            if interval is None:
+                return FusedAdamEMA(state, lr=lr, betas=betas, eps=eps, device_step=device_step)
+            r = interval / (interval + 1)                                            # lazy regularisation: training_loop.py:245-248
+            return FusedAdamEMA(state, lr=lr * r, betas=[b ** r for b in betas], eps=eps, device_step=device_step)
+        # main and regularisation phases of a network share one optimiser, like the reference's (name + 'main', name + 'reg') pairs
+        self.G_opt = make_opt(self.G_state, self.G_reg_interval)
+        self.D_opt = make_opt(self.D_state, self.D_reg_interval)
+        self.cur_nimg = 0
+        self.it = 0
+
+    def ema_beta(self):
+        nimg = self.ema_kimg * 1000
+        if self.ema_rampup is not None:
+            nimg = min(nimg, self.cur_nimg * self.ema_rampup)
+        return 0.5 ** (self.batch_size / max(nimg, 1e-8))                            # training_loop.py:393-396
+
+    def _finish(self, state, opt, ema_beta=None):
+        state.all_reduce()                                                           # SUM over ranks; 1/world is applied by the update kernel
+        opt.step(ema_beta=ema_beta, zero_grad=True)
+        if ema_beta is not None:
+            # buffers are copied, not averaged (training_loop.py:399-400); w_avg is the only G buffer that changes during training
+            self.G_ema.mapping.w_avg.copy_(self.G.mapping.w_avg)
+
+    def _grad_mode(self, train_G):
+        self.G.requires_grad_(train_G)
+        self.D.requires_grad_(not train_G)
+
+    def step(self, real_img, real_t, z, t, c=None, real_c=None, **synthesis_kwargs):
+        """One iteration: real_img [B*F, 3, R, R], real_t / t [B, F], z [B, z_dim].  EMA is applied with the G main phase's update
+        (the reference applies it after all phases of the iteration, training_loop.py:392-400 — same values, since only G phases change G
+        and the regularisation phase's update is folded in when it runs)."""
+        B = z.shape[0]
+        c = torch.zeros(B, 0, device=z.device) if c is None else c
+        real_c = torch.zeros(B, 0, device=z.device) if real_c is None else real_c
+        out = {}
+        do_greg = self.G_reg_interval is not None and self.it % self.G_reg_interval == 0
+        do_dreg = self.D_reg_interval is not None and self.it % self.D_reg_interval == 0
+        self.cur_nimg += self.batch_size
+        # ---- G phases
+        self._grad_mode(True)
+        loss = generator_main_loss(self.G, self.D, z, c, t, **synthesis_kwargs)
+        loss.backward()
+        out['Gmain'] = loss.detach()
+        self._finish(self.G_state, self.G_opt, ema_beta=None if do_greg else self.ema_beta())
+        if do_greg:
+            loss = generator_path_length_loss(self.G, z, c, t, self.pl_mean, self.pl_weight, **synthesis_kwargs)
+            loss.mul(self.G_reg_interval).backward()
+            out['Greg'] = loss.detach()
+            self._finish(self.G_state, self.G_opt, ema_beta=self.ema_beta())
+        # ---- D phases
+        self._grad_mode(False)
+        loss_gen, loss_real = discriminator_main_loss(self.G, self.D, real_img, real_c, real_t, z, c, t, **synthesis_kwargs)
+        (loss_gen + loss_real).backward()
+        out['Dmain'] = (loss_gen + loss_real).detach()
+        self._finish(self.D_state, self.D_opt)
+        if do_dreg:
+            loss = discriminator_r1_loss(self.D, real_img, real_c, real_t, self.r1_gamma)
+            loss.mul(self.D_reg_interval).backward()
+            out['Dreg'] = loss.detach()
+            self._finish(self.D_state, self.D_opt)
+        self.it += 1
+        return out

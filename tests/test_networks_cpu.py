@@ -62,14 +62,13 @@ def test_mapping_network_vs_reference_golden():
     g, _ = load_golden('discriminator_tiny.npz')
     M = MappingNetwork(z_dim=16, c_dim=0, w_dim=24, num_ws=5, num_layers=2)
     sd = {k[2:]: _t(g[k]) for k in g.files if k.startswith('m:')}
-    sd['w_avg'] = torch.zeros(24)                 # the golden state was saved after one training-mode call; restart from the initial average
     assert set(sd) == set(M.state_dict())
     M.load_state_dict(sd)
     M.train()
     z = _t(g['map_z'])
     ws = M(z, torch.zeros(4, 0))
     assert rel_err(ws, _t(g['map_ws'])) < 1e-6
-    assert rel_err(M.w_avg, _t(g['m:w_avg'])) < 1e-6                             # moving average after that one update
+    assert rel_err(M.w_avg, _t(g['map_w_avg_after'])) < 1e-6                     # moving average after that one update (layers.py:86-88)
     M.eval()
     assert rel_err(M(z, torch.zeros(4, 0), truncation_psi=0.7, truncation_cutoff=3), _t(g['map_ws_trunc'])) < 1e-6
 
