@@ -122,6 +122,119 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_gd_step(args):
+    """BASELINE configs[2]: 256x256 G + D training step, forward + backward, no regularisation phases, 3 frames / clip, 16 clips / GPU,
+    synthetic frames; phases Gmain + Dmain (loss.py:84-99,121-147) each followed by the all-reduce and the fused Adam (+ EMA) update.
+    frames/s = 48 frames per GPU and step / step time.  A secondary line: the headline metric stays `synthesis`."""
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device: the b200 implementation has no CPU path'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from stylegan_v_b200 import _lib
+    from stylegan_v_b200.networks import Generator, Discriminator
+    from stylegan_v_b200.train_step import TrainingPhases
+    args.warmup = max(args.warmup, 3)
+    torch.manual_seed(rank)
+    B, Fr = 16, 3
+    G = Generator(img_resolution=RES).to(dev).train()
+    D = Discriminator(img_resolution=RES, mbstd_group_size=4).to(dev).train()
+    tp = TrainingPhases(G, D, lr=0.0025, r1_gamma=0.0, pl_weight=0.0, batch_size=B * world, device_step=not args.no_graph)
+    h_real = torch.randn(B * Fr, 3, RES, RES).clamp_(-1, 1).pin_memory()
+    h_z = torch.randn(B, G.z_dim).pin_memory()
+    base = torch.randint(0, 900, (B, 1)).float()
+    h_t = (base + torch.tensor([[0.0, 5.0, 9.0]])).pin_memory()
+    s_real, s_z, s_t = h_real.to(dev), h_z.to(dev), h_t.to(dev)
+    h_out = torch.zeros(2).pin_memory()
+
+    def compute():
+        out = tp.step(s_real, s_t, s_z, s_t)
+        return torch.stack([out['Gmain'], out['Dmain']])
+    graph, graph_launches, s_loss = None, 0, None
+    if not args.no_graph and world == 1:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    compute()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                s_loss = compute()
+            graph_launches = _lib.launch_count() - l0
+        except Exception as e:
+            if rank == 0:
+                sys.stderr.write(f'[bench] CUDA graph capture failed ({type(e).__name__}: {e}); eager launches\n')
+            graph = None
+            torch.cuda.synchronize()
+
+    def step():
+        if graph is not None:
+            graph.replay()
+            return s_loss
+        return compute()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), _lib.launch_count() - l0
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches = timed(step, args.steps, args.warmup)
+    if graph is not None:
+        launches = graph_launches * args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    def e2e_step():
+        s_real.copy_(h_real, non_blocking=True); s_z.copy_(h_z, non_blocking=True); s_t.copy_(h_t, non_blocking=True)
+        h_out.copy_(step().detach(), non_blocking=True)
+    ms_e2e, _ = timed(e2e_step, args.steps, 1)
+    if rank == 0:
+        frames = B * Fr * world
+        ms_step = ms_total / args.steps
+        line = dict(metric='gd_training_step_frames_per_sec_256', value=frames / (ms_step * 1e-3), unit='frames/s', n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='tf32 (fp32 storage, TF32 tensor-core products, fp32 accumulate)', data='synthetic',
+                    config=dict(workload='BASELINE configs[2]: 256x256 G+D training step fwd+bwd (Gmain + Dmain, no reg), 3 frames/clip, 16 clips/GPU, '
+                                         'all-reduce + fused Adam/EMA update per phase', clips_per_gpu=B, frames_per_clip=Fr, parallelism=f'dp{world}',
+                                cuda_graph=graph is not None, l2='per-step activation working set >> 126 MB L2; no explicit flush',
+                                G_params=int(tp.G_state.numel), D_params=int(tp.D_state.numel)),
+                    e2e=dict(value=frames / (ms_e2e / args.steps * 1e-3), unit='frames/s',
+                             h2d_bytes_per_step=(h_real.numel() + h_z.numel() + h_t.numel()) * 4, d2h_bytes_per_step=8),
+                    gpu_launches=launches, clocks=clocks)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -130,9 +243,14 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph of the step')
+    ap.add_argument('--no-optimizer', action='store_true', help='time forward + backward only (no fused Adam update at the end of the step)')
+    ap.add_argument('--workload', default='synthesis', choices=['synthesis', 'gd_step'],
+                    help="synthesis = BASELINE metric (256x256 SynthesisNetwork fwd+bwd, configs[1] batch); gd_step = configs[2] (G+D training step, no reg)")
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.workload == 'gd_step':
+        return run_gd_step(args)
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
@@ -150,13 +268,16 @@ def main():
 
     from stylegan_v_b200 import _lib, conv as C, plugin
     from stylegan_v_b200.synthesis import SynthesisNetwork
-    from stylegan_v_b200.ddp import FlatGradReducer
+    from stylegan_v_b200.optim import FlatModuleState, FusedAdamEMA
     from stylegan_v_b200.ops import upfirdn2d as U
     from oracle import synthesis_ref as sr     # FLOP model + cpu_baseline only
 
     torch.manual_seed(rank)
     net = SynthesisNetwork(img_resolution=RES).to(dev).train()
-    reducer = FlatGradReducer(net.parameters())
+    # parameters / gradients / Adam moments in flat buffers: one all-reduce (N > 1) and one fused nan_to_num + Adam launch per step
+    # (training_loop.py:381-386 semantics; lr as train.py:160).  --no-optimizer times forward + backward alone.
+    state = FlatModuleState(list(net.parameters()))
+    opt = None if args.no_optimizer else FusedAdamEMA(state, lr=0.0025, betas=(0.0, 0.99), eps=1e-8)
     N = FRAMES_PER_GPU
     L = net.motion_encoder.traj_len()
     # host-side (pinned) inputs for the end-to-end measurement
@@ -168,7 +289,8 @@ def main():
     h_out = torch.zeros(1).pin_memory()
 
     def step_compute(ws, t, mz):
-        reducer.zero()
+        if opt is None:
+            state.zero_grad()                  # with the optimiser, its update kernel re-zeroes the gradient buffer
         ws = ws.requires_grad_(True)
         img = net(ws, t, motion_z=mz)
         loss = (img * dimg).sum()
@@ -199,6 +321,7 @@ def main():
                 sys.stderr.write(f'[bench] CUDA graph capture failed ({type(e).__name__}: {e}); falling back to eager launches\n')
             graph = None
             torch.cuda.synchronize()
+    state.zero_grad()                          # warm-up / capture passes accumulated into the buffer
 
     def step(ws, t, mz):
         if graph is not None:
@@ -208,7 +331,11 @@ def main():
             loss = s_loss
         else:
             loss = step_compute(ws, t, mz)
-        reducer.all_reduce()
+        state.all_reduce()                     # SUM over ranks; the 1/world of the average is applied inside the update kernel
+        if opt is not None:
+            opt.step(zero_grad=True)
+        elif world > 1:
+            state.grad.div_(world)
         return loss
 
     def timed(fn, steps, warmup):
@@ -240,7 +367,7 @@ def main():
     ms_total, launches = timed(lambda: step(s_ws if graph is not None else d_ws.detach(), s_t if graph is not None else d_t, s_mz if graph is not None else d_mz),
                                args.steps, args.warmup)
     if graph is not None:
-        launches = graph_launches * args.steps      # launches recorded at capture time, replayed once per step
+        launches = (graph_launches + (1 if opt is not None else 0)) * args.steps      # launches recorded at capture time, replayed once per step (+ the update kernel)
     clocks = sampler.stop() if rank == 0 else None
 
     # (2) end to end: H2D of the step's inputs from pinned memory, D2H of the loss, every step
@@ -322,7 +449,8 @@ def main():
     line = dict(metric='synthesis_fwd_bwd_frames_per_sec_256', value=value, unit='frames/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='tf32 (fp32 storage, TF32 tensor-core products, fp32 accumulate)',
                 data='synthetic',
-                config=dict(workload='256x256 SynthesisNetwork forward+backward, 32 frames/GPU (32 latents x 1 frame), fmaps 0.5, random-init weights',
+                config=dict(workload='256x256 SynthesisNetwork forward+backward' + (' + fused nan_to_num/Adam update of all parameters' if opt is not None else '') +
+                                     ', 32 frames/GPU (32 latents x 1 frame), fmaps 0.5, random-init weights', optimizer_step=opt is not None,
                             frames_per_gpu=N, parallelism=f'dp{world}', cuda_graph=graph is not None, l2='activation working set per step (>= 134 MB per layer at res >= 64, ~6 GB total) exceeds the 126 MB L2; no explicit flush',
                             conv_gflop_per_frame_fwd=conv_gflop_fwd),
                 e2e=dict(value=e2e_value, unit='frames/s', h2d_bytes_per_step=(h_ws.numel() + h_t.numel() + h_mz.numel()) * 4, d2h_bytes_per_step=4),

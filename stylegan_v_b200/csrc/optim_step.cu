@@ -122,9 +122,15 @@ extern "C" int sgv_adam_ema_step(const sgv_adam_params* q, void* stream_)
     void (*kern)(AdamArgs) = ema ? (zero ? adam_ema_kernel<true, true> : adam_ema_kernel<true, false>)
                                  : (zero ? adam_ema_kernel<false, true> : adam_ema_kernel<false, false>);
     // persistent grid: exactly the CTAs that are co-resident (register-limited), so every SM streams for the whole kernel
-    int per_sm = 0;
-    SGV_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
-    if (per_sm < 1) per_sm = 1;
+    static std::atomic<int> occupancy[4];                  // per template variant; all devices of a box are the same part
+    const int variant = (ema ? 2 : 0) + (zero ? 1 : 0);
+    int per_sm = occupancy[variant].load(std::memory_order_relaxed);
+    if (per_sm == 0)
+    {
+        SGV_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+        if (per_sm < 1) per_sm = 1;
+        occupancy[variant].store(per_sm, std::memory_order_relaxed);
+    }
     const long long nvec = q->numel >> 2;
     long long want = (nvec + 2 * 256 - 1) / (2 * 256);
     const long long cap = (long long)num_sms() * per_sm;

@@ -104,6 +104,9 @@ def test_fused_adam_device_step_counter_in_cuda_graph(cuda):
     ref = train_ref.OptimizerRef([p.detach().cpu() for p in params], None, lr=0.01, betas=(0.5, 0.99), eps=1e-8)
     st = FlatModuleState(params)
     opt = FusedAdamEMA(st, lr=0.01, betas=(0.5, 0.99), eps=1e-8, device_step=True)
+    # first launches of these kernels (module load, occupancy query) must not happen inside a stream capture: warm up on a throwaway state
+    FusedAdamEMA(FlatModuleState(_make([(8,)], 3, cuda)), device_step=True).step()
+    torch.cuda.synchronize()
     gstat = [torch.randn(s, generator=torch.Generator().manual_seed(7)) for s in shapes]
     for p, gr in zip(params, gstat):
         p.grad.copy_(gr.to(cuda))
