@@ -140,7 +140,10 @@ def run_gd_step(args):
     torch.backends.cuda.matmul.allow_tf32 = False
     from stylegan_v_b200 import _lib
     from stylegan_v_b200.networks import Generator, Discriminator
+    from stylegan_v_b200 import train_step
     from stylegan_v_b200.train_step import TrainingPhases
+    if args.fused_d is not None:
+        train_step.FUSED_DISCRIMINATOR = bool(args.fused_d)
     args.warmup = max(args.warmup, 3)
     torch.manual_seed(rank)
     B, Fr = 16, 3
@@ -225,7 +228,8 @@ def run_gd_step(args):
                     dtype='tf32 (fp32 storage, TF32 tensor-core products, fp32 accumulate)', data='synthetic',
                     config=dict(workload='BASELINE configs[2]: 256x256 G+D training step fwd+bwd (Gmain + Dmain, no reg), 3 frames/clip, 16 clips/GPU, '
                                          'all-reduce + fused Adam/EMA update per phase', clips_per_gpu=B, frames_per_clip=Fr, parallelism=f'dp{world}',
-                                cuda_graph=graph is not None, l2='per-step activation working set >> 126 MB L2; no explicit flush',
+                                cuda_graph=graph is not None, fused_discriminator_layers=bool(train_step.FUSED_DISCRIMINATOR),
+                                l2='per-step activation working set >> 126 MB L2; no explicit flush',
                                 G_params=int(tp.G_state.numel), D_params=int(tp.D_state.numel)),
                     e2e=dict(value=frames / (ms_e2e / args.steps * 1e-3), unit='frames/s',
                              h2d_bytes_per_step=(h_real.numel() + h_z.numel() + h_t.numel()) * 4, d2h_bytes_per_step=8),
@@ -244,6 +248,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph of the step')
     ap.add_argument('--no-optimizer', action='store_true', help='time forward + backward only (no fused Adam update at the end of the step)')
+    ap.add_argument('--fused-d', type=int, default=None, help='gd_step: 1 / 0 = discriminator conv layers on the fused conv+bias+act nodes or on the drop-in ops')
     ap.add_argument('--workload', default='synthesis', choices=['synthesis', 'gd_step'],
                     help="synthesis = BASELINE metric (256x256 SynthesisNetwork fwd+bwd, configs[1] batch); gd_step = configs[2] (G+D training step, no reg)")
     args = ap.parse_args()
@@ -433,6 +438,14 @@ def main():
                    peak_source=peaks['source'], nchw=dict(kernel='fir_nchw_tiled, same extents in NCHW (odd row pitch: not TMA-addressable)', achieved=fir_bytes / fir_nchw_ms / 1e6,
                                                           frac=fir_bytes / fir_nchw_ms / 1e6 / peaks['hbm_gbs']))
     del xf
+    # the parameter update of the step: one streaming pass over the flat state (4 loads + 4 stores of 4 B per parameter incl. gradient zeroing)
+    optimizer = None
+    if opt is not None:
+        opt_ms = kernel_ms(lambda: opt.step(zero_grad=True))
+        opt_bytes = opt.algorithmic_bytes(False, True)
+        optimizer = dict(bound='hbm', kernel=f'adam_ema_kernel<EMA=0,ZERO=1> over {state.numel} fp32 parameters (flat state)', ms=opt_ms,
+                         achieved=opt_bytes / opt_ms / 1e6, peak=peaks['hbm_gbs'], unit='GB/s', frac=opt_bytes / opt_ms / 1e6 / peaks['hbm_gbs'],
+                         algorithmic_bytes_per_launch=opt_bytes)
 
     cfg = sr.SynthesisConfig(img_resolution=RES)
     conv_gflop_fwd = sr.conv_flops_per_frame(cfg) / 1e9
@@ -454,7 +467,7 @@ def main():
                             frames_per_gpu=N, parallelism=f'dp{world}', cuda_graph=graph is not None, l2='activation working set per step (>= 134 MB per layer at res >= 64, ~6 GB total) exceeds the 126 MB L2; no explicit flush',
                             conv_gflop_per_frame_fwd=conv_gflop_fwd),
                 e2e=dict(value=e2e_value, unit='frames/s', h2d_bytes_per_step=(h_ws.numel() + h_t.numel() + h_mz.numel()) * 4, d2h_bytes_per_step=4),
-                gpu_launches=launches, clocks=clocks, roofline=roofline, upfirdn2d=upfirdn, cpu_baseline=cpu_baseline,
+                gpu_launches=launches, clocks=clocks, roofline=roofline, upfirdn2d=upfirdn, optimizer=optimizer, cpu_baseline=cpu_baseline,
                 model_tflops_fwd_bwd=3 * conv_gflop_fwd * frames / ms_step / 1e3 / world)
     print(json.dumps(line))
     if world > 1:

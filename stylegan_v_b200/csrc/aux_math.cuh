@@ -101,6 +101,14 @@ SGV_HD void time_encoder_bwd_elem(const float* h, int nf, int f, float freq, flo
 
 struct AdamScalars { float one_minus_b1, b2, one_minus_b2, eps, step_size, bc2_sqrt, ema_beta, grad_scale, grad_clamp; };
 
+SGV_HD AdamScalars make_adam_scalars(float beta1, float beta2, float eps, float step_size, float bc2_sqrt, float ema_beta, float grad_scale, float grad_clamp)
+{
+    AdamScalars s;
+    s.one_minus_b1 = 1.f - beta1; s.b2 = beta2; s.one_minus_b2 = 1.f - beta2; s.eps = eps;
+    s.step_size = step_size; s.bc2_sqrt = bc2_sqrt; s.ema_beta = ema_beta; s.grad_scale = grad_scale; s.grad_clamp = grad_clamp;
+    return s;
+}
+
 SGV_HD void adam_bias_corrections(float lr, float beta1, float beta2, double t, float* step_size, float* bc2_sqrt)
 {
     // in double like torch.optim.Adam: step_size = lr / (1 - beta1^t), bias_correction2_sqrt = (1 - beta2^t)^0.5

@@ -29,11 +29,11 @@ __global__ void adam_step_advance_kernel(int* step_count) { *step_count += 1; }
 template <bool EMA, bool ZERO>
 __global__ void __launch_bounds__(256) adam_ema_kernel(AdamArgs a)
 {
-    AdamScalars s;
-    s.one_minus_b1 = 1.f - a.beta1; s.b2 = a.beta2; s.one_minus_b2 = 1.f - a.beta2; s.eps = a.eps;
-    s.step_size = a.step_size; s.bc2_sqrt = a.bc2_sqrt; s.ema_beta = a.ema_beta;
+    // every field of the per-launch scalars is set in ONE place shared with the host harness (aux_math.cuh::make_adam_scalars)
+    float step_size = a.step_size, bc2_sqrt = a.bc2_sqrt;
     if (a.step_count)      // graph-replay mode: the step number lives on the device
-        adam_bias_corrections(a.lr, a.beta1, a.beta2, (double)*a.step_count, &s.step_size, &s.bc2_sqrt);
+        adam_bias_corrections(a.lr, a.beta1, a.beta2, (double)*a.step_count, &step_size, &bc2_sqrt);
+    const AdamScalars s = make_adam_scalars(a.beta1, a.beta2, a.eps, step_size, bc2_sqrt, a.ema_beta, a.grad_scale, a.grad_clamp);
 
     const long long nvec = a.numel >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;

@@ -7,7 +7,7 @@ Covered (everything the synthesis and discriminator blocks issue, conv2d_resampl
   conv_transpose2d  k = 3, stride 2, padding 0 (generator up path)     -> 4 polyphase launches into the (2h+1) lattice
   conv_transpose2d  k in {1,3}, stride 1 (data gradient of conv2d)     -> one launch with transposed weights
 and the matching weight gradients (stylegan_v_b200/csrc/wgrad_tf32.cu).  Requirements: CUDA fp32, groups = 1,
-dilation 1, GEMM-K channels % 32 == 0, GEMM-N channels % 32 == 0 (16 allowed for the forward kernels).
+dilation 1, GEMM-K channels % 32 == 0, GEMM-N channels 32 or a multiple of 64.
 Anything else returns None and the caller uses the library (cuDNN) call exactly like the reference.
 
 Tensors are converted to channels_last (NHWC) on entry if necessary and results are returned channels_last — the
@@ -22,8 +22,10 @@ enabled = True
 
 
 def _ok_channels(k_ch, n_ch):
-    """forward / data-gradient kernel: GEMM-K channels % 32, GEMM-N channels % 64 (or exactly 16 / 32)"""
-    return k_ch % 32 == 0 and (n_ch % 64 == 0 or n_ch in (16, 32))
+    """forward / data-gradient kernel: GEMM-K channels % 32, GEMM-N channels % 64 (or exactly 32).  16 output channels are NOT routed here:
+    that tile shape produced wrong results for the 32 -> 16 channel down layers of a tiny discriminator (round-1 GPU run, scripts/debug_d_layers.py)
+    and no configuration of the reference has it (narrowest layers: 64 channels at 256^2, 32 at 1024^2) — such calls take the library path."""
+    return k_ch % 32 == 0 and (n_ch % 64 == 0 or n_ch == 32)
 
 
 def _common_ok(x, w, dilation, groups):

@@ -14,6 +14,7 @@ the fp32 contract of BASELINE.json applies.
 import numpy as np
 import torch
 
+from . import dconv
 from .ops import bias_act, conv2d_resample, upfirdn2d
 from .synthesis import SynthesisNetwork
 
@@ -109,9 +110,22 @@ class Conv2dLayer(torch.nn.Module):
             else:
                 self.bias = None
 
-    def forward(self, x, gain=1):
+    def forward(self, x, gain=1, fused=False):
+        """fused=True: layers inside the native envelope run as [FIR] + ONE implicit-GEMM launch with the bias / activation epilogue
+        (stylegan_v_b200/dconv.py; first-order differentiable); everything else — and fused=False — is conv2d_resample + bias_act."""
         w = self.weight * self.weight_gain
         b = self.bias.to(x.dtype) if self.bias is not None else None
+        if fused and self.up == 1 and self.down in (1, 2) and self.conv_clamp is None and self.activation in ('linear', 'lrelu'):
+            k = self.weight.shape[2]
+            # down layers (conv2d_resample.py:100-110,119-122): k = 3 -> low-pass at full resolution, then the convolution strides;
+            #                                                    k = 1 -> the FIR decimates, then a 1x1 convolution
+            stride, pad = (2, 0) if (self.down == 2 and k == 3) else (1, self.padding if self.down == 1 else 0)
+            if dconv.supported(x, w, stride, pad):
+                if self.down == 2:
+                    fw = self.resample_filter.shape[-1]
+                    p0, p1 = self.padding + (fw - self.down + 1) // 2, self.padding + (fw - self.down) // 2       # conv2d_resample.py:100-104
+                    x = upfirdn2d.upfirdn2d(x, self.resample_filter, down=(1 if k == 3 else 2), padding=[p0, p1, p0, p1])
+                return dconv.fused_conv_act(x, w, b, stride=stride, padding=pad, act=self.activation, gain=self.act_gain * gain)
         x = conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down, padding=self.padding,
                                             flip_weight=(self.up == 1))
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
@@ -143,22 +157,22 @@ class DiscriminatorBlock(torch.nn.Module):
         if architecture == 'resnet':
             self.skip = Conv2dLayer(conv0_in, out_channels, 1, bias=False, down=2, trainable=trainable(), resample_filter=resample_filter)
 
-    def forward(self, x, img):
+    def forward(self, x, img, fused=False):
         if x is not None:
             assert x.shape[1] == self.in_channels and x.shape[2] == x.shape[3] == self.resolution
             x = x.to(torch.float32)
         if self.in_channels == 0 or self.architecture == 'skip':
             assert img.shape[1] == self.img_channels and img.shape[2] == img.shape[3] == self.resolution
             img = img.to(torch.float32)
-            y = self.fromrgb(img)
+            y = self.fromrgb(img, fused=fused)
             x = x + y if x is not None else y
             img = upfirdn2d.downsample2d(img, self.resample_filter) if self.architecture == 'skip' else None
         if self.architecture == 'resnet':
-            y = self.skip(x, gain=np.sqrt(0.5))
-            x = self.conv1(self.conv0(x), gain=np.sqrt(0.5))
+            y = self.skip(x, gain=np.sqrt(0.5), fused=fused)
+            x = self.conv1(self.conv0(x, fused=fused), gain=np.sqrt(0.5), fused=fused)
             x = y.add_(x)
         else:
-            x = self.conv1(self.conv0(x))
+            x = self.conv1(self.conv0(x, fused=fused), fused=fused)
         return x, img
 
 
@@ -300,8 +314,11 @@ class Discriminator(torch.nn.Module):
         self.b4 = DiscriminatorEpilogue(ch[4], cmap_dim, 4, img_channels, architecture=architecture, mbstd_group_size=mbstd_group_size,
                                         mbstd_num_channels=mbstd_num_channels, conv_clamp=conv_clamp)
 
-    def forward(self, img, c, t):
+    def forward(self, img, c, t, fused=None):
+        """fused=None: CUDA inputs use the fused conv + bias + activation nodes when no second-order gradient can be requested, i.e.
+        when gradient mode is off or the caller says so explicitly; TrainingPhases passes fused=True for the main phases and False for R1."""
         assert t.ndim == 2 and len(img) == t.shape[0] * t.shape[1]
+        fused = bool(fused) if fused is not None else (img.is_cuda and not torch.is_grad_enabled())
         if self.time_encoder is not None:
             c = torch.cat([c, self.time_encoder(t.reshape(-1, self.num_frames_per_video))], dim=1)
             if self.dummy_c:
@@ -310,7 +327,7 @@ class Discriminator(torch.nn.Module):
         for res in self.block_resolutions:
             if res == self.concat_res:
                 x = x.contiguous().reshape(-1, self.num_frames_per_video * x.shape[1], *x.shape[2:])     # [B, F*C, h, w] in (frame, channel) order
-            x, img = getattr(self, f'b{res}')(x, img)
+            x, img = getattr(self, f'b{res}')(x, img, fused=fused)
         cmap = self.mapping(None, c) if c.shape[1] > 0 else None
         return {'image_logits': self.b4(x, img, cmap).squeeze(1)}
 

@@ -23,23 +23,32 @@ from .ops import conv2d_gradfix
 from .optim import FlatModuleState, FusedAdamEMA
 
 
+# fused=True routes the discriminator's conv layers through the first-order-only fused nodes (stylegan_v_b200/dconv.py); the R1 term below
+# differentiates D twice and therefore never does.
+FUSED_DISCRIMINATOR = False
+
+
+def _d_kwargs(x):
+    return dict(fused=True) if (FUSED_DISCRIMINATOR and x.is_cuda) else dict(fused=False)
+
+
 def generator_main_loss(G, D, z, c, t, **synthesis_kwargs):
     img = G(z, c, t, **synthesis_kwargs)
-    return F.softplus(-D(img, c, t)['image_logits']).mean()
+    return F.softplus(-D(img, c, t, **_d_kwargs(img))['image_logits']).mean()
 
 
 def discriminator_main_loss(G, D, real_img, real_c, real_t, z, c, t, **synthesis_kwargs):
     """Returns (loss on generated frames, loss on real frames); the reference backpropagates them separately (loss.py:139,173)."""
     with torch.no_grad():
         fake = G(z, c, t, **synthesis_kwargs)
-    loss_gen = F.softplus(D(fake, c, t)['image_logits']).mean()
-    loss_real = F.softplus(-D(real_img, real_c, real_t)['image_logits']).mean()
+    loss_gen = F.softplus(D(fake, c, t, **_d_kwargs(fake))['image_logits']).mean()
+    loss_real = F.softplus(-D(real_img, real_c, real_t, **_d_kwargs(fake))['image_logits']).mean()
     return loss_gen, loss_real
 
 
 def discriminator_r1_loss(D, real_img, real_c, real_t, r1_gamma):
     img = real_img.detach().requires_grad_(True)
-    logits = D(img, real_c, real_t)['image_logits']
+    logits = D(img, real_c, real_t, fused=False)['image_logits']
     with conv2d_gradfix.no_weight_gradients():
         grads, = torch.autograd.grad([logits.sum()], [img], create_graph=True, only_inputs=True)
     penalty = grads.square().sum([1, 2, 3]) * (r1_gamma / 2)                      # per frame

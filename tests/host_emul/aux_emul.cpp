@@ -34,10 +34,9 @@ extern "C" void emul_time_encoder_bwd(const float* dout, const float* hl, const 
 extern "C" void emul_adam_ema(float* p, float* g, float* m, float* v, float* pe, int64_t numel, float lr, float beta1, float beta2, float eps,
                               float ema_beta, float grad_scale, float grad_clamp, int step, int zero_grad)
 {
-    AdamScalars s;
-    s.one_minus_b1 = 1.f - beta1; s.b2 = beta2; s.one_minus_b2 = 1.f - beta2; s.eps = eps;
-    s.ema_beta = ema_beta; s.grad_scale = grad_scale; s.grad_clamp = grad_clamp;
-    adam_bias_corrections(lr, beta1, beta2, (double)step, &s.step_size, &s.bc2_sqrt);
+    float step_size, bc2_sqrt;
+    adam_bias_corrections(lr, beta1, beta2, (double)step, &step_size, &bc2_sqrt);
+    const AdamScalars s = make_adam_scalars(beta1, beta2, eps, step_size, bc2_sqrt, ema_beta, grad_scale, grad_clamp);
     for (int64_t k = 0; k < numel; k++)
     {
         adam_one(p[k], g[k], m[k], v[k], s);

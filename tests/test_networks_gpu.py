@@ -42,3 +42,46 @@ def test_path_length_cuda_vs_reference_golden(cuda):
     g, meta = load_golden('path_length_tiny.npz')
     net, _ = make_synthesis(g, meta)
     path_length_checks(net.to(cuda), g, cuda, 2e-2)
+
+
+def _d128(cuda, seed=0):
+    from stylegan_v_b200.networks import Discriminator
+    torch.manual_seed(seed)
+    D = Discriminator(c_dim=0, img_resolution=32, channel_base=4096, channel_max=128, num_frames_per_video=3, concat_res=16,
+                      num_frames_div_factor=2, mbstd_group_size=2)
+    with torch.no_grad():
+        for n, p in D.named_parameters():
+            if n.endswith('.bias'):
+                p.normal_(0, 0.1)
+    return D
+
+
+def test_discriminator_fused_conv_layers_match_unfused(cuda):
+    """128-channel discriminator: every block conv (conv0, conv1 down 2, 1x1 skip down 2, incl. the 192-channel concat layer) is inside the
+    native envelope, so fused=True runs them as [FIR +] one launch with the epilogue.  Same logits and gradients as the unfused drop-in
+    ops on the GPU and as the fp32 CPU evaluation of the same module."""
+    D = _d128(cuda)
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(6, 3, 32, 32, generator=g)
+    t = torch.tensor([[0.0, 5.0, 9.0], [100.0, 101.0, 131.0]])
+    c = torch.zeros(2, 0)
+    names = [n for n, _ in D.named_parameters()]
+
+    def run(dev, fused):
+        Dd = D.to(dev).train()
+        x = img.to(dev).requires_grad_(True)
+        logits = Dd(x, c.to(dev), t.to(dev), fused=fused)['image_logits']
+        grads = torch.autograd.grad(torch.nn.functional.softplus(-logits).mean(), [x] + list(Dd.parameters()), allow_unused=True)
+        return logits.detach().cpu(), [None if a is None else a.detach().cpu() for a in grads]
+    l_cpu, g_cpu = run(torch.device('cpu'), False)
+    n0 = _lib.launch_count()
+    l_unf, g_unf = run(cuda, False)
+    n1 = _lib.launch_count()
+    l_fus, g_fus = run(cuda, True)
+    n2 = _lib.launch_count()
+    assert n2 - n1 < n1 - n0                                     # fewer kernels: bias_act forward / backward passes are gone
+    assert rel_err(l_unf, l_cpu) < 3e-3 and rel_err(l_fus, l_cpu) < 3e-3
+    for n, a, b, r in zip(['img'] + names, g_fus, g_unf, g_cpu):
+        assert (a is None) == (r is None), n
+        if a is not None:
+            assert rel_err(a, r) < 5e-2 and rel_err(b, r) < 5e-2, (n, rel_err(a, r), rel_err(b, r))

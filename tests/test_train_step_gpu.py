@@ -35,7 +35,9 @@ def test_phase_gradients_cuda_vs_reference_loss(cuda, phase):
     check_phase(phase, module, g, 3e-2, 5e-2)
 
 
-def test_training_phases_step(cuda):
+@pytest.mark.parametrize('fused_d', [False, True])
+def test_training_phases_step(cuda, fused_d, monkeypatch):
+    monkeypatch.setattr(ts, 'FUSED_DISCRIMINATOR', fused_d)
     g, meta = load_golden('loss_phases_tiny.npz')
     G, D = make_gd(g, meta)
     G, D = G.to(cuda), D.to(cuda)
