@@ -25,7 +25,7 @@ from .optim import FlatModuleState, FusedAdamEMA
 
 # fused=True routes the discriminator's conv layers through the first-order-only fused nodes (stylegan_v_b200/dconv.py); the R1 term below
 # differentiates D twice and therefore never does.
-FUSED_DISCRIMINATOR = False
+FUSED_DISCRIMINATOR = True
 
 
 def _d_kwargs(x):
