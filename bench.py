@@ -92,12 +92,23 @@ def cpu_reference_step(frames, threads):
     t = torch.zeros(frames, 1)
     mz = torch.randn(frames, sr.max_traj_len(cfg, 0.0), cfg.motion_z_dim, generator=g)
 
+    from oracle import train_ref
+    names = list(P.keys())
+    opt = torch.optim.Adam([P[n] for n in names], lr=0.0025, betas=(0.0, 0.99), eps=1e-8)     # train.py:192-193
+
     def step():
         t0 = time.perf_counter()
         img = sr.synthesis_forward(P, cfg, ws, t, motion_z=mz, fused_modconv=False)
         dimg = torch.ones_like(img)
-        torch.autograd.grad(img, [ws] + list(P.values()), dimg, allow_unused=True)
-        return time.perf_counter() - t0
+        grads = torch.autograd.grad(img, [ws] + [P[n] for n in names], dimg, allow_unused=True)
+        # the parameter update the b200 arm performs with its fused kernel: per-tensor nan_to_num + Adam (training_loop.py:381-386)
+        t1 = time.perf_counter()
+        for n, g in zip(names, grads[1:]):
+            P[n].grad = train_ref.nan_to_num_ref(g) if g is not None else None
+        opt.step()
+        t2 = time.perf_counter()
+        # the update happens once per 32-frame step: charge the sampled frames their share of it
+        return (t1 - t0) + (t2 - t1) * frames / FRAMES_PER_GPU
     return step
 
 
@@ -115,8 +126,8 @@ def run_reference(args):
     fps = sample_frames / sec
     line = dict(metric='synthesis_fwd_bwd_frames_per_sec_256', value=fps, unit='frames/s', n_gpus=args.gpus, steps=len(times), warmup=1,
                 ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
-                config=dict(workload='256x256 SynthesisNetwork fwd+bwd (oracle CPU port of the reference path, fused_modconv=False)',
-                            frames_per_step=sample_frames, note='bounded sample of the 32-frame workload; CPU frames/s is batch-size insensitive'),
+                config=dict(workload='256x256 SynthesisNetwork fwd+bwd + nan_to_num/Adam update (oracle CPU port of the reference path, fused_modconv=False)',
+                            frames_per_step=sample_frames, note='bounded sample of the 32-frame workload; forward/backward time of the sample + its 1/32 share of the once-per-step parameter update'),
                 cpu_baseline=dict(value=fps, unit='frames/s', cores=threads, kind='port', sample=f'{sample_frames} frames fwd+bwd, median of {len(times)}'),
                 e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))

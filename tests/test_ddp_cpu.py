@@ -37,3 +37,41 @@ def test_flat_grad_reducer_world2():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def _worker_flat_state(rank, world, port, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from stylegan_v_b200.optim import FlatModuleState
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(5, 3)
+    conv = torch.nn.Conv2d(2, 2, 3)
+    ema = [torch.nn.Parameter(p.detach().clone()) for p in list(lin.parameters()) + list(conv.parameters())]
+    params = list(lin.parameters()) + list(conv.parameters())
+    before = [p.detach().clone() for p in params]
+    st = FlatModuleState(params, ema)
+    same_values = all(torch.equal(p.detach(), b) for p, b in zip(params, before))          # re-homing keeps the values
+    aligned = all(o % 64 == 0 for o in st.offsets) and params[1].data_ptr() == st.param.data_ptr() + st.offsets[1] * 4
+    y = lin(torch.full((4, 5), float(rank + 1))).sum() + conv(torch.ones(1, 2, 5, 5) * (rank + 1)).sum()
+    y.backward()
+    local = st.grad.clone()
+    st.all_reduce()                                               # SUM (the 1/world lives in the update kernel's grad_scale)
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    ok = same_values and aligned and torch.allclose(st.grad, sum(gathered)) and st.world_size() == world
+    # padding between parameters stays zero, so the flat update never sees garbage there
+    mask = torch.ones_like(st.grad, dtype=torch.bool)
+    for p, o in zip(params, st.offsets):
+        mask[o:o + p.numel()] = False
+    ok = ok and not st.grad[mask].any() and not st.param[mask].any()
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_flat_module_state_world2():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_flat_state, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]
