@@ -250,6 +250,160 @@ def run_gd_step(args):
         dist.destroy_process_group()
 
 
+def _dist_setup():
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device: the b200 implementation has no CPU path'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return dist, rank, local_rank, world, dev
+
+
+def _timed(dist, world, dev, fn, steps, warmup):
+    from stylegan_v_b200 import _lib
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _lib.launch_count()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()), _lib.launch_count() - l0
+
+
+def run_synthesis_fwd(args):
+    """BASELINE configs[1] / configs[4]: SynthesisNetwork forward only (no_grad), 256^2 x 32 frames or 1024^2 x 8 frames (fmaps 1), replicas at N > 1."""
+    dist, rank, local_rank, world, dev = _dist_setup()
+    from stylegan_v_b200 import _lib
+    from stylegan_v_b200.synthesis import SynthesisNetwork
+    from oracle import synthesis_ref as sr     # FLOP model only
+    args.warmup = max(args.warmup, 3)
+    res = args.res
+    N = 32 if res <= 256 else 8
+    cb = 16384 if res < 512 else 32768
+    torch.manual_seed(rank)
+    net = SynthesisNetwork(img_resolution=res, channel_base=cb).to(dev).eval().requires_grad_(False)
+    h_ws = torch.randn(N, net.num_ws, net.w_dim).pin_memory()
+    h_t = torch.zeros(N, 1).pin_memory()
+    h_mz = torch.randn(N, net.motion_encoder.traj_len(), net.motion_encoder.z_dim).pin_memory()
+    s_ws, s_t, s_mz = h_ws.to(dev), h_t.to(dev), h_mz.to(dev)
+    h_out = torch.zeros(1).pin_memory()
+
+    def compute():
+        with torch.no_grad():
+            return net(s_ws, s_t, motion_z=s_mz).mean()
+    graph, graph_launches, s_out = None, 0, None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    compute()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                s_out = compute()
+            graph_launches = _lib.launch_count() - l0
+        except Exception as e:
+            sys.stderr.write(f'[bench] CUDA graph capture failed ({type(e).__name__}: {e}); eager launches\n')
+            graph = None
+            torch.cuda.synchronize()
+
+    def step():
+        if graph is not None:
+            graph.replay()
+            return s_out
+        return compute()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches = _timed(dist, world, dev, step, args.steps, args.warmup)
+    if graph is not None:
+        launches = graph_launches * args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    def e2e_step():
+        s_ws.copy_(h_ws, non_blocking=True); s_t.copy_(h_t, non_blocking=True); s_mz.copy_(h_mz, non_blocking=True)
+        h_out.copy_(step().reshape(1), non_blocking=True)
+    ms_e2e, _ = _timed(dist, world, dev, e2e_step, args.steps, 1)
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        frames = N * world
+        gflop = sr.conv_flops_per_frame(sr.SynthesisConfig(img_resolution=res, channel_base=cb)) / 1e9
+        line = dict(metric=f'synthesis_fwd_frames_per_sec_{res}', value=frames / (ms_step * 1e-3), unit='frames/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='tf32 (fp32 storage, TF32 tensor-core products, fp32 accumulate)',
+                    data='synthetic', config=dict(workload=f'{res}x{res} SynthesisNetwork forward, {N} frames/GPU, random-init weights (BASELINE configs[{1 if res <= 256 else 4}])',
+                                                  frames_per_gpu=N, parallelism=f'replicas x{world}', cuda_graph=graph is not None, conv_gflop_per_frame_fwd=gflop,
+                                                  l2='activations per layer exceed the 126 MB L2 at res >= 64; no explicit flush'),
+                    e2e=dict(value=frames / (ms_e2e / args.steps * 1e-3), unit='frames/s', h2d_bytes_per_step=(h_ws.numel() + h_t.numel() + h_mz.numel()) * 4, d2h_bytes_per_step=4),
+                    gpu_launches=launches, clocks=clocks, model_tflops_fwd=gflop * N / ms_step / 1e3)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_full_loop(args):
+    """BASELINE configs[3]: the full training iteration with lazy regularisation — R1 every 16 iterations, path-length every 4 (training_loop.py:116-117),
+    8 clips x 3 frames per GPU (global batch 64 on 8 GPUs), DDP gradient all-reduce + fused Adam/EMA per phase.  A step here = 16 iterations (one complete
+    regularisation cycle: 16 Gmain, 4 Greg, 16 Dmain, 1 Dreg), eager launches (the phase mix changes per iteration)."""
+    dist, rank, local_rank, world, dev = _dist_setup()
+    from stylegan_v_b200.networks import Generator, Discriminator
+    from stylegan_v_b200.train_step import TrainingPhases
+    torch.manual_seed(rank)
+    B, Fr, CYCLE = 8, 3, 16
+    G = Generator(img_resolution=RES).to(dev).train()
+    D = Discriminator(img_resolution=RES, mbstd_group_size=4).to(dev).train()
+    tp = TrainingPhases(G, D, lr=0.0025, r1_gamma=0.2048, pl_weight=2.0, G_reg_interval=4, D_reg_interval=16, batch_size=B * world)
+    real = torch.randn(B * Fr, 3, RES, RES, device=dev).clamp_(-1, 1)
+    z = torch.randn(B, G.z_dim, device=dev)
+    t = (torch.randint(0, 900, (B, 1)).float() + torch.tensor([[0.0, 5.0, 9.0]])).to(dev)
+
+    def cycle():
+        for _ in range(CYCLE):
+            out = tp.step(real, t, z, t)
+        return out
+    steps = max(1, min(args.steps, 3))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches = _timed(dist, world, dev, cycle, steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        ms_iter = ms_total / steps / CYCLE
+        frames = B * Fr * world
+        line = dict(metric='full_training_loop_frames_per_sec_256', value=frames / (ms_iter * 1e-3), unit='frames/s', n_gpus=world, steps=steps * CYCLE, warmup=CYCLE,
+                    ms_per_step=ms_iter, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='tf32 (fp32 storage, TF32 tensor-core products, fp32 accumulate)',
+                    data='synthetic', config=dict(workload='BASELINE configs[3]: 256x256 full training loop, R1 every 16 + path length every 4, 3 frames/clip, 8 clips/GPU',
+                                                  clips_per_gpu=B, frames_per_clip=Fr, parallelism=f'dp{world}', cuda_graph=False, iterations_timed=steps * CYCLE,
+                                                  note='ms_per_step = mean iteration time over whole 16-iteration regularisation cycles'),
+                    gpu_launches=launches, clocks=clocks)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -260,13 +414,18 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph of the step')
     ap.add_argument('--no-optimizer', action='store_true', help='time forward + backward only (no fused Adam update at the end of the step)')
     ap.add_argument('--fused-d', type=int, default=None, help='gd_step: 1 / 0 = discriminator conv layers on the fused conv+bias+act nodes or on the drop-in ops')
-    ap.add_argument('--workload', default='synthesis', choices=['synthesis', 'gd_step'],
+    ap.add_argument('--res', type=int, default=256, help='synthesis_fwd: 256 (BASELINE configs[1], 32 frames) or 1024 (configs[4], 8 frames, fmaps 1)')
+    ap.add_argument('--workload', default='synthesis', choices=['synthesis', 'gd_step', 'synthesis_fwd', 'full_loop'],
                     help="synthesis = BASELINE metric (256x256 SynthesisNetwork fwd+bwd, configs[1] batch); gd_step = configs[2] (G+D training step, no reg)")
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
     if args.workload == 'gd_step':
         return run_gd_step(args)
+    if args.workload == 'synthesis_fwd':
+        return run_synthesis_fwd(args)
+    if args.workload == 'full_loop':
+        return run_full_loop(args)
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
