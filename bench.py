@@ -358,7 +358,7 @@ def run_synthesis_fwd(args):
                                                   frames_per_gpu=N, parallelism=f'replicas x{world}', cuda_graph=graph is not None, conv_gflop_per_frame_fwd=gflop,
                                                   l2='activations per layer exceed the 126 MB L2 at res >= 64; no explicit flush'),
                     e2e=dict(value=frames / (ms_e2e / args.steps * 1e-3), unit='frames/s', h2d_bytes_per_step=(h_ws.numel() + h_t.numel() + h_mz.numel()) * 4, d2h_bytes_per_step=4),
-                    gpu_launches=launches, clocks=clocks, model_tflops_fwd=gflop * N / ms_step / 1e3)
+                    gpu_launches=launches, clocks=clocks, model_tflops_fwd=gflop * N / ms_step)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -638,7 +638,7 @@ def main():
                             conv_gflop_per_frame_fwd=conv_gflop_fwd),
                 e2e=dict(value=e2e_value, unit='frames/s', h2d_bytes_per_step=(h_ws.numel() + h_t.numel() + h_mz.numel()) * 4, d2h_bytes_per_step=4),
                 gpu_launches=launches, clocks=clocks, roofline=roofline, upfirdn2d=upfirdn, optimizer=optimizer, cpu_baseline=cpu_baseline,
-                model_tflops_fwd_bwd=3 * conv_gflop_fwd * frames / ms_step / 1e3 / world)
+                model_tflops_fwd_bwd=3 * conv_gflop_fwd * frames / ms_step / world)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
