@@ -301,6 +301,58 @@ def gen_path_length(ref):
     np.savez_compressed(os.path.join(OUT, 'path_length_tiny.npz'), **out)
 
 
+def gen_mixed_precision(ref):
+    """The reference's mixed-precision mode (train.py:173-174: num_fp16_res highest resolutions in fp16, conv_clamp 256) on the tiny
+    synthesis network (fp16 in the 16^2 and 32^2 blocks) and the tiny discriminator (fp16 in its 32^2 and 16^2 blocks), CPU."""
+    cfg = sr.SynthesisConfig(**TINY)
+    rcfg = ref_loader.to_cfg(cfg.reference_generator_cfg())
+    torch.manual_seed(0)
+    S = ref.networks.SynthesisNetwork(w_dim=cfg.w_dim, img_resolution=cfg.img_resolution, img_channels=3, channel_base=cfg.channel_base,
+                                      channel_max=cfg.channel_max, cfg=rcfg, num_fp16_res=2, conv_clamp=256)
+    g = torch.Generator().manual_seed(31)
+    with torch.no_grad():
+        for n, p in S.named_parameters():
+            if n.endswith('.bias') and 'affine' not in n:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    B = 2
+    ws = torch.randn(B, S.num_ws, cfg.w_dim, generator=g).requires_grad_(True)
+    t = torch.tensor([[0.0, 5.25], [100.5, 130.75]])
+    c = torch.zeros(B, 0)
+    mz = torch.randn(B, sr.max_traj_len(cfg, float(t.max())), cfg.motion_z_dim, generator=g)
+    S.train()
+    img = S(ws, t=t, c=c, motion_z=mz)
+    dimg = torch.randn(img.shape, generator=g)
+    keep = ['b32.conv0.weight', 'b16.conv1.bias', 'b8.conv1.weight', 'b32.torgb.weight']
+    P = dict(S.named_parameters())
+    grads = torch.autograd.grad(img, [ws] + [P[n] for n in keep], dimg)
+    S.eval()
+    with torch.no_grad():
+        img_eval = S(ws, t=t, c=c, motion_z=mz)
+        img_eval_b1 = S(ws[:1], t=t[:1], c=c[:1], motion_z=mz[:1])          # batch of one latent: fused_modconv rule of networks.py:232
+    out = {'p:' + k: v.detach().numpy().copy() for k, v in S.state_dict().items()}
+    out.update(ws=ws.detach().numpy(), t=t.numpy(), motion_z=mz.numpy(), dimg=dimg.numpy(), img_train=img.detach().numpy(),
+               img_eval=img_eval.numpy(), img_eval_b1=img_eval_b1.numpy(), d_ws=grads[0].numpy())
+    for n, a in zip(keep, grads[1:]):
+        out['g:' + n] = a.numpy()
+    # discriminator
+    d = TINY_D
+    dcfg = ref_loader.to_cfg(dict(sampling=dict(num_frames_per_video=3, max_num_frames=d['max_num_frames'], type='random'),
+                                  concat_res=d['concat_res'], num_frames_div_factor=d['num_frames_div_factor'], dummy_c=False))
+    torch.manual_seed(3)
+    D = ref.networks.Discriminator(c_dim=0, img_resolution=d['img_resolution'], img_channels=3, channel_base=d['channel_base'],
+                                   channel_max=d['channel_max'], cfg=dcfg, mapping_kwargs=dict(num_layers=d['mapping_layers']),
+                                   epilogue_kwargs=dict(mbstd_group_size=d['mbstd_group_size']), num_fp16_res=2, conv_clamp=256)
+    dimg_in = torch.randn(6, 3, 32, 32, generator=g).requires_grad_(True)
+    dt = torch.tensor([[0.0, 5.0, 9.0], [100.0, 101.0, 131.0]])
+    D.train()
+    logits = D(dimg_in, torch.zeros(2, 0), dt)['image_logits']
+    gin, gw = torch.autograd.grad(logits.sum(), [dimg_in, D.b8.conv0.weight])
+    out.update({'d:' + k: v.detach().numpy().copy() for k, v in D.state_dict().items()})
+    out.update(d_img=dimg_in.detach().numpy(), d_t=dt.numpy(), d_logits=logits.detach().numpy(), d_gin=gin.numpy(), d_gw_b8_conv0=gw.numpy())
+    out['meta'] = np.frombuffer(json.dumps(dict(G=TINY, D=TINY_D, num_fp16_res=2, conv_clamp=256)).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, 'mixed_precision_tiny.npz'), **out)
+
+
 def gen_loss_phases(ref):
     """The reference's StyleGAN2Loss.accumulate_gradients (loss.py:73-173) on tiny reference G and D, one call per phase with fixed RNG
     state: per-parameter gradient sums and norms (+ a few full tensors) for Gmain, Dmain and Dreg (R1)."""
@@ -360,6 +412,7 @@ def main():
     gen_discriminator(ref)
     gen_path_length(ref)
     gen_loss_phases(ref)
+    gen_mixed_precision(ref)
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
 

@@ -137,10 +137,11 @@ class DiscriminatorBlock(torch.nn.Module):
     'resnet', the 1x1 down-2 skip branch; both branches scaled by sqrt(1/2)."""
 
     def __init__(self, in_channels, tmp_channels, out_channels, resolution, img_channels, first_layer_idx, architecture='resnet',
-                 activation='lrelu', resample_filter=(1, 3, 3, 1), conv_clamp=None, freeze_layers=0):
+                 activation='lrelu', resample_filter=(1, 3, 3, 1), conv_clamp=None, freeze_layers=0, use_fp16=False):
         assert architecture in ('orig', 'skip', 'resnet')
         super().__init__()
         self.in_channels, self.resolution, self.img_channels, self.architecture = in_channels, resolution, img_channels, architecture
+        self.use_fp16 = use_fp16                                   # mixed-precision mode of the reference (networks.py:462); unfused ops only
         self.register_buffer('resample_filter', upfirdn2d.setup_filter(list(resample_filter)))
         self.num_layers = 0
 
@@ -158,12 +159,19 @@ class DiscriminatorBlock(torch.nn.Module):
             self.skip = Conv2dLayer(conv0_in, out_channels, 1, bias=False, down=2, trainable=trainable(), resample_filter=resample_filter)
 
     def forward(self, x, img, fused=False):
+        dtype = torch.float16 if self.use_fp16 else torch.float32
+        fused = fused and not self.use_fp16
         if x is not None:
             assert x.shape[1] == self.in_channels and x.shape[2] == x.shape[3] == self.resolution
-            x = x.to(torch.float32)
+            x = x.to(dtype)
         if self.in_channels == 0 or self.architecture == 'skip':
             assert img.shape[1] == self.img_channels and img.shape[2] == img.shape[3] == self.resolution
-            img = img.to(torch.float32)
+            img = img.to(dtype)
+            if fused and img.is_cuda:
+                # 3-channel NHWC view of the frames (37 MB at 48 x 256^2): the library 1x1 conv then writes its 64-channel output channels_last,
+                # i.e. already in the layout of the fused conv0 that follows — otherwise that 805 MB activation is transposed once forward and
+                # once backward per discriminator pass (profiles/timeline_gd_step_r1.txt: 10.9 ms of strided-copy kernels per G+D step)
+                img = img.contiguous(memory_format=torch.channels_last)
             y = self.fromrgb(img, fused=fused)
             x = x + y if x is not None else y
             img = upfirdn2d.downsample2d(img, self.resample_filter) if self.architecture == 'skip' else None
@@ -284,13 +292,14 @@ class Discriminator(torch.nn.Module):
     def __init__(self, c_dim=0, img_resolution=256, img_channels=3, architecture='resnet', channel_base=16384, channel_max=512,
                  conv_clamp=None, cmap_dim=None, num_frames_per_video=3, max_num_frames=1024, sampling_type='random', concat_res=16,
                  num_frames_div_factor=2, dummy_c=False, mbstd_group_size=4, mbstd_num_channels=1, mapping_layers=2, freeze_layers=0,
-                 resample_filter=(1, 3, 3, 1)):
+                 resample_filter=(1, 3, 3, 1), num_fp16_res=0):
         super().__init__()
         self.c_dim, self.img_resolution, self.img_channels = c_dim, img_resolution, img_channels
         self.num_frames_per_video, self.concat_res, self.dummy_c = num_frames_per_video, concat_res, dummy_c
         log2 = int(np.log2(img_resolution))
         self.block_resolutions = [2 ** i for i in range(log2, 2, -1)]
         ch = {res: min(channel_base // res, channel_max) for res in self.block_resolutions + [4]}
+        fp16_resolution = max(2 ** (log2 + 1 - num_fp16_res), 8)                                       # networks.py:611
         if cmap_dim is None:
             cmap_dim = ch[4]
         self.time_encoder = TemporalDifferenceEncoder(num_frames_per_video, max_num_frames, sampling_type) if num_frames_per_video > 1 else None
@@ -306,7 +315,7 @@ class Discriminator(torch.nn.Module):
             if res == concat_res:
                 cin = (cin // num_frames_div_factor) * num_frames_per_video
             block = DiscriminatorBlock(cin, ch[res], cout, res, img_channels, layer_idx, architecture=architecture, conv_clamp=conv_clamp,
-                                       freeze_layers=freeze_layers, resample_filter=resample_filter)
+                                       freeze_layers=freeze_layers, resample_filter=resample_filter, use_fp16=(res >= fp16_resolution))
             setattr(self, f'b{res}', block)
             layer_idx += block.num_layers
         if c_dim > 0 or self.time_encoder is not None:

@@ -58,19 +58,20 @@ class SynthesisLayer(torch.nn.Module):
                                     torgb_wmod=torgb_wmod, torgb_bias=torgb_bias, wbox=plan['wbox'])
 
 
-def _layer_unfused(layer, x, w, fused_modconv, gain=1.0):
+def _layer_unfused(layer, x, w, fused_modconv, gain=1.0, conv_clamp=None):
     """SynthesisLayer.forward of the reference (networks.py:124-144, use_noise = false) on the drop-in ops."""
     styles = layer.affine(w)
     x = _modulated_conv2d(x=x, weight=layer.weight, styles=styles, up=layer.up, padding=1, resample_filter=layer.resample_filter,
                           flip_weight=(layer.up == 1), fused_modconv=fused_modconv)
-    return _bias_act.bias_act(x, layer.bias.to(x.dtype), act='lrelu', gain=float(np.sqrt(2)) * gain)
+    clamp = conv_clamp * gain if conv_clamp is not None else None
+    return _bias_act.bias_act(x, layer.bias.to(x.dtype), act='lrelu', gain=float(np.sqrt(2)) * gain, clamp=clamp)
 
 
-def _torgb_unfused(layer, x, w, fused_modconv):
+def _torgb_unfused(layer, x, w, fused_modconv, conv_clamp=None):
     """ToRGBLayer.forward of the reference (networks.py:159-163) on the drop-in ops."""
     styles = layer.affine(w) * layer.weight_gain
     x = _modulated_conv2d(x=x, weight=layer.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
-    return _bias_act.bias_act(x, layer.bias.to(x.dtype))
+    return _bias_act.bias_act(x, layer.bias.to(x.dtype), clamp=conv_clamp)
 
 
 class _ToRGB(torch.autograd.Function):
@@ -143,9 +144,11 @@ class _GenInput(torch.nn.Module):
 
 
 class SynthesisBlock(torch.nn.Module):
-    def __init__(self, in_channels, out_channels, w_dim, motion_v_dim, resolution, img_channels, resample_filter=(1, 3, 3, 1)):
+    def __init__(self, in_channels, out_channels, w_dim, motion_v_dim, resolution, img_channels, resample_filter=(1, 3, 3, 1),
+                 use_fp16=False, conv_clamp=None):
         super().__init__()
         self.in_channels, self.resolution = in_channels, resolution
+        self.use_fp16, self.conv_clamp = use_fp16, conv_clamp            # mixed-precision mode of the reference (train.py:173-174); unfused path only
         self.register_buffer('resample_filter', _setup_filter(list(resample_filter)))
         self.num_conv = 0
         if in_channels == 0:
@@ -182,18 +185,23 @@ class SynthesisBlock(torch.nn.Module):
         img = img.add_(y) if img is not None else y
         return x, img
 
-    def forward_unfused(self, x, img, ws, motion_v=None, fused_modconv=False):
-        """SynthesisBlock.forward of the reference (networks.py:224-266, 'skip' architecture, fp32) layer by layer on the drop-in ops:
-        differentiable to any order and runnable on CPU tensors.  ws [N, num_conv + num_torgb, w_dim]."""
+    def forward_unfused(self, x, img, ws, motion_v=None, fused_modconv=None, force_fp32=False):
+        """SynthesisBlock.forward of the reference (networks.py:224-266, 'skip' architecture) layer by layer on the drop-in ops:
+        differentiable to any order, runnable on CPU tensors, and the home of the reference's mixed-precision mode (fp16 activations +
+        conv_clamp in the `use_fp16` blocks).  ws [N, num_conv + num_torgb, w_dim]."""
         w_iter = iter(ws.unbind(dim=1))
+        dtype = torch.float16 if self.use_fp16 and not force_fp32 else torch.float32
+        if fused_modconv is None:               # networks.py:232: per-sample-weight conv in eval mode, unless fp16 with a batch
+            fused_modconv = (not self.training) and (dtype == torch.float32 or (x is not None and int(x.shape[0]) == 1))
         if self.in_channels == 0:
             x = self.input(motion_v).contiguous()
         else:
-            x = _layer_unfused(self.conv0, x, next(w_iter), fused_modconv)
-        x = _layer_unfused(self.conv1, x, next(w_iter), fused_modconv)
+            x = _layer_unfused(self.conv0, x.to(dtype), next(w_iter), fused_modconv, conv_clamp=self.conv_clamp)
+        x = _layer_unfused(self.conv1, x, next(w_iter), fused_modconv, conv_clamp=self.conv_clamp)
         if img is not None:
             img = _upfirdn2d.upsample2d(img, self.resample_filter)
-        y = _torgb_unfused(self.torgb, x, next(w_iter), fused_modconv).to(dtype=torch.float32, memory_format=torch.contiguous_format)
+        y = _torgb_unfused(self.torgb, x, next(w_iter), fused_modconv, conv_clamp=self.conv_clamp)
+        y = y.to(dtype=torch.float32, memory_format=torch.contiguous_format)
         img = img.add_(y) if img is not None else y
         return x, img
 
@@ -201,9 +209,13 @@ class SynthesisBlock(torch.nn.Module):
 class SynthesisNetwork(torch.nn.Module):
     def __init__(self, w_dim=512, img_resolution=256, img_channels=3, channel_base=16384, channel_max=512,
                  motion_z_dim=512, motion_v_dim=512, motion_kernel_size=11, motion_z_distance=16, time_enc_dim=256,
-                 min_period_len=16, max_period_len=1024, max_num_frames=1024, resample_filter=(1, 3, 3, 1)):
+                 min_period_len=16, max_period_len=1024, max_num_frames=1024, resample_filter=(1, 3, 3, 1), num_fp16_res=0, conv_clamp=None):
         assert img_resolution >= 4 and img_resolution & (img_resolution - 1) == 0
         super().__init__()
+        # the reference's mixed-precision mode (fp16 in the num_fp16_res highest resolutions + activation clamp, train.py:173-174,
+        # networks.py:292,305).  The fused NHWC layers are fp32-storage / TF32-math only, so a network built with it runs the unfused ops.
+        self.mixed_precision = num_fp16_res > 0 or conv_clamp is not None
+        fp16_resolution = max(2 ** (int(np.log2(img_resolution)) + 1 - num_fp16_res), 8)
         self.w_dim, self.img_resolution, self.img_channels = w_dim, img_resolution, img_channels
         self.block_resolutions = [2 ** i for i in range(2, int(np.log2(img_resolution)) + 1)]
         self.motion_encoder = MotionMappingNetwork(motion_z_dim, motion_v_dim, motion_kernel_size, motion_z_distance,
@@ -212,7 +224,8 @@ class SynthesisNetwork(torch.nn.Module):
         ch = {res: min(channel_base // res, channel_max) for res in self.block_resolutions}
         self.num_ws = 0
         for res in self.block_resolutions:
-            block = SynthesisBlock(ch[res // 2] if res > 4 else 0, ch[res], w_dim, self.motion_v_dim, res, img_channels, resample_filter)
+            block = SynthesisBlock(ch[res // 2] if res > 4 else 0, ch[res], w_dim, self.motion_v_dim, res, img_channels, resample_filter,
+                                   use_fp16=(res >= fp16_resolution), conv_clamp=conv_clamp)
             self.num_ws += block.num_conv
             if res == img_resolution:
                 self.num_ws += block.num_torgb
@@ -254,17 +267,16 @@ class SynthesisNetwork(torch.nn.Module):
         unfused=None (default): CUDA inputs run the fused NHWC layers (first-order differentiable); CPU inputs, or unfused=True,
         run the layer-by-layer formulation on the drop-in ops (any-order differentiable: path-length regularisation).
         fused_modconv only applies to the unfused formulation: None = the reference's rule (grouped per-sample-weight conv in eval
-        mode, shared-weight conv in training mode, networks.py:232)."""
+        mode, shared-weight conv in training mode, networks.py:232).  Networks built with num_fp16_res / conv_clamp always run unfused."""
         assert t.ndim == 2 and len(ws) == len(t)
         assert ws.shape[1] == self.num_ws and ws.shape[2] == self.w_dim
         if motion_v is None:
             motion_v = self.motion_encoder(t, motion_z=motion_z, t_max=t_max)['motion_v']
         ws = ws.to(torch.float32).repeat_interleave(t.shape[1], dim=0)
         if unfused is None:
-            unfused = not ws.is_cuda
+            unfused = (not ws.is_cuda) or self.mixed_precision
+        assert unfused or not self.mixed_precision, 'fp16 / conv_clamp blocks run on the unfused ops only'
         if unfused:
-            if fused_modconv is None:
-                fused_modconv = not self.training
             x = img = None
             w_idx = 0
             for res in self.block_resolutions:

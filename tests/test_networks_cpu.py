@@ -162,3 +162,43 @@ def test_generator_wraps_mapping_and_synthesis():
     img = G(z, torch.zeros(2, 0), t)
     assert img.shape == (4, 3, 32, 32) and torch.isfinite(img).all()
     assert {k.split('.')[0] for k in G.state_dict()} == {'synthesis', 'mapping'}
+
+
+def test_mixed_precision_mode_vs_reference_golden():
+    """num_fp16_res / conv_clamp (the reference's default training precision, train.py:173-174): fp16 activations + clamp 256 in the
+    high-resolution blocks of G and D, fp16 pre-normalisation of weights and styles (networks.py:50-52), fused_modconv rule of
+    networks.py:232 — on the unfused ops, against the reference run the same way on CPU."""
+    g, meta = load_golden('mixed_precision_tiny.npz')
+    cfg = sr.SynthesisConfig(**meta['G'])
+    kw = dict(w_dim=cfg.w_dim, img_resolution=cfg.img_resolution, channel_base=cfg.channel_base, channel_max=cfg.channel_max,
+              motion_z_dim=cfg.motion_z_dim, motion_v_dim=cfg.motion_v_dim, time_enc_dim=cfg.time_enc_dim)
+    net = SynthesisNetwork(num_fp16_res=meta['num_fp16_res'], conv_clamp=meta['conv_clamp'], **kw)
+    net.load_state_dict({k[2:]: _t(g[k]) for k in g.files if k.startswith('p:')})
+    assert [getattr(net, f'b{r}').use_fp16 for r in net.block_resolutions] == [False, False, True, True]
+    ws, t, mz = _t(g['ws']).requires_grad_(True), _t(g['t']), _t(g['motion_z'])
+    net.train()
+    img = net(ws, t, motion_z=mz)
+    assert img.dtype == torch.float32 and rel_err(img, _t(g['img_train'])) < 2e-3           # fp16 activations: half-ulp flips allowed
+    names = [k[2:] for k in g.files if k.startswith('g:')]
+    P = dict(net.named_parameters())
+    grads = torch.autograd.grad(img, [ws] + [P[n] for n in names], _t(g['dimg']))
+    assert rel_err(grads[0], _t(g['d_ws'])) < 1e-2
+    for n, a in zip(names, grads[1:]):
+        assert rel_err(a, _t(g['g:' + n])) < 1e-2, n
+    net.eval()
+    with torch.no_grad():
+        assert rel_err(net(ws, t, motion_z=mz), _t(g['img_eval'])) < 2e-3
+        assert rel_err(net(ws[:1], t[:1], motion_z=mz[:1]), _t(g['img_eval_b1'])) < 2e-3
+    md = meta['D']
+    D = Discriminator(c_dim=0, img_resolution=md['img_resolution'], channel_base=md['channel_base'], channel_max=md['channel_max'],
+                      num_frames_per_video=md['num_frames_per_video'], max_num_frames=md['max_num_frames'], concat_res=md['concat_res'],
+                      num_frames_div_factor=md['num_frames_div_factor'], mbstd_group_size=md['mbstd_group_size'], mapping_layers=md['mapping_layers'],
+                      num_fp16_res=meta['num_fp16_res'], conv_clamp=meta['conv_clamp'])
+    D.load_state_dict({k[2:]: _t(g[k]) for k in g.files if k.startswith('d:')})
+    assert [getattr(D, f'b{r}').use_fp16 for r in D.block_resolutions] == [True, True, False]
+    x = _t(g['d_img']).requires_grad_(True)
+    D.train()
+    logits = D(x, torch.zeros(2, 0), _t(g['d_t']))['image_logits']
+    assert rel_err(logits, _t(g['d_logits'])) < 2e-3
+    gin, gw = torch.autograd.grad(logits.sum(), [x, D.b8.conv0.weight])
+    assert rel_err(gin, _t(g['d_gin'])) < 1e-2 and rel_err(gw, _t(g['d_gw_b8_conv0'])) < 1e-2
