@@ -55,6 +55,8 @@ def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, ga
     _require(out_w >= 1 and out_h >= 1, 'output must be at least 1x1')
     y = torch.empty([N, C, out_h, out_w], dtype=x.dtype, device=x.device, memory_format=_suggest_format(x))
     _require(y.numel() <= INT_MAX, 'output is too large')
+    if y.numel() == 0:            # empty batch / no channels: nothing to launch (the reference's zero-sized grid raises instead)
+        return y
 
     p = _lib.UpfirdnParams()
     p.x, p.f, p.y = x.data_ptr(), f.data_ptr(), y.data_ptr()
