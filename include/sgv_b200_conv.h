@@ -42,7 +42,7 @@ int sgv_conv_prep_weights_pair(const float* w, int32_t out_ch, int32_t in_ch, in
  * Out-of-range input pixels read as zero.  Output element (n, oy, ox, o) lives at
  *   y + n*out_stride_n + oy*out_stride_y + ox*out_stride_x + o        (element strides; lets one call write a
  *   polyphase sub-lattice of a larger tensor, which is how the stride-2 transposed convolution is issued).
- * Requirements: cin % 32 == 0, cout % 64 == 0 (or cout in {16, 32}), x and wp 16-byte aligned, y and strides multiples of 4 elements.
+ * Requirements: cin % 32 == 0, cout % 64 == 0 (or cout == 32), x and wp 16-byte aligned, y and strides multiples of 4 elements.
  */
 typedef struct sgv_conv_params {
     const float* x;            /* [n, h, w, cin] NHWC */

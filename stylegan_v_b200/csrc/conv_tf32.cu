@@ -415,7 +415,10 @@ extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
     SGV_CHECK_ARG(p->x && p->wp && p->y, "sgv_conv2d_tf32: x, wp and y must be non-NULL");
     SGV_CHECK_ARG(p->n >= 1 && p->h >= 1 && p->w >= 1 && p->out_h >= 1 && p->out_w >= 1, "extents must be positive");
     SGV_CHECK_ARG(p->cin >= 32 && p->cin % 32 == 0, "cin must be a multiple of 32 (got %d)", p->cin);
-    SGV_CHECK_ARG(p->cout % 64 == 0 || p->cout == 32 || p->cout == 16, "cout must be a multiple of 64, or 16/32 (got %d)", p->cout);
+    // 16 output channels are rejected: the epilogue reads the accumulator in 32-column TMEM slices (tmem_ld_32x32), so a 16-wide N tile ran
+    // zero epilogue iterations and stored nothing (found on the GPU in round 1, profiles/debug_d_layers_cout16_r1.txt).  No reference
+    // configuration has such a layer; callers take the library path for it (stylegan_v_b200/native_conv.py::_ok_channels).
+    SGV_CHECK_ARG(p->cout % 64 == 0 || p->cout == 32, "cout must be a multiple of 64, or 32 (got %d)", p->cout);
     SGV_CHECK_ARG(p->ntaps >= 1 && p->ntaps <= SGV_CONV_MAX_TAPS, "ntaps must be in [1, %d]", SGV_CONV_MAX_TAPS);
     SGV_CHECK_ARG(p->in_stride == 1 || p->in_stride == 2, "in_stride must be 1 or 2");
     SGV_CHECK_ARG(p->act == 1 || p->act == 3, "act must be 1 (linear) or 3 (lrelu)");
@@ -498,6 +501,6 @@ extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
         case 128: return launch_conv<128, 6>(tmx, tmw, a, grid, stream);
         case 64:  return launch_conv<64, 8>(tmx, tmw, a, grid, stream);
         case 32:  return launch_conv<32, 8>(tmx, tmw, a, grid, stream);
-        default:  return launch_conv<16, 8>(tmx, tmw, a, grid, stream);
+        default:  return fail(SGV_ERR_UNSUPPORTED, "sgv_conv2d_tf32: no kernel for an N tile of %d columns", bn);
     }
 }

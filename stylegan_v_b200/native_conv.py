@@ -22,9 +22,10 @@ enabled = True
 
 
 def _ok_channels(k_ch, n_ch):
-    """forward / data-gradient kernel: GEMM-K channels % 32, GEMM-N channels % 64 (or exactly 32).  16 output channels are NOT routed here:
-    that tile shape produced wrong results for the 32 -> 16 channel down layers of a tiny discriminator (round-1 GPU run, scripts/debug_d_layers.py)
-    and no configuration of the reference has it (narrowest layers: 64 channels at 256^2, 32 at 1024^2) — such calls take the library path."""
+    """forward / data-gradient kernel: GEMM-K channels % 32, GEMM-N channels % 64 (or exactly 32).  16 output channels are NOT routed here: the
+    kernel's epilogue works in 32-column TMEM slices, so a 16-wide tile stored nothing (wrong 32 -> 16 channel down layers of a tiny
+    discriminator in the round-1 GPU run, scripts/debug_d_layers.py); no configuration of the reference has such a layer (narrowest: 64
+    channels at 256^2, 32 at 1024^2) — those calls take the library path, and the C ABI rejects them."""
     return k_ch % 32 == 0 and (n_ch % 64 == 0 or n_ch == 32)
 
 
