@@ -353,6 +353,41 @@ def gen_mixed_precision(ref):
     np.savez_compressed(os.path.join(OUT, 'mixed_precision_tiny.npz'), **out)
 
 
+AUG_CASES = [
+    # name, constructor kwargs (train.py:271-279 'bgc' = blit + geom + color, all multipliers 1), p, input shape
+    dict(name='bgc', kw=dict(xflip=1, rotate90=1, xint=1, scale=1, rotate=1, aniso=1, xfrac=1, brightness=1, contrast=1, lumaflip=1, hue=1, saturation=1), p=0.8, shape=[4, 3, 32, 32]),
+    dict(name='bgc_clip', kw=dict(xflip=1, rotate90=1, xint=1, scale=1, rotate=1, aniso=1, xfrac=1, brightness=1, contrast=1, lumaflip=1, hue=1, saturation=1), p=1.0, shape=[3, 9, 24, 40]),
+    dict(name='blit', kw=dict(xflip=1, rotate90=1, xint=1), p=1.0, shape=[5, 3, 16, 16]),
+    dict(name='color_gray', kw=dict(brightness=1, contrast=1, lumaflip=1), p=1.0, shape=[3, 1, 16, 16]),
+    dict(name='filter_noise_cutout', kw=dict(imgfilter=1, noise=1, cutout=1), p=1.0, shape=[3, 3, 32, 32]),
+    dict(name='bgc_debug', kw=dict(xflip=1, rotate90=1, xint=1, scale=1, rotate=1, aniso=1, xfrac=1, brightness=1, contrast=1, lumaflip=1, hue=1, saturation=1,
+                                   imgfilter=1, noise=1, cutout=1), p=1.0, shape=[2, 3, 32, 32], debug_percentile=0.7),
+]
+
+
+def gen_augment(ref):
+    """Reference AugmentPipe (augment.py:117-436) outputs for fixed generator seeds: the whole random-number stream is part of the contract."""
+    out = {}
+    g = torch.Generator().manual_seed(41)
+    for case in AUG_CASES:
+        pipe = ref.augment.AugmentPipe(**case['kw'])
+        pipe.p.copy_(torch.as_tensor(case['p']))
+        x = torch.randn(case['shape'], generator=g).requires_grad_(True)
+        torch.manual_seed(1234)
+        y = pipe(x, debug_percentile=case.get('debug_percentile'))
+        dy = torch.randn(y.shape, generator=g)
+        dx, = torch.autograd.grad(y, [x], dy)
+        out[case['name'] + ':x'] = x.detach().numpy()
+        out[case['name'] + ':y'] = y.detach().numpy()
+        out[case['name'] + ':dy'] = dy.numpy()
+        out[case['name'] + ':dx'] = dx.numpy()
+        if case['name'] == 'bgc':
+            for k, v in pipe.state_dict().items():
+                out['buf:' + k] = v.numpy().copy()
+    out['meta'] = np.frombuffer(json.dumps(AUG_CASES).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, 'augment_cases.npz'), **out)
+
+
 def gen_loss_phases(ref):
     """The reference's StyleGAN2Loss.accumulate_gradients (loss.py:73-173) on tiny reference G and D, one call per phase with fixed RNG
     state: per-parameter gradient sums and norms (+ a few full tensors) for Gmain, Dmain and Dreg (R1)."""
@@ -396,7 +431,20 @@ def gen_loss_phases(ref):
         for n in keep:
             out[f'grad:{phase}:{n}'] = dict(module.named_parameters())[n].grad.numpy().copy()
     out['w_avg_after'] = G.mapping.w_avg.numpy().copy()
-    out['meta'] = np.frombuffer(json.dumps(dict(G=TINY, D=TINY_D, r1_gamma=0.5)).encode(), dtype=np.uint8)
+    # the same Dmain phase with the ADA pipe in front of D, video-consistent (loss.py:58-70): generator stream = motion noise, then the
+    # pipe's draws for the generated clip, then for the real clip
+    loss.cfg = ref_loader.to_cfg(dict(model=dict(loss_kwargs=dict(video_consistent_aug=True)), sampling=dict(num_frames_per_video=3)))
+    loss.augment_pipe = ref.augment.AugmentPipe(**AUG_CASES[0]['kw'])
+    loss.augment_pipe.p.copy_(torch.as_tensor(0.6))
+    G.requires_grad_(False); D.requires_grad_(True)
+    for p in D.parameters():
+        p.grad = None
+    torch.manual_seed(100)
+    loss.accumulate_gradients(phase='Dmain', real_img=real, real_c=c, real_t=real_t, gen_z=z, gen_c=c, gen_t=gen_t, sync=True, gain=1)
+    stats = {n: [float(p.grad.double().sum()), float(p.grad.double().norm())] for n, p in D.named_parameters() if p.grad is not None}
+    out['stats:Dmain_aug'] = np.frombuffer(json.dumps(stats).encode(), dtype=np.uint8)
+    out['grad:Dmain_aug:b32.conv1.weight'] = D.b32.conv1.weight.grad.numpy().copy()
+    out['meta'] = np.frombuffer(json.dumps(dict(G=TINY, D=TINY_D, r1_gamma=0.5, aug=AUG_CASES[0]['kw'], aug_p=0.6)).encode(), dtype=np.uint8)
     np.savez_compressed(os.path.join(OUT, 'loss_phases_tiny.npz'), **out)
 
 
@@ -413,6 +461,7 @@ def main():
     gen_path_length(ref)
     gen_loss_phases(ref)
     gen_mixed_precision(ref)
+    gen_augment(ref)
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
 

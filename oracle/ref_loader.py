@@ -80,5 +80,6 @@ def load():
     ns.layers = importlib.import_module('training.layers')
     ns.motion = importlib.import_module('training.motion')
     ns.loss = importlib.import_module('training.loss')
+    ns.augment = importlib.import_module('training.augment')
     _loaded = ns
     return ns

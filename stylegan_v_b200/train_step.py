@@ -32,23 +32,36 @@ def _d_kwargs(x):
     return dict(fused=True) if (FUSED_DISCRIMINATOR and x.is_cuda) else dict(fused=False)
 
 
-def generator_main_loss(G, D, z, c, t, **synthesis_kwargs):
+def run_discriminator(D, img, c, t, augment_pipe=None, video_consistent_aug=True, **d_kwargs):
+    """D on (optionally augmented) frames — loss.py:58-72.  With video_consistent_aug the F frames of a clip enter the pipe as one
+    [B, F*3, H, W] image so that they receive the same geometric and colour transform."""
+    if augment_pipe is not None:
+        if video_consistent_aug:
+            nf, ch, h, w = img.shape
+            f = t.shape[1]
+            img = augment_pipe(img.view(nf // f, f * ch, h, w)).view(nf, ch, h, w)
+        else:
+            img = augment_pipe(img)
+    return D(img, c, t, **d_kwargs)
+
+
+def generator_main_loss(G, D, z, c, t, augment_pipe=None, video_consistent_aug=True, **synthesis_kwargs):
     img = G(z, c, t, **synthesis_kwargs)
-    return F.softplus(-D(img, c, t, **_d_kwargs(img))['image_logits']).mean()
+    return F.softplus(-run_discriminator(D, img, c, t, augment_pipe, video_consistent_aug, **_d_kwargs(img))['image_logits']).mean()
 
 
-def discriminator_main_loss(G, D, real_img, real_c, real_t, z, c, t, **synthesis_kwargs):
+def discriminator_main_loss(G, D, real_img, real_c, real_t, z, c, t, augment_pipe=None, video_consistent_aug=True, **synthesis_kwargs):
     """Returns (loss on generated frames, loss on real frames); the reference backpropagates them separately (loss.py:139,173)."""
     with torch.no_grad():
         fake = G(z, c, t, **synthesis_kwargs)
-    loss_gen = F.softplus(D(fake, c, t, **_d_kwargs(fake))['image_logits']).mean()
-    loss_real = F.softplus(-D(real_img, real_c, real_t, **_d_kwargs(fake))['image_logits']).mean()
+    loss_gen = F.softplus(run_discriminator(D, fake, c, t, augment_pipe, video_consistent_aug, **_d_kwargs(fake))['image_logits']).mean()
+    loss_real = F.softplus(-run_discriminator(D, real_img, real_c, real_t, augment_pipe, video_consistent_aug, **_d_kwargs(fake))['image_logits']).mean()
     return loss_gen, loss_real
 
 
-def discriminator_r1_loss(D, real_img, real_c, real_t, r1_gamma):
+def discriminator_r1_loss(D, real_img, real_c, real_t, r1_gamma, augment_pipe=None, video_consistent_aug=True):
     img = real_img.detach().requires_grad_(True)
-    logits = D(img, real_c, real_t, fused=False)['image_logits']
+    logits = run_discriminator(D, img, real_c, real_t, augment_pipe, video_consistent_aug, fused=False)['image_logits']
     with conv2d_gradfix.no_weight_gradients():
         grads, = torch.autograd.grad([logits.sum()], [img], create_graph=True, only_inputs=True)
     penalty = grads.square().sum([1, 2, 3]) * (r1_gamma / 2)                      # per frame
@@ -79,10 +92,11 @@ class TrainingPhases:
     values (tensors; no host sync)."""
 
     def __init__(self, G, D, lr=0.0025, betas=(0.0, 0.99), eps=1e-8, r1_gamma=0.2048, pl_weight=0.0, G_reg_interval=4, D_reg_interval=16,
-                 ema_kimg=20.0, ema_rampup=None, batch_size=64, process_group=None, device_step=False):
+                 ema_kimg=20.0, ema_rampup=None, batch_size=64, process_group=None, device_step=False, augment_pipe=None, video_consistent_aug=True):
         assert next(G.parameters()).is_cuda, 'TrainingPhases drives the CUDA path only'
         conv2d_gradfix.enabled = True                                               # training_loop.py:143
         self.G, self.D = G, D
+        self.aug = dict(augment_pipe=augment_pipe, video_consistent_aug=video_consistent_aug)      # ADA pipe in front of D (loss.py:58-70); None = off
         if getattr(G.synthesis, '_pstream', None) is not None:
             G.synthesis._pstream = None                                             # a CUDA stream handle is not deep-copyable; it is re-created lazily
         self.G_ema = copy.deepcopy(G).eval().requires_grad_(False)
@@ -135,7 +149,7 @@ class TrainingPhases:
         self.cur_nimg += self.batch_size
         # ---- G phases
         self._grad_mode(True)
-        loss = generator_main_loss(self.G, self.D, z, c, t, **synthesis_kwargs)
+        loss = generator_main_loss(self.G, self.D, z, c, t, **self.aug, **synthesis_kwargs)
         loss.backward()
         out['Gmain'] = loss.detach()
         self._finish(self.G_state, self.G_opt, ema_beta=None if do_greg else self.ema_beta())
@@ -146,12 +160,12 @@ class TrainingPhases:
             self._finish(self.G_state, self.G_opt, ema_beta=self.ema_beta())
         # ---- D phases
         self._grad_mode(False)
-        loss_gen, loss_real = discriminator_main_loss(self.G, self.D, real_img, real_c, real_t, z, c, t, **synthesis_kwargs)
+        loss_gen, loss_real = discriminator_main_loss(self.G, self.D, real_img, real_c, real_t, z, c, t, **self.aug, **synthesis_kwargs)
         (loss_gen + loss_real).backward()
         out['Dmain'] = (loss_gen + loss_real).detach()
         self._finish(self.D_state, self.D_opt)
         if do_dreg:
-            loss = discriminator_r1_loss(self.D, real_img, real_c, real_t, self.r1_gamma)
+            loss = discriminator_r1_loss(self.D, real_img, real_c, real_t, self.r1_gamma, **self.aug)
             loss.mul(self.D_reg_interval).backward()
             out['Dreg'] = loss.detach()
             self._finish(self.D_state, self.D_opt)

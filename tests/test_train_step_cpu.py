@@ -86,3 +86,23 @@ def test_w_avg_tracks_both_generator_calls():
     run_phase('Gmain', G, D, g, torch.device('cpu'), meta['r1_gamma'])
     run_phase('Dmain', G, D, g, torch.device('cpu'), meta['r1_gamma'])
     assert rel_err(G.mapping.w_avg, _t(g['w_avg_after'])) < 1e-5
+
+
+def test_dmain_with_video_consistent_augmentation_vs_reference_loss():
+    """Dmain with the ADA pipe in front of D (loss.py:58-70, video_consistent_aug): same generator stream (motion noise, pipe draws for
+    the generated clips, pipe draws for the real clips) and same discriminator gradients as the reference loss."""
+    from stylegan_v_b200.augment import AugmentPipe
+    g, meta = load_golden('loss_phases_tiny.npz')
+    G, D = make_gd(g, meta)
+    pipe = AugmentPipe(**meta['aug'])
+    pipe.p.copy_(torch.as_tensor(meta['aug_p']))
+    real = _t(g['real'])
+    real = real.view(-1, *real.shape[2:])
+    real_t, gen_t, z = _t(g['real_t']), _t(g['gen_t']), _t(g['z'])
+    c = torch.zeros(len(z), 0)
+    G.requires_grad_(False)
+    D.requires_grad_(True)
+    torch.manual_seed(100)
+    a, b = ts.discriminator_main_loss(G, D, real, c, real_t, z, c, gen_t, augment_pipe=pipe, video_consistent_aug=True)
+    (a + b).backward()
+    check_phase('Dmain_aug', D, g, 1e-4, 1e-4)
