@@ -164,3 +164,49 @@ int NAME(const T* xin, const T* bin, const T* xrefin, const T* yrefin, const T* 
 
 DEFINE_BIAS_ACT(oracle_bias_act_f32, float, expf, logf)
 DEFINE_BIAS_ACT(oracle_bias_act_f64, double, exp, log)
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * oracle_time_encoder_tail_f32 — plain-C restatement of the elementwise tail of the continuous Fourier time-encoder:
+ * /root/reference/src/training/motion.py:111-115 (t_left = t - t % d, t_right = t_left + d, interp = (t % d) / d; Python / torch
+ * remainder semantics) and :198-212 (periods = tanh(.) + 1; raw = freqs * periods * tau + phases * phase_scales for tau in
+ * {t, t_left, t_right}; [sin, cos]; pos - lerp(left, right) + lerp(aligners_left, aligners_right)), every product / sum rounded to
+ * fp32 on its own like the chain of PyTorch kernels (the file is built with -ffp-contract=off; volatile stores stop x87-style excess
+ * precision).  heads_left [m, 4F] = [P u_L | Phi u_L | A u_L], aligners_right [m, 2F], out [m, 2F].
+ */
+static float r32(float v) { volatile float r = v; return r; }
+
+void oracle_time_encoder_tail_f32(const float* heads_left, const float* aligners_right, const float* t, const float* freqs,
+                                  const float* phase_scales, float* out, int m, int nf, float d)
+{
+    for (int row = 0; row < m; row++)
+    {
+        float rem = fmodf(t[row], d);                               /* torch remainder: fmod, then shifted to the sign of d */
+        if (rem != 0.f && ((rem < 0.f) != (d < 0.f))) rem = r32(rem + d);
+        const float t_left = r32(t[row] - rem);                     /* motion.py:111 */
+        const float t_right = r32(t_left + d);                      /* :112 */
+        const float a = r32(rem / d);                               /* :114 */
+        const float na = r32(1.f - a);
+        const float* h = heads_left + (size_t)row * 4 * nf;
+        const float* ar = aligners_right + (size_t)row * 2 * nf;
+        float* o = out + (size_t)row * 2 * nf;
+        for (int f = 0; f < nf; f++)
+        {
+            const float periods = r32(tanhf(h[f]) + 1.f);           /* :198 */
+            const float base = r32(freqs[f] * periods);             /* :203 freqs * periods ... */
+            const float shift = r32(h[nf + f] * phase_scales[f]);   /*      ... phases * phase_scales */
+            const float taus[3] = {t[row], t_left, t_right};
+            float s[3], c[3];
+            for (int k = 0; k < 3; k++)
+            {
+                const float raw = r32(r32(base * taus[k]) + shift); /* :203-205 */
+                s[k] = sinf(raw); c[k] = cosf(raw);                 /* :207-209 */
+            }
+            const float rem_s = r32(r32(s[1] * na) + r32(s[2] * a));                        /* :212 */
+            const float rem_c = r32(r32(c[1] * na) + r32(c[2] * a));
+            const float add_s = r32(r32(h[2 * nf + f] * na) + r32(ar[f] * a));              /* :213 */
+            const float add_c = r32(r32(h[3 * nf + f] * na) + r32(ar[nf + f] * a));
+            o[f] = r32(r32(s[0] - rem_s) + add_s);                                          /* :214 */
+            o[nf + f] = r32(r32(c[0] - rem_c) + add_c);
+        }
+    }
+}

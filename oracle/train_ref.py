@@ -34,6 +34,20 @@ def time_encoder_tail_ref(heads_left, aligners_right, t, freqs, phase_scales, d)
     return emb(t) - remove + add                                          # :214
 
 
+def time_encoder_tail_c(heads_left, aligners_right, t, freqs, phase_scales, d):
+    """The same tail through the plain-C port (oracle/c/sgv_oracle.c::oracle_time_encoder_tail_f32): scalar loops, libm sin/cos/tanh."""
+    import ctypes
+    from . import ops_ref
+    L = ops_ref.lib()
+    hl, ar = heads_left.contiguous().float(), aligners_right.contiguous().float()
+    tt, fr, ps = t.reshape(-1).contiguous().float(), freqs.reshape(-1).contiguous().float(), phase_scales.reshape(-1).contiguous().float()
+    m, nf = tt.numel(), fr.numel()
+    out = torch.empty(m, 2 * nf)
+    vp = lambda x: ctypes.c_void_p(x.data_ptr())
+    L.oracle_time_encoder_tail_f32(vp(hl), vp(ar), vp(tt), vp(fr), vp(ps), vp(out), ctypes.c_int(m), ctypes.c_int(nf), ctypes.c_float(float(d)))
+    return out
+
+
 def nan_to_num_ref(g, nan=0.0, posinf=1e5, neginf=-1e5):
     """torch_utils/misc.py:49-56 — note that it clamps finite values as well."""
     assert nan == 0

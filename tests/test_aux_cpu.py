@@ -80,6 +80,22 @@ def test_kernel_arithmetic_time_encoder_fwd(emul):
     assert float((torch.from_numpy(out) - ref).abs().max()) < 5e-4
 
 
+def test_c_port_of_the_tail_and_kernel_arithmetic_bit_exact(emul):
+    """Three statements of the same arithmetic: the torch restatement (pinned to the reference golden above), the plain-C port, and the
+    kernel's per-element code compiled for the host.  The C port and the kernel arithmetic share libm, so they must agree BIT FOR BIT
+    (operation order, separate roundings, remainder semantics); the torch version differs only by its vectorised sin / cos / tanh."""
+    hl, ar, t, freqs, ps = _tail_inputs(m=53, nf=40, seed=7)
+    t[6:10] = torch.tensor([1008.0, 1022.99, 0.001, 511.5])
+    c_out = train_ref.time_encoder_tail_c(hl, ar, t, freqs, ps, 16.0)
+    m, nf = t.numel(), freqs.numel()
+    k_out = np.zeros([m, 2 * nf], np.float32)
+    a = [x.numpy().copy() for x in (hl, ar, t, freqs, ps)]
+    emul.emul_time_encoder_fwd(*[_ptr(x) for x in a], _ptr(k_out), m, nf, ctypes.c_float(16.0))
+    assert np.array_equal(c_out.numpy(), k_out)
+    ref = train_ref.time_encoder_tail_ref(hl, ar, t, freqs, ps, 16.0)
+    assert float((c_out - ref).abs().max()) < 5e-4
+
+
 def test_kernel_arithmetic_time_encoder_bwd(emul):
     hl, ar, t, freqs, ps = _tail_inputs(seed=1, tmax=200.0)
     m, nf = t.numel(), freqs.numel()
