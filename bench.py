@@ -543,7 +543,6 @@ def main():
                                args.steps, args.warmup)
     if graph is not None:
         launches = (graph_launches + (1 if opt is not None else 0)) * args.steps      # launches recorded at capture time, replayed once per step (+ the update kernel)
-    clocks = sampler.stop() if rank == 0 else None
 
     # (2) end to end: H2D of the step's inputs from pinned memory, D2H of the loss, every step
     def e2e_step():
@@ -551,6 +550,7 @@ def main():
         loss = step(ws, t, mz)
         h_out.copy_(loss.detach().reshape(1), non_blocking=True)
     ms_e2e, _ = timed(e2e_step, args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions (device-resident and end-to-end)
 
     ms_step = ms_total / args.steps
     frames = N * world
