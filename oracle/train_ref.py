@@ -9,7 +9,10 @@ CPU restatement of the pieces either side of the contraction stack:
 * `optimizer_step_ref` — the parameter update of one training phase (training_loop.py:381-386: nan_to_num = clamp(nansum),
   torch_utils/misc.py:49-56; then torch.optim.Adam.step(), the very optimiser class the reference constructs,
   train.py:192-193) and the G_ema update (training_loop.py:392-400).  torch.optim.Adam is third-party arithmetic for the
-  reference too (torch, pinned by environment.yaml:8-10); it is CALLED here, not restated.
+  reference too (torch; environment.yaml:8-10 pins pytorch 1.7.1, environment-ampere.yaml:15-17 pytorch 1.9); it is CALLED here
+  (torch 2.11 in this image), not restated.  Its published algorithm for the options the reference passes (no weight decay, no
+  amsgrad): m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps) — unchanged between
+  those versions.
 """
 import torch
 
