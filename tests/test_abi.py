@@ -95,3 +95,21 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
                 assert 'oracle/' not in src or f.endswith('.md'), f
+
+
+def test_aux_entry_points_have_no_cpu_path():
+    """Time-encoder tail, fused optimiser step and the fused layer nodes refuse CPU tensors / a missing device instead of computing elsewhere."""
+    import torch
+    from stylegan_v_b200.optim import FlatModuleState, FusedAdamEMA
+    from stylegan_v_b200.time_encoder import _TimeEncoderTail
+    from stylegan_v_b200 import dconv
+    with pytest.raises(Exception):
+        _TimeEncoderTail.apply(torch.zeros(2, 16), torch.zeros(2, 8), torch.zeros(2), torch.ones(4), torch.ones(4), 16.0)
+    with pytest.raises(AssertionError):
+        FusedAdamEMA(FlatModuleState([torch.nn.Parameter(torch.zeros(8))]))
+    assert not dconv.supported(torch.zeros(1, 64, 8, 8), torch.zeros(64, 64, 3, 3), 1, 1)          # CPU tensors never take the fused node
+    L = _lib.lib()
+    if not torch.cuda.is_available():
+        buf = (ctypes.c_float * 64)()
+        rc = L.sgv_time_encoder_fwd(buf, buf, buf, buf, buf, buf, 1, 4, ctypes.c_float(16.0), None)
+        assert rc == 4 and b'no CPU path' in L.sgv_last_error()                                    # SGV_ERR_NO_DEVICE
