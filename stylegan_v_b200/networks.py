@@ -323,6 +323,19 @@ class Discriminator(torch.nn.Module):
         self.b4 = DiscriminatorEpilogue(ch[4], cmap_dim, 4, img_channels, architecture=architecture, mbstd_group_size=mbstd_group_size,
                                         mbstd_num_channels=mbstd_num_channels, conv_clamp=conv_clamp)
 
+    @classmethod
+    def from_reference_cfg(cls, cfg, img_resolution, img_channels=3, c_dim=0, channel_base=16384, channel_max=512, mbstd_group_size=4,
+                           mapping_layers=2, **kwargs):
+        """Builds the module from the reference's `cfg.model.discriminator` node (configs/model/stylegan-v.yaml:47-51 + `sampling`), given as a
+        nested dict / attribute object, the way train.py:166-178 assembles D_kwargs."""
+        get = (lambda o, k, d=None: o.get(k, d) if hasattr(o, 'get') else getattr(o, k, d))
+        sampling = get(cfg, 'sampling')
+        return cls(c_dim=c_dim, img_resolution=img_resolution, img_channels=img_channels, channel_base=channel_base, channel_max=channel_max,
+                   num_frames_per_video=get(sampling, 'num_frames_per_video'), max_num_frames=get(sampling, 'max_num_frames'),
+                   sampling_type=get(sampling, 'type', 'random'), concat_res=get(cfg, 'concat_res', 16),
+                   num_frames_div_factor=get(cfg, 'num_frames_div_factor', 2), dummy_c=get(cfg, 'dummy_c', False),
+                   mbstd_group_size=mbstd_group_size, mapping_layers=mapping_layers, **kwargs)
+
     def forward(self, img, c, t, fused=None):
         """fused=None: CUDA inputs use the fused conv + bias + activation nodes when no second-order gradient can be requested, i.e.
         when gradient mode is off or the caller says so explicitly; TrainingPhases passes fused=True for the main phases and False for R1."""
@@ -350,6 +363,32 @@ class Generator(torch.nn.Module):
         self.synthesis = SynthesisNetwork(w_dim=w_dim, img_resolution=img_resolution, img_channels=img_channels, **synthesis_kwargs)
         self.num_ws = self.synthesis.num_ws
         self.mapping = MappingNetwork(z_dim=z_dim, c_dim=c_dim, w_dim=w_dim, num_ws=self.num_ws, num_layers=mapping_layers)
+
+    @classmethod
+    def from_reference_cfg(cls, cfg, img_resolution, img_channels=3, channel_base=16384, channel_max=512, mapping_layers=2, **kwargs):
+        """Builds the module from the reference's `cfg.model.generator` node (configs/model/stylegan-v.yaml:3-45 + `sampling`), nested dict or
+        attribute object, the way train.py:163-172 assembles G_kwargs.  Options this implementation does not cover raise instead of being ignored."""
+        get = (lambda o, k, d=None: o.get(k, d) if hasattr(o, 'get') else getattr(o, k, d))
+        motion, tenc, sampling = get(cfg, 'motion'), get(cfg, 'time_enc'), get(cfg, 'sampling')
+        unsupported = []
+        if get(cfg, 'use_noise', False):
+            unsupported.append('use_noise=true')
+        if get(get(cfg, 'input', {}), 'type', 'temporal') != 'temporal':
+            unsupported.append('input.type != temporal')
+        if get(tenc, 'cond_type', 'concat_const') != 'concat_const':
+            unsupported.append('time_enc.cond_type != concat_const')
+        if get(motion, 'gen_strategy', 'conv') != 'conv' or not get(motion, 'fourier', True):
+            unsupported.append('motion.gen_strategy != conv / fourier=false')
+        if get(cfg, 'c_dim', 0) not in (0, None):
+            unsupported.append('c_dim > 0')
+        if unsupported:
+            raise NotImplementedError('generator options outside the stylegan-v.yaml model: ' + ', '.join(unsupported))
+        return cls(z_dim=get(cfg, 'z_dim', 512), c_dim=0, w_dim=get(cfg, 'w_dim', 512), img_resolution=img_resolution, img_channels=img_channels,
+                   mapping_layers=mapping_layers, channel_base=channel_base, channel_max=channel_max,
+                   motion_z_dim=get(motion, 'z_dim', 512), motion_v_dim=get(motion, 'v_dim', 512), motion_kernel_size=get(motion, 'kernel_size', 11),
+                   motion_z_distance=get(motion, 'motion_z_distance', get(tenc, 'min_period_len', 16)), time_enc_dim=get(tenc, 'dim', 256),
+                   min_period_len=get(tenc, 'min_period_len', 16), max_period_len=get(tenc, 'max_period_len', 1024),
+                   max_num_frames=get(sampling, 'max_num_frames', 1024), **kwargs)
 
     def forward(self, z, c, t, truncation_psi=1, truncation_cutoff=None, **synthesis_kwargs):
         assert len(z) == len(c) == len(t) and t.ndim == 2

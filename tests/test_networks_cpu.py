@@ -202,3 +202,23 @@ def test_mixed_precision_mode_vs_reference_golden():
     assert rel_err(logits, _t(g['d_logits'])) < 2e-3
     gin, gw = torch.autograd.grad(logits.sum(), [x, D.b8.conv0.weight])
     assert rel_err(gin, _t(g['d_gin'])) < 1e-2 and rel_err(gw, _t(g['d_gw_b8_conv0'])) < 1e-2
+
+
+def test_modules_from_reference_cfg_nodes():
+    """Generator / Discriminator built from the reference's own config nodes (stylegan-v.yaml values) have the reference's state-dict keys and shapes."""
+    g, meta = load_golden('loss_phases_tiny.npz')
+    cfg = sr.SynthesisConfig(**meta['G'])
+    G = Generator.from_reference_cfg(cfg.reference_generator_cfg(), img_resolution=cfg.img_resolution, channel_base=cfg.channel_base,
+                                     channel_max=cfg.channel_max, mapping_layers=2)
+    want = {k[2:]: tuple(g[k].shape) for k in g.files if k.startswith('g:')}
+    assert {k: tuple(v.shape) for k, v in G.state_dict().items()} == want
+    md = meta['D']
+    dcfg = dict(sampling=dict(num_frames_per_video=md['num_frames_per_video'], max_num_frames=md['max_num_frames'], type='random'),
+                concat_res=md['concat_res'], num_frames_div_factor=md['num_frames_div_factor'], dummy_c=False)
+    D = Discriminator.from_reference_cfg(dcfg, img_resolution=md['img_resolution'], channel_base=md['channel_base'], channel_max=md['channel_max'],
+                                         mbstd_group_size=md['mbstd_group_size'], mapping_layers=md['mapping_layers'])
+    want = {k[2:]: tuple(g[k].shape) for k in g.files if k.startswith('d:')}
+    assert {k: tuple(v.shape) for k, v in D.state_dict().items()} == want
+    bad = dict(cfg.reference_generator_cfg(), use_noise=True)
+    with pytest.raises(NotImplementedError):
+        Generator.from_reference_cfg(bad, img_resolution=32)
