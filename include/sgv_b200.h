@@ -11,7 +11,8 @@
  *     `stream` argument (a cudaStream_t passed as void*; NULL = legacy default stream);
  *   - the caller selects the device (cudaSetDevice) before calling — reference: OptionalCUDAGuard,
  *     upfirdn2d.cpp:31, bias_act.cpp:54;
- *   - re-entrant, no mutable global state besides a thread-local error string;
+ *   - re-entrant; global state is limited to a thread-local error string, a launch counter and per-device caches of
+ *     one-time set-up (kernel attributes, occupancy, SM count) kept in atomics;
  *   - returns 0 on success, non-zero on error (sgv_last_error() describes it) — the reference raises
  *     through TORCH_CHECK / AT_CUDA_CHECK (upfirdn2d.cpp:19-28,92; bias_act.cpp:35-51,88);
  *   - sizes are int32 like the reference (numel <= INT_MAX, upfirdn2d.cpp:22-23,36; bias_act.cpp:40);
@@ -27,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SGV_ABI_VERSION 1
+#define SGV_ABI_VERSION 2
 
 enum sgv_dtype { SGV_F32 = 0, SGV_F16 = 1, SGV_F64 = 2 };
 
@@ -53,7 +54,8 @@ int64_t     sgv_kernel_launch_count(void); /* kernels launched by this library i
  * Any dense/strided NCHW or channels_last layout is accepted through the strides.
  *
  * Optional fused epilogue (not in the reference plugin; used by the native synthesis layers):
- *   y = act((fir(x) * scale[n,c] ) + bias[c]) * act_gain, clamp   with act in {linear(1), lrelu(3)}
+ *   y = act((fir(x) * scale[n,c] + noise[n,oy,ox]) + bias[c]) * act_gain, clamp   with act in {linear(1), lrelu(3)}
+ * (the order of modulated_conv2d's fma(x, dcoefs, noise) followed by bias_act: networks.py:68-69,141-143)
  * disabled when epi_scale == epi_bias == NULL and epi_act == 0.
  */
 typedef struct sgv_upfirdn2d_params {
@@ -78,6 +80,10 @@ typedef struct sgv_upfirdn2d_params {
     float   epi_alpha, epi_gain, epi_clamp;   /* clamp < 0 disables */
     int32_t epi_round_tf32;                   /* != 0 (needs epi_act != 0): round the result to TF32 (nearest, ties away) — lets a tensor-core
                                                  consumer skip its operand-rounding pass; channels_last 4x4 up=down=1 kernels only */
+    const float* epi_noise;                   /* per-pixel noise plane(s), already multiplied by the noise strength, or NULL (needs epi_act != 0):
+                                                 element (n, oy, ox) at epi_noise[n*epi_noise_stride_n + oy*epi_noise_stride_y + ox*epi_noise_stride_x];
+                                                 stride_n = 0 broadcasts one plane over the batch (noise_mode='const', networks.py:133-134) */
+    int64_t epi_noise_stride_n, epi_noise_stride_y, epi_noise_stride_x;
 } sgv_upfirdn2d_params;
 
 int sgv_upfirdn2d_out_size(int in_size, int up, int pad0, int pad1, int fsize, int down);

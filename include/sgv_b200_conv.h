@@ -9,7 +9,12 @@
  *
  * Layout: activations are NHWC fp32 (torch channels_last); weights are pre-arranged once per call by
  * sgv_conv_prep_weights into [tap][out_channel][in_channel] fp32 rounded to TF32 (round-to-nearest).
- * Arithmetic: TF32 x TF32 products, fp32 accumulation in TMEM (tcgen05.mma.kind::tf32).
+ * Arithmetic, two modes:
+ *   tf32x1 (default)  TF32 x TF32 products, fp32 accumulation in TMEM (tcgen05.mma.kind::tf32): <= 1e-3 of fp32 per contraction.
+ *   tf32x3            fp32-grade: every operand is split into hi = tf32(v) and lo = tf32(v - hi); the kernels accumulate
+ *                     hi*hi + lo*hi + hi*lo (three tensor-core products per term, fp32 accumulation): ~1e-6 of fp32, the mode that
+ *                     corresponds to the reference's torch.backends.cudnn.allow_tf32 = False (training_loop.py:141-142).
+ *                     Selected per call: sgv_conv_params.wp_lo != NULL, sgv_wgrad_params.precision = 1.
  * Same contract as include/sgv_b200.h: caller-owned buffers, no allocation, no synchronisation, work is
  * enqueued on `stream`, 0 on success.
  */
@@ -29,6 +34,11 @@ extern "C" {
 int sgv_conv_prep_weights(const float* w, int64_t stride_row, int64_t stride_col, int64_t stride_ky, int64_t stride_kx,
                           int32_t rows, int32_t cols, int32_t ntaps, const int32_t* tap_ky, const int32_t* tap_kx,
                           float* wp, void* stream);
+/* The same with a scale folded in (equalised-lr weight gain, layers.py:131,361) and, for the tf32x3 mode, the hi/lo split:
+ *   v = w[...] * w_scale;   wp[t][r][k] = tf32_rn(v);   wp_lo[t][r][k] = tf32_rn(v - wp[t][r][k])   (wp_lo may be NULL) */
+int sgv_conv_prep_weights_ex(const float* w, int64_t stride_row, int64_t stride_col, int64_t stride_ky, int64_t stride_kx,
+                             int32_t rows, int32_t cols, int32_t ntaps, const int32_t* tap_ky, const int32_t* tap_kx,
+                             float w_scale, float* wp, float* wp_lo, void* stream);
 
 /* Both slab sets of a layer from one read of a DENSE weight w[out_ch][in_ch][kh][kw] (1x1 or 3x3, channel counts % 32 == 0):
  *   wp_a[t][o][i] = tf32_rn(w[o][i][a_ky[t]][a_kx[t]])   (forward contraction: rows = out_ch)          — skipped when wp_a is NULL
@@ -36,9 +46,14 @@ int sgv_conv_prep_weights(const float* w, int64_t stride_row, int64_t stride_col
 int sgv_conv_prep_weights_pair(const float* w, int32_t out_ch, int32_t in_ch, int32_t kh, int32_t kw,
                                int32_t ntaps_a, const int32_t* a_ky, const int32_t* a_kx, float* wp_a,
                                int32_t ntaps_b, const int32_t* b_ky, const int32_t* b_kx, float* wp_b, void* stream);
+/* tf32x3 variant: additionally writes the residual slabs wp_a_lo / wp_b_lo (same shapes; lo = tf32_rn(w - tf32_rn(w))); each may be NULL
+ * together with its hi set. */
+int sgv_conv_prep_weights_pair_x3(const float* w, int32_t out_ch, int32_t in_ch, int32_t kh, int32_t kw,
+                                  int32_t ntaps_a, const int32_t* a_ky, const int32_t* a_kx, float* wp_a, float* wp_a_lo,
+                                  int32_t ntaps_b, const int32_t* b_ky, const int32_t* b_kx, float* wp_b, float* wp_b_lo, void* stream);
 
 /* y[n, oy, ox, o] = epilogue( sum_{t, i}  x[n, oy*in_stride + tap_dy[t], ox*in_stride + tap_dx[t], i] * a_scale[n, i] * wp[t][o][i] )
- *   epilogue(v) = clamp( act( v * o_scale[n, o] + bias[o] ) * gain )        (each piece optional)
+ *   epilogue(v) = clamp( act( v * o_scale[n, o] + noise[n, oy, ox] + bias[o] ) * gain )        (each piece optional)
  * Out-of-range input pixels read as zero.  Output element (n, oy, ox, o) lives at
  *   y + n*out_stride_n + oy*out_stride_y + ox*out_stride_x + o        (element strides; lets one call write a
  *   polyphase sub-lattice of a larger tensor, which is how the stride-2 transposed convolution is issued).
@@ -71,9 +86,24 @@ typedef struct sgv_conv_params {
     /* optional: x already holds TF32-representable values and needs no scaling (a_scale must be NULL): the persistent kernel skips its
      * operand-staging pass over the activation patches (they go TMA -> MMA directly) */
     int32_t      a_ready;
+    /* optional, tf32x3 mode: residual slabs [ntaps, cout, cin] from sgv_conv_prep_weights_ex / _pair_x3 (same allocation as wp, at a
+     * non-negative offset that is a multiple of cin elements).  a_ready must be 0 (the activations are split inside the kernel). */
+    const float* wp_lo;
+    /* optional noise-add of the modulated convolution (networks.py:68-69,130-134; fma.py:15): per-pixel plane(s) already multiplied by
+     * the noise strength, added after o_scale and before the bias; element (n, oy, ox) at noise[n*noise_stride_n + oy*noise_stride_y +
+     * ox*noise_stride_x]; noise_stride_n = 0 broadcasts one plane over the batch.  Not with accumulate = 1. */
+    const float* noise;
+    int64_t      noise_stride_n, noise_stride_y, noise_stride_x;
 } sgv_conv_params;
 
 int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream);
+
+/* Which kernel variant sgv_conv2d_tf32 would launch for *p (no launch, no device work): lets tests assert that a shape really
+ * exercises the variant a benchmark runs.  kernel = 1 per-tap kernel (conv_tf32.cu), 3 persistent halo-patch
+ * kernel (conv_tf32_v3.cu); bn = N tile (output channels per CTA or CTA pair), mh = 128-pixel M halves per tile, cluster =
+ * CTAs sharing weight slabs by TMA multicast, cta_pair = 1 when the MMAs are issued as tcgen05 cta_group::2, x3 = 1 in tf32x3 mode. */
+typedef struct sgv_conv_variant { int32_t kernel, bn, mh, cluster, cta_pair, x3; } sgv_conv_variant;
+int sgv_conv2d_tf32_variant(const sgv_conv_params* p, sgv_conv_variant* out);
 
 /* Weight gradient of the same contraction (replaces aten::cudnn_convolution_backward_weight /
  * cudnn_convolution_transpose_backward_weight, conv2d_gradfix.py:140-148), with both per-sample scalings fused:
@@ -106,9 +136,15 @@ typedef struct sgv_wgrad_params {
     /* optional: the operand already holds TF32-representable values with its scale applied (g_scale / x_scale must then be NULL): the
      * kernel skips that operand's staging pass (scale + round in shared memory), which is its bottleneck (profiles/wgrad_ablation_r1.txt) */
     int32_t g_ready, x_ready;
+    int32_t precision;         /* 0 = tf32x1, 1 = tf32x3 (three passes over the hi / lo parts of both operands; g_ready / x_ready must be 0) */
 } sgv_wgrad_params;
 
 int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream);
+
+/* Variant query for the weight gradient (see sgv_conv2d_tf32_variant): kernel = 1 per-tap kernel, 2 grouped-tap kernel; nt = N tile
+ * (input channels per CTA), stages = pipeline depth, ksplit = split-K factor, passes = launches issued (3 in tf32x3 mode). */
+typedef struct sgv_wgrad_variant { int32_t kernel, nt, stages, ksplit, passes; } sgv_wgrad_variant;
+int sgv_conv2d_wgrad_tf32_variant(const sgv_wgrad_params* p, sgv_wgrad_variant* out);
 
 /* ---- one-pass NHWC companions of the fused layer (csrc/layer_elementwise.cu) -------------------------------------------
  * All tensors float32; activations [n, hw, c] (NHWC, c % 4 == 0, 256 % (c/4) == 0); accumulation outputs (db, dd, ds, dwmod)

@@ -207,6 +207,43 @@ def gen_synthesis(ref):
     np.savez_compressed(os.path.join(OUT, 'synthesis_tiny.npz'), **out)
 
 
+def gen_synthesis_noise(ref):
+    """The reference SynthesisNetwork with use_noise = true (networks.py:119-121,130-134), noise_mode='const', non-zero strengths:
+    image + gradients incl. d(noise_strength).  Pins the noise-add of the fused layers (a6)."""
+    tiny = dict(TINY, img_resolution=16)
+    cfg = sr.SynthesisConfig(**tiny, use_noise=True)
+    rcfg = ref_loader.to_cfg(cfg.reference_generator_cfg())
+    torch.manual_seed(3)
+    S = ref.networks.SynthesisNetwork(w_dim=cfg.w_dim, img_resolution=cfg.img_resolution, img_channels=3,
+                                      channel_base=cfg.channel_base, channel_max=cfg.channel_max, cfg=rcfg)
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for n, p in S.named_parameters():
+            if n.endswith('.bias') and 'affine' not in n:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+            if n.endswith('.noise_strength'):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+    B, Fr = 2, 2
+    ws = torch.randn(B, S.num_ws, cfg.w_dim, generator=g).requires_grad_(True)
+    t = torch.tensor([[0.0, 5.25], [100.5, 130.75]])
+    c = torch.zeros(B, 0)
+    mz = torch.randn(B, sr.max_traj_len(cfg, float(t.max())), cfg.motion_z_dim, generator=g)
+    S.train()
+    img = S(ws, t=t, c=c, motion_z=mz, noise_mode='const')
+    dimg = torch.randn(img.shape, generator=g)
+    params = dict(S.named_parameters())
+    names = sorted(params.keys())
+    grads = torch.autograd.grad(img, [ws] + [params[n] for n in names], dimg)
+    out = {}
+    for k, v in S.state_dict().items():
+        out['p:' + k] = v.detach().numpy()
+    out.update(ws=ws.detach().numpy(), t=t.numpy(), motion_z=mz.numpy(), img_train=img.detach().numpy(), dimg=dimg.numpy(), d_ws=grads[0].numpy())
+    for n, gr in zip(names, grads[1:]):
+        out['g:' + n] = gr.numpy()
+    out['meta'] = np.frombuffer(json.dumps(dict(tiny, use_noise=True)).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, 'synthesis_noise_tiny.npz'), **out)
+
+
 TINY_D = dict(img_resolution=32, channel_base=1024, channel_max=32, num_frames_per_video=3, max_num_frames=1024, concat_res=16,
               num_frames_div_factor=2, mbstd_group_size=2, mapping_layers=2)
 
@@ -448,15 +485,20 @@ def gen_loss_phases(ref):
     np.savez_compressed(os.path.join(OUT, 'loss_phases_tiny.npz'), **out)
 
 
-def main():
+def main(only=None):
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.load()
     torch.set_num_threads(4)
+    if only:            # python -m oracle.make_goldens gen_synthesis_noise ...  (re-mint selected files only)
+        for name in only:
+            globals()[name](ref)
+        return
     gen_upfirdn2d(ref)
     gen_bias_act(ref)
     gen_modconv(ref)
     gen_conv2d_resample(ref)
     gen_synthesis(ref)
+    gen_synthesis_noise(ref)
     gen_discriminator(ref)
     gen_path_length(ref)
     gen_loss_phases(ref)
@@ -467,4 +509,5 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    import sys
+    main(sys.argv[1:])

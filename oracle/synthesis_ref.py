@@ -148,10 +148,13 @@ def motion_encoder(P, cfg: SynthesisConfig, t, motion_z, prefix='motion_encoder.
 # ----------------------------------------------------------------------------------------------
 # synthesis layers
 
-def synthesis_layer(P, name, x, w, up, resample_filter, fused_modconv, gain=1.0, conv_clamp=None):
+def synthesis_layer(P, name, x, w, up, resample_filter, fused_modconv, gain=1.0, conv_clamp=None, noise_mode='none'):
     styles = fully_connected(w, P[name + '.affine.weight'], P[name + '.affine.bias'])
     weight = P[name + '.weight']
-    x = ops_ref.modulated_conv2d_ref(x, weight, styles, noise=None, up=up, padding=weight.shape[2] // 2,
+    noise = None                                                                     # networks.py:130-134 ('random' draws are the caller's business)
+    if noise_mode == 'const' and (name + '.noise_const') in P:
+        noise = P[name + '.noise_const'] * P[name + '.noise_strength']
+    x = ops_ref.modulated_conv2d_ref(x, weight, styles, noise=noise, up=up, padding=weight.shape[2] // 2,
                                      resample_filter=resample_filter, flip_weight=(up == 1), fused_modconv=fused_modconv)
     act_gain = float(np.sqrt(2)) * gain
     act_clamp = conv_clamp * gain if conv_clamp is not None else None
@@ -166,7 +169,7 @@ def torgb_layer(P, name, x, w, fused_modconv, conv_clamp=None):
 
 
 def synthesis_forward(P, cfg: SynthesisConfig, ws, t, motion_z=None, motion_v=None, fused_modconv=False,
-                      return_features=False):
+                      return_features=False, noise_mode='none'):
     """ws [B, num_ws, w_dim], t [B, F] -> img [B*F, 3, R, R] (networks.py:324-366, cond_type concat_const)."""
     B, Fr = t.shape
     assert ws.shape[1] == cfg.num_ws
@@ -187,10 +190,10 @@ def synthesis_forward(P, cfg: SynthesisConfig, ws, t, motion_z=None, motion_v=No
             const = P[b + '.input.input.const']                                         # layers.py:246-249
             x = torch.cat([const.repeat(B * Fr, 1, 1, 1),
                            motion_v.unsqueeze(2).unsqueeze(3).repeat(1, 1, 4, 4)], dim=1)
-            x = synthesis_layer(P, b + '.conv1', x, next(wi), 1, f, fused_modconv, conv_clamp=cfg.conv_clamp)
+            x = synthesis_layer(P, b + '.conv1', x, next(wi), 1, f, fused_modconv, conv_clamp=cfg.conv_clamp, noise_mode=noise_mode)
         else:
-            x = synthesis_layer(P, b + '.conv0', x, next(wi), 2, f, fused_modconv, conv_clamp=cfg.conv_clamp)
-            x = synthesis_layer(P, b + '.conv1', x, next(wi), 1, f, fused_modconv, conv_clamp=cfg.conv_clamp)
+            x = synthesis_layer(P, b + '.conv0', x, next(wi), 2, f, fused_modconv, conv_clamp=cfg.conv_clamp, noise_mode=noise_mode)
+            x = synthesis_layer(P, b + '.conv1', x, next(wi), 1, f, fused_modconv, conv_clamp=cfg.conv_clamp, noise_mode=noise_mode)
         if img is not None:
             img = ops_ref.upfirdn2d_ref_torch(img, f, up=2, padding=[2, 1, 2, 1], gain=4)   # upsample2d (upfirdn2d.py:308-343)
         y = torgb_layer(P, b + '.torgb', x, next(wi), fused_modconv, conv_clamp=cfg.conv_clamp)

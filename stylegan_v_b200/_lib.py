@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libsgv_b200.so')
 c_int, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 
 SGV_F32, SGV_F16, SGV_F64 = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class UpfirdnParams(ctypes.Structure):
@@ -30,6 +30,7 @@ class UpfirdnParams(ctypes.Structure):
         ('out_stride_x', c_i64), ('out_stride_y', c_i64), ('out_stride_c', c_i64), ('out_stride_n', c_i64),
         ('epi_scale', c_vp), ('epi_bias', c_vp), ('epi_act', c_int),
         ('epi_alpha', c_f32), ('epi_gain', c_f32), ('epi_clamp', c_f32), ('epi_round_tf32', c_int),
+        ('epi_noise', c_vp), ('epi_noise_stride_n', c_i64), ('epi_noise_stride_y', c_i64), ('epi_noise_stride_x', c_i64),
     ]
 
 
@@ -60,7 +61,18 @@ class ConvParams(ctypes.Structure):
         ('act', c_int), ('alpha', c_f32), ('gain', c_f32), ('clamp', c_f32),
         ('in_stride_n', c_i64), ('in_stride_y', c_i64), ('in_stride_x', c_i64), ('accumulate', c_int),
         ('red_x', c_vp), ('red_out', c_vp), ('a_ready', c_int),
+        ('wp_lo', c_vp), ('noise', c_vp), ('noise_stride_n', c_i64), ('noise_stride_y', c_i64), ('noise_stride_x', c_i64),
     ]
+
+
+class ConvVariant(ctypes.Structure):
+    """struct sgv_conv_variant"""
+    _fields_ = [('kernel', c_int), ('bn', c_int), ('mh', c_int), ('cluster', c_int), ('cta_pair', c_int), ('x3', c_int)]
+
+
+class WgradVariant(ctypes.Structure):
+    """struct sgv_wgrad_variant"""
+    _fields_ = [('kernel', c_int), ('nt', c_int), ('stages', c_int), ('ksplit', c_int), ('passes', c_int)]
 
 
 class WgradParams(ctypes.Structure):
@@ -73,7 +85,7 @@ class WgradParams(ctypes.Structure):
         ('g_scale', c_vp), ('x_scale', c_vp),
         ('x_stride_n', c_i64), ('x_stride_y', c_i64), ('x_stride_x', c_i64),
         ('use_dw_slot', c_int), ('dw_slot', c_int * CONV_MAX_TAPS),
-        ('g_ready', c_int), ('x_ready', c_int),
+        ('g_ready', c_int), ('x_ready', c_int), ('precision', c_int),
     ]
 
 
@@ -89,7 +101,7 @@ class AdamParams(ctypes.Structure):
 
 
 STRUCTS = {'sgv_upfirdn2d_params': UpfirdnParams, 'sgv_bias_act_params': BiasActParams, 'sgv_conv_params': ConvParams,
-           'sgv_wgrad_params': WgradParams, 'sgv_adam_params': AdamParams}
+           'sgv_wgrad_params': WgradParams, 'sgv_adam_params': AdamParams, 'sgv_conv_variant': ConvVariant, 'sgv_wgrad_variant': WgradVariant}
 
 # every symbol include/sgv_b200*.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -104,8 +116,14 @@ SYMBOLS = [
                                       ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_vp, c_vp]),
     ('sgv_conv_prep_weights_pair', c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_vp,
                                            c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_vp, c_vp]),
+    ('sgv_conv_prep_weights_ex', c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int,
+                                         ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_f32, c_vp, c_vp, c_vp]),
+    ('sgv_conv_prep_weights_pair_x3', c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_vp, c_vp,
+                                              c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_vp, c_vp, c_vp]),
     ('sgv_conv2d_tf32', c_int, [ctypes.POINTER(ConvParams), c_vp]),
+    ('sgv_conv2d_tf32_variant', c_int, [ctypes.POINTER(ConvParams), ctypes.POINTER(ConvVariant)]),
     ('sgv_conv2d_wgrad_tf32', c_int, [ctypes.POINTER(WgradParams), c_vp]),
+    ('sgv_conv2d_wgrad_tf32_variant', c_int, [ctypes.POINTER(WgradParams), ctypes.POINTER(WgradVariant)]),
     ('sgv_modconv_act_bwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),
     ('sgv_modconv_act_bwd_rgb', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),
     ('sgv_modconv_act_bwd_ex', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),

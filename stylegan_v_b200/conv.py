@@ -7,6 +7,7 @@ import ctypes
 import torch
 
 from . import _lib
+from . import precision as _precision
 
 
 def _stream(device):
@@ -18,67 +19,89 @@ def _req(cond, msg):
         raise RuntimeError(msg)
 
 
-def prep_weights(w, taps, rows_dim=0, cols_dim=1):
-    """[rows, cols, kh, kw]-like weight (any strides) -> [ntaps, rows, cols] TF32-rounded slab for the kernel.
+def prep_weights(w, taps, rows_dim=0, cols_dim=1, scale=1.0, x3=None):
+    """[rows, cols, kh, kw]-like weight (any strides) -> TF32 slabs for the kernel: [ntaps, rows, cols], or in tf32x3 mode
+    [2, ntaps, rows, cols] (hi parts, then the TF32 residuals).  `scale` is multiplied in before rounding (equalised-lr gain).
 
     taps: list of (ky, kx) kernel positions; rows_dim / cols_dim say which weight dims play GEMM-N (output
-    channels of the contraction) and GEMM-K (its input channels)."""
+    channels of the contraction) and GEMM-K (its input channels).  x3=None follows stylegan_v_b200.precision."""
     _req(w.is_cuda and w.dtype == torch.float32 and w.ndim == 4, 'weight must be a CUDA float32 4-D tensor')
     L = _lib.lib()
+    x3 = _precision.is_x3() if x3 is None else bool(x3)
     rows, cols = w.shape[rows_dim], w.shape[cols_dim]
     nt = len(taps)
-    wp = torch.empty([nt, rows, cols], dtype=torch.float32, device=w.device)
+    wp = torch.empty([2, nt, rows, cols] if x3 else [nt, rows, cols], dtype=torch.float32, device=w.device)
     ky = (ctypes.c_int32 * nt)(*[int(t[0]) for t in taps])
     kx = (ctypes.c_int32 * nt)(*[int(t[1]) for t in taps])
     with torch.cuda.device(w.device):
-        _lib.check(L.sgv_conv_prep_weights(w.data_ptr(), w.stride(rows_dim), w.stride(cols_dim), w.stride(2), w.stride(3),
-                                           rows, cols, nt, ky, kx, wp.data_ptr(), _stream(w.device)), 'sgv_conv_prep_weights')
+        _lib.check(L.sgv_conv_prep_weights_ex(w.data_ptr(), w.stride(rows_dim), w.stride(cols_dim), w.stride(2), w.stride(3),
+                                              rows, cols, nt, ky, kx, float(scale), wp.data_ptr(), wp[1].data_ptr() if x3 else None,
+                                              _stream(w.device)), 'sgv_conv_prep_weights_ex')
     return wp
 
 
-def prep_weights_pair(w, taps_fwd, taps_dgrad):
+def prep_weights_pair(w, taps_fwd, taps_dgrad, x3=None):
     """Dense [O, I, kh, kw] weight -> (wp_fwd [len(taps_fwd), O, I], wp_dgrad [len(taps_dgrad), I, O]), TF32-rounded, ONE launch
-    (sgv_conv_prep_weights_pair).  Equivalent to prep_weights(w, taps_fwd) and prep_weights(w, taps_dgrad, rows_dim=1, cols_dim=0)."""
+    (sgv_conv_prep_weights_pair[_x3]); in tf32x3 mode each gets a leading [2] = (hi, residual).
+    Equivalent to prep_weights(w, taps_fwd) and prep_weights(w, taps_dgrad, rows_dim=1, cols_dim=0)."""
     _req(w.is_cuda and w.dtype == torch.float32 and w.ndim == 4 and w.is_contiguous(), 'weight must be a dense CUDA float32 [O, I, kh, kw] tensor')
+    x3 = _precision.is_x3() if x3 is None else bool(x3)
     O, I, kh, kw = w.shape
     na, nb = len(taps_fwd), len(taps_dgrad)
-    wa = torch.empty([na, O, I], dtype=torch.float32, device=w.device)
-    wb = torch.empty([nb, I, O], dtype=torch.float32, device=w.device)
+    wa = torch.empty(([2] if x3 else []) + [na, O, I], dtype=torch.float32, device=w.device)
+    wb = torch.empty(([2] if x3 else []) + [nb, I, O], dtype=torch.float32, device=w.device)
     arr = lambda taps, j: (ctypes.c_int32 * max(len(taps), 1))(*[int(t[j]) for t in taps])
     L = _lib.lib()
     with torch.cuda.device(w.device):
-        _lib.check(L.sgv_conv_prep_weights_pair(w.data_ptr(), O, I, kh, kw, na, arr(taps_fwd, 0), arr(taps_fwd, 1), wa.data_ptr(),
-                                                nb, arr(taps_dgrad, 0), arr(taps_dgrad, 1), wb.data_ptr(), _stream(w.device)), 'sgv_conv_prep_weights_pair')
+        _lib.check(L.sgv_conv_prep_weights_pair_x3(w.data_ptr(), O, I, kh, kw, na, arr(taps_fwd, 0), arr(taps_fwd, 1), wa.data_ptr(),
+                                                   wa[1].data_ptr() if x3 else None, nb, arr(taps_dgrad, 0), arr(taps_dgrad, 1), wb.data_ptr(),
+                                                   wb[1].data_ptr() if x3 else None, _stream(w.device)), 'sgv_conv_prep_weights_pair_x3')
     return wa, wb
+
+
+def slab_taps(wp, start, stop):
+    """Taps [start, stop) of a slab tensor from prep_weights / prep_weights_pair (tap axis = -3), in either precision layout."""
+    return wp[..., start:stop, :, :]
 
 
 def igemm_conv(x, wp, tap_offsets, out=None, out_hw=None, out_view=None, in_stride=1,
                a_scale=None, o_scale=None, bias=None, act='linear', alpha=0.2, gain=1.0, clamp=None, accumulate=False,
-               red_x=None, red_out=None, a_ready=False):
+               red_x=None, red_out=None, a_ready=False, noise=None, query=False):
     """y[n,oy,ox,o] = epi(sum_{t,i} x[n, oy*in_stride+dy_t, ox*in_stride+dx_t, i] * a_scale[n,i] * wp[t,o,i]).
 
-    x: [N, Cin, H, W] channels_last fp32.  wp: [ntaps, Cout, Cin] from prep_weights.  tap_offsets: [(dy, dx)].
+    x: [N, Cin, H, W] channels_last fp32.  wp: [ntaps, Cout, Cin] from prep_weights — or [2, ntaps, Cout, Cin] (hi, residual),
+    which selects the fp32-grade tf32x3 arithmetic.  tap_offsets: [(dy, dx)].
+    noise: [N or 1, 1, out_h, out_w] (or [out_h, out_w]) plane added after o_scale, before the bias (modulated_conv2d's noise-add).
     Output: a new channels_last [N, Cout, out_h, out_w] tensor, or — for polyphase writes — `out_view`, a strided
-    view [N, Cout, out_h, out_w] (channel stride 1) of a larger channels_last tensor."""
+    view [N, Cout, out_h, out_w] (channel stride 1) of a larger channels_last tensor.
+    query=True: nothing is launched; returns the kernel variant the call would run (sgv_conv2d_tf32_variant) as a dict."""
     _req(x.is_cuda and x.dtype == torch.float32 and x.ndim == 4, 'x must be a CUDA float32 [N,C,H,W] tensor')
     N, Cin, H, W = x.shape
     dense = x.stride(1) == 1 and x.stride(3) == Cin and x.stride(2) == W * Cin and x.stride(0) == H * W * Cin
     _req(dense or (x.stride(1) == 1 and all(st % 4 == 0 for st in (x.stride(0), x.stride(2), x.stride(3)))),
          'x must be channels_last (NHWC), dense or a pixel-strided view with unit channel stride')
-    nt, Cout, Cin2 = wp.shape
-    _req(Cin2 == Cin and nt == len(tap_offsets) and wp.is_contiguous(), 'wp does not match x / taps')
+    x3 = wp.ndim == 4
+    _req(wp.ndim in (3, 4) and (not x3 or wp.shape[0] == 2), 'wp must be [ntaps, Cout, Cin] or [2, ntaps, Cout, Cin]')
+    nt, Cout, Cin2 = wp.shape[-3:]
+    wp_hi, wp_lo = (wp[0], wp[1]) if x3 else (wp, None)
+    _req(Cin2 == Cin and nt == len(tap_offsets) and wp_hi.is_contiguous() and (wp_lo is None or wp_lo.is_contiguous()), 'wp does not match x / taps')
+    if query:
+        out_view, y = None, None
     if out_view is not None:
         y = out_view
         oh, ow = y.shape[2], y.shape[3]
         _req(y.shape[0] == N and y.shape[1] == Cout and y.stride(1) == 1, 'out_view must be [N,Cout,oh,ow] with unit channel stride')
     else:
         oh, ow = out_hw if out_hw is not None else (H, W)
-        y = torch.empty([N, Cout, oh, ow], dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
-        if Cout == 1 or (oh == 1 and ow == 1):
-            y = torch.empty([N, oh, ow, Cout], dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
+        shape = [1, 1, 1, 4] if query else [N, oh, ow, Cout]          # a variant query touches no output
+        y = torch.empty(shape, dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
+        if query:
+            y = y.as_strided([N, Cout, oh, ow], [oh * ow * Cout, 1, ow * Cout, Cout])
     L = _lib.lib()
     p = _lib.ConvParams()
-    p.x, p.wp, p.y = x.data_ptr(), wp.data_ptr(), y.data_ptr()
+    p.x, p.wp, p.y = x.data_ptr(), wp_hi.data_ptr(), y.data_ptr()
+    if x3:
+        p.wp_lo = wp_lo.data_ptr()
     p.n, p.h, p.w, p.cin, p.cout = N, H, W, Cin, Cout
     p.out_h, p.out_w = oh, ow
     p.out_stride_n, p.out_stride_y, p.out_stride_x = y.stride(0), y.stride(2), y.stride(3)
@@ -98,12 +121,24 @@ def igemm_conv(x, wp, tap_offsets, out=None, out_hw=None, out_view=None, in_stri
     if not dense:
         p.in_stride_n, p.in_stride_y, p.in_stride_x = x.stride(0), x.stride(2), x.stride(3)
     p.accumulate = int(bool(accumulate))
-    p.a_ready = int(bool(a_ready and a_scale is None))      # x is already TF32-exact: no staging pass (persistent kernel)
+    p.a_ready = int(bool(a_ready and a_scale is None and not x3))      # x is already TF32-exact: no staging pass (persistent kernel)
+    if noise is not None:
+        nz = noise.to(torch.float32)
+        nz = nz.reshape(1, oh, ow) if nz.ndim == 2 else nz.reshape(nz.shape[0], oh, ow)
+        _req(nz.shape[0] in (1, N) and nz.device == x.device, 'noise must be [N or 1, 1, out_h, out_w] on the same device')
+        keep.append(nz)
+        p.noise = nz.data_ptr()
+        p.noise_stride_n, p.noise_stride_y, p.noise_stride_x = (nz.stride(0) if nz.shape[0] == N and N > 1 else 0), nz.stride(1), nz.stride(2)
     if red_out is not None:
         _req(red_x is not None and red_x.shape == y.shape and red_x.stride() == y.stride() and red_x.dtype == torch.float32,
              'red_x must have the shape and strides of the output')
         _req(red_out.dtype == torch.float32 and red_out.is_contiguous() and tuple(red_out.shape) == (N, Cout), 'red_out must be a contiguous float32 [N, Cout] buffer')
         p.red_x, p.red_out = red_x.data_ptr(), red_out.data_ptr()
+    if query:
+        v = _lib.ConvVariant()
+        with torch.cuda.device(x.device):
+            _lib.check(L.sgv_conv2d_tf32_variant(ctypes.byref(p), ctypes.byref(v)), 'sgv_conv2d_tf32_variant')
+        return {k: int(getattr(v, k)) for k, _ in v._fields_}
     with torch.cuda.device(x.device):
         _lib.check(L.sgv_conv2d_tf32(ctypes.byref(p), _stream(x.device)), 'sgv_conv2d_tf32')
     return y
@@ -117,12 +152,16 @@ def conv3x3_taps():
     return TAPS_3x3, [(ky - 1, kx - 1) for ky, kx in TAPS_3x3]
 
 
-def igemm_wgrad(g, x, taps_g, taps_x, out_hw, g_stride=1, x_stride=1, g_scale=None, x_scale=None, out=None, slots=None, g_ready=False, x_ready=False):
+def igemm_wgrad(g, x, taps_g, taps_x, out_hw, g_stride=1, x_stride=1, g_scale=None, x_scale=None, out=None, slots=None, g_ready=False, x_ready=False,
+                x3=None, query=False):
     """dw[t,o,i] = sum_{n,p} g[n, p*gs + dg_t, o] * g_scale[n,o] * x[n, p*xs + dx_t, i] * x_scale[n,i]  ->  [ntaps, Cout, Cin].
 
     g: [N, Cout, gh, gw], x: [N, Cin, xh, xw], both channels_last fp32; taps_*: per-tap (dy, dx) pixel offsets.
     g_ready / x_ready: that operand already holds TF32-representable, fully scaled values (its scale must be None): no staging pass.
-    out / slots: accumulate tap t into out[slots[t]] of a caller-provided (zeroed) [S, Cout, Cin] buffer instead of a fresh result."""
+    out / slots: accumulate tap t into out[slots[t]] of a caller-provided (zeroed) [S, Cout, Cin] buffer instead of a fresh result.
+    x3: fp32-grade tf32x3 arithmetic (three passes over hi / residual operand parts; None follows stylegan_v_b200.precision).
+    query=True: nothing is launched; returns the kernel variant (sgv_conv2d_wgrad_tf32_variant) as a dict."""
+    x3 = _precision.is_x3() if x3 is None else bool(x3)
     for name, t in (('g', g), ('x', x)):
         _req(t.is_cuda and t.dtype == torch.float32 and t.ndim == 4, f'{name} must be a CUDA float32 [N,C,H,W] tensor')
     _req(_is_nhwc(g), 'g must be dense channels_last (NHWC)')
@@ -134,7 +173,7 @@ def igemm_wgrad(g, x, taps_g, taps_x, out_hw, g_stride=1, x_stride=1, g_scale=No
     _req(N == N2 and len(taps_g) == len(taps_x), 'g / x / taps mismatch')
     nt = len(taps_g)
     if out is None:
-        dw = torch.zeros([nt, Cout, Cin], dtype=torch.float32, device=x.device)
+        dw = torch.zeros([nt, Cout, Cin] if not query else [4], dtype=torch.float32, device=x.device)
     else:
         dw = out
         _req(slots is not None and len(slots) == nt and dw.is_contiguous() and dw.dtype == torch.float32 and tuple(dw.shape[1:]) == (Cout, Cin)
@@ -157,11 +196,17 @@ def igemm_wgrad(g, x, taps_g, taps_x, out_hw, g_stride=1, x_stride=1, g_scale=No
             setattr(p, name, t.data_ptr())
     if not x_dense:
         p.x_stride_n, p.x_stride_y, p.x_stride_x = x.stride(0), x.stride(2), x.stride(3)
-    p.g_ready, p.x_ready = int(bool(g_ready and g_scale is None)), int(bool(x_ready and x_scale is None))
+    p.g_ready, p.x_ready = int(bool(g_ready and g_scale is None and not x3)), int(bool(x_ready and x_scale is None and not x3))
+    p.precision = int(x3)
     if out is not None:
         p.use_dw_slot = 1
         for i, sl in enumerate(slots):
             p.dw_slot[i] = int(sl)
+    if query:
+        v = _lib.WgradVariant()
+        with torch.cuda.device(x.device):
+            _lib.check(L.sgv_conv2d_wgrad_tf32_variant(ctypes.byref(p), ctypes.byref(v)), 'sgv_conv2d_wgrad_tf32_variant')
+        return {k: int(getattr(v, k)) for k, _ in v._fields_}
     with torch.cuda.device(x.device):
         _lib.check(L.sgv_conv2d_wgrad_tf32(ctypes.byref(p), _stream(x.device)), 'sgv_conv2d_wgrad_tf32')
     return dw

@@ -24,6 +24,30 @@ void count_launch(int n = 1);
     return ::sgv::fail(SGV_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); ::sgv::count_launch(); } while (0)
 
 int num_sms();   // SM count of the current device (cached per device)
+int current_device_slot();                       // cudaGetDevice() clamped to [0, kMaxDevices); -1 on failure
+int env_int(const char* name, int dflt);         // integer tuning switch from the environment (read by callers ONCE, into a static const)
+constexpr int kMaxDevices = 64;
+
+// Kernel attributes (cudaFuncSetAttribute) and occupancy answers belong to a device context, and entry points are called from several
+// threads (forward thread + autograd workers): cache them per device in zero-initialised atomics.
+struct PerDeviceInt
+{
+    std::atomic<int> v[kMaxDevices];
+    int get(int dev) const { return (dev >= 0 && dev < kMaxDevices) ? v[dev].load(std::memory_order_acquire) : 0; }
+    void set(int dev, int x) { if (dev >= 0 && dev < kMaxDevices) v[dev].store(x, std::memory_order_release); }
+};
+
+// opt a kernel into more than 48 KB of dynamic shared memory, once per device
+#define SGV_OPT_IN_SMEM(kern, bytes) do { static ::sgv::PerDeviceInt done__; const int dev__ = ::sgv::current_device_slot(); \
+    if (!done__.get(dev__)) { SGV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); done__.set(dev__, 1); } } while (0)
+
+// Ablation switches (skip staging / epilogue / MMAs: wrong results, timing only) exist only in builds with -DSGV_ABLATION; release
+// kernels carry no such branches.
+#ifdef SGV_ABLATION
+#define SGV_ABL(flags, bit) (((flags) & (bit)) != 0)
+#else
+#define SGV_ABL(flags, bit) false
+#endif
 
 template <class T> struct acc_type            { typedef float  type; };
 template <>        struct acc_type<double>    { typedef double type; };

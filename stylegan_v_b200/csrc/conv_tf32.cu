@@ -24,13 +24,13 @@
 #include "../../include/sgv_b200_conv.h"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace sgv {
 
 using namespace ptx;
 
-int conv2d_tf32_v2(const sgv_conv_params* p, cudaStream_t stream);     // conv_tf32_v2.cu
-int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream);     // conv_tf32_v3.cu
+int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream, sgv_conv_variant* query);     // conv_tf32_v3.cu
 
 constexpr int kConvThreads = 192;
 constexpr int kBM = 128;
@@ -49,6 +49,10 @@ struct ConvArgs
     int act; float alpha, gain, clamp;
     int accumulate;
     const float* red_x; float* red_out;
+    // tf32x3 (fp32-grade) mode: every (chunk, tap) k-step is issued three times — part 0: tf32(x*s) x hi slab, part 1: tf32 residual of
+    // x*s x hi slab, part 2: tf32(x*s) x lo slab; lo_row0 = first row of the lo slab set in the [rows, cin] slab tensor
+    int parts; int lo_row0;
+    const float* noise; long long nsn, nsy, nsx;
 };
 
 template <int BN, int STAGES>
@@ -83,7 +87,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int ox0 = tile_x * p.tw, oy0 = tile_y * p.th;
     const int nb0 = blockIdx.y * BN;                 // first output channel of this CTA
     const int kchunks = p.cin / kBK;
-    const int ksteps = kchunks * p.ntaps;
+    const int ksteps = kchunks * p.ntaps * p.parts;
 
     if (threadIdx.x == 0)
     {
@@ -111,15 +115,16 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             int stage = 0; uint32_t phase = 0;
             for (int kc = 0; kc < kchunks; kc++)
                 for (int t = 0; t < p.ntaps; t++)
-                {
-                    mbar_wait(empty_bar + stage, phase ^ 1);
-                    uint8_t* sa = smem + stage * L::kStageBytes;
-                    uint8_t* sb = sa + kATileBytes;
-                    mbar_expect_tx(full_bar + stage, L::kStageBytes);
-                    tma_load_4d(sa, &tmap_x, full_bar + stage, kc * kBK, ox0 * p.in_stride + p.tap_dx[t], oy0 * p.in_stride + p.tap_dy[t], n0);
-                    tma_load_2d(sb, &tmap_w, full_bar + stage, kc * kBK, t * p.cout + nb0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
+                    for (int part = 0; part < p.parts; part++)
+                    {
+                        mbar_wait(empty_bar + stage, phase ^ 1);
+                        uint8_t* sa = smem + stage * L::kStageBytes;
+                        uint8_t* sb = sa + kATileBytes;
+                        mbar_expect_tx(full_bar + stage, L::kStageBytes);
+                        tma_load_4d(sa, &tmap_x, full_bar + stage, kc * kBK, ox0 * p.in_stride + p.tap_dx[t], oy0 * p.in_stride + p.tap_dy[t], n0);
+                        tma_load_2d(sb, &tmap_w, full_bar + stage, kc * kBK, (part == 2 ? p.lo_row0 : 0) + t * p.cout + nb0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
         }
     }
     else if (warp == 1)
@@ -176,19 +181,33 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < kBK; j++) sv[j] = 1.f;
                 }
-                for (int t = 0; t < p.ntaps; t++)
+                for (int tp = 0; tp < p.ntaps * p.parts; tp++)
                 {
+                    const bool lo_part = (p.parts == 3) && (tp % 3 == 1);
                     mbar_wait(full_bar + stage, phase);
                     const uint32_t arow = smem_u32(smem + stage * L::kStageBytes) + (uint32_t)row * 128u;
                     float4 v[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++) v[j] = lds128(arow + (uint32_t)((j ^ (row & 7)) << 4));   // logical 16-byte chunk j
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
+                    if (!lo_part)
                     {
-                        v[j].x = tf32_rn(v[j].x * sv[4 * j + 0]); v[j].y = tf32_rn(v[j].y * sv[4 * j + 1]);
-                        v[j].z = tf32_rn(v[j].z * sv[4 * j + 2]); v[j].w = tf32_rn(v[j].w * sv[4 * j + 3]);
-                        sts128(arow + (uint32_t)((j ^ (row & 7)) << 4), v[j]);
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                        {
+                            v[j].x = tf32_rn(v[j].x * sv[4 * j + 0]); v[j].y = tf32_rn(v[j].y * sv[4 * j + 1]);
+                            v[j].z = tf32_rn(v[j].z * sv[4 * j + 2]); v[j].w = tf32_rn(v[j].w * sv[4 * j + 3]);
+                            sts128(arow + (uint32_t)((j ^ (row & 7)) << 4), v[j]);
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                        {
+                            v[j].x = tf32_lo(__fmul_rn(v[j].x, sv[4 * j + 0])); v[j].y = tf32_lo(__fmul_rn(v[j].y, sv[4 * j + 1]));
+                            v[j].z = tf32_lo(__fmul_rn(v[j].z, sv[4 * j + 2])); v[j].w = tf32_lo(__fmul_rn(v[j].w, sv[4 * j + 3]));
+                            sts128(arow + (uint32_t)((j ^ (row & 7)) << 4), v[j]);
+                        }
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
@@ -204,6 +223,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         float* yrow = p.y + (long long)nc * p.osn + (long long)oy * p.osy + (long long)ox * p.osx + nb0;
         const float* osc = p.o_scale ? p.o_scale + (long long)nc * p.cout + nb0 : nullptr;
         const float* bia = p.bias ? p.bias + nb0 : nullptr;
+        const float nz = (p.noise && valid) ? __ldg(p.noise + (long long)nc * p.nsn + (long long)oy * p.nsy + (long long)ox * p.nsx) : 0.f;
 #pragma unroll 1
         for (int cc = 0; cc < BN / 32; cc++)
         {
@@ -247,6 +267,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         const int col = cc * 32 + j * 4 + e;
                         float f = __uint_as_float(v[j * 4 + e]);
                         if (osc) f = __fmul_rn(f, __ldg(osc + col));
+                        if (p.noise) f = __fadd_rn(f, nz);
                         if (bia) f = __fadd_rn(f, __ldg(bia + col));
                         if (p.act == 3) f = (f > 0.f) ? f : f * p.alpha;
                         f *= p.gain;
@@ -270,7 +291,8 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 struct TapTable { int ky[SGV_CONV_MAX_TAPS]; int kx[SGV_CONV_MAX_TAPS]; };
 
 __global__ void __launch_bounds__(256) conv_prep_weights_kernel(const float* __restrict__ w, long long sr, long long sc, long long sky, long long skx,
-                                                                  int rows, int cols, int ntaps, TapTable taps, float* __restrict__ wp)
+                                                                  int rows, int cols, int ntaps, TapTable taps, float w_scale, float* __restrict__ wp,
+                                                                  float* __restrict__ wp_lo)
 {
     const long long total = (long long)ntaps * rows * cols;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
@@ -278,7 +300,9 @@ __global__ void __launch_bounds__(256) conv_prep_weights_kernel(const float* __r
         const int k = (int)(i % cols);
         const int r = (int)((i / cols) % rows);
         const int t = (int)(i / ((long long)cols * rows));
-        wp[i] = ptx::tf32_rn(w[r * sr + k * sc + taps.ky[t] * sky + taps.kx[t] * skx]);
+        const float v = __fmul_rn(w[r * sr + k * sc + taps.ky[t] * sky + taps.kx[t] * skx], w_scale);
+        wp[i] = ptx::tf32_rn(v);
+        if (wp_lo) wp_lo[i] = ptx::tf32_lo(v);
     }
 }
 
@@ -290,25 +314,38 @@ __global__ void __launch_bounds__(256) conv_prep_weights_kernel(const float* __r
 struct TapPair { int na, nb; int a[SGV_CONV_MAX_TAPS]; int b[SGV_CONV_MAX_TAPS]; };      // tap = ky * kw + kx
 
 template <int KK>
-__global__ void __launch_bounds__(256) conv_prep_pair_kernel(const float* __restrict__ w, int O, int I, TapPair taps, float* __restrict__ wa, float* __restrict__ wb)
+__global__ void __launch_bounds__(256) conv_prep_pair_kernel(const float* __restrict__ w, int O, int I, TapPair taps, float* __restrict__ wa, float* __restrict__ wb,
+                                                               float* __restrict__ wa_lo, float* __restrict__ wb_lo)
 {
     __shared__ float tile[32][32 * KK + 1];
     const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+    const bool split = wa_lo != nullptr || wb_lo != nullptr;      // tf32x3: the tile keeps the fp32 value, hi / lo are formed at the store
     for (int idx = threadIdx.x; idx < 32 * 32 * KK; idx += 256)
     {
         const int ol = idx / (32 * KK), rem = idx - ol * (32 * KK);
-        tile[ol][rem] = ptx::tf32_rn(w[((long long)(o0 + ol) * I + i0) * KK + rem]);
+        const float v = w[((long long)(o0 + ol) * I + i0) * KK + rem];
+        tile[ol][rem] = split ? v : ptx::tf32_rn(v);
     }
     __syncthreads();
     const int lo = threadIdx.x & 31, hi = threadIdx.x >> 5;      // 8 row groups
     if (wa)
         for (int t = 0; t < taps.na; t++)
             for (int ol = hi; ol < 32; ol += 8)
-                wa[((long long)t * O + o0 + ol) * I + i0 + lo] = tile[ol][lo * KK + taps.a[t]];
+            {
+                const float v = tile[ol][lo * KK + taps.a[t]];
+                const long long at = ((long long)t * O + o0 + ol) * I + i0 + lo;
+                wa[at] = ptx::tf32_rn(v);
+                if (wa_lo) wa_lo[at] = ptx::tf32_lo(v);
+            }
     if (wb)
         for (int t = 0; t < taps.nb; t++)
             for (int il = hi; il < 32; il += 8)
-                wb[((long long)t * I + i0 + il) * O + o0 + lo] = tile[lo][il * KK + taps.b[t]];
+            {
+                const float v = tile[lo][il * KK + taps.b[t]];
+                const long long at = ((long long)t * I + i0 + il) * O + o0 + lo;
+                wb[at] = ptx::tf32_rn(v);
+                if (wb_lo) wb_lo[at] = ptx::tf32_lo(v);
+            }
 }
 
 // ---- host ----
@@ -348,12 +385,7 @@ static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvA
 {
     using L = ConvSmem<BN, STAGES>;
     auto kern = conv_tf32_kernel<BN, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        SGV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-        attr_set = true;
-    }
+    SGV_OPT_IN_SMEM(kern, L::kTotal);
     kern<<<grid, kConvThreads, L::kTotal, stream>>>(tx, tw, a);
     SGV_LAUNCH_OK("conv_tf32_kernel");
     return SGV_OK;
@@ -365,9 +397,17 @@ extern "C" int sgv_conv_prep_weights_pair(const float* w, int32_t out_ch, int32_
                                           int32_t ntaps_a, const int32_t* a_ky, const int32_t* a_kx, float* wp_a,
                                           int32_t ntaps_b, const int32_t* b_ky, const int32_t* b_kx, float* wp_b, void* stream_)
 {
+    return sgv_conv_prep_weights_pair_x3(w, out_ch, in_ch, kh, kw, ntaps_a, a_ky, a_kx, wp_a, nullptr, ntaps_b, b_ky, b_kx, wp_b, nullptr, stream_);
+}
+
+extern "C" int sgv_conv_prep_weights_pair_x3(const float* w, int32_t out_ch, int32_t in_ch, int32_t kh, int32_t kw,
+                                             int32_t ntaps_a, const int32_t* a_ky, const int32_t* a_kx, float* wp_a, float* wp_a_lo,
+                                             int32_t ntaps_b, const int32_t* b_ky, const int32_t* b_kx, float* wp_b, float* wp_b_lo, void* stream_)
+{
     using namespace sgv;
     cudaStream_t stream = (cudaStream_t)stream_;
     SGV_CHECK_ARG(w && (wp_a || wp_b), "sgv_conv_prep_weights_pair: NULL argument");
+    SGV_CHECK_ARG((wp_a || !wp_a_lo) && (wp_b || !wp_b_lo), "a lo slab set needs its hi set");
     SGV_CHECK_ARG((kh == 3 && kw == 3) || (kh == 1 && kw == 1), "kernel must be 1x1 or 3x3");
     SGV_CHECK_ARG(out_ch % 32 == 0 && in_ch % 32 == 0 && out_ch > 0 && in_ch > 0, "channel counts must be positive multiples of 32");
     SGV_CHECK_ARG(ntaps_a >= 0 && ntaps_a <= SGV_CONV_MAX_TAPS && ntaps_b >= 0 && ntaps_b <= SGV_CONV_MAX_TAPS, "ntaps must be in [0, %d]", SGV_CONV_MAX_TAPS);
@@ -378,8 +418,8 @@ extern "C" int sgv_conv_prep_weights_pair(const float* w, int32_t out_ch, int32_
     for (int t = 0; t < tp.na; t++) { SGV_CHECK_ARG(a_ky[t] >= 0 && a_ky[t] < kh && a_kx[t] >= 0 && a_kx[t] < kw, "tap out of range"); tp.a[t] = a_ky[t] * kw + a_kx[t]; }
     for (int t = 0; t < tp.nb; t++) { SGV_CHECK_ARG(b_ky[t] >= 0 && b_ky[t] < kh && b_kx[t] >= 0 && b_kx[t] < kw, "tap out of range"); tp.b[t] = b_ky[t] * kw + b_kx[t]; }
     dim3 grid((unsigned)(in_ch / 32), (unsigned)(out_ch / 32));
-    if (kh == 3) conv_prep_pair_kernel<9><<<grid, 256, 0, stream>>>(w, out_ch, in_ch, tp, wp_a, wp_b);
-    else conv_prep_pair_kernel<1><<<grid, 256, 0, stream>>>(w, out_ch, in_ch, tp, wp_a, wp_b);
+    if (kh == 3) conv_prep_pair_kernel<9><<<grid, 256, 0, stream>>>(w, out_ch, in_ch, tp, wp_a, wp_b, wp_a_lo, wp_b_lo);
+    else conv_prep_pair_kernel<1><<<grid, 256, 0, stream>>>(w, out_ch, in_ch, tp, wp_a, wp_b, wp_a_lo, wp_b_lo);
     SGV_LAUNCH_OK("conv_prep_pair_kernel");
     return SGV_OK;
 }
@@ -387,6 +427,13 @@ extern "C" int sgv_conv_prep_weights_pair(const float* w, int32_t out_ch, int32_
 extern "C" int sgv_conv_prep_weights(const float* w, int64_t stride_row, int64_t stride_col, int64_t stride_ky, int64_t stride_kx,
                                      int32_t rows, int32_t cols, int32_t ntaps, const int32_t* tap_ky, const int32_t* tap_kx,
                                      float* wp, void* stream_)
+{
+    return sgv_conv_prep_weights_ex(w, stride_row, stride_col, stride_ky, stride_kx, rows, cols, ntaps, tap_ky, tap_kx, 1.0f, wp, nullptr, stream_);
+}
+
+extern "C" int sgv_conv_prep_weights_ex(const float* w, int64_t stride_row, int64_t stride_col, int64_t stride_ky, int64_t stride_kx,
+                                        int32_t rows, int32_t cols, int32_t ntaps, const int32_t* tap_ky, const int32_t* tap_kx,
+                                        float w_scale, float* wp, float* wp_lo, void* stream_)
 {
     using namespace sgv;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -399,7 +446,7 @@ extern "C" int sgv_conv_prep_weights(const float* w, int64_t stride_row, int64_t
     for (int t = 0; t < SGV_CONV_MAX_TAPS; t++) { taps.ky[t] = t < ntaps ? tap_ky[t] : 0; taps.kx[t] = t < ntaps ? tap_kx[t] : 0; }
     const long long total = (long long)ntaps * rows * cols;
     const unsigned grid = (unsigned)min((long long)num_sms() * 8, (total + 255) / 256);
-    conv_prep_weights_kernel<<<grid, 256, 0, stream>>>(w, stride_row, stride_col, stride_ky, stride_kx, rows, cols, ntaps, taps, wp);
+    conv_prep_weights_kernel<<<grid, 256, 0, stream>>>(w, stride_row, stride_col, stride_ky, stride_kx, rows, cols, ntaps, taps, w_scale, wp, wp_lo);
     SGV_LAUNCH_OK("conv_prep_weights_kernel");
     return SGV_OK;
 }
@@ -407,10 +454,23 @@ extern "C" int sgv_conv_prep_weights(const float* w, int64_t stride_row, int64_t
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
+static int conv2d_tf32_dispatch(const sgv_conv_params* p, cudaStream_t stream, sgv_conv_variant* query);
+
 extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
 {
+    return conv2d_tf32_dispatch(p, (cudaStream_t)stream_, nullptr);
+}
+
+extern "C" int sgv_conv2d_tf32_variant(const sgv_conv_params* p, sgv_conv_variant* out)
+{
+    SGV_CHECK_ARG(out != nullptr, "sgv_conv2d_tf32_variant: out is NULL");
+    memset(out, 0, sizeof(*out));
+    return conv2d_tf32_dispatch(p, nullptr, out);
+}
+
+static int conv2d_tf32_dispatch(const sgv_conv_params* p, cudaStream_t stream, sgv_conv_variant* query)
+{
     using namespace sgv;
-    cudaStream_t stream = (cudaStream_t)stream_;
     SGV_CHECK_ARG(p != nullptr, "sgv_conv2d_tf32: params is NULL");
     SGV_CHECK_ARG(p->x && p->wp && p->y, "sgv_conv2d_tf32: x, wp and y must be non-NULL");
     SGV_CHECK_ARG(p->n >= 1 && p->h >= 1 && p->w >= 1 && p->out_h >= 1 && p->out_w >= 1, "extents must be positive");
@@ -432,20 +492,19 @@ extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
     SGV_CHECK_ARG((p->in_stride_x == 0 && p->in_stride_y == 0 && p->in_stride_n == 0) ||
                   (p->in_stride_x % 4 == 0 && p->in_stride_y % 4 == 0 && p->in_stride_n % 4 == 0 && p->in_stride_x > 0),
                   "input view strides must be positive multiples of 4 elements (or all zero for a dense tensor)");
+    const bool x3 = p->wp_lo != nullptr;
+    SGV_CHECK_ARG(!x3 || (p->wp_lo >= p->wp && (p->wp_lo - p->wp) % p->cin == 0 && (p->wp_lo - p->wp) / p->cin < 0x40000000LL &&
+                          (reinterpret_cast<uintptr_t>(p->wp_lo) & 15) == 0), "wp_lo must follow wp in the same allocation at a multiple of cin elements");
+    SGV_CHECK_ARG(!x3 || !p->a_ready, "tf32x3 mode splits the activations inside the kernel: a_ready must be 0");
+    SGV_CHECK_ARG(!p->noise || !p->accumulate, "noise cannot be combined with accumulate=1");
     int rc = sgv_device_check();
     if (rc != SGV_OK) return rc;
 
-    // v2 (halo patch + shifted descriptors, csrc/conv_tf32_v2.cu) covers stride-1 inputs on planes >= 12x12; SGV_CONV_V1=1 forces v1
-    static const bool force_v1 = getenv("SGV_CONV_V1") != nullptr;
-    static const bool no_v3 = getenv("SGV_CONV_NO_V3") != nullptr;
-    if (!force_v1 && !no_v3)
-    {
-        rc = conv2d_tf32_v3(p, stream);      // persistent (csrc/conv_tf32_v3.cu)
-        if (rc != SGV_ERR_UNSUPPORTED) return rc;
-    }
+    // the persistent halo-patch kernel (csrc/conv_tf32_v3.cu) covers planes >= 12x12; SGV_CONV_V1=1 forces the per-tap kernel below (A/B runs)
+    static const bool force_v1 = env_int("SGV_CONV_V1", 0) != 0;
     if (!force_v1)
     {
-        rc = conv2d_tf32_v2(p, stream);
+        rc = conv2d_tf32_v3(p, stream, query);
         if (rc != SGV_ERR_UNSUPPORTED) return rc;
     }
 
@@ -458,6 +517,9 @@ extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
     a.act = p->act; a.alpha = p->alpha; a.gain = p->gain; a.clamp = p->clamp;
     a.accumulate = p->accumulate;
     a.red_x = p->red_x; a.red_out = p->red_out;
+    a.parts = x3 ? 3 : 1;
+    a.lo_row0 = x3 ? (int)((p->wp_lo - p->wp) / p->cin) : 0;
+    a.noise = p->noise; a.nsn = p->noise_stride_n; a.nsy = p->noise_stride_y; a.nsx = p->noise_stride_x;
 
     // activation box of 128 output pixels: as square as the plane allows, spilling into the batch dimension for tiny planes
     int tw = pow2_floor(p->out_w < 16 ? p->out_w : 16);
@@ -474,6 +536,11 @@ extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
     int bn = (p->cout % 256 == 0) ? 256 : (p->cout % 128 == 0) ? 128 : (p->cout % 64 == 0) ? 64 : p->cout;
     while (bn > 64 && p->cout % (bn / 2) == 0 && mtiles_total * (p->cout / bn) < num_sms()) bn /= 2;
 
+    if (query)
+    {
+        query->kernel = 1; query->bn = bn; query->mh = 1; query->cluster = 1; query->cta_pair = 0; query->x3 = x3 ? 1 : 0;
+        return SGV_OK;
+    }
     CUtensorMap tmx, tmw;
     {
         const uint64_t dims[4] = {(uint64_t)p->cin, (uint64_t)p->w, (uint64_t)p->h, (uint64_t)p->n};
@@ -487,7 +554,7 @@ extern "C" int sgv_conv2d_tf32(const sgv_conv_params* p, void* stream_)
         if (rc != SGV_OK) return rc;
     }
     {
-        const uint64_t dims[2] = {(uint64_t)p->cin, (uint64_t)p->ntaps * p->cout};
+        const uint64_t dims[2] = {(uint64_t)p->cin, (uint64_t)a.lo_row0 + (uint64_t)p->ntaps * p->cout};
         const uint64_t strides[1] = {(uint64_t)p->cin * 4};
         const uint32_t box[2] = {(uint32_t)kBK, (uint32_t)bn};
         const uint32_t es[2] = {1, 1};

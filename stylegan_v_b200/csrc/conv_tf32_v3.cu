@@ -1,14 +1,14 @@
-// Implicit-GEMM convolution v3 for sm_100a: PERSISTENT version of v2 (haloed patch + shifted descriptors + 2 M-halves).
+// Implicit-GEMM convolution for sm_100a, persistent halo-patch kernel ("v3"; haloed patch + shifted descriptors + 2-4 M-halves).
 //
-// v2 launches one CTA per 256-pixel tile.  For the high-resolution, few-channel layers a tile is only ~2.4 us of MMA work,
-// so the serial chain  TMA latency -> transform -> MMA -> TMEM read-out -> stores  (plus barrier init, TMEM alloc and
-// descriptor fetch per CTA) left the tensor pipe 24 % active (ncu: profiles/ncu_tc_r1l_summary.txt).  v3 keeps one CTA per
+// Its round-1 predecessor launched one CTA per 256-pixel tile.  For the high-resolution, few-channel layers a tile is only ~2.4 us
+// of MMA work, so the serial chain  TMA latency -> transform -> MMA -> TMEM read-out -> stores  (plus barrier init, TMEM alloc and
+// descriptor fetch per CTA) left the tensor pipe 24 % active (ncu: profiles/ncu_tc_r1l_summary.txt).  This kernel keeps one CTA per
 // SM alive and walks tiles round-robin (tile = blockIdx.x + i * gridDim.x):
 //   * the TMA producer, the transform warps and the MMA issuer run ahead ACROSS tile boundaries through the same rings;
 //   * the accumulator is double-buffered in TMEM (when 2 * MH * BN <= 512 columns);
 //   * four dedicated epilogue warps drain tile i (TMEM -> regs -> dcoefs/bias/lrelu/gain -> NHWC stores) while tile i+1
 //     is being multiplied.
-// Operand staging is v2's: per 32-channel chunk ONE TMA box = output tile (16 rows x 16 cols) + halo; every tap's A matrix is
+// Operand staging: per 32-channel chunk ONE TMA box = output tile (16 rows x 16 cols) + halo; every tap's A matrix is
 // that patch through a shifted K-major SWIZZLE_128B descriptor (start row = (dy-dy_min)*PW + (dx-dx_min) + 8*half,
 // SBO = PW*128; legal because tcgen05 swizzles on absolute smem address bits — profiles/umma_probe_r1.txt).
 // Warps: 0 activation-patch TMA producer, 1 MMA issuer + TMEM owner, 2-5 transform (styles * x, round to TF32), 6-13 epilogue
@@ -28,27 +28,32 @@ using namespace ptx;
 
 constexpr int kV3Threads = 64 + 128 + 256 + 32;
 constexpr int kV3TileH = 16;
+constexpr int kV3MaxCls = 8;                              // 4 parity classes (stride 2) x {hi, lo} operand part (tf32x3)
+constexpr int kV3MaxTaps = 3 * SGV_CONV_MAX_TAPS;         // tf32x3: every tap is issued three times (hi*hi, hi*lo, lo*hi)
 
 struct ConvV3Args
 {
     float* y; const float* a_scale; const float* o_scale; const float* bias;
     int n, cin, cout, out_h, out_w;
     long long osn, osy, osx;
-    int ntaps;
+    int ntaps;      // class-ordered MMA taps (tf32x3: 3 per tap of the contraction)
     // Taps are grouped into patch CLASSES: all taps of a class read the same TMA box (origin cls_ox/oy relative to the tile's first
     // input pixel, sampled with the input stride) through shifted descriptors.  Stride 1: one class.  Stride 2 (data gradient of the
     // stride-2 transposed conv): one class per (dy, dx) parity, i.e. 4 boxes of every-other pixel per 32-channel chunk.
+    // tf32x3 (fp32-grade) mode doubles the classes: class (c, hi) stages tf32(x*s) and is multiplied with the hi AND the lo weight slabs,
+    // class (c, lo) stages tf32(x*s - tf32(x*s)) from a second TMA load of the same box and is multiplied with the hi slabs only.
     int in_stride, ncls;
-    int cls_ntaps[4], cls_ox[4], cls_oy[4];
-    int tap_row[SGV_CONV_MAX_TAPS];        // class-ordered: start row of the tap's A matrix inside its class patch
-    int tap_slab[SGV_CONV_MAX_TAPS];       // class-ordered: index of the tap's weight slab in wp
+    int cls_ntaps[kV3MaxCls], cls_ox[kV3MaxCls], cls_oy[kV3MaxCls], cls_lo[kV3MaxCls];
+    int tap_row[kV3MaxTaps];               // class-ordered: start row of the tap's A matrix inside its class patch
+    int tap_slab[kV3MaxTaps];              // class-ordered: first row of the tap's weight slab in the [rows, cin] slab tensor (hi set, then lo set)
     int pw, ph;
     int tiles_x, tiles_y, ntiles_n, total_groups;      // group = CL pixel tiles x one n-tile, one tile per CTA of a cluster
     int act; float alpha, gain, clamp;
     int accumulate;
     const float* red_x; float* red_out;
     int a_ready;    // activation patches need no staging pass
-    int debug;      // ablation switches, env SGV_V3_DEBUG (measurement only; profiles/conv_v3_ablation_r1.txt): 1 skip transform, 2 skip epilogue, 4 skip MMAs
+    const float* noise; long long nsn, nsy, nsx;      // per-pixel noise plane(s), added after o_scale (element strides; nsn = 0: shared plane)
+    int debug;      // ablation switches, only honoured by -DSGV_ABLATION builds (profiles/conv_v3_ablation_r1.txt): 1 skip transform, 2 skip epilogue, 4 skip MMAs
 };
 
 template <int BN, int MH, int SA, int SB>
@@ -160,10 +165,10 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         mbar_wait(empty_b + sb, pb ^ 1);
                         mbar_expect_tx(full_b + sb, L::kBTile);
                         if (CL == 1)
-                            tma_load_2d(smem + L::kBOffset + sb * L::kBTile, &tmap_w, full_b + sb, kc * 32, p.tap_slab[t] * p.cout + nb0);
+                            tma_load_2d(smem + L::kBOffset + sb * L::kBTile, &tmap_w, full_b + sb, kc * 32, p.tap_slab[t] + nb0);
                         else    // this CTA fetches rows [crank * BN/CL, +BN/CL) of the slab once and multicasts them to the whole cluster
                             tma_load_2d_mc(smem + L::kBOffset + sb * L::kBTile + crank * (BN / CL) * 128, &tmap_w, full_b + sb, kc * 32,
-                                           p.tap_slab[t] * p.cout + nb0 + crank * (BN / CL), kMask);
+                                           p.tap_slab[t] + nb0 + crank * (BN / CL), kMask);
                         if (++sb == SB) { sb = 0; pb ^= 1; }
                     }
                 }
@@ -211,7 +216,7 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                             for (int h = 0; h < MH; h++)
 #pragma unroll
                                 for (int k = 0; k < 4; k++)
-                                    if (!(p.debug & 4))
+                                    if (!SGV_ABL(p.debug, 4))
                                         mma_tf32(acc + (uint32_t)(h * BN), desc(a_lo + (uint32_t)(h * 64 + k * 2), a_hi), desc(b_lo + (uint32_t)(k * 2), b_hi), idesc,
                                                  (kc > 0 || t > 0 || k > 0) ? 1u : 0u);
                             if (CL == 1) mma_commit(empty_b + sb); else mma_commit_mc(empty_b + sb, kMask);
@@ -256,18 +261,32 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 {
                     mbar_wait(full_a + sa, pa);
                     const uint32_t patch = smem_u32(smem + sa * L::kPatch);
-                    for (int row = tid; row < (((p.debug & 1) || p.a_ready) ? 0 : nrows); row += 128)
+                    const bool lo_part = p.cls_lo[c] != 0;
+                    for (int row = tid; row < ((SGV_ABL(p.debug, 1) || p.a_ready) ? 0 : nrows); row += 128)
                     {
                         const uint32_t arow = patch + (uint32_t)row * 128u;
                         float4 v[8];
 #pragma unroll
                         for (int j = 0; j < 8; j++) v[j] = lds128(arow + (uint32_t)((j ^ (row & 7)) << 4));
-#pragma unroll
-                        for (int j = 0; j < 8; j++)
+                        if (!lo_part)
                         {
-                            v[j].x = tf32_rn(v[j].x * sv[4 * j + 0]); v[j].y = tf32_rn(v[j].y * sv[4 * j + 1]);
-                            v[j].z = tf32_rn(v[j].z * sv[4 * j + 2]); v[j].w = tf32_rn(v[j].w * sv[4 * j + 3]);
-                            sts128(arow + (uint32_t)((j ^ (row & 7)) << 4), v[j]);
+#pragma unroll
+                            for (int j = 0; j < 8; j++)
+                            {
+                                v[j].x = tf32_rn(v[j].x * sv[4 * j + 0]); v[j].y = tf32_rn(v[j].y * sv[4 * j + 1]);
+                                v[j].z = tf32_rn(v[j].z * sv[4 * j + 2]); v[j].w = tf32_rn(v[j].w * sv[4 * j + 3]);
+                                sts128(arow + (uint32_t)((j ^ (row & 7)) << 4), v[j]);
+                            }
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int j = 0; j < 8; j++)
+                            {
+                                v[j].x = tf32_lo(__fmul_rn(v[j].x, sv[4 * j + 0])); v[j].y = tf32_lo(__fmul_rn(v[j].y, sv[4 * j + 1]));
+                                v[j].z = tf32_lo(__fmul_rn(v[j].z, sv[4 * j + 2])); v[j].w = tf32_lo(__fmul_rn(v[j].w, sv[4 * j + 3]));
+                                sts128(arow + (uint32_t)((j ^ (row & 7)) << 4), v[j]);
+                            }
                         }
                     }
                     fence_proxy_async_smem();
@@ -301,10 +320,11 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             const uint32_t acc = tmem_base + (uint32_t)(buf * MH * BN);
             const int oy = tc.oy0 + (row >> 3);
 #pragma unroll 1
-            for (int h = 0; h < ((p.debug & 2) ? 0 : MH); h++)
+            for (int h = 0; h < (SGV_ABL(p.debug, 2) ? 0 : MH); h++)
             {
                 const int ox = tc.ox0 + 8 * h + (row & 7);
                 const bool valid = (oy < p.out_h) && (ox < p.out_w);
+                const float nz = (p.noise && valid) ? __ldg(p.noise + (long long)tc.n * p.nsn + (long long)oy * p.nsy + (long long)ox * p.nsx) : 0.f;
 #pragma unroll 1
                 for (int cc = grp; cc < BN / 32; cc += 2)
                 {
@@ -342,6 +362,7 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     {
                         float o[4] = {__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])};
                         if (osc) { const float4 sv = __ldg(osc + j); o[0] = __fmul_rn(o[0], sv.x); o[1] = __fmul_rn(o[1], sv.y); o[2] = __fmul_rn(o[2], sv.z); o[3] = __fmul_rn(o[3], sv.w); }
+                        if (p.noise) { o[0] = __fadd_rn(o[0], nz); o[1] = __fadd_rn(o[1], nz); o[2] = __fadd_rn(o[2], nz); o[3] = __fadd_rn(o[3], nz); }
                         if (bia) { const float4 bv = __ldg(bia + j); o[0] = __fadd_rn(o[0], bv.x); o[1] = __fadd_rn(o[1], bv.y); o[2] = __fadd_rn(o[2], bv.z); o[3] = __fadd_rn(o[3], bv.w); }
 #pragma unroll
                         for (int e = 0; e < 4; e++)
@@ -364,7 +385,7 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     }
                 }
             }
-            if (p.debug & 2) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(acc_empty + buf); }
+            if (SGV_ABL(p.debug, 2)) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(acc_empty + buf); }
         }
         if (issuer) bulk_wait_all();
     }
@@ -379,26 +400,28 @@ static int launch_v3(const CUtensorMap& tx, const CUtensorMap& tw, const CUtenso
 {
     using L = ConvV3Smem<BN, MH, SA, SB>;
     auto kern = conv_tf32_v3_kernel<BN, MH, SA, SB, CL>;
-    static int max_clusters = 0;
+    static PerDeviceInt max_clusters;      // co-resident clusters of this variant, per device
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.blockDim = dim3(kV3Threads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = stream;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (max_clusters == 0)
+    const int dev = current_device_slot();
+    int nc = max_clusters.get(dev);
+    if (nc == 0)
     {
         SGV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-        int nc = num_sms() / CL;
+        nc = num_sms() / CL;
         if (CL > 1)
         {
             cfg.gridDim = dim3((unsigned)(nc * CL));
             SGV_CUDA_OK(cudaOccupancyMaxActiveClusters(&nc, kern, &cfg));     // GPC granularity can leave fewer than num_sms / CL co-resident
         }
         SGV_CHECK_ARG(nc >= 1, "conv_tf32_v3: no co-resident cluster of this size");
-        max_clusters = nc;
+        max_clusters.set(dev, nc);
     }
-    const int clusters = a.total_groups < max_clusters ? a.total_groups : max_clusters;
+    const int clusters = a.total_groups < nc ? a.total_groups : nc;
     cfg.gridDim = dim3((unsigned)(clusters * CL));
     ConvV3Args args = a;
     SGV_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tx, tw, ty, args));
@@ -419,43 +442,51 @@ static int launch_v3_bn(int bn, int mh, const CUtensorMap& tx, const CUtensorMap
     }
 }
 
-// thread-block cluster size (CTAs sharing each weight slab through TMA multicast); SGV_CONV_CLUSTER=1|2|4 overrides
-static int v3_cluster_pref()
+// Tuning switches, read from the environment ONCE per process (thread-safe static initialisation), never per launch.
+struct V3Tuning
 {
-    static int pref = -1;
-    if (pref < 0)
+    int cluster;      // SGV_CONV_CLUSTER=1|2|4: CTAs sharing each weight slab through TMA multicast
+    int mh4;          // SGV_V3_MH4=0: no 16x32-pixel tiles for 64-channel layers
+    int max_bn;       // SGV_V3_MAXBN
+    int wide_cin;     // SGV_V3_WIDE_CIN: smallest cin that takes the 256-column N tile
+    int debug;        // SGV_V3_DEBUG: ablation switches (honoured by -DSGV_ABLATION builds only)
+    V3Tuning()
     {
-        const char* e = getenv("SGV_CONV_CLUSTER");
-        pref = e ? atoi(e) : 2;
-        if (pref != 1 && pref != 2 && pref != 4) pref = 2;
+        cluster = env_int("SGV_CONV_CLUSTER", 2);
+        if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
+        mh4 = env_int("SGV_V3_MH4", 1) ? 1 : 0;
+        max_bn = env_int("SGV_V3_MAXBN", 256);
+        wide_cin = env_int("SGV_V3_WIDE_CIN", 512);
+        debug = env_int("SGV_V3_DEBUG", 0);
     }
-    return pref;
-}
+};
+static const V3Tuning& v3_tuning() { static const V3Tuning t; return t; }
 
-// Returns SGV_ERR_UNSUPPORTED when the shape is outside the envelope (caller falls back to v2 / v1).
-int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
+// Returns SGV_ERR_UNSUPPORTED when the shape is outside the envelope (caller falls back to the per-tap kernel).  With `query` the chosen variant is
+// reported and nothing is launched.
+int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream, sgv_conv_variant* query)
 {
     if ((p->in_stride != 1 && p->in_stride != 2) || p->out_h < 12 || p->out_w < 12 || p->cout % 64 != 0) return SGV_ERR_UNSUPPORTED;
     if (p->in_stride == 2 && p->in_stride_x != 0) return SGV_ERR_UNSUPPORTED;      // strided sampling of a strided view: not needed by any caller
+    const V3Tuning& tune = v3_tuning();
     const int st = p->in_stride;
+    const bool x3 = p->wp_lo != nullptr;
     // 64 output channels: each weight slab feeds only 128 x 64 MMAs, so slabs re-streamed per tile saturate the ~40 B/clk L2 -> SM path
     // (profiles/conv_v3_ablation_r1.txt); tiles of 4 halves (16 x 32 pixels) halve that traffic and still fit two accumulator buffers.
-    static int mh4 = -1;
-    if (mh4 < 0) { const char* e = getenv("SGV_V3_MH4"); mh4 = (e && !atoi(e)) ? 0 : 1; }
-    const int mh = (mh4 && p->cout % 128 != 0 && p->out_w >= 32) ? 4 : 2;
+    const int mh = (tune.mh4 && p->cout % 128 != 0 && p->out_w >= 32) ? 4 : 2;
     ConvV3Args a;
     memset(&a, 0, sizeof(a));
     // group the taps into patch classes by the parity of (dy, dx) modulo the input stride
     int cls_of[SGV_CONV_MAX_TAPS], cmin_x[4], cmin_y[4], cmax_x[4], cmax_y[4], ckey[4];
-    a.ncls = 0;
+    int ncls = 0;
     for (int t = 0; t < p->ntaps; t++)
     {
         const int key = (((p->tap_dy[t] % st) + st) % st) * st + (((p->tap_dx[t] % st) + st) % st);
         int c = -1;
-        for (int j = 0; j < a.ncls; j++) if (ckey[j] == key) c = j;
+        for (int j = 0; j < ncls; j++) if (ckey[j] == key) c = j;
         if (c < 0)
         {
-            c = a.ncls++;
+            c = ncls++;
             ckey[c] = key; cmin_x[c] = cmax_x[c] = p->tap_dx[t]; cmin_y[c] = cmax_y[c] = p->tap_dy[t];
         }
         cmin_x[c] = min(cmin_x[c], p->tap_dx[t]); cmax_x[c] = max(cmax_x[c], p->tap_dx[t]);
@@ -463,48 +494,58 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
         cls_of[t] = c;
     }
     int ext_x = 0, ext_y = 0;
-    for (int c = 0; c < a.ncls; c++) { ext_x = max(ext_x, (cmax_x[c] - cmin_x[c]) / st); ext_y = max(ext_y, (cmax_y[c] - cmin_y[c]) / st); }
+    for (int c = 0; c < ncls; c++) { ext_x = max(ext_x, (cmax_x[c] - cmin_x[c]) / st); ext_y = max(ext_y, (cmax_y[c] - cmin_y[c]) / st); }
     if (ext_x > 2 || ext_y > 2) return SGV_ERR_UNSUPPORTED;
     a.y = p->y; a.a_scale = p->a_scale; a.o_scale = p->o_scale; a.bias = p->bias;
     a.n = p->n; a.cin = p->cin; a.cout = p->cout; a.out_h = p->out_h; a.out_w = p->out_w;
     a.osn = p->out_stride_n; a.osy = p->out_stride_y; a.osx = p->out_stride_x;
-    a.ntaps = p->ntaps; a.in_stride = st;
+    a.in_stride = st;
     a.pw = 8 * mh + ext_x; a.ph = kV3TileH + ext_y;
+    // rows of the slab tensor [rows, cin] the weight tensor map covers: the hi set, then (tf32x3) the lo set wherever the caller put it
+    const long long lo_row0 = x3 ? (long long)(p->wp_lo - p->wp) / p->cin : 0;
+    const long long slab_rows = (x3 ? lo_row0 : 0) + (long long)p->ntaps * p->cout;
     {
         int j = 0;
-        for (int c = 0; c < a.ncls; c++)
-        {
-            a.cls_ox[c] = cmin_x[c]; a.cls_oy[c] = cmin_y[c]; a.cls_ntaps[c] = 0;
-            for (int t = 0; t < p->ntaps; t++)
-                if (cls_of[t] == c)
-                {
-                    a.tap_row[j] = (p->tap_dy[t] - cmin_y[c]) / st * a.pw + (p->tap_dx[t] - cmin_x[c]) / st;
-                    a.tap_slab[j] = t;
-                    a.cls_ntaps[c]++; j++;
-                }
-        }
+        a.ncls = 0;
+        for (int c = 0; c < ncls; c++)
+            for (int part = 0; part < (x3 ? 2 : 1); part++)      // part 0 = hi operand, part 1 = lo operand (tf32x3 only)
+            {
+                const int cc = a.ncls++;
+                a.cls_ox[cc] = cmin_x[c]; a.cls_oy[cc] = cmin_y[c]; a.cls_ntaps[cc] = 0; a.cls_lo[cc] = part;
+                for (int wpart = 0; wpart < ((x3 && part == 0) ? 2 : 1); wpart++)      // hi activations meet the hi and the lo slabs; lo activations the hi slabs
+                    for (int t = 0; t < p->ntaps; t++)
+                        if (cls_of[t] == c)
+                        {
+                            a.tap_row[j] = (p->tap_dy[t] - cmin_y[c]) / st * a.pw + (p->tap_dx[t] - cmin_x[c]) / st;
+                            a.tap_slab[j] = (int)((wpart ? lo_row0 : 0) + (long long)t * p->cout);
+                            a.cls_ntaps[cc]++; j++;
+                        }
+            }
+        a.ntaps = j;
     }
     a.tiles_x = ceil_div(p->out_w, 8 * mh); a.tiles_y = ceil_div(p->out_h, kV3TileH);
     a.act = p->act; a.alpha = p->alpha; a.gain = p->gain; a.clamp = p->clamp;
     a.accumulate = p->accumulate;
     a.red_x = p->red_x; a.red_out = p->red_out;
-    a.a_ready = p->a_ready && !p->a_scale;
-    { const char* e = getenv("SGV_V3_DEBUG"); a.debug = e ? atoi(e) : 0; }
+    a.a_ready = p->a_ready && !p->a_scale && !x3;
+    a.noise = p->noise; a.nsn = p->noise_stride_n; a.nsy = p->noise_stride_y; a.nsx = p->noise_stride_x;
+    a.debug = tune.debug;
     const int pixel_tiles = a.tiles_x * a.tiles_y * p->n;
     // N tile: 256 columns leave no room to double-buffer the accumulator (2 halves x 256 = all 512 TMEM columns), so the drain of a
     // tile is exposed; that only pays off when K is long (cin >= 512) and there are enough tiles to fill the SMs.  Measured
     // (profiles/conv_v3_ablation_r1.txt): 256->256 ch 0.263 vs 0.242 ms, 512->512 ch 0.230 vs 0.267 ms for BN = 256 vs 128.
-    static int max_bn = 0;
-    if (max_bn == 0) { const char* e = getenv("SGV_V3_MAXBN"); max_bn = e ? atoi(e) : 256; }
-    static int wide_cin = 0;
-    if (wide_cin == 0) { const char* e = getenv("SGV_V3_WIDE_CIN"); wide_cin = e ? atoi(e) : 512; }
-    const bool wide = p->cout % 256 == 0 && max_bn >= 256 && p->cin >= wide_cin && pixel_tiles * (p->cout / 256) >= num_sms();
-    const int bn = wide ? 256 : (p->cout % 128 == 0 && max_bn >= 128) ? 128 : 64;
+    const bool wide = p->cout % 256 == 0 && tune.max_bn >= 256 && p->cin >= tune.wide_cin && pixel_tiles * (p->cout / 256) >= num_sms();
+    const int bn = wide ? 256 : (p->cout % 128 == 0 && tune.max_bn >= 128) ? 128 : 64;
     a.ntiles_n = p->cout / bn;
     if (st == 2 && pixel_tiles * a.ntiles_n < (3 * num_sms()) / 4) return SGV_ERR_UNSUPPORTED;     // too few tiles for one CTA per SM: the per-tap kernel's finer grid wins
-    int cl = v3_cluster_pref();
+    int cl = tune.cluster;
     while (cl > 1 && (pixel_tiles % cl != 0 || pixel_tiles / cl * a.ntiles_n < num_sms() / cl)) cl >>= 1;   // small problems: fill the SMs first
     a.total_groups = pixel_tiles / cl * a.ntiles_n;
+    if (query)
+    {
+        query->kernel = 3; query->bn = bn; query->mh = mh; query->cluster = cl; query->cta_pair = 0; query->x3 = x3 ? 1 : 0;
+        return SGV_OK;
+    }
 
     CUtensorMap tmx, tmw, tmy;
     {
@@ -518,7 +559,7 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream)
         if (rc != SGV_OK) return rc;
     }
     {
-        const uint64_t dims[2] = {(uint64_t)p->cin, (uint64_t)p->ntaps * p->cout};
+        const uint64_t dims[2] = {(uint64_t)p->cin, (uint64_t)slab_rows};
         const uint64_t strides[1] = {(uint64_t)p->cin * 4};
         const uint32_t box[2] = {32, (uint32_t)(bn / cl)};
         const uint32_t es[2] = {1, 1};

@@ -249,4 +249,11 @@ __device__ __forceinline__ float tf32_rn(float x)
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
+// Residual of the TF32 rounding, itself rounded to TF32: x = tf32_rn(x) + tf32_lo(x) to ~2^-22 relative (x - tf32_rn(x) is exact in fp32).
+// The tf32x3 (fp32-grade) mode multiplies hi*hi + lo*hi + hi*lo.
+__device__ __forceinline__ float tf32_lo(float x)
+{
+    return tf32_rn(__fsub_rn(x, tf32_rn(x)));
+}
+
 }} // namespace sgv::ptx

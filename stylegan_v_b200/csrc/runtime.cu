@@ -1,6 +1,7 @@
 // libsgv_b200 housekeeping: error text, device check, launch accounting.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace sgv {
 
@@ -20,18 +21,31 @@ int fail(int code, const char* fmt, ...)
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int current_device_slot()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+    return dev;
+}
+
+int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 int num_sms()
 {
-    static int cached[64] = {0};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-    if (cached[dev] == 0)
+    static PerDeviceInt cached;
+    const int dev = current_device_slot();
+    if (dev < 0) return 148;
+    int n = cached.get(dev);
+    if (n == 0)
     {
-        int n = 0;
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        cached[dev] = n;
+        cached.set(dev, n);
     }
-    return cached[dev];
+    return n;
 }
 
 } // namespace sgv

@@ -31,7 +31,14 @@ struct FirArgs
     int f_w, f_h; long long fsx, fsy;
     int out_w, out_h; long long osx, osy, osc, osn;
     const float* escale; const float* ebias; int eact; float ealpha, egain, eclamp; int eround;
+    const float* enoise; long long ensn, ensy, ensx;      // per-pixel noise plane(s) added after the scale (fma(x, dcoefs, noise), networks.py:68-69)
 };
+
+__device__ __forceinline__ float fir_noise(const FirArgs& p, int n, int oy, int ox)
+{
+    // callers may evaluate the epilogue for the (masked) columns past a ragged edge: keep the read in range
+    return __ldg(p.enoise + (long long)n * p.ensn + (long long)min(oy, p.out_h - 1) * p.ensy + (long long)min(ox, p.out_w - 1) * p.ensx);
+}
 
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
@@ -39,11 +46,12 @@ __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 
 template <class A, bool EPI = true>
-__device__ __forceinline__ A fir_epilogue(A v, const FirArgs& p, int n, int c)
+__device__ __forceinline__ A fir_epilogue(A v, const FirArgs& p, int n, int c, int oy, int ox)
 {
     if (!EPI || p.eact == 0) return v;
     // separate roundings (no FMA contraction) so the fused result equals the unfused op sequence bit for bit
     if (p.escale) v = mul_rn(v, (A)p.escale[(long long)n * p.in_c + c]);
+    if (p.enoise) v = add_rn(v, (A)fir_noise(p, n, oy, ox));
     if (p.ebias) v = add_rn(v, (A)p.ebias[c]);
     if (p.eact == 3) v = (v > 0) ? v : v * (A)p.ealpha;
     v *= (A)p.egain;
@@ -96,7 +104,7 @@ __global__ void __launch_bounds__(256) fir_generic(FirArgs p, int channels_fast,
             fp += stepY - w * stepX;
         }
         v *= (A)p.gain;
-        v = fir_epilogue<A>(v, p, n, c);
+        v = fir_epilogue<A>(v, p, n, c, outY, outX);
         ((T*)p.y)[outX * p.osx + outY * p.osy + c * p.osc + n * p.osn] = (T)v;
     }
 }
@@ -309,7 +317,7 @@ __global__ void __launch_bounds__(kFirThreads) fir_nchw_tiled(FirArgs p, FirTile
         if (relOutY0 + r >= t.tile_out_h || outY >= p.out_h) continue;
         float o[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) o[k] = fir_epilogue<float, EPI>(acc[r][k] * p.gain, p, n, c);
+        for (int k = 0; k < 4; k++) o[k] = fir_epilogue<float, EPI>(acc[r][k] * p.gain, p, n, c, outY, outX0 + k);
         float* dst = yg + (plane * p.out_h + outY) * (long long)p.out_w + outX0;
         if (t.out_vec_ok && outX0 + 3 < p.out_w && relOutX0 + 3 < t.tile_out_w)
             __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
@@ -341,14 +349,14 @@ __device__ __forceinline__ void nhwc_store(const FirArgs& p, typename vec_t<VEC>
     if constexpr (VEC == 4)
     {
         float4 o;
-        o.x = fir_epilogue<float, EPI>(v.x * p.gain, p, n, c0 + 0);
-        o.y = fir_epilogue<float, EPI>(v.y * p.gain, p, n, c0 + 1);
-        o.z = fir_epilogue<float, EPI>(v.z * p.gain, p, n, c0 + 2);
-        o.w = fir_epilogue<float, EPI>(v.w * p.gain, p, n, c0 + 3);
+        o.x = fir_epilogue<float, EPI>(v.x * p.gain, p, n, c0 + 0, outY, outX);
+        o.y = fir_epilogue<float, EPI>(v.y * p.gain, p, n, c0 + 1, outY, outX);
+        o.z = fir_epilogue<float, EPI>(v.z * p.gain, p, n, c0 + 2, outY, outX);
+        o.w = fir_epilogue<float, EPI>(v.w * p.gain, p, n, c0 + 3, outY, outX);
         __stcs(reinterpret_cast<float4*>(dst), o);
     }
     else
-        *dst = fir_epilogue<float, EPI>(v * p.gain, p, n, c0);
+        *dst = fir_epilogue<float, EPI>(v * p.gain, p, n, c0, outY, outX);
 }
 
 // FAST: up = 1 in both dims, compile-time FWxFH filter, ROWS = 2 output rows per thread.
@@ -467,6 +475,7 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_slide44(FirArgs p, long long 
             {
                 // separate roundings (no FMA contraction): bit-identical to the unfused op sequence, like fir_epilogue
                 if (p.escale) { o.x = __fmul_rn(o.x, esc.x); o.y = __fmul_rn(o.y, esc.y); o.z = __fmul_rn(o.z, esc.z); o.w = __fmul_rn(o.w, esc.w); }
+                if (p.enoise) { const float nz = fir_noise(p, n, outY, outX); o.x = __fadd_rn(o.x, nz); o.y = __fadd_rn(o.y, nz); o.z = __fadd_rn(o.z, nz); o.w = __fadd_rn(o.w, nz); }
                 if (p.ebias) { o.x = __fadd_rn(o.x, ebi.x); o.y = __fadd_rn(o.y, ebi.y); o.z = __fadd_rn(o.z, ebi.z); o.w = __fadd_rn(o.w, ebi.w); }
                 if (p.eact == 3) { o.x = o.x > 0.f ? o.x : o.x * p.ealpha; o.y = o.y > 0.f ? o.y : o.y * p.ealpha; o.z = o.z > 0.f ? o.z : o.z * p.ealpha; o.w = o.w > 0.f ? o.w : o.w * p.ealpha; }
                 o.x *= p.egain; o.y *= p.egain; o.z *= p.egain; o.w *= p.egain;
@@ -614,6 +623,7 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_tma44(const __grid_constant__
                 {
                     // separate roundings (no FMA contraction): bit-identical to the unfused op sequence, like fir_epilogue
                     if (p.escale) { o.x = __fmul_rn(o.x, esc.x); o.y = __fmul_rn(o.y, esc.y); o.z = __fmul_rn(o.z, esc.z); o.w = __fmul_rn(o.w, esc.w); }
+                    if (p.enoise) { const float nz = fir_noise(p, n, oy, ox); o.x = __fadd_rn(o.x, nz); o.y = __fadd_rn(o.y, nz); o.z = __fadd_rn(o.z, nz); o.w = __fadd_rn(o.w, nz); }
                     if (p.ebias) { o.x = __fadd_rn(o.x, ebi.x); o.y = __fadd_rn(o.y, ebi.y); o.z = __fadd_rn(o.z, ebi.z); o.w = __fadd_rn(o.w, ebi.w); }
                     if (p.eact == 3) { o.x = o.x > 0.f ? o.x : o.x * p.ealpha; o.y = o.y > 0.f ? o.y : o.y * p.ealpha; o.z = o.z > 0.f ? o.z : o.z * p.ealpha; o.w = o.w > 0.f ? o.w : o.w * p.ealpha; }
                     o.x *= p.egain; o.y *= p.egain; o.z *= p.egain; o.w *= p.egain;
@@ -784,6 +794,8 @@ extern "C" int sgv_upfirdn2d(const sgv_upfirdn2d_params* p, void* stream_)
     a.osx = p->out_stride_x; a.osy = p->out_stride_y; a.osc = p->out_stride_c; a.osn = p->out_stride_n;
     a.escale = p->epi_scale; a.ebias = p->epi_bias; a.eact = p->epi_act;
     a.ealpha = p->epi_alpha; a.egain = p->epi_gain; a.eclamp = p->epi_clamp; a.eround = p->epi_round_tf32;
+    a.enoise = p->epi_noise; a.ensn = p->epi_noise_stride_n; a.ensy = p->epi_noise_stride_y; a.ensx = p->epi_noise_stride_x;
+    SGV_CHECK_ARG(!a.enoise || a.eact != 0, "epi_noise needs a fused epilogue (epi_act != 0)");
     SGV_CHECK_ARG(!a.eround || a.eact != 0, "epi_round_tf32 needs a fused epilogue (epi_act != 0)");
     // the rounding flag is honoured by the two channels_last 4x4 kernels below; any other route rejects it rather than ignore it
     const bool round_ok = p->dtype == SGV_F32 && a.upx == 1 && a.upy == 1 && a.downx == 1 && a.downy == 1 && a.f_w == 4 && a.f_h == 4 && a.in_c % 4 == 0 && a.in_c > 1
@@ -814,8 +826,7 @@ extern "C" int sgv_upfirdn2d(const sgv_upfirdn2d_params* p, void* stream_)
                 const bool epi = a.eact != 0;
 #define SGV_NHWC_FAST(V, D) do { if (epi) fir_nhwc_fast<V, D, 4, 4, true><<<grid, 256, 0, stream>>>(a, work); \
                                  else fir_nhwc_fast<V, D, 4, 4, false><<<grid, 256, 0, stream>>>(a, work); } while (0)
-                static int use_tma = -1;
-                if (use_tma < 0) { const char* e = getenv("SGV_FIR_NO_TMA"); use_tma = (e && atoi(e)) ? 0 : 1; }
+                static const int use_tma = env_int("SGV_FIR_NO_TMA", 0) ? 0 : 1;
                 if (v4 && a.downx == 1 && use_tma && a.in_c % 32 == 0 && ow >= kFtTW && oh >= kFtTH)
                 {
                     CUtensorMap tm;
@@ -829,13 +840,8 @@ extern "C" int sgv_upfirdn2d(const sgv_upfirdn2d_params* p, void* stream_)
                     const long long tiles = (long long)tiles_x * tiles_y * cblocks * a.in_n;
                     SGV_CHECK_ARG(tiles <= 0x7fffffffLL, "too many tiles");
                     const unsigned g3 = (unsigned)min((long long)sms * 2, tiles);
-                    static bool attr_set = false;
-                    if (!attr_set)
-                    {
-                        SGV_CUDA_OK(cudaFuncSetAttribute(fir_nhwc_tma44<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmem));
-                        SGV_CUDA_OK(cudaFuncSetAttribute(fir_nhwc_tma44<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtSmem));
-                        attr_set = true;
-                    }
+                    SGV_OPT_IN_SMEM(fir_nhwc_tma44<true>, kFtSmem);
+                    SGV_OPT_IN_SMEM(fir_nhwc_tma44<false>, kFtSmem);
                     if (epi) fir_nhwc_tma44<true><<<g3, 256, kFtSmem, stream>>>(tm, a, tiles_x, tiles_y, cblocks, (int)tiles);
                     else fir_nhwc_tma44<false><<<g3, 256, kFtSmem, stream>>>(tm, a, tiles_x, tiles_y, cblocks, (int)tiles);
                 }

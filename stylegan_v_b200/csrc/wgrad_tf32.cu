@@ -23,7 +23,8 @@ namespace sgv {
 
 using namespace ptx;
 
-int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, cudaStream_t stream);
+// g_lo / x_lo: stage the TF32 residual tf32(v - tf32(v)) of that operand instead of tf32(v) (one pass of the tf32x3 mode)
+int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, int g_lo, int x_lo, cudaStream_t stream, sgv_wgrad_variant* query);
 
 constexpr int kWgThreads = 192;
 constexpr int kWgM = 128;
@@ -40,6 +41,7 @@ struct WgArgs
     int tiles_x, tiles_y, tiles_nb;
     int mtiles, ktiles, ksplit;
     int dw_slot[SGV_CONV_MAX_TAPS];   // dw block each tap accumulates into
+    int g_lo, x_lo;                   // tf32x3 pass: stage the TF32 residual of that operand
 };
 
 template <int BN, int STAGES>
@@ -52,7 +54,7 @@ struct WgSmem
 };
 
 // scales one staged 128-byte row (32 channels of one pixel) by sc[0..31] and rounds to TF32, in place
-__device__ __forceinline__ void wg_transform_row(uint8_t* rowp_generic, int row, const float* __restrict__ sc)
+__device__ __forceinline__ void wg_transform_row(uint8_t* rowp_generic, int row, const float* __restrict__ sc, bool lo)
 {
     const uint32_t rowp = smem_u32(rowp_generic);
     const int flip = (row >> 2) & 1;          // chunk order that keeps a quarter-warp's 8 rows on 8 distinct bank groups
@@ -69,7 +71,9 @@ __device__ __forceinline__ void wg_transform_row(uint8_t* rowp_generic, int row,
     {
         const int jj = j ^ flip;
         const float4 s = sc ? __ldg(reinterpret_cast<const float4*>(sc) + jj) : make_float4(1.f, 1.f, 1.f, 1.f);
-        v[j].x = tf32_rn(v[j].x * s.x); v[j].y = tf32_rn(v[j].y * s.y); v[j].z = tf32_rn(v[j].z * s.z); v[j].w = tf32_rn(v[j].w * s.w);
+        v[j].x = __fmul_rn(v[j].x, s.x); v[j].y = __fmul_rn(v[j].y, s.y); v[j].z = __fmul_rn(v[j].z, s.z); v[j].w = __fmul_rn(v[j].w, s.w);
+        if (lo) { v[j].x = tf32_lo(v[j].x); v[j].y = tf32_lo(v[j].y); v[j].z = tf32_lo(v[j].z); v[j].w = tf32_lo(v[j].w); }
+        else { v[j].x = tf32_rn(v[j].x); v[j].y = tf32_rn(v[j].y); v[j].z = tf32_rn(v[j].z); v[j].w = tf32_rn(v[j].w); }
         sts128(rowp + (uint32_t)(((((jj >> 1) ^ (row & 3)) << 1) | (jj & 1)) << 4), v[j]);
     }
 }
@@ -175,7 +179,7 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                         const int n = min(nb0 + pix / box_hw, p.n - 1);
                         const int ch = m0 + blk * 32;
                         const float* sc = (p.g_scale && ch < p.cout) ? p.g_scale + (long long)n * p.cout + ch : nullptr;
-                        if (ch < p.cout) wg_transform_row(sa + tid * 128, tid, sc);
+                        if (ch < p.cout) wg_transform_row(sa + tid * 128, tid, sc, p.g_lo != 0);
                     }
 #pragma unroll
                     for (int rr = 0; rr < (BN + 127) / 128; rr++)
@@ -187,7 +191,7 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                             const int n = min(nb0 + pix / box_hw, p.n - 1);
                             const int ch = c0 + blk * 32;
                             const float* sc = (p.x_scale && ch < p.cin) ? p.x_scale + (long long)n * p.cin + ch : nullptr;
-                            if (ch < p.cin) wg_transform_row(sa + kWgATile + row * 128, row, sc);
+                            if (ch < p.cin) wg_transform_row(sa + kWgATile + row * 128, row, sc, p.x_lo != 0);
                         }
                     }
                     fence_proxy_async_smem();
@@ -229,12 +233,7 @@ static int launch_wgrad(const CUtensorMap& tg, const CUtensorMap& tx, const WgAr
 {
     using L = WgSmem<BN, STAGES>;
     auto kern = wgrad_tf32_kernel<BN, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        SGV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-        attr_set = true;
-    }
+    SGV_OPT_IN_SMEM(kern, L::kTotal);
     kern<<<grid, kWgThreads, L::kTotal, stream>>>(tg, tx, a);
     SGV_LAUNCH_OK("wgrad_tf32_kernel");
     return SGV_OK;
@@ -251,11 +250,39 @@ static int make_blocked_tmap(CUtensorMap* m, const float* base, int c, int w, in
 
 } // namespace sgv
 
-extern "C" int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream_)
+static int wgrad_pass(const sgv_wgrad_params* p, int g_lo, int x_lo, cudaStream_t stream, sgv_wgrad_variant* query);
+
+static int wgrad_dispatch(const sgv_wgrad_params* p, cudaStream_t stream, sgv_wgrad_variant* query)
 {
     using namespace sgv;
-    cudaStream_t stream = (cudaStream_t)stream_;
     SGV_CHECK_ARG(p != nullptr, "sgv_conv2d_wgrad_tf32: params is NULL");
+    SGV_CHECK_ARG(p->precision == 0 || p->precision == 1, "precision must be 0 (tf32x1) or 1 (tf32x3)");
+    if (p->precision == 0) return wgrad_pass(p, 0, 0, stream, query);
+    // tf32x3: dw += g_hi*x_hi + g_lo*x_hi + g_hi*x_lo — three passes of the same kernel into the same accumulation buffer, each staging
+    // the hi or lo part of its operands (the staging warps form the parts from the fp32 values in shared memory)
+    SGV_CHECK_ARG(!p->g_ready && !p->x_ready, "tf32x3 mode needs unrounded operands: g_ready / x_ready must be 0");
+    int rc = wgrad_pass(p, 1, 0, stream, query);           // small terms first
+    if (rc != SGV_OK || query) { if (query) query->passes = 3; return rc; }
+    rc = wgrad_pass(p, 0, 1, stream, nullptr);
+    if (rc != SGV_OK) return rc;
+    return wgrad_pass(p, 0, 0, stream, nullptr);
+}
+
+extern "C" int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream_)
+{
+    return wgrad_dispatch(p, (cudaStream_t)stream_, nullptr);
+}
+
+extern "C" int sgv_conv2d_wgrad_tf32_variant(const sgv_wgrad_params* p, sgv_wgrad_variant* out)
+{
+    SGV_CHECK_ARG(out != nullptr, "sgv_conv2d_wgrad_tf32_variant: out is NULL");
+    memset(out, 0, sizeof(*out));
+    return wgrad_dispatch(p, nullptr, out);
+}
+
+static int wgrad_pass(const sgv_wgrad_params* p, int g_lo, int x_lo, cudaStream_t stream, sgv_wgrad_variant* query)
+{
+    using namespace sgv;
     SGV_CHECK_ARG(p->g && p->x && p->dw, "sgv_conv2d_wgrad_tf32: g, x and dw must be non-NULL");
     SGV_CHECK_ARG(p->cin >= 32 && p->cin % 32 == 0 && p->cout >= 32 && p->cout % 32 == 0, "cin and cout must be multiples of 32 (got %d, %d)", p->cin, p->cout);
     SGV_CHECK_ARG(p->ntaps >= 1 && p->ntaps <= SGV_CONV_MAX_TAPS, "ntaps must be in [1, %d]", SGV_CONV_MAX_TAPS);
@@ -266,10 +293,10 @@ extern "C" int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream_)
     int rc = sgv_device_check();
     if (rc != SGV_OK) return rc;
 
-    static const bool force_v1 = getenv("SGV_WGRAD_V1") != nullptr;
+    static const bool force_v1 = env_int("SGV_WGRAD_V1", 0) != 0;
     if (!force_v1)
     {
-        rc = conv2d_wgrad_tf32_v2(p, stream);
+        rc = conv2d_wgrad_tf32_v2(p, g_lo, x_lo, stream, query);
         if (rc != SGV_ERR_UNSUPPORTED) return rc;
     }
     if (p->x_stride_x != 0) return sgv::fail(SGV_ERR_UNSUPPORTED, "strided x views are only supported by the grouped-tap kernel (stride 1, out_w >= 8, out_h >= 4)");
@@ -293,6 +320,12 @@ extern "C" int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream_)
     if (ksplit > a.ktiles) ksplit = a.ktiles;
     if (ksplit < 1) ksplit = 1;
     a.ksplit = ksplit;
+    a.g_lo = g_lo; a.x_lo = x_lo;
+    if (query)
+    {
+        query->kernel = 1; query->nt = bn; query->stages = bn == 256 ? 4 : bn == 128 ? 6 : 8; query->ksplit = ksplit; query->passes = 1;
+        return SGV_OK;
+    }
 
     CUtensorMap tg, tx;
     rc = make_blocked_tmap(&tg, p->g, p->cout, p->gw, p->gh, p->n, tw, th, tn, p->g_stride, kWgM / 32);
@@ -337,7 +370,8 @@ struct Wg2Args
     int dx_min, pw;
     int tiles_x, tiles_y, mtiles, ktiles, ksplit;
     int g_ready, x_ready;     // operand needs no staging pass
-    int debug;      // ablation switches, env SGV_WG_DEBUG (measurement only; profiles/wgrad_ablation_r1.txt): 1 skip transform, 2 skip epilogue, 4 skip MMAs
+    int g_lo, x_lo;           // tf32x3 pass: stage the TF32 residual of that operand
+    int debug;      // ablation switches, only honoured by -DSGV_ABLATION builds (profiles/wgrad_ablation_r1.txt): 1 skip transform, 2 skip epilogue, 4 skip MMAs
 };
 
 template <int NT, int STAGES>
@@ -429,7 +463,7 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
 #pragma unroll
                         for (int k = 0; k < 4; k++)        // image row k of the 8x4 tile = 8 consecutive pixel rows
                         {
-                            if (p.debug & 4) continue;
+                            if (SGV_ABL(p.debug, 4)) continue;
                             const uint64_t da = umma_desc_mn_sw128_32b(sg + k * 1024, 32 * 128, 512);
                             const uint64_t db = umma_desc_mn_sw128_32b(sx + (uint32_t)(p.grp_col[grp][t] + k * p.pw) * 128u, (uint32_t)xblock, 512);
                             mma_tf32(tmem_base + (uint32_t)(t * NT), da, db, idesc, (ks > 0 || k > 0) ? 1u : 0u);
@@ -453,13 +487,14 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
             float sv[2][32];
             int cur_n = -1;
             const FastDiv div_plane((uint32_t)(p.tiles_x * p.tiles_y));
-            int rr[2]; const float* sbase[2]; int sstride[2]; bool act[2];
+            int rr[2]; const float* sbase[2]; int sstride[2]; bool act[2]; bool lo[2];
 #pragma unroll
             for (int s = 0; s < 2; s++)
             {
                 rr[s] = tid + s * 256;
                 act[s] = rr[s] < total_rows;
                 sbase[s] = nullptr; sstride[s] = 0;
+                lo[s] = (rr[s] < 128 ? p.g_lo : p.x_lo) != 0;
                 if (act[s])
                 {
                     if (rr[s] < 128) { const int ch = m0 + (rr[s] >> 5) * 32; act[s] = ch < p.cout && !p.g_ready; if (p.g_scale) { sbase[s] = p.g_scale + ch; sstride[s] = p.cout; } }
@@ -490,7 +525,7 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
 #pragma unroll
                     for (int s = 0; s < 2; s++)
                     {
-                        if (!act[s] || (p.debug & 1)) continue;
+                        if (!act[s] || SGV_ABL(p.debug, 1)) continue;
                         const int row = rr[s] < 128 ? rr[s] : rr[s] - 128;
                         const uint32_t rowp = smem_u32(sg) + (uint32_t)(rr[s] < 128 ? 0 : kW2GTile) + (uint32_t)row * 128u;
                         // logical 16-byte chunk jj = j ^ bit2(row): the 8 rows a quarter-warp touches then hit 8 distinct physical
@@ -511,7 +546,9 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
                             const float s1 = flip ? sv[s][4 * (j ^ 1) + 1] : sv[s][4 * j + 1];
                             const float s2 = flip ? sv[s][4 * (j ^ 1) + 2] : sv[s][4 * j + 2];
                             const float s3 = flip ? sv[s][4 * (j ^ 1) + 3] : sv[s][4 * j + 3];
-                            v[j].x = tf32_rn(v[j].x * s0); v[j].y = tf32_rn(v[j].y * s1); v[j].z = tf32_rn(v[j].z * s2); v[j].w = tf32_rn(v[j].w * s3);
+                            v[j].x = __fmul_rn(v[j].x, s0); v[j].y = __fmul_rn(v[j].y, s1); v[j].z = __fmul_rn(v[j].z, s2); v[j].w = __fmul_rn(v[j].w, s3);
+                            if (lo[s]) { v[j].x = tf32_lo(v[j].x); v[j].y = tf32_lo(v[j].y); v[j].z = tf32_lo(v[j].z); v[j].w = tf32_lo(v[j].w); }
+                            else { v[j].x = tf32_rn(v[j].x); v[j].y = tf32_rn(v[j].y); v[j].z = tf32_rn(v[j].z); v[j].w = tf32_rn(v[j].w); }
                             sts128(rowp + (uint32_t)(((((jj >> 1) ^ (row & 3)) << 1) | (jj & 1)) << 4), v[j]);
                         }
                     }
@@ -536,7 +573,7 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NT + cc * 32), v);
                     tmem_ld_wait();
-                    if (o < p.cout && c0 + cc * 32 < p.cin && !(p.debug & 2))
+                    if (o < p.cout && c0 + cc * 32 < p.cin && !SGV_ABL(p.debug, 2))
                     {
 #pragma unroll
                         for (int j = 0; j < 8; j++)
@@ -558,18 +595,13 @@ static int launch_wgrad_v2(const CUtensorMap& tg, const CUtensorMap& tx, const W
 {
     using L = Wg2Smem<NT, STAGES>;
     auto kern = wgrad_tf32_v2_kernel<NT, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set)
-    {
-        SGV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-        attr_set = true;
-    }
+    SGV_OPT_IN_SMEM(kern, L::kTotal);
     kern<<<grid, kWg2Threads, L::kTotal, stream>>>(tg, tx, a);
     SGV_LAUNCH_OK("wgrad_tf32_v2_kernel");
     return SGV_OK;
 }
 
-int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, cudaStream_t stream)
+int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, int g_lo, int x_lo, cudaStream_t stream, sgv_wgrad_variant* query)
 {
     if (p->g_stride != 1 || p->x_stride != 1 || p->out_w < 8 || p->out_h < 4) return SGV_ERR_UNSUPPORTED;
     int dx_min = p->x_dx[0], dx_max = p->x_dx[0];
@@ -609,9 +641,16 @@ int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, cudaStream_t stream)
     while (ksplit > 1 && a.ktiles / ksplit < 48) ksplit--;
     if (ksplit > a.ktiles) ksplit = a.ktiles;
     a.ksplit = ksplit;
-    { const char* e = getenv("SGV_WG_DEBUG"); a.debug = e ? atoi(e) : 0; }
-    a.g_ready = p->g_ready && !p->g_scale; a.x_ready = p->x_ready && !p->x_scale;
+    static const int debug_flags = env_int("SGV_WG_DEBUG", 0);
+    a.debug = debug_flags;
+    a.g_ready = p->g_ready && !p->g_scale && !p->precision; a.x_ready = p->x_ready && !p->x_scale && !p->precision;
+    a.g_lo = g_lo; a.x_lo = x_lo;
 
+    if (query)
+    {
+        query->kernel = 2; query->nt = nt; query->stages = nt == 128 ? 5 : nt == 64 ? 7 : 8; query->ksplit = a.ksplit; query->passes = 1;
+        return SGV_OK;
+    }
     CUtensorMap tg, tx;
     int rc = make_blocked_tmap(&tg, p->g, p->cout, p->gw, p->gh, p->n, 8, 4, 1, 1, kWgM / 32);
     if (rc != SGV_OK) return rc;

@@ -60,13 +60,13 @@ def _fir(device):
     return _FIR_1331
 
 
-def _wgrad_native(gout, x, styles, dscale, w_shape, up, g_ready=False):
+def _wgrad_native(gout, x, styles, dscale, w_shape, up, g_ready=False, x3=False):
     """Weight gradient on the tcgen05 split-K kernel (csrc/wgrad_tf32.cu) with styles / dcoefs folded into operand staging."""
     O, I, kh, kw = w_shape
     N, _, H, W = x.shape
     if up == 1:
         taps_x = _OFFS3_FWD if kh == 3 else [(0, 0)]
-        dw = _conv.igemm_wgrad(gout, x, [(0, 0)] * len(taps_x), taps_x, (H, W), g_scale=dscale, x_scale=styles, g_ready=g_ready)
+        dw = _conv.igemm_wgrad(gout, x, [(0, 0)] * len(taps_x), taps_x, (H, W), g_scale=dscale, x_scale=styles, g_ready=g_ready, x3=x3)
     elif H >= 8 and W >= 8:
         # transposed (stride-2) conv: per polyphase sub-lattice (a, b) of the output gradient, a stride-1 correlation between the
         # unshifted input (M side) and the pixel-strided VIEW gout[:, :, a::2, b::2] shifted by (ky//2, kx//2) (N side): the grouped-tap
@@ -77,10 +77,10 @@ def _wgrad_native(gout, x, styles, dscale, w_shape, up, g_ready=False):
                 taps = [(ky, kx) for ky in range(a, 3, 2) for kx in range(b, 3, 2)]
                 offs = [(ky // 2, kx // 2) for ky, kx in taps]
                 _conv.igemm_wgrad(x, gout[:, :, a::2, b::2], [(0, 0)] * len(taps), offs, (H, W), g_scale=styles, x_scale=dscale,
-                                  out=dwt, slots=[ky * kw + kx for ky, kx in taps], x_ready=g_ready)
+                                  out=dwt, slots=[ky * kw + kx for ky, kx in taps], x_ready=g_ready, x3=x3)
         return dwt.reshape(kh, kw, I, O).permute(3, 2, 0, 1)
     else:
-        dw = _conv.igemm_wgrad(gout, x, _TAPS3, [(0, 0)] * 9, (H, W), g_stride=2, g_scale=dscale, x_scale=styles)
+        dw = _conv.igemm_wgrad(gout, x, _TAPS3, [(0, 0)] * 9, (H, W), g_stride=2, g_scale=dscale, x_scale=styles, x3=x3)
     return dw.reshape(kh, kw, O, I).permute(2, 3, 0, 1)
 
 
@@ -91,7 +91,8 @@ PRESCALE_GRADIENT = os.environ.get('SGV_PRESCALE', '1') != '0'     # fold dcoefs
 def prepare_weights(weight, up, flip_weight):
     """Tap-major TF32 weight slabs of one layer for the forward and the data-gradient launches (non-differentiable; the weight
     gradient is produced directly by the wgrad kernel).  Depends on the weight only, so a caller may build it ahead of the layer
-    (SynthesisNetwork does, on its parameter stream) and hand it to fused_modulated_conv(prep=...)."""
+    (SynthesisNetwork does, on its parameter stream) and hand it to fused_modulated_conv(prep=...).  In the tf32x3 precision mode
+    (stylegan_v_b200.precision) the slabs carry their TF32 residuals too ([2, ntaps, ., .]); the layer then runs fp32-grade."""
     O, I, kh, kw = weight.shape
     # a flipped kernel is the same weight read with mirrored tap indices: no flip kernel
     flipped = (not flip_weight) if up == 1 else flip_weight      # conv2d_resample.py:35-36 (up = 1) / :138 (transposed conv: flag inverted)
@@ -111,7 +112,7 @@ def prepare_weights(weight, up, flip_weight):
         wd = _conv.prep_weights(wsrc, base, rows_dim=1, cols_dim=0)
     fwd, start = [], 0
     for g in groups:
-        fwd.append(wf[start:start + len(g)])
+        fwd.append(_conv.slab_taps(wf, start, start + len(g)))
         start += len(g)
     return dict(fwd=fwd, dgrad=wd)
 
@@ -158,7 +159,7 @@ def _placeholder(like):
 
 class _FusedModConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, styles, dcoefs, bias, up, act, gain, flip_weight, prep, wmod=None, rgb_bias=None, wbox=None):
+    def forward(ctx, x, weight, styles, dcoefs, bias, up, act, gain, flip_weight, prep, wmod=None, rgb_bias=None, wbox=None, noise=None):
         assert x.is_cuda and x.dtype == torch.float32, 'the fused layer op is CUDA / float32 only (no CPU path)'
         x = _nhwc(x)
         O, I, kh, kw = weight.shape
@@ -166,17 +167,22 @@ class _FusedModConv(torch.autograd.Function):
         assert kh == kw and kh in (1, 3)
         if prep is None:
             prep = prepare_weights(weight, up, flip_weight)
+        ctx.x3 = prep['dgrad'].ndim == 4          # the precision mode the slabs were prepared in; backward follows it
+        if noise is not None:
+            noise = noise.detach().to(torch.float32).contiguous()
         if up == 1:
             offs = _OFFS3_FWD if kh == 3 else [(0, 0)]
-            y = _conv.igemm_conv(x, prep['fwd'][0], offs, a_scale=styles, o_scale=dcoefs, bias=bias, act=act, gain=gain)
+            y = _conv.igemm_conv(x, prep['fwd'][0], offs, a_scale=styles, o_scale=dcoefs, bias=bias, act=act, gain=gain, noise=noise)
         else:
             assert up == 2 and kh == 3
             u = torch.empty([N, O, 2 * H + 1, 2 * W + 1], dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
             for j, (a, b) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
                 _conv.igemm_conv(x, prep['fwd'][j], _phase_taps(a, b)[1], a_scale=styles, out_view=u[:, :, a::2, b::2])
             y = _plugin.upfirdn2d(u, _fir(x.device), 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0,
-                                  epilogue=dict(scale=dcoefs, bias=bias, act=act, alpha=0.2, gain=gain, clamp=None))
-        ctx.save_for_backward(x, weight, styles, dcoefs if dcoefs is not None else x.new_empty(0), bias if bias is not None else x.new_empty(0), y)
+                                  epilogue=dict(scale=dcoefs, bias=bias, act=act, alpha=0.2, gain=gain, clamp=None, noise=noise))
+        ctx.save_for_backward(x, weight, styles, dcoefs if dcoefs is not None else x.new_empty(0), bias if bias is not None else x.new_empty(0), y,
+                              noise if noise is not None else x.new_empty(0))
+        ctx.has_noise = noise is not None
         ctx.cfg = (up, act, gain, flip_weight, dcoefs is not None, bias is not None)
         ctx.wp_dgrad = prep['dgrad']
         ctx.wbox = wbox
@@ -191,7 +197,7 @@ class _FusedModConv(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy, drgb=None):
-        x, weight, styles, dcoefs, bias, y = ctx.saved_tensors
+        x, weight, styles, dcoefs, bias, y, noise = ctx.saved_tensors
         up, act, gain, flip_weight, has_d, has_b = ctx.cfg
         O, I, kh, kw = weight.shape
         N, _, H, W = x.shape
@@ -205,15 +211,30 @@ class _FusedModConv(torch.autograd.Function):
         # operand both contractions below need — they then skip scaling, and the weight-gradient kernel skips the staging pass of
         # that operand altogether (`ready`).  db / dd are reduced from the unscaled gradient inside the same kernel.
         native_w = USE_NATIVE_WGRAD and I % 32 == 0 and O % 32 == 0
-        prescale = PRESCALE_GRADIENT and has_d and native_w
+        # (not in the tf32x3 mode, whose contractions split the UNROUNDED gradient themselves, and not with a noise input, whose own
+        #  gradient needs the unscaled dz)
+        x3 = ctx.x3
+        prescale = PRESCALE_GRADIENT and has_d and native_w and not x3 and not ctx.has_noise
         osc = dcoefs if prescale else None
         if ctx.wmod is not None and drgb is not None:
             dz, db, dd, dwmod = _conv.act_bwd(dy, y, bias if has_b else None, act, gain, want_db, want_dd, dyimg=drgb, wmod=ctx.wmod, oscale=osc)
             drgb_bias = drgb.sum(dim=[0, 2, 3])
         else:
             if dy is None:
-                return (None,) * 13
+                return (None,) * 14
             dz, db, dd = _conv.act_bwd(dy, y, bias if has_b else None, act, gain, want_db, want_dd, oscale=osc)
+        dnoise = None
+        if ctx.has_noise:
+            # y = act(conv * dcoefs + noise + bias): the pre-bias value the kernel recovers from y contains the noise, so its part of the
+            # dcoefs reduction is taken out again, and d(noise)[n, hw] = sum_c dz (fma.py:36-58).  Two extra passes over dz, only in this
+            # (non-default: configs/model/stylegan-v.yaml use_noise = false) mode.
+            nz = noise.reshape(-1, 1, y.shape[2], y.shape[3])
+            if want_dd:
+                dd = dd - (dz * nz).sum(dim=[2, 3])
+            if ctx.needs_input_grad[13]:
+                dnoise = dz.sum(dim=1, keepdim=True)
+                if nz.shape[0] == 1 and N > 1:
+                    dnoise = dnoise.sum(dim=0, keepdim=True)
         ddcoefs = dd / dcoefs if want_dd else None
         dscale = dcoefs if (has_d and not prescale) else None
         wp = ctx.wp_dgrad
@@ -236,7 +257,7 @@ class _FusedModConv(torch.autograd.Function):
         # ---- weight gradient ----
         def weight_grad():
             if native_w:
-                dw = _wgrad_native(gout, x, styles, dscale, (O, I, kh, kw), up, g_ready=prescale)
+                dw = _wgrad_native(gout, x, styles, dscale, (O, I, kh, kw), up, g_ready=prescale, x3=x3)
             else:
                 xs = x * styles.reshape(N, I, 1, 1)
                 g = gout * dscale.reshape(N, O, 1, 1) if has_d else gout
@@ -261,20 +282,22 @@ class _FusedModConv(torch.autograd.Function):
                         t.record_stream(box.stream)
                 box.job = weight_grad
                 dw = _placeholder(weight)
-        return dx, dw, ds, ddcoefs, db, None, None, None, None, None, dwmod, drgb_bias, None
+        return dx, dw, ds, ddcoefs, db, None, None, None, None, None, dwmod, drgb_bias, None, dnoise
 
 
 def fused_modulated_conv(x, weight, styles, bias=None, up=1, demodulate=True, act='lrelu', gain=None, flip_weight=True, dcoefs=None, prep=None,
-                         torgb_wmod=None, torgb_bias=None, wbox=None):
-    """y = clamp-free bias_act(modulated_conv2d(x, weight, styles, up, demodulate), bias, act, gain) on NHWC fp32 tensors.
+                         torgb_wmod=None, torgb_bias=None, wbox=None, noise=None):
+    """y = clamp-free bias_act(modulated_conv2d(x, weight, styles, noise, up, demodulate), bias, act, gain) on NHWC fp32 tensors.
 
-    Equivalent (up to TF32 rounding of the contraction operands) to the reference's training-mode sequence
-    modulated_conv2d(..., fused_modconv=False) + bias_act (networks.py:30-86,141-143)."""
+    Equivalent (up to TF32 rounding of the contraction operands; fp32-grade in the tf32x3 precision mode) to the reference's
+    training-mode sequence modulated_conv2d(..., fused_modconv=False) + bias_act (networks.py:30-86,141-143).
+    noise: [N or 1, 1, H_out, W_out] plane(s) already multiplied by the noise strength (networks.py:130-134), added inside the
+    contraction's epilogue (up = 1) / the FIR pass's epilogue (up = 2) between the demodulation and the bias."""
     if gain is None:
         gain = float(np.sqrt(2)) if act == 'lrelu' else 1.0
     if dcoefs is None and demodulate:
         dcoefs = demod_coefs(weight, styles)
     if torgb_wmod is not None:
         # -> (y, rgb): rgb[n,j,hw] = sum_c y[n,hw,c] * torgb_wmod[n,j,c] + torgb_bias[j]  (ToRGBLayer arithmetic, one autograd node)
-        return _FusedModConv.apply(x, weight, styles, dcoefs, bias, up, act, float(gain), flip_weight, prep, torgb_wmod, torgb_bias, wbox)
-    return _FusedModConv.apply(x, weight, styles, dcoefs, bias, up, act, float(gain), flip_weight, prep, None, None, wbox)
+        return _FusedModConv.apply(x, weight, styles, dcoefs, bias, up, act, float(gain), flip_weight, prep, torgb_wmod, torgb_bias, wbox, noise)
+    return _FusedModConv.apply(x, weight, styles, dcoefs, bias, up, act, float(gain), flip_weight, prep, None, None, wbox, noise)

@@ -371,8 +371,6 @@ class Generator(torch.nn.Module):
         get = (lambda o, k, d=None: o.get(k, d) if hasattr(o, 'get') else getattr(o, k, d))
         motion, tenc, sampling = get(cfg, 'motion'), get(cfg, 'time_enc'), get(cfg, 'sampling')
         unsupported = []
-        if get(cfg, 'use_noise', False):
-            unsupported.append('use_noise=true')
         if get(get(cfg, 'input', {}), 'type', 'temporal') != 'temporal':
             unsupported.append('input.type != temporal')
         if get(tenc, 'cond_type', 'concat_const') != 'concat_const':
@@ -388,7 +386,7 @@ class Generator(torch.nn.Module):
                    motion_z_dim=get(motion, 'z_dim', 512), motion_v_dim=get(motion, 'v_dim', 512), motion_kernel_size=get(motion, 'kernel_size', 11),
                    motion_z_distance=get(motion, 'motion_z_distance', get(tenc, 'min_period_len', 16)), time_enc_dim=get(tenc, 'dim', 256),
                    min_period_len=get(tenc, 'min_period_len', 16), max_period_len=get(tenc, 'max_period_len', 1024),
-                   max_num_frames=get(sampling, 'max_num_frames', 1024), **kwargs)
+                   max_num_frames=get(sampling, 'max_num_frames', 1024), use_noise=bool(get(cfg, 'use_noise', False)), **kwargs)
 
     def forward(self, z, c, t, truncation_psi=1, truncation_cutoff=None, **synthesis_kwargs):
         assert len(z) == len(c) == len(t) and t.ndim == 2

@@ -36,7 +36,7 @@ def _suggest_format(x):
 
 def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain, *, epilogue=None):
     """One FIR resampling pass on the GPU.  `epilogue` (optional, not part of the reference plugin) is a dict
-    with keys scale [N,C] / bias [C] / act ('linear'|'lrelu') / alpha / gain / clamp applied to the result."""
+    with keys scale [N,C] / noise [N|1,1,oh,ow] / bias [C] / act ('linear'|'lrelu') / alpha / gain / clamp applied to the result."""
     _require(x.is_cuda, 'x must reside on CUDA device')
     _require(f.device == x.device, 'f must reside on the same device as x')
     _require(f.dtype == torch.float32, 'f must be float32')
@@ -87,6 +87,15 @@ def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, ga
         cl = epilogue.get('clamp')
         p.epi_clamp = float(cl) if cl is not None else -1.0
         p.epi_round_tf32 = int(bool(epilogue.get('round_tf32', False)))
+        nz = epilogue.get('noise')
+        if nz is not None:      # [N or 1, 1, out_h, out_w] (or [out_h, out_w]) plane added after the scale, before the bias
+            nz = nz.to(torch.float32)
+            nz = nz.reshape(1, out_h, out_w) if nz.ndim == 2 else nz.reshape(nz.shape[0], out_h, out_w)
+            _require(nz.shape[0] in (1, N) and nz.device == x.device, 'epilogue noise must be [N or 1, 1, out_h, out_w] on the same device')
+            keep.append(nz)
+            p.epi_noise = nz.data_ptr()
+            p.epi_noise_stride_n = nz.stride(0) if (nz.shape[0] == N and N > 1) else 0
+            p.epi_noise_stride_y, p.epi_noise_stride_x = nz.stride(1), nz.stride(2)
     with torch.cuda.device(x.device):
         _lib.check(L.sgv_upfirdn2d(ctypes.byref(p), _stream_ptr(x.device)), 'sgv_upfirdn2d')
     return y

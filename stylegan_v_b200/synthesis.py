@@ -30,13 +30,26 @@ def _setup_filter(taps):
 
 
 class SynthesisLayer(torch.nn.Module):
-    def __init__(self, in_channels, out_channels, w_dim, resolution, kernel_size=3, up=1, resample_filter=(1, 3, 3, 1)):
+    def __init__(self, in_channels, out_channels, w_dim, resolution, kernel_size=3, up=1, resample_filter=(1, 3, 3, 1), use_noise=False):
         super().__init__()
-        self.resolution, self.up = resolution, up
+        self.resolution, self.up, self.use_noise = resolution, up, use_noise
         self.register_buffer('resample_filter', _setup_filter(list(resample_filter)))
         self.affine = EqualizedLinear(w_dim, in_channels, bias_init=1)
         self.weight = torch.nn.Parameter(torch.randn(out_channels, in_channels, kernel_size, kernel_size))
+        if use_noise:                                   # networks.py:119-121 (same registration order => same state dict / RNG draws)
+            self.register_buffer('noise_const', torch.randn([resolution, resolution]))
+            self.noise_strength = torch.nn.Parameter(torch.zeros([]))
         self.bias = torch.nn.Parameter(torch.zeros(out_channels))
+
+    def make_noise(self, batch, noise_mode, device):
+        """The noise input of modulated_conv2d (networks.py:130-134): [N,1,res,res] fresh Gaussian draws ('random') or the stored
+        plane ('const'), times the learned strength; None without use_noise / for 'none'."""
+        assert noise_mode in ('random', 'const', 'none')
+        if not self.use_noise or noise_mode == 'none':
+            return None
+        if noise_mode == 'random':
+            return torch.randn([batch, 1, self.resolution, self.resolution], device=device) * self.noise_strength
+        return (self.noise_const * self.noise_strength).reshape(1, 1, self.resolution, self.resolution)
 
     def plan(self, styles, async_wgrad_stream=None):
         """Everything of this layer that depends on parameters and styles only (not on activations): demodulation coefficients
@@ -49,19 +62,23 @@ class SynthesisLayer(torch.nn.Module):
             plan['weight'] = WeightGradNode.apply(self.weight, plan['wbox'])
         return plan
 
-    def forward(self, x, w=None, styles=None, gain=1.0, plan=None, torgb_wmod=None, torgb_bias=None):
-        """With torgb_wmod [N,3,C] / torgb_bias [3] the block's ToRGB layer is evaluated in the same autograd node: returns (x, rgb)."""
+    def forward(self, x, w=None, styles=None, gain=1.0, plan=None, torgb_wmod=None, torgb_bias=None, noise_mode='random', noise=None):
+        """With torgb_wmod [N,3,C] / torgb_bias [3] the block's ToRGB layer is evaluated in the same autograd node: returns (x, rgb).
+        noise: explicit [N|1,1,res,res] noise input (already scaled) overriding noise_mode (tests feed the oracle's draws)."""
         if plan is None:
             plan = dict(styles=styles if styles is not None else self.affine(w), dcoefs=None, prep=None, weight=self.weight, wbox=None)
+        if noise is None:
+            noise = self.make_noise(x.shape[0], noise_mode, x.device)
         return fused_modulated_conv(x, plan['weight'], plan['styles'], self.bias, up=self.up, demodulate=True, act='lrelu',
                                     gain=float(np.sqrt(2)) * gain, flip_weight=(self.up == 1), dcoefs=plan['dcoefs'], prep=plan['prep'],
-                                    torgb_wmod=torgb_wmod, torgb_bias=torgb_bias, wbox=plan['wbox'])
+                                    torgb_wmod=torgb_wmod, torgb_bias=torgb_bias, wbox=plan['wbox'], noise=noise)
 
 
-def _layer_unfused(layer, x, w, fused_modconv, gain=1.0, conv_clamp=None):
-    """SynthesisLayer.forward of the reference (networks.py:124-144, use_noise = false) on the drop-in ops."""
+def _layer_unfused(layer, x, w, fused_modconv, gain=1.0, conv_clamp=None, noise_mode='random'):
+    """SynthesisLayer.forward of the reference (networks.py:124-144) on the drop-in ops."""
     styles = layer.affine(w)
-    x = _modulated_conv2d(x=x, weight=layer.weight, styles=styles, up=layer.up, padding=1, resample_filter=layer.resample_filter,
+    noise = layer.make_noise(x.shape[0], noise_mode, x.device)
+    x = _modulated_conv2d(x=x, weight=layer.weight, styles=styles, noise=noise, up=layer.up, padding=1, resample_filter=layer.resample_filter,
                           flip_weight=(layer.up == 1), fused_modconv=fused_modconv)
     clamp = conv_clamp * gain if conv_clamp is not None else None
     return _bias_act.bias_act(x, layer.bias.to(x.dtype), act='lrelu', gain=float(np.sqrt(2)) * gain, clamp=clamp)
@@ -145,7 +162,7 @@ class _GenInput(torch.nn.Module):
 
 class SynthesisBlock(torch.nn.Module):
     def __init__(self, in_channels, out_channels, w_dim, motion_v_dim, resolution, img_channels, resample_filter=(1, 3, 3, 1),
-                 use_fp16=False, conv_clamp=None):
+                 use_fp16=False, conv_clamp=None, use_noise=False):
         super().__init__()
         self.in_channels, self.resolution = in_channels, resolution
         self.use_fp16, self.conv_clamp = use_fp16, conv_clamp            # mixed-precision mode of the reference (train.py:173-174); unfused path only
@@ -155,10 +172,10 @@ class SynthesisBlock(torch.nn.Module):
             self.input = _GenInput(out_channels, motion_v_dim)
             conv1_in = self.input.total_dim
         else:
-            self.conv0 = SynthesisLayer(in_channels, out_channels, w_dim, resolution, up=2, resample_filter=resample_filter)
+            self.conv0 = SynthesisLayer(in_channels, out_channels, w_dim, resolution, up=2, resample_filter=resample_filter, use_noise=use_noise)
             self.num_conv += 1
             conv1_in = out_channels
-        self.conv1 = SynthesisLayer(conv1_in, out_channels, w_dim, resolution, resample_filter=resample_filter)
+        self.conv1 = SynthesisLayer(conv1_in, out_channels, w_dim, resolution, resample_filter=resample_filter, use_noise=use_noise)
         self.num_conv += 1
         self.torgb = ToRGBLayer(out_channels, img_channels, w_dim)
         self.num_torgb = 1
@@ -166,26 +183,26 @@ class SynthesisBlock(torch.nn.Module):
     def layers(self):
         return ([] if self.in_channels == 0 else [self.conv0]) + [self.conv1, self.torgb]
 
-    def forward(self, x, img, plans, motion_v=None):
+    def forward(self, x, img, plans, motion_v=None, noise_mode='random'):
         """plans: list of per-layer plans in layer order (conv0?, conv1, torgb); each is a callable returning the plan dict
         (it makes the compute stream wait for the parameter stream first)."""
         it = iter(plans)
         if self.in_channels == 0:
             x = self.input(motion_v)
         else:
-            x = self.conv0(x, plan=next(it)())
+            x = self.conv0(x, plan=next(it)(), noise_mode=noise_mode)
         conv1_plan, rgb_plan = next(it)(), next(it)()
         if rgb_plan['wmod'].shape[1] == 3:
-            x, y = self.conv1(x, plan=conv1_plan, torgb_wmod=rgb_plan['wmod'], torgb_bias=self.torgb.bias)    # conv1 + ToRGB: one node
+            x, y = self.conv1(x, plan=conv1_plan, torgb_wmod=rgb_plan['wmod'], torgb_bias=self.torgb.bias, noise_mode=noise_mode)    # conv1 + ToRGB: one node
         else:
-            x = self.conv1(x, plan=conv1_plan)
+            x = self.conv1(x, plan=conv1_plan, noise_mode=noise_mode)
             y = self.torgb(x, plan=rgb_plan)
         if img is not None:
             img = _upfirdn2d.upsample2d(img, self.resample_filter)
         img = img.add_(y) if img is not None else y
         return x, img
 
-    def forward_unfused(self, x, img, ws, motion_v=None, fused_modconv=None, force_fp32=False):
+    def forward_unfused(self, x, img, ws, motion_v=None, fused_modconv=None, force_fp32=False, noise_mode='random'):
         """SynthesisBlock.forward of the reference (networks.py:224-266, 'skip' architecture) layer by layer on the drop-in ops:
         differentiable to any order, runnable on CPU tensors, and the home of the reference's mixed-precision mode (fp16 activations +
         conv_clamp in the `use_fp16` blocks).  ws [N, num_conv + num_torgb, w_dim]."""
@@ -196,8 +213,8 @@ class SynthesisBlock(torch.nn.Module):
         if self.in_channels == 0:
             x = self.input(motion_v).contiguous()
         else:
-            x = _layer_unfused(self.conv0, x.to(dtype), next(w_iter), fused_modconv, conv_clamp=self.conv_clamp)
-        x = _layer_unfused(self.conv1, x, next(w_iter), fused_modconv, conv_clamp=self.conv_clamp)
+            x = _layer_unfused(self.conv0, x.to(dtype), next(w_iter), fused_modconv, conv_clamp=self.conv_clamp, noise_mode=noise_mode)
+        x = _layer_unfused(self.conv1, x, next(w_iter), fused_modconv, conv_clamp=self.conv_clamp, noise_mode=noise_mode)
         if img is not None:
             img = _upfirdn2d.upsample2d(img, self.resample_filter)
         y = _torgb_unfused(self.torgb, x, next(w_iter), fused_modconv, conv_clamp=self.conv_clamp)
@@ -209,7 +226,8 @@ class SynthesisBlock(torch.nn.Module):
 class SynthesisNetwork(torch.nn.Module):
     def __init__(self, w_dim=512, img_resolution=256, img_channels=3, channel_base=16384, channel_max=512,
                  motion_z_dim=512, motion_v_dim=512, motion_kernel_size=11, motion_z_distance=16, time_enc_dim=256,
-                 min_period_len=16, max_period_len=1024, max_num_frames=1024, resample_filter=(1, 3, 3, 1), num_fp16_res=0, conv_clamp=None):
+                 min_period_len=16, max_period_len=1024, max_num_frames=1024, resample_filter=(1, 3, 3, 1), num_fp16_res=0, conv_clamp=None,
+                 use_noise=False):
         assert img_resolution >= 4 and img_resolution & (img_resolution - 1) == 0
         super().__init__()
         # the reference's mixed-precision mode (fp16 in the num_fp16_res highest resolutions + activation clamp, train.py:173-174,
@@ -225,7 +243,7 @@ class SynthesisNetwork(torch.nn.Module):
         self.num_ws = 0
         for res in self.block_resolutions:
             block = SynthesisBlock(ch[res // 2] if res > 4 else 0, ch[res], w_dim, self.motion_v_dim, res, img_channels, resample_filter,
-                                   use_fp16=(res >= fp16_resolution), conv_clamp=conv_clamp)
+                                   use_fp16=(res >= fp16_resolution), conv_clamp=conv_clamp, use_noise=use_noise)
             self.num_ws += block.num_conv
             if res == img_resolution:
                 self.num_ws += block.num_torgb
@@ -238,7 +256,7 @@ class SynthesisNetwork(torch.nn.Module):
                    channel_max=cfg.channel_max, motion_z_dim=cfg.motion_z_dim, motion_v_dim=cfg.motion_v_dim,
                    motion_kernel_size=cfg.motion_kernel_size, motion_z_distance=cfg.motion_z_distance, time_enc_dim=cfg.time_enc_dim,
                    min_period_len=cfg.min_period_len, max_period_len=cfg.max_period_len, max_num_frames=cfg.max_num_frames,
-                   resample_filter=tuple(cfg.resample_filter))
+                   resample_filter=tuple(cfg.resample_filter), use_noise=bool(getattr(cfg, 'use_noise', False)))
 
     def _all_styles(self, ws):
         """Evaluates every style affine of the forward pass with one stacked GEMM per distinct w index.
@@ -261,7 +279,7 @@ class SynthesisNetwork(torch.nn.Module):
                 out[id(l)] = piece
         return out
 
-    def forward(self, ws, t, c=None, motion_z=None, motion_v=None, t_max=None, unfused=None, fused_modconv=None):
+    def forward(self, ws, t, c=None, motion_z=None, motion_v=None, t_max=None, unfused=None, fused_modconv=None, noise_mode='random'):
         """ws [B, num_ws, w_dim], t [B, F] -> img [B*F, 3, R, R] (fp32, NCHW) — networks.py:324-366 semantics.
 
         unfused=None (default): CUDA inputs run the fused NHWC layers (first-order differentiable); CPU inputs, or unfused=True,
@@ -282,14 +300,14 @@ class SynthesisNetwork(torch.nn.Module):
             for res in self.block_resolutions:
                 block = getattr(self, f'b{res}')
                 x, img = block.forward_unfused(x, img, ws.narrow(1, w_idx, block.num_conv + block.num_torgb), motion_v=motion_v,
-                                               fused_modconv=fused_modconv)
+                                               fused_modconv=fused_modconv, noise_mode=noise_mode)
                 w_idx += block.num_conv
             return img
         plans = self._plan_layers(ws)
         x = img = None
         for res in self.block_resolutions:
             block = getattr(self, f'b{res}')
-            x, img = block(x, img, [plans[id(l)] for l in block.layers()], motion_v=motion_v)
+            x, img = block(x, img, [plans[id(l)] for l in block.layers()], motion_v=motion_v, noise_mode=noise_mode)
         return img
 
     # evaluate the per-layer plans on a second CUDA stream (SGV_PARAM_STREAM=0 or False: same stream, for A/B measurements)

@@ -22,6 +22,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
+from . import precision as _precision
 
 
 class _TimeEncoderTail(torch.autograd.Function):
@@ -92,6 +93,7 @@ class _Conv1dFp32Fwd(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b):
         ctx.save_for_backward(x, w)
+        ctx.tf32_backward = not _precision.is_x3()          # fp32-grade mode: the backward is true fp32 as well
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             return F.conv1d(x, w, b)
 
@@ -99,7 +101,7 @@ class _Conv1dFp32Fwd(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=True):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=ctx.tf32_backward):
             gx, gw, gb = torch.ops.aten.convolution_backward(gy, x, w, [w.shape[0]], [1], [0], [1], False, [0], 1,
                                                             [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]])
         return gx, gw, gb

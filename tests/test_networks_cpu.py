@@ -219,6 +219,8 @@ def test_modules_from_reference_cfg_nodes():
                                          mbstd_group_size=md['mbstd_group_size'], mapping_layers=md['mapping_layers'])
     want = {k[2:]: tuple(g[k].shape) for k in g.files if k.startswith('d:')}
     assert {k: tuple(v.shape) for k, v in D.state_dict().items()} == want
-    bad = dict(cfg.reference_generator_cfg(), use_noise=True)
+    noisy = Generator.from_reference_cfg(dict(cfg.reference_generator_cfg(), use_noise=True), img_resolution=32, channel_base=1024, channel_max=32)
+    assert 'synthesis.b8.conv0.noise_strength' in noisy.state_dict() and tuple(noisy.synthesis.b16.conv1.noise_const.shape) == (16, 16)
+    bad = dict(cfg.reference_generator_cfg(), input=dict(type='const'))
     with pytest.raises(NotImplementedError):
         Generator.from_reference_cfg(bad, img_resolution=32)

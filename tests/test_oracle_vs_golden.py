@@ -113,6 +113,38 @@ def test_synthesis_network_restatement():
     assert cfg.num_ws == ws.shape[1]
 
 
+def test_synthesis_network_with_noise_restatement_and_native_cpu_path():
+    """use_noise = true / noise_mode = 'const' (networks.py:119-121,130-134): the oracle restatement and the native network's
+    layer-by-layer CPU formulation against the golden minted from the reference (image, d ws, every parameter gradient incl. noise_strength)."""
+    from stylegan_v_b200.synthesis import SynthesisNetwork
+    g, meta = load_golden('synthesis_noise_tiny.npz')
+    cfg = sr.SynthesisConfig(**meta)
+    skip = ('resample_filter', 'freqs', 'phase_scales')
+    P = {k[2:]: _t(g[k]).clone().requires_grad_(not k.endswith('noise_const')) for k in g.files if k.startswith('p:') and not k.endswith(skip)}
+    ws = _t(g['ws']).requires_grad_(True)
+    t = _t(g['t']); mz = _t(g['motion_z'])
+    names = sorted(k[2:] for k in g.files if k.startswith('g:'))
+    assert sum(n.endswith('noise_strength') for n in names) == 5
+    img = sr.synthesis_forward(P, cfg, ws, t, motion_z=mz, fused_modconv=False, noise_mode='const')
+    assert rel_err(img, _t(g['img_train'])) < 1e-5
+    grads = torch.autograd.grad(img, [ws] + [P[n] for n in names], _t(g['dimg']))
+    for n, gr in zip(['ws'] + names, grads):
+        assert rel_err(gr, _t(g['d_ws'] if n == 'ws' else g['g:' + n])) < 1e-4, n
+    net = SynthesisNetwork.from_config(cfg)
+    net.load_state_dict({k[2:]: _t(g[k]) for k in g.files if k.startswith('p:')}, strict=True)
+    net.train()
+    ws2 = _t(g['ws']).requires_grad_(True)
+    img2 = net(ws2, t, motion_z=mz, noise_mode='const')
+    assert rel_err(img2, _t(g['img_train'])) < 1e-5
+    params = dict(net.named_parameters())
+    grads2 = torch.autograd.grad(img2, [params[n] for n in names], _t(g['dimg']))
+    for n, gr in zip(names, grads2):
+        assert rel_err(gr, _t(g['g:' + n])) < 1e-4, n
+    with torch.no_grad():      # 'none' drops the noise, 'random' draws fresh planes
+        assert rel_err(net(ws2, t, motion_z=mz, noise_mode='none'), img2) > 1e-3
+        assert rel_err(net(ws2, t, motion_z=mz, noise_mode='random'), img2) > 1e-3
+
+
 def test_flop_model_matches_baseline_md():
     # BASELINE.md §2: 29.870 GFLOP/frame at 256^2, 15.336 at 64^2, 148.596 at 1024^2
     assert abs(sr.conv_flops_per_frame(sr.SynthesisConfig(img_resolution=256)) / 1e9 - 29.870) < 0.01

@@ -1,8 +1,6 @@
 """The reference's mixed-precision mode (num_fp16_res / conv_clamp) on CUDA: fp16 activations through the FIR / bias_act kernels (SGV_F16
 dispatch) and the library contraction, against the reference golden minted on CPU.
-NOTE: written after the round-1 GPU budget was spent and never executed on a GPU yet — opt-in (SGV_RUN_UNVERIFIED=1), sorts last."""
-import os
-
+(Round 1 shipped this test opt-in because it had never run on a GPU; it is a normal member of the GPU suite now.)"""
 import pytest
 import torch
 
@@ -12,8 +10,7 @@ from stylegan_v_b200.networks import Discriminator
 from stylegan_v_b200.synthesis import SynthesisNetwork
 from test_networks_cpu import _t
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get('SGV_RUN_UNVERIFIED') != '1',
-                                                reason='not yet executed on a GPU (round-1 budget spent); set SGV_RUN_UNVERIFIED=1')]
+pytestmark = pytest.mark.gpu
 
 
 def test_mixed_precision_cuda_vs_reference_golden(cuda):
