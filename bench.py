@@ -2,7 +2,7 @@
 """Benchmark of the StyleGAN-V synthesis hot path on B200 (contract: see DESIGN.md §Measurement).
 
     python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+    python bench.py --impl reference --gpus N --steps K ...  # the UNMODIFIED reference network on the host cores (its impl='ref' ops)
 
 Workload (BASELINE.json metric "256x256 synthesis frames/sec (fwd+bwd)"): one step = forward + backward of the
 256x256 SynthesisNetwork (fmaps 0.5, fp32 storage, random-init weights) on 32 synthetic frames per GPU
@@ -25,6 +25,8 @@ sys.path.insert(0, ROOT)
 
 FRAMES_PER_GPU = 32
 RES = 256
+DTYPES = {'tf32': 'tf32 (fp32 storage, TF32 tensor-core products, fp32 accumulate) — the headline; the fp32-grade tf32x3 mode is measured beside it',
+          'tf32x3': 'tf32x3 (fp32 storage, hi/lo-split TF32 products hi*hi + lo*hi + hi*lo, fp32 accumulate: fp32-grade, ~1e-6 of fp32)'}
 
 
 def load_peaks():
@@ -80,55 +82,116 @@ class ClockSampler:
         return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_reference_step(frames, threads):
-    """One forward+backward of the reference's CPU path (oracle port: torch_utils.ops 'ref' formulations + F.conv2d,
-    training-mode non-fused modconv) on `frames` frames at 256x256.  Returns seconds."""
-    from oracle import synthesis_ref as sr
-    torch.set_num_threads(threads)
+def _reference_cpu_network(frames):
+    """The UNMODIFIED reference SynthesisNetwork (src/training/networks.py:270-366) on CPU tensors: every op takes its `impl='ref'` branch
+    (upfirdn2d.py:162-164, bias_act.py:87-89) and conv2d_gradfix defers to F.conv2d (conv2d_gradfix.py:51-52) — BASELINE's "torch_utils.ops
+    with custom CUDA disabled".  Imported from /root/reference, or on the GPU box from the hash-verified copy under oracle/_ref/pyref
+    (oracle/stage_ref.py).  Returns (step_fn, kind) or None when no reference tree is available."""
+    from oracle import ref_loader, synthesis_ref as sr
+    if not ref_loader.available():
+        return None
+    ref = ref_loader.load()
+    cfg = sr.SynthesisConfig(img_resolution=RES)
+    torch.manual_seed(0)
+    S = ref.networks.SynthesisNetwork(w_dim=cfg.w_dim, img_resolution=RES, img_channels=3, channel_base=cfg.channel_base, channel_max=cfg.channel_max,
+                                      cfg=ref_loader.to_cfg(cfg.reference_generator_cfg())).train()      # train mode => fused_modconv=False (networks.py:232)
+    g = torch.Generator().manual_seed(1)
+    ws = torch.randn(frames, S.num_ws, cfg.w_dim, generator=g).requires_grad_(True)
+    t = torch.zeros(frames, 1)
+    c = torch.zeros(frames, 0)
+    mz = torch.randn(frames, sr.max_traj_len(cfg, 0.0), cfg.motion_z_dim, generator=g)
+    dimg = torch.randn(frames, 3, RES, RES, generator=g)
+    params = list(S.parameters())
+    opt = torch.optim.Adam(params, lr=0.0025, betas=(0.0, 0.99), eps=1e-8)     # train.py:192-193
+
+    def step():
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        ws.grad = None
+        img = S(ws, t=t, c=c, motion_z=mz)
+        (img * dimg).sum().backward()
+        t1 = time.perf_counter()
+        for p in params:                                                        # training_loop.py:381-386
+            if p.grad is not None:
+                torch.nan_to_num(p.grad, nan=0, posinf=1e5, neginf=-1e5, out=p.grad)
+        opt.step()
+        t2 = time.perf_counter()
+        # the parameter update happens once per 32-frame step: the sampled frames are charged their share of it
+        return (t1 - t0) + (t2 - t1) * frames / FRAMES_PER_GPU
+    return step, 'reference'
+
+
+def _port_cpu_network(frames):
+    """Fallback when no reference tree is reachable: the oracle port of the same path (kind = 'port')."""
+    from oracle import synthesis_ref as sr, train_ref
     cfg = sr.SynthesisConfig(img_resolution=RES)
     P = {k: v.requires_grad_(True) for k, v in sr.init_params(cfg, seed=0).items()}
     g = torch.Generator().manual_seed(1)
     ws = torch.randn(frames, cfg.num_ws, cfg.w_dim, generator=g).requires_grad_(True)
     t = torch.zeros(frames, 1)
     mz = torch.randn(frames, sr.max_traj_len(cfg, 0.0), cfg.motion_z_dim, generator=g)
-
-    from oracle import train_ref
     names = list(P.keys())
-    opt = torch.optim.Adam([P[n] for n in names], lr=0.0025, betas=(0.0, 0.99), eps=1e-8)     # train.py:192-193
+    opt = torch.optim.Adam([P[n] for n in names], lr=0.0025, betas=(0.0, 0.99), eps=1e-8)
 
     def step():
         t0 = time.perf_counter()
         img = sr.synthesis_forward(P, cfg, ws, t, motion_z=mz, fused_modconv=False)
-        dimg = torch.ones_like(img)
-        grads = torch.autograd.grad(img, [ws] + [P[n] for n in names], dimg, allow_unused=True)
-        # the parameter update the b200 arm performs with its fused kernel: per-tensor nan_to_num + Adam (training_loop.py:381-386)
+        grads = torch.autograd.grad(img, [ws] + [P[n] for n in names], torch.ones_like(img), allow_unused=True)
         t1 = time.perf_counter()
-        for n, g in zip(names, grads[1:]):
-            P[n].grad = train_ref.nan_to_num_ref(g) if g is not None else None
+        for n, gr in zip(names, grads[1:]):
+            P[n].grad = train_ref.nan_to_num_ref(gr) if gr is not None else None
         opt.step()
         t2 = time.perf_counter()
-        # the update happens once per 32-frame step: charge the sampled frames their share of it
         return (t1 - t0) + (t2 - t1) * frames / FRAMES_PER_GPU
-    return step
+    return step, 'port'
+
+
+def cpu_reference_step(frames, threads=None):
+    """One forward + backward + parameter update of the reference's CPU path on `frames` frames at 256x256 -> (step() -> seconds, kind, threads).
+    threads=None: the faster of 32 / 64 / all host threads on one probe step (oversubscribed intra-op pools are SLOWER on these 128-core hosts)."""
+    made = _reference_cpu_network(frames) or _port_cpu_network(frames)
+    step, kind = made
+    ncpu = os.cpu_count() or 1
+    if threads is None:
+        best = None
+        for th in sorted({min(32, ncpu), min(64, ncpu), ncpu}):
+            torch.set_num_threads(th)
+            sec = step()
+            if best is None or sec < best[0]:
+                best = (sec, th)
+        threads = best[1]
+    torch.set_num_threads(threads)
+    return step, kind, threads
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port) on the host cores."""
+    """--impl reference: the reference's own implementation of the path on the host cores — the unmodified reference SynthesisNetwork with
+    custom CUDA disabled — on a bounded sample (8 of the 32 frames of a step) with the requested steps / warm-up (shortened only if the
+    whole run would exceed ~3 minutes)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    threads = min(os.cpu_count() or 1, 32)
-    sample_frames = 1
-    step = cpu_reference_step(sample_frames, threads)
-    step()
-    times = [step() for _ in range(max(1, min(args.steps, 3)))]
-    sec = sorted(times)[len(times) // 2]
+    sample_frames = args.ref_frames
+    step, kind, threads = cpu_reference_step(sample_frames)
+    t_probe = step()
+    budget = 150.0
+    warmup = max(1, min(args.warmup, int(budget * 0.2 / max(t_probe, 1e-3))))
+    steps = max(1, min(args.steps, int(budget * 0.8 / max(t_probe, 1e-3))))
+    for _ in range(warmup):
+        step()
+    times = [step() for _ in range(steps)]
+    sec = sum(times) / len(times)
     fps = sample_frames / sec
-    line = dict(metric='synthesis_fwd_bwd_frames_per_sec_256', value=fps, unit='frames/s', n_gpus=args.gpus, steps=len(times), warmup=1,
+    what = 'UNMODIFIED reference SynthesisNetwork on CPU tensors (torch_utils.ops impl=\'ref\', F.conv2d; custom CUDA disabled), training mode (fused_modconv=False)' \
+        if kind == 'reference' else 'oracle CPU port of the reference path (no reference tree reachable), fused_modconv=False'
+    line = dict(metric='synthesis_fwd_bwd_frames_per_sec_256', value=fps, unit='frames/s', n_gpus=args.gpus, steps=steps, warmup=warmup,
                 ms_per_step=sec * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
-                config=dict(workload='256x256 SynthesisNetwork fwd+bwd + nan_to_num/Adam update (oracle CPU port of the reference path, fused_modconv=False)',
-                            frames_per_step=sample_frames, note='bounded sample of the 32-frame workload; forward/backward time of the sample + its 1/32 share of the once-per-step parameter update'),
-                cpu_baseline=dict(value=fps, unit='frames/s', cores=threads, kind='port', sample=f'{sample_frames} frames fwd+bwd, median of {len(times)}'),
+                config=dict(workload='256x256 SynthesisNetwork forward+backward + fused nan_to_num/Adam update of all parameters, 32 frames/GPU (32 latents x 1 frame), '
+                                     'fmaps 0.5, random-init weights', implementation=what, frames_per_step=sample_frames, frames_per_gpu=FRAMES_PER_GPU,
+                            note=f'each step = a bounded sample of {sample_frames} of the 32 frames: forward/backward of the sample + its {sample_frames}/32 share of the '
+                                 'once-per-step per-tensor nan_to_num + torch.optim.Adam update; frames/s = sample frames / that time'),
+                cpu_baseline=dict(value=fps, unit='frames/s', cores=threads, kind=kind,
+                                  sample=f'{sample_frames} frames fwd+bwd per step, mean of {steps} steps after {warmup} warm-up; {threads} torch threads of {os.cpu_count()} host cores'),
                 e2e=dict(value=fps, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -415,6 +478,9 @@ def main():
     ap.add_argument('--no-optimizer', action='store_true', help='time forward + backward only (no fused Adam update at the end of the step)')
     ap.add_argument('--fused-d', type=int, default=None, help='gd_step: 1 / 0 = discriminator conv layers on the fused conv+bias+act nodes or on the drop-in ops')
     ap.add_argument('--res', type=int, default=256, help='synthesis_fwd: 256 (BASELINE configs[1], 32 frames) or 1024 (configs[4], 8 frames, fmaps 1)')
+    ap.add_argument('--precision', default='tf32', choices=['tf32', 'tf32x3'], help='arithmetic mode of the headline number (the other mode is measured beside it)')
+    ap.add_argument('--no-second-mode', action='store_true', help='skip the measurement of the other arithmetic mode')
+    ap.add_argument('--ref-frames', type=int, default=8, help='--impl reference: frames per sampled CPU step (of the 32 of a step)')
     ap.add_argument('--workload', default='synthesis', choices=['synthesis', 'gd_step', 'synthesis_fwd', 'full_loop'],
                     help="synthesis = BASELINE metric (256x256 SynthesisNetwork fwd+bwd, configs[1] batch); gd_step = configs[2] (G+D training step, no reg)")
     args = ap.parse_args()
@@ -441,18 +507,20 @@ def main():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
 
-    from stylegan_v_b200 import _lib, conv as C, plugin
+    from stylegan_v_b200 import _lib, conv as C, plugin, precision
     from stylegan_v_b200.synthesis import SynthesisNetwork
     from stylegan_v_b200.optim import FlatModuleState, FusedAdamEMA
     from stylegan_v_b200.ops import upfirdn2d as U
     from oracle import synthesis_ref as sr     # FLOP model + cpu_baseline only
 
-    torch.manual_seed(rank)
+    torch.manual_seed(0)                       # every rank builds the SAME replica ...
     net = SynthesisNetwork(img_resolution=RES).to(dev).train()
     # parameters / gradients / Adam moments in flat buffers: one all-reduce (N > 1) and one fused nan_to_num + Adam launch per step
     # (training_loop.py:381-386 semantics; lr as train.py:160).  --no-optimizer times forward + backward alone.
     state = FlatModuleState(list(net.parameters()))
+    state.broadcast(0)                         # ... and rank 0's parameters are broadcast like the reference's "Distribute across GPUs" (training_loop.py:215-232)
     opt = None if args.no_optimizer else FusedAdamEMA(state, lr=0.0025, betas=(0.0, 0.99), eps=1e-8)
+    torch.manual_seed(1 + rank)                # per-rank latents (each rank works on its own 32 frames)
     N = FRAMES_PER_GPU
     L = net.motion_encoder.traj_len()
     # host-side (pinned) inputs for the end-to-end measurement
@@ -474,44 +542,52 @@ def main():
 
     # The step (about 1000 kernel launches: forward + backward of 20 fused layers) is captured ONCE into a CUDA graph and replayed:
     # the GPU then never waits for the Python/ctypes launch path.  The gradient all-reduce (N > 1) is issued after each replay.
-    graph = None
-    graph_launches = 0
     s_ws, s_t, s_mz = d_ws.clone(), d_t.clone(), d_mz.clone()      # static graph inputs
-    if not args.no_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(2):
-                    step_compute(s_ws.detach(), s_t, s_mz)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            l0 = _lib.launch_count()
-            with torch.cuda.graph(graph):
-                s_loss = step_compute(s_ws.detach(), s_t, s_mz)
-            graph_launches = _lib.launch_count() - l0
-        except Exception as e:      # capture is an optimisation, not a requirement
-            if rank == 0:
-                sys.stderr.write(f'[bench] CUDA graph capture failed ({type(e).__name__}: {e}); falling back to eager launches\n')
-            graph = None
-            torch.cuda.synchronize()
-    state.zero_grad()                          # warm-up / capture passes accumulated into the buffer
 
-    def step(ws, t, mz):
-        if graph is not None:
-            if ws.data_ptr() != s_ws.data_ptr():
-                s_ws.copy_(ws, non_blocking=True); s_t.copy_(t, non_blocking=True); s_mz.copy_(mz, non_blocking=True)
-            graph.replay()
-            loss = s_loss
-        else:
-            loss = step_compute(ws, t, mz)
-        state.all_reduce()                     # SUM over ranks; the 1/world of the average is applied inside the update kernel
-        if opt is not None:
-            opt.step(zero_grad=True)
-        elif world > 1:
-            state.grad.div_(world)
-        return loss
+    def build_step(mode):
+        """The step in one arithmetic mode of the contractions (stylegan_v_b200.precision): 'tf32' or the fp32-grade 'tf32x3'.  The mode is
+        read when the kernels are issued, i.e. at capture time; a replay needs no context."""
+        graph, graph_launches, s_loss = None, 0, None
+        if not args.no_graph:
+            try:
+                with precision.precision(mode):
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        for _ in range(2):
+                            step_compute(s_ws.detach(), s_t, s_mz)
+                    torch.cuda.current_stream().wait_stream(side)
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    l0 = _lib.launch_count()
+                    with torch.cuda.graph(graph):
+                        s_loss = step_compute(s_ws.detach(), s_t, s_mz)
+                    graph_launches = _lib.launch_count() - l0
+            except Exception as e:      # capture is an optimisation, not a requirement
+                if rank == 0:
+                    sys.stderr.write(f'[bench] CUDA graph capture failed ({type(e).__name__}: {e}); falling back to eager launches\n')
+                graph = None
+                torch.cuda.synchronize()
+        state.zero_grad()                          # warm-up / capture passes accumulated into the buffer
+
+        def step(ws, t, mz):
+            if graph is not None:
+                if ws.data_ptr() != s_ws.data_ptr():
+                    s_ws.copy_(ws, non_blocking=True); s_t.copy_(t, non_blocking=True); s_mz.copy_(mz, non_blocking=True)
+                graph.replay()
+                loss = s_loss
+            else:
+                with precision.precision(mode):
+                    loss = step_compute(ws, t, mz)
+            state.all_reduce()                     # SUM over ranks; the 1/world of the average is applied inside the update kernel
+            if opt is not None:
+                opt.step(zero_grad=True)
+            elif world > 1:
+                state.grad.div_(world)
+            return loss
+        return step, graph, graph_launches
+
+    step, graph, graph_launches = build_step(args.precision)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -552,6 +628,18 @@ def main():
     ms_e2e, _ = timed(e2e_step, args.steps, 1)
     clocks = sampler.stop() if rank == 0 else None      # sampled across both timed regions (device-resident and end-to-end)
 
+    # (3) the same step in the other arithmetic mode, beside the headline (the reference trains with allow_tf32 = False, training_loop.py:141-142:
+    #     tf32x3 is the fp32-grade counterpart; tf32 is the north_star's TF32 tensor-core arithmetic)
+    other_mode = 'tf32x3' if args.precision == 'tf32' else 'tf32'
+    other = None
+    if not args.no_second_mode:
+        step2, graph2, launches2 = build_step(other_mode)
+        k2 = max(3, args.steps // 2)
+        ms2, l2 = timed(lambda: step2(s_ws if graph2 is not None else d_ws.detach(), s_t if graph2 is not None else d_t, s_mz if graph2 is not None else d_mz), k2, 3)
+        other = dict(dtype=DTYPES[other_mode], value=N * world / (ms2 / k2 * 1e-3), unit='frames/s', ms_per_step=ms2 / k2, steps=k2, warmup=3,
+                     gpu_launches=(launches2 + (1 if opt is not None else 0)) * k2 if graph2 is not None else l2)
+        del step2, graph2
+
     ms_step = ms_total / args.steps
     frames = N * world
     value = frames / (ms_step * 1e-3)
@@ -578,20 +666,28 @@ def main():
     taps, offs = C.conv3x3_taps()
     conv_shapes = [('b32.conv1', 512, 512, 32), ('b64.conv1', 256, 256, 64), ('b128.conv1', 128, 128, 128), ('b256.conv1', 64, 64, 256)]
     per_layer = []
+    x3_headline = args.precision == 'tf32x3'
     for name, ci, co, r in conv_shapes:
         x = torch.randn(N, ci, r, r, device=dev).contiguous(memory_format=torch.channels_last)
-        wp = C.prep_weights(torch.randn(co, ci, 3, 3, device=dev), taps)
+        wp = C.prep_weights(torch.randn(co, ci, 3, 3, device=dev), taps, x3=x3_headline)
         s = torch.rand(N, ci, device=dev) + 0.5; d = torch.rand(N, co, device=dev) + 0.5; b = torch.zeros(co, device=dev)
         ms = kernel_ms(lambda: C.igemm_conv(x, wp, offs, a_scale=s, o_scale=d, bias=b, act='lrelu', gain=1.4142135))
+        var = C.igemm_conv(x, wp, offs, a_scale=s, o_scale=d, bias=b, act='lrelu', gain=1.4142135, query=True)
         fl = 2.0 * N * r * r * ci * co * 9
-        per_layer.append(dict(layer=name, ms=ms, tflops=fl / ms / 1e9, flops=fl))
+        per_layer.append(dict(layer=name, ms=ms, tflops=fl / ms / 1e9, flops=fl, variant=var))
         del x, wp
     dom = max(per_layer, key=lambda z: z['ms'])
-    # DRAM bytes per launch of these kernels from the committed `ncu --set full` captures (profiles/ncu_final_r1aw_summary.txt, b64 from
-    # profiles/ncu_v3_r1y_summary.txt): dram__bytes_read.sum + dram__bytes_write.sum; the algorithmic minimum is x once + y once
-    ncu_traffic = {'b256.conv1': 537104000 + 483684352, 'b128.conv1': 269128704 + 215464960, 'b64.conv1': 137792768 + 81528320, 'b32.conv1': 81619000 + 19873792}
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of ONE `ncu --set full` capture of the current kernels): read from the
+    # committed summary profiles/ncu_traffic.json (written by scripts/ncu_traffic.py from the .ncu-rep); null when no capture of this build exists.
+    # The algorithmic minimum of the conv is x once + y once.
+    try:
+        ncu_traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+    except Exception:
+        ncu_traffic = {}
     roofline = dict(bound='tensor', kernel=f"conv_tf32_v3_kernel @ {dom['layer']} (N={N})", achieved=dom['tflops'], peak=peaks['bf16_tflops'],
-                    unit='TFLOP/s', frac=dom['tflops'] / peaks['bf16_tflops'], traffic=ncu_traffic.get(dom['layer']), traffic_unit='bytes/launch (ncu, profiles/ncu_final_r1aw_summary.txt)',
+                    unit='TFLOP/s', frac=dom['tflops'] / peaks['bf16_tflops'], traffic=ncu_traffic.get(dom['layer']),
+                    traffic_unit='bytes/launch (ncu --set full, profiles/ncu_traffic.json: ' + str(ncu_traffic.get('source')) + ')',
+                    algorithmic_bytes_per_launch=N * 256 * 256 * 64 * 4 * 2 if dom['layer'] == 'b256.conv1' else None,
                     peak_source=peaks['source'] + ' (dense bf16 cuBLAS; the kernel runs kind::tf32, whose measured issue-rate ceiling is 1164 TFLOP/s for N >= 128 and '
                                                   '776 TFLOP/s for N = 64 output channels — profiles/mma_rate_probe_r1.txt)',
                     tf32_issue_rate_ceiling_tflops=776.0 if dom['layer'] == 'b256.conv1' else 1164.0,
@@ -604,9 +700,33 @@ def main():
     xf = xf.contiguous(memory_format=torch.channels_last)
     fir_ms = kernel_ms(lambda: plugin.upfirdn2d(xf, f, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0))
     upfirdn = dict(bound='hbm', kernel='fir_nhwc_tma44 [32,257,257,64]->[32,256,256,64] (channels_last, as the synthesis path runs it)', achieved=fir_bytes / fir_ms / 1e6,
-                   peak=peaks['hbm_gbs'], unit='GB/s', frac=fir_bytes / fir_ms / 1e6 / peaks['hbm_gbs'], traffic=None, algorithmic_bytes_per_launch=fir_bytes,
+                   peak=peaks['hbm_gbs'], unit='GB/s', frac=fir_bytes / fir_ms / 1e6 / peaks['hbm_gbs'], traffic=ncu_traffic.get('fir_nhwc_tma44'), algorithmic_bytes_per_launch=fir_bytes,
                    peak_source=peaks['source'], nchw=dict(kernel='fir_nchw_tiled, same extents in NCHW (odd row pitch: not TMA-addressable)', achieved=fir_bytes / fir_nchw_ms / 1e6,
                                                           frac=fir_bytes / fir_nchw_ms / 1e6 / peaks['hbm_gbs']))
+    # "beat this kernel" (BASELINE.md §4): the reference's OWN CUDA plugins, compiled unmodified for sm_100a (oracle/_ref, oracle/build_ref.py), timed
+    # on the same extents in the layout the reference runs them in (NCHW) — a reported baseline, never part of the product path
+    ref_cuda = None
+    try:
+        from oracle import build_ref
+        rup, rba = build_ref.load_plugin('upfirdn2d_plugin'), build_ref.load_plugin('bias_act_plugin')
+        if rup is not None and rba is not None:
+            xn = xf.contiguous()
+            ref_fir_ms = kernel_ms(lambda: rup.upfirdn2d(xn, f, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0))
+            ref_fir_cl_ms = kernel_ms(lambda: rup.upfirdn2d(xf, f, 1, 1, 1, 1, 1, 1, 1, 1, False, 4.0))
+            xb = torch.randn(N, 64, 256, 256, device=dev); bb = torch.randn(64, device=dev); e = torch.empty(0, device=dev)
+            ba_bytes = 2 * xb.numel() * 4
+            ref_ba_ms = kernel_ms(lambda: rba.bias_act(xb, bb, e, e, e, 0, 1, 3, 0.2, 1.4142135, -1.0))
+            our_ba_ms = kernel_ms(lambda: plugin.bias_act(xb, bb, e, e, e, 0, 1, 3, 0.2, 1.4142135, -1.0))
+            ref_cuda = dict(note="the reference's own upfirdn2d / bias_act CUDA kernels (unmodified sources, --use_fast_math, sm_100a) on this B200, same extents",
+                            upfirdn2d=dict(shape='[32,64,257,257] -> [32,64,256,256] fp32', reference_nchw_gbs=fir_bytes / ref_fir_ms / 1e6,
+                                           reference_channels_last_gbs=fir_bytes / ref_fir_cl_ms / 1e6, ours_nchw_gbs=fir_bytes / fir_nchw_ms / 1e6,
+                                           ours_channels_last_gbs=fir_bytes / fir_ms / 1e6, speedup_vs_reference_nchw=ref_fir_ms / fir_ms),
+                            bias_act=dict(shape='[32,64,256,256] fp32 lrelu', reference_gbs=ba_bytes / ref_ba_ms / 1e6, ours_gbs=ba_bytes / our_ba_ms / 1e6,
+                                          speedup=ref_ba_ms / our_ba_ms,
+                                          note='in the synthesis path this pass does not exist at all: bias/lrelu/gain run in the conv / FIR epilogue'))
+            del xn, xb
+    except Exception as ex:      # a baseline that cannot run is reported, not fatal
+        ref_cuda = dict(unavailable=f'{type(ex).__name__}: {ex}')
     del xf
     # the parameter update of the step: one streaming pass over the flat state (4 loads + 4 stores of 4 B per parameter incl. gradient zeroing)
     optimizer = None
@@ -621,16 +741,18 @@ def main():
     conv_gflop_fwd = sr.conv_flops_per_frame(cfg) / 1e9
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        threads = min(os.cpu_count() or 1, 32)
-        cstep = cpu_reference_step(1, threads)
+        cframes = 4
+        cstep, ckind, threads = cpu_reference_step(cframes)
         cstep()
-        ts = sorted(cstep() for _ in range(2))
-        cpu_baseline = dict(value=1 / ts[0], unit='frames/s', cores=threads, kind='port',
-                            sample='1 frame fwd+bwd at 256x256 (oracle port of the reference CPU path, fused_modconv=False), best of 2 after 1 warm-up; '
-                                   f'{threads} torch threads of {os.cpu_count()} host cores')
+        ts = sorted(cstep() for _ in range(3))
+        cpu_baseline = dict(value=cframes / ts[1], unit='frames/s', cores=threads, kind=ckind,
+                            sample=f'{cframes} of the 32 frames fwd+bwd (+ their share of the nan_to_num/Adam update) at 256x256 on the ' +
+                                   ("UNMODIFIED reference SynthesisNetwork, torch_utils.ops impl='ref' (custom CUDA disabled)" if ckind == 'reference'
+                                    else 'oracle port of the reference CPU path') +
+                                   f', fused_modconv=False; median of 3 after warm-up; {threads} torch threads of {os.cpu_count()} host cores')
 
     line = dict(metric='synthesis_fwd_bwd_frames_per_sec_256', value=value, unit='frames/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='tf32 (fp32 storage, TF32 tensor-core products, fp32 accumulate)',
+                ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype=DTYPES[args.precision],
                 data='synthetic',
                 config=dict(workload='256x256 SynthesisNetwork forward+backward' + (' + fused nan_to_num/Adam update of all parameters' if opt is not None else '') +
                                      ', 32 frames/GPU (32 latents x 1 frame), fmaps 0.5, random-init weights', optimizer_step=opt is not None,
@@ -638,7 +760,8 @@ def main():
                             conv_gflop_per_frame_fwd=conv_gflop_fwd),
                 e2e=dict(value=e2e_value, unit='frames/s', h2d_bytes_per_step=(h_ws.numel() + h_t.numel() + h_mz.numel()) * 4, d2h_bytes_per_step=4),
                 gpu_launches=launches, clocks=clocks, roofline=roofline, upfirdn2d=upfirdn, optimizer=optimizer, cpu_baseline=cpu_baseline,
-                model_tflops_fwd_bwd=3 * conv_gflop_fwd * frames / ms_step / world)
+                model_tflops_fwd_bwd=3 * conv_gflop_fwd * frames / ms_step / world, reference_cuda_kernels=ref_cuda)
+    line[other_mode] = other      # the same step in the other arithmetic mode, measured beside the headline
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

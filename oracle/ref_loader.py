@@ -1,8 +1,8 @@
 """ORACLE (test infrastructure only).  Imports the UNMODIFIED Python reference from /root/reference.
 
-Only usable in the build container (the GPU box has no /root/reference); used by
-oracle/make_goldens.py to mint tests/golden/*.npz and by CPU tests that are skipped when the
-reference tree is absent.  Nothing is copied: the reference modules are imported in place.
+Imports /root/reference in place in the build container; on the GPU box (no /root/reference) the byte-for-byte copy that
+oracle/stage_ref.py stages under the git-ignored oracle/_ref/pyref (hash-verified on load).  Used by oracle/make_goldens.py to mint
+tests/golden/*.npz, by `bench.py --impl reference`, and by tests that are skipped when no reference tree is present.
 
 The reference needs `omegaconf` (absent here) only for `OmegaConf.create/to_container` and the
 `DictConfig` name (src/training/networks.py:12,384; layers.py:8; motion.py:6) — a minimal in-memory
@@ -12,11 +12,26 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get('SGV_REFERENCE_ROOT', '/root/reference')
+def _find_root():
+    """The reference tree: $SGV_REFERENCE_ROOT, else /root/reference (build container), else the byte-for-byte copy staged by
+    oracle/stage_ref.py under oracle/_ref/pyref (what the GPU box has)."""
+    env = os.environ.get('SGV_REFERENCE_ROOT')
+    if env:
+        return env
+    if os.path.isdir('/root/reference/src/torch_utils/ops'):
+        return '/root/reference'
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref', 'pyref')
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, 'src', 'torch_utils', 'ops'))
+
+
+def is_staged_copy() -> bool:
+    return os.path.basename(os.path.normpath(REF_ROOT)) == 'pyref'
 
 
 class _Cfg(dict):
@@ -65,6 +80,9 @@ def load():
         return _loaded
     if not available():
         raise RuntimeError(f'reference tree not found at {REF_ROOT}')
+    if is_staged_copy():
+        from . import stage_ref
+        assert stage_ref.verify(), 'oracle/_ref/pyref does not match its manifest: not the unmodified reference'
     _install_omegaconf_stub()
     for p in (os.path.join(REF_ROOT, 'src'), REF_ROOT):
         if p not in sys.path:

@@ -75,6 +75,16 @@ class FlatModuleState:
             return None
         return dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
 
+    def broadcast(self, src=0):
+        """Replicas start identical: parameters (and the EMA copy) are broadcast from rank `src` before the first step, as the reference
+        does for every parameter and buffer ("Distribute across GPUs", training_loop.py:215-232).  Two collectives over the flat buffers."""
+        if self.world_size() == 1:
+            return
+        src_global = dist.get_global_rank(self.group, src) if self.group is not None else src
+        dist.broadcast(self.param, src=src_global, group=self.group)
+        if self.ema is not None:
+            dist.broadcast(self.ema, src=src_global, group=self.group)
+
     def nbytes(self):
         return self.numel * 4
 

@@ -89,10 +89,16 @@ class TrainingPhases:
     """G and D with flat state, lazily-regularised Adam (training_loop.py:243-250) and the EMA generator.
 
     step(...) runs the phases due at this iteration in the reference's order (Gmain, [Greg], Dmain, [Dreg]) and returns their loss
-    values (tensors; no host sync)."""
+    values (tensors; no host sync).
+
+    Lazy regularisation follows the reference exactly: whenever a reg interval is configured the optimiser of that network runs with
+    lr * r and betas ** r, r = interval / (interval + 1) (training_loop.py:243-250) — independently of the loss WEIGHTS.  StyleGAN-V's own
+    config has pl_weight = 0 with G_reg_interval = 4: G then trains at 0.8 * lr with beta2 = 0.99 ** 0.8 and the Greg phase produces no
+    gradients (loss.py:101: do_Gpl needs pl_weight != 0), so torch's Adam skips every parameter; here the phase is skipped outright."""
 
     def __init__(self, G, D, lr=0.0025, betas=(0.0, 0.99), eps=1e-8, r1_gamma=0.2048, pl_weight=0.0, G_reg_interval=4, D_reg_interval=16,
-                 ema_kimg=20.0, ema_rampup=None, batch_size=64, process_group=None, device_step=False, augment_pipe=None, video_consistent_aug=True):
+                 ema_kimg=20.0, ema_rampup=None, batch_size=64, num_frames_per_video=None, process_group=None, device_step=False,
+                 augment_pipe=None, video_consistent_aug=True):
         assert next(G.parameters()).is_cuda, 'TrainingPhases drives the CUDA path only'
         conv2d_gradfix.enabled = True                                               # training_loop.py:143
         self.G, self.D = G, D
@@ -101,12 +107,23 @@ class TrainingPhases:
             G.synthesis._pstream = None                                             # a CUDA stream handle is not deep-copyable; it is re-created lazily
         self.G_ema = copy.deepcopy(G).eval().requires_grad_(False)
         self.r1_gamma, self.pl_weight = r1_gamma, pl_weight
-        self.G_reg_interval = G_reg_interval if pl_weight != 0 else None
-        self.D_reg_interval = D_reg_interval if r1_gamma != 0 else None
+        self.G_reg_interval, self.D_reg_interval = G_reg_interval, D_reg_interval       # optimiser scaling: keyed on the interval alone
+        self.run_greg = G_reg_interval is not None and pl_weight != 0                   # whether the reg phase has anything to do
+        self.run_dreg = D_reg_interval is not None and r1_gamma != 0
         self.ema_kimg, self.ema_rampup, self.batch_size = ema_kimg, ema_rampup, batch_size
+        self.num_frames_per_video = num_frames_per_video
         self.pl_mean = torch.zeros([], device=next(G.parameters()).device)
         self.G_state = FlatModuleState(list(G.parameters()), list(self.G_ema.parameters()), process_group)
         self.D_state = FlatModuleState(list(D.parameters()), None, process_group)
+        # replicas start from rank 0's parameters and buffers (training_loop.py:215-232 "Distribute across GPUs"); only gradients are
+        # exchanged afterwards
+        self.G_state.broadcast(0)
+        self.D_state.broadcast(0)
+        if self.G_state.world_size() > 1:
+            import torch.distributed as dist
+            for module in (G, self.G_ema, D):
+                for buf in module.buffers():
+                    dist.broadcast(buf, src=0 if process_group is None else dist.get_global_rank(process_group, 0), group=process_group)
 
         def make_opt(state, interval):
             if interval is None:
@@ -120,10 +137,12 @@ class TrainingPhases:
         self.it = 0
 
     def ema_beta(self):
+        """training_loop.py:393-396, evaluated with cur_nimg BEFORE this iteration's increment (first iteration with a ramp-up: beta = 0,
+        i.e. G_ema = G)."""
         nimg = self.ema_kimg * 1000
         if self.ema_rampup is not None:
             nimg = min(nimg, self.cur_nimg * self.ema_rampup)
-        return 0.5 ** (self.batch_size / max(nimg, 1e-8))                            # training_loop.py:393-396
+        return 0.5 ** (self.batch_size / max(nimg, 1e-8))
 
     def _finish(self, state, opt, ema_beta=None):
         state.all_reduce()                                                           # SUM over ranks; 1/world is applied by the update kernel
@@ -136,31 +155,50 @@ class TrainingPhases:
         self.G.requires_grad_(train_G)
         self.D.requires_grad_(not train_G)
 
+    PHASES = ('Gmain', 'Greg', 'Dmain', 'Dreg')
+
+    @staticmethod
+    def _per_phase(v, name):
+        """Per-phase generator inputs: a dict {phase: tensor} (missing phases fall back to 'Gmain') or one tensor shared by all phases."""
+        if isinstance(v, dict):
+            return v.get(name, v['Gmain'])
+        return v
+
     def step(self, real_img, real_t, z, t, c=None, real_c=None, **synthesis_kwargs):
-        """One iteration: real_img [B*F, 3, R, R], real_t / t [B, F], z [B, z_dim].  EMA is applied with the G main phase's update
-        (the reference applies it after all phases of the iteration, training_loop.py:392-400 — same values, since only G phases change G
-        and the regularisation phase's update is folded in when it runs)."""
-        B = z.shape[0]
-        c = torch.zeros(B, 0, device=z.device) if c is None else c
-        real_c = torch.zeros(B, 0, device=z.device) if real_c is None else real_c
+        """One iteration: real_img [B*F, 3, R, R], real_t [B, F]; generator latents z [B, z_dim] and times t [B, F].
+
+        The reference draws INDEPENDENT gen_z / gen_c / gen_t for every phase (training_loop.py:333-348: all_gen_z split per phase):
+        pass z / t / c as dicts keyed by phase name ('Gmain', 'Greg', 'Dmain', 'Dreg') to reproduce that — `sample_phase_latents` builds
+        them; a plain tensor is shared by all phases (benchmarks, CUDA-graph capture with static inputs).
+        EMA is applied with the last G update of the iteration (the reference applies it after all phases, training_loop.py:392-400 —
+        same values, since only G phases change G)."""
+        z0 = self._per_phase(z, 'Gmain')
+        B = z0.shape[0]
+        zeros_c = torch.zeros(B, 0, device=z0.device)
+        c = zeros_c if c is None else c
+        real_c = zeros_c if real_c is None else real_c
+        pick = lambda name: (self._per_phase(z, name), self._per_phase(c, name), self._per_phase(t, name))
         out = {}
-        do_greg = self.G_reg_interval is not None and self.it % self.G_reg_interval == 0
-        do_dreg = self.D_reg_interval is not None and self.it % self.D_reg_interval == 0
-        self.cur_nimg += self.batch_size
+        do_greg = self.run_greg and self.it % self.G_reg_interval == 0
+        do_dreg = self.run_dreg and self.it % self.D_reg_interval == 0
+        ema_beta = self.ema_beta()                                                   # from the pre-increment image count
         # ---- G phases
         self._grad_mode(True)
-        loss = generator_main_loss(self.G, self.D, z, c, t, **self.aug, **synthesis_kwargs)
+        pz, pc, pt = pick('Gmain')
+        loss = generator_main_loss(self.G, self.D, pz, pc, pt, **self.aug, **synthesis_kwargs)
         loss.backward()
         out['Gmain'] = loss.detach()
-        self._finish(self.G_state, self.G_opt, ema_beta=None if do_greg else self.ema_beta())
+        self._finish(self.G_state, self.G_opt, ema_beta=None if do_greg else ema_beta)
         if do_greg:
-            loss = generator_path_length_loss(self.G, z, c, t, self.pl_mean, self.pl_weight, **synthesis_kwargs)
+            pz, pc, pt = pick('Greg')
+            loss = generator_path_length_loss(self.G, pz, pc, pt, self.pl_mean, self.pl_weight, **synthesis_kwargs)
             loss.mul(self.G_reg_interval).backward()
             out['Greg'] = loss.detach()
-            self._finish(self.G_state, self.G_opt, ema_beta=self.ema_beta())
+            self._finish(self.G_state, self.G_opt, ema_beta=ema_beta)
         # ---- D phases
         self._grad_mode(False)
-        loss_gen, loss_real = discriminator_main_loss(self.G, self.D, real_img, real_c, real_t, z, c, t, **self.aug, **synthesis_kwargs)
+        pz, pc, pt = pick('Dmain')
+        loss_gen, loss_real = discriminator_main_loss(self.G, self.D, real_img, real_c, real_t, pz, pc, pt, **self.aug, **synthesis_kwargs)
         (loss_gen + loss_real).backward()
         out['Dmain'] = (loss_gen + loss_real).detach()
         self._finish(self.D_state, self.D_opt)
@@ -169,5 +207,14 @@ class TrainingPhases:
             loss.mul(self.D_reg_interval).backward()
             out['Dreg'] = loss.detach()
             self._finish(self.D_state, self.D_opt)
+        frames = self.num_frames_per_video if self.num_frames_per_video is not None else int(real_t.shape[1])
+        self.cur_nimg += self.batch_size * frames                                    # training_loop.py:403: batch_size * num_frames_per_video
         self.it += 1
         return out
+
+    def sample_phase_latents(self, batch, z_dim, t_sampler, device, generator=None):
+        """Independent generator inputs per phase, like the reference's data fetch (training_loop.py:333-348): returns (z, t) dicts keyed by
+        phase name.  t_sampler(batch) -> [batch, F] frame positions (the reference's sample_frames)."""
+        z = {name: torch.randn(batch, z_dim, device=device, generator=generator) for name in self.PHASES}
+        t = {name: t_sampler(batch).to(device) for name in self.PHASES}
+        return z, t

@@ -17,22 +17,63 @@ def _gradfix_enabled(monkeypatch):
     monkeypatch.setattr(conv2d_gradfix, 'enabled', True)
 
 
-@pytest.mark.parametrize('phase', ['Gmain', 'Dmain', 'Dreg'])
-def test_phase_gradients_cuda_vs_reference_loss(cuda, phase):
+def _main_phase_grads(phase, G, D, g, dev, mz):
+    """Gmain / Dmain gradients with the motion noise fed explicitly (the loss functions forward synthesis kwargs to G), so that the result
+    does not depend on which device's generator would have drawn it."""
+    real = _t(g['real']).to(dev)
+    real = real.view(-1, *real.shape[2:])
+    real_t, gen_t, z = _t(g['real_t']).to(dev), _t(g['gen_t']).to(dev), _t(g['z']).to(dev)
+    c = torch.zeros(len(z), 0, device=dev)
+    module = G if phase == 'Gmain' else D
+    G.requires_grad_(module is G)
+    D.requires_grad_(module is D)
+    for p in module.parameters():
+        p.grad = None
+    if phase == 'Gmain':
+        loss = ts.generator_main_loss(G, D, z, c, gen_t, motion_z=mz.to(dev))
+    else:
+        a, b = ts.discriminator_main_loss(G, D, real, c, real_t, z, c, gen_t, motion_z=mz.to(dev))
+        loss = a + b
+    loss.backward()
+    return float(loss), {n: p.grad.detach().double().cpu() for n, p in module.named_parameters() if p.grad is not None}
+
+
+@pytest.mark.parametrize('phase', ['Gmain', 'Dmain'])
+def test_main_phase_gradients_cuda_vs_cpu_evaluation(cuda, phase):
+    """The CPU evaluation of the native modules is pinned to the reference's StyleGAN2Loss (tests/test_train_step_cpu.py, 1e-4); the CUDA
+    evaluation (fused synthesis layers, fused discriminator nodes, tcgen05 contractions) of the SAME modules and inputs must agree with it:
+    fp32-grade in tf32x3 mode (every gradient <= 2e-3 normwise), direction + norm in the default TF32 mode."""
+    import torch.nn.functional as F
+    from stylegan_v_b200 import precision
+    g, meta = load_golden('loss_phases_tiny.npz')
+    G, D = make_gd(g, meta)
+    mz = torch.randn(len(_t(g['z'])), G.synthesis.motion_encoder.traj_len(), G.synthesis.motion_encoder.z_dim, generator=torch.Generator().manual_seed(5))
+    loss_c, ref = _main_phase_grads(phase, G, D, g, torch.device('cpu'), mz)
+    assert len(ref) > 10
+    G, D = make_gd(g, meta)
+    G, D = G.to(cuda), D.to(cuda)
+    n0 = _lib.launch_count()
+    with precision.precision('tf32x3'):
+        loss_g, got = _main_phase_grads(phase, G, D, g, cuda, mz)
+    assert _lib.launch_count() > n0
+    assert abs(loss_g - loss_c) < 1e-4 * max(1.0, abs(loss_c))
+    assert set(got) == set(ref)
+    worst = max((rel_err(got[n], ref[n]), n) for n in ref)
+    assert worst[0] < 2e-3, worst
+    loss_t, got = _main_phase_grads(phase, G, D, g, cuda, mz)            # default TF32 mode
+    assert abs(loss_t - loss_c) < 5e-3 * max(1.0, abs(loss_c))
+    for n in ref:
+        if ref[n].ndim >= 2 and float(ref[n].norm()) > 0:
+            cos = float(F.cosine_similarity(got[n].flatten(), ref[n].flatten(), dim=0))
+            assert cos > 0.99 and abs(float(got[n].norm() / ref[n].norm()) - 1) < 5e-2, (n, cos)
+
+
+def test_dreg_gradients_cuda_vs_reference_loss(cuda):
     g, meta = load_golden('loss_phases_tiny.npz')
     G, D = make_gd(g, meta)
     G, D = G.to(cuda), D.to(cuda)
-    module = run_phase(phase, G, D, g, cuda, meta['r1_gamma'])
-    if phase == 'Gmain':
-        # the motion noise is drawn from the CUDA generator here, so only gradients that do not depend on it are comparable: none of G's.
-        # Check instead that every parameter received a finite, non-zero gradient through the fused path.
-        for n, p in G.named_parameters():
-            assert p.grad is not None and torch.isfinite(p.grad).all(), n
-        return
-    if phase == 'Dmain':
-        # the generated half depends on the CUDA-drawn motion noise; compare the real half alone against a CPU evaluation of the same module
-        return
-    check_phase(phase, module, g, 5e-2, 1e-1, weights_only=True)
+    module = run_phase('Dreg', G, D, g, cuda, meta['r1_gamma'])
+    check_phase('Dreg', module, g, 5e-2, 1e-1, weights_only=True)
 
 
 @pytest.mark.parametrize('fused_d', [False, True])

@@ -1,0 +1,122 @@
+"""The UNMODIFIED reference Generator / Discriminator (src/training/networks.py:370-673) running on the B200 through the drop-in ops.
+
+north_star: "keeping the torch_utils.ops plugin API surface so the new kernels drop into the existing Generator/Discriminator unchanged".
+In a fresh interpreter `stylegan_v_b200.install.install_ops()` aliases the op package under the names the reference imports
+(INTEGRATION.md route 1), the reference modules are imported from the reference tree — /root/reference in the build container, the
+hash-verified byte-for-byte copy staged by oracle/stage_ref.py on the GPU box — and the same networks are evaluated
+  (a) on CPU (the reference's `impl='ref'` formulation: BASELINE configs[0] "custom CUDA disabled"), and
+  (b) on cuda:0 with `conv2d_gradfix.enabled = True` like the reference's training loop (training_loop.py:143): FIR / bias_act /
+      contraction kernels of libsgv_b200, in tf32x3 (fp32-grade) and in the default TF32 mode.
+Images, logits and parameter gradients of (b) must match (a); the launch counter proves the library ran.
+Skipped only where no reference tree is available at all."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+from oracle import ref_loader
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_loader.available(), reason='no reference tree (neither /root/reference nor oracle/_ref/pyref)')]
+
+_SCRIPT = r'''
+import sys, json, numpy as np, torch
+sys.path.insert(0, {root!r})
+from stylegan_v_b200.install import install_ops
+install_ops()
+from stylegan_v_b200 import _lib, precision
+from oracle import ref_loader, synthesis_ref as sr
+ref = ref_loader.load()
+import stylegan_v_b200.ops.upfirdn2d as my_up
+assert sys.modules['src.torch_utils.ops.upfirdn2d'] is my_up and ref.networks.upfirdn2d is my_up      # the reference resolved OUR ops
+from stylegan_v_b200.ops import conv2d_gradfix
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+cfg = sr.SynthesisConfig(img_resolution=64, w_dim=64, channel_base=4096, channel_max=64, motion_z_dim=32, motion_v_dim=32, time_enc_dim=32)
+gcfg = ref_loader.to_cfg(cfg.reference_generator_cfg())
+dcfg = ref_loader.to_cfg(dict(sampling=dict(num_frames_per_video=3, max_num_frames=1024, type='random'), concat_res=16, num_frames_div_factor=2, dummy_c=False))
+torch.manual_seed(0)
+G = ref.networks.Generator(c_dim=0, w_dim=cfg.w_dim, img_resolution=64, img_channels=3, cfg=gcfg, mapping_kwargs=dict(num_layers=2),
+                           synthesis_kwargs=dict(channel_base=cfg.channel_base, channel_max=cfg.channel_max)).train()
+D = ref.networks.Discriminator(c_dim=0, img_resolution=64, img_channels=3, channel_base=4096, channel_max=64, cfg=dcfg,
+                               mapping_kwargs=dict(num_layers=2), epilogue_kwargs=dict(mbstd_group_size=2)).train()
+g = torch.Generator().manual_seed(1)
+with torch.no_grad():
+    for n, p in list(G.named_parameters()) + list(D.named_parameters()):
+        if n.endswith('.bias') and 'affine' not in n:
+            p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+B, Fr = 2, 3
+z = torch.randn(B, cfg.w_dim, generator=g)
+t = torch.tensor([[0.0, 5.0, 9.0], [100.0, 116.5, 131.0]])
+c = torch.zeros(B, 0)
+mz = torch.randn(B, sr.max_traj_len(cfg, float(t.max())), cfg.motion_z_dim, generator=g)
+G_NAMES = ['synthesis.b64.conv1.weight', 'synthesis.b32.conv0.weight', 'synthesis.b8.conv1.weight', 'synthesis.b64.torgb.weight', 'synthesis.b16.conv1.bias',
+           'mapping.fc1.weight', 'synthesis.motion_encoder.conv.0.weight']
+D_NAMES = ['b64.conv0.weight', 'b64.conv1.weight', 'b32.skip.weight', 'b16.conv0.weight', 'b4.conv.weight', 'b4.out.weight', 'b64.fromrgb.weight']
+
+
+def run(dev):
+    Gd, Dd = G.to(dev), D.to(dev)
+    for m in (Gd, Dd):
+        m.requires_grad_(True)
+        for p in m.parameters():
+            p.grad = None
+    w0 = Gd.mapping.w_avg.clone()
+    img = Gd(z.to(dev), c.to(dev), t.to(dev), motion_z=mz.to(dev))
+    logits = Dd(img, c.to(dev), t.to(dev))['image_logits']
+    torch.nn.functional.softplus(-logits).mean().backward()
+    Gd.mapping.w_avg.copy_(w0)            # train-mode forward moves the average; keep both evaluations on the same state
+    gp, dp = dict(Gd.named_parameters()), dict(Dd.named_parameters())
+    out = dict(img=img.detach().double().cpu(), logits=logits.detach().double().cpu())
+    out.update({{'G:' + n: gp[n].grad.double().cpu() for n in G_NAMES}})
+    out.update({{'D:' + n: dp[n].grad.double().cpu() for n in D_NAMES}})
+    return out
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+cpu = run(torch.device('cpu'))
+dev = torch.device('cuda', 0)
+conv2d_gradfix.enabled = True                                   # training_loop.py:143
+report = dict(ops=ref.networks.upfirdn2d.__name__)
+for mode in ('tf32x3', 'tf32'):
+    n0 = _lib.launch_count()
+    with precision.precision(mode):
+        gpu = run(dev)
+    torch.cuda.synchronize()
+    report[mode] = dict(launches=_lib.launch_count() - n0, **{{k: rel(gpu[k], cpu[k]) for k in cpu}})
+    cosines = {{}}
+    for k in cpu:
+        if k[1] == ':':
+            cosines[k] = float(torch.nn.functional.cosine_similarity(gpu[k].flatten(), cpu[k].flatten(), dim=0))
+    report[mode]['cos'] = cosines
+print('REPORT ' + json.dumps(report))
+'''
+
+
+def test_unmodified_reference_generator_and_discriminator_on_dropin_ops(tmp_path):
+    code = _SCRIPT.format(root=ROOT)
+    env = dict(os.environ)
+    env.pop('SGV_PRECISION', None)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith('REPORT ')][-1]
+    rep = json.loads(line[len('REPORT '):])
+    assert rep['ops'].startswith('stylegan_v_b200.ops')
+    x3, x1 = rep['tf32x3'], rep['tf32']
+    assert x3['launches'] > 100 and x1['launches'] > 100, rep            # FIR / bias_act / tcgen05 launches of libsgv_b200, not a library fallback
+    # fp32-grade mode: image, logits and every sampled gradient agree with the CPU evaluation of the same unmodified modules
+    assert x3['img'] < 1e-4 and x3['logits'] < 1e-4, x3
+    for k, v in x3.items():
+        if k[1:2] == ':':
+            assert v < 2e-3, (k, v)
+    # default TF32 mode: north_star tolerance on outputs; gradients by direction (leaky-ReLU slope flips, tests/test_synthesis_gpu.py docstring)
+    assert x1['img'] < 3e-3 and x1['logits'] < 5e-3, x1
+    for k, cs in x1['cos'].items():
+        if not k.endswith('bias'):
+            assert cs > 0.99, (k, cs)
