@@ -85,26 +85,27 @@ def igemm_conv(x, wp, tap_offsets, out=None, out_hw=None, out_view=None, in_stri
     nt, Cout, Cin2 = wp.shape[-3:]
     wp_hi, wp_lo = (wp[0], wp[1]) if x3 else (wp, None)
     _req(Cin2 == Cin and nt == len(tap_offsets) and wp_hi.is_contiguous() and (wp_lo is None or wp_lo.is_contiguous()), 'wp does not match x / taps')
-    if query:
-        out_view, y = None, None
     if out_view is not None:
         y = out_view
         oh, ow = y.shape[2], y.shape[3]
         _req(y.shape[0] == N and y.shape[1] == Cout and y.stride(1) == 1, 'out_view must be [N,Cout,oh,ow] with unit channel stride')
+        y_ptr, y_strides = y.data_ptr(), (y.stride(0), y.stride(2), y.stride(3))
     else:
         oh, ow = out_hw if out_hw is not None else (H, W)
-        shape = [1, 1, 1, 4] if query else [N, oh, ow, Cout]          # a variant query touches no output
-        y = torch.empty(shape, dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
-        if query:
-            y = y.as_strided([N, Cout, oh, ow], [oh * ow * Cout, 1, ow * Cout, Cout])
+        y_strides = (oh * ow * Cout, ow * Cout, Cout)                 # NHWC, exact strides also for 1-pixel / 1-channel extents
+        if query:                                                     # a variant query touches no output: any non-NULL, 16-byte aligned address will do
+            y, y_ptr = None, x.data_ptr()
+        else:
+            y = torch.empty_strided([N, Cout, oh, ow], [y_strides[0], 1, y_strides[1], y_strides[2]], dtype=torch.float32, device=x.device)
+            y_ptr = y.data_ptr()
     L = _lib.lib()
     p = _lib.ConvParams()
-    p.x, p.wp, p.y = x.data_ptr(), wp_hi.data_ptr(), y.data_ptr()
+    p.x, p.wp, p.y = x.data_ptr(), wp_hi.data_ptr(), y_ptr
     if x3:
         p.wp_lo = wp_lo.data_ptr()
     p.n, p.h, p.w, p.cin, p.cout = N, H, W, Cin, Cout
     p.out_h, p.out_w = oh, ow
-    p.out_stride_n, p.out_stride_y, p.out_stride_x = y.stride(0), y.stride(2), y.stride(3)
+    p.out_stride_n, p.out_stride_y, p.out_stride_x = y_strides
     p.in_stride, p.ntaps = in_stride, nt
     for i, (dy, dx) in enumerate(tap_offsets):
         p.tap_dy[i], p.tap_dx[i] = int(dy), int(dx)
@@ -130,8 +131,8 @@ def igemm_conv(x, wp, tap_offsets, out=None, out_hw=None, out_view=None, in_stri
         p.noise = nz.data_ptr()
         p.noise_stride_n, p.noise_stride_y, p.noise_stride_x = (nz.stride(0) if nz.shape[0] == N and N > 1 else 0), nz.stride(1), nz.stride(2)
     if red_out is not None:
-        _req(red_x is not None and red_x.shape == y.shape and red_x.stride() == y.stride() and red_x.dtype == torch.float32,
-             'red_x must have the shape and strides of the output')
+        _req(red_x is not None and tuple(red_x.shape) == (N, Cout, oh, ow) and (red_x.stride(0), red_x.stride(2), red_x.stride(3)) == tuple(y_strides)
+             and red_x.stride(1) == 1 and red_x.dtype == torch.float32, 'red_x must have the shape and strides of the output')
         _req(red_out.dtype == torch.float32 and red_out.is_contiguous() and tuple(red_out.shape) == (N, Cout), 'red_out must be a contiguous float32 [N, Cout] buffer')
         p.red_x, p.red_out = red_x.data_ptr(), red_out.data_ptr()
     if query:

@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import dconv
+from . import dense as _dense
 from .ops import bias_act, conv2d_resample, upfirdn2d
 from .synthesis import SynthesisNetwork
 
@@ -34,7 +35,13 @@ class FullyConnectedLayer(torch.nn.Module):
         self.weight_gain = lr_multiplier / np.sqrt(in_features)
         self.bias_gain = lr_multiplier
 
-    def forward(self, x):
+    def forward(self, x, fused=False):
+        """fused=True (first-order callers): ONE tcgen05 contraction with the weight gain folded into its weight pass and bias / leaky ReLU /
+        gain in its epilogue (stylegan_v_b200/dense.py, fp32-grade arithmetic); otherwise the reference's addmm / matmul + bias_act
+        formulation, differentiable to any order (the R1 penalty differentiates the discriminator's dense layers twice)."""
+        if fused and x.ndim == 2 and self.activation in ('linear', 'lrelu') and _dense.supported(x, self.weight, self.activation):
+            return _dense.linear(x, self.weight, self.bias, self.weight_gain, self.bias_gain, act=self.activation,
+                                 gain=bias_act.activation_funcs[self.activation].def_gain)
         w = self.weight.to(x.dtype) * self.weight_gain
         b = self.bias
         if b is not None:
@@ -73,7 +80,9 @@ class MappingNetwork(torch.nn.Module):
             parts.append(normalize_2nd_moment(self.embed(c.to(torch.float32))))
         x = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
         for i in range(self.num_layers):
-            x = getattr(self, f'fc{i}')(x)
+            # the mapping network is only ever differentiated once (path length and R1 differentiate the synthesis / discriminator bodies twice,
+            # and reach the mapping through a plain first-order backward): its layers always take the kernel route where the shape allows
+            x = getattr(self, f'fc{i}')(x, fused=True)
         if self.w_avg_beta is not None and self.training and not skip_w_avg_update:
             self.w_avg.copy_(x.detach().mean(dim=0).lerp(self.w_avg, self.w_avg_beta))
         if self.num_ws is not None:
@@ -217,7 +226,7 @@ class DiscriminatorEpilogue(torch.nn.Module):
         self.fc = FullyConnectedLayer(in_channels * resolution ** 2, in_channels, activation=activation)
         self.out = FullyConnectedLayer(in_channels, 1 if cmap_dim == 0 else cmap_dim)
 
-    def forward(self, x, img, cmap):
+    def forward(self, x, img, cmap, fused=False):
         assert x.shape[1] == self.in_channels and x.shape[2] == x.shape[3] == self.resolution
         x = x.to(dtype=torch.float32, memory_format=torch.contiguous_format)
         if self.architecture == 'skip':
@@ -226,7 +235,7 @@ class DiscriminatorEpilogue(torch.nn.Module):
             x = self.mbstd(x)
         x = self.conv(x)
         # flatten in (C, H, W) order like the reference, whatever memory format the conv returned
-        x = self.out(self.fc(x.contiguous().flatten(1)))
+        x = self.out(self.fc(x.contiguous().flatten(1), fused=fused), fused=fused)
         if self.cmap_dim > 0:
             assert cmap.shape[1] == self.cmap_dim
             x = (x * cmap).sum(dim=1, keepdim=True) * (1 / np.sqrt(self.cmap_dim))
@@ -351,7 +360,7 @@ class Discriminator(torch.nn.Module):
                 x = x.contiguous().reshape(-1, self.num_frames_per_video * x.shape[1], *x.shape[2:])     # [B, F*C, h, w] in (frame, channel) order
             x, img = getattr(self, f'b{res}')(x, img, fused=fused)
         cmap = self.mapping(None, c) if c.shape[1] > 0 else None
-        return {'image_logits': self.b4(x, img, cmap).squeeze(1)}
+        return {'image_logits': self.b4(x, img, cmap, fused=fused).squeeze(1)}
 
 
 class Generator(torch.nn.Module):

@@ -63,6 +63,11 @@ def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_paddi
 def _forward_op(x, w, b, transpose, stride, padding, output_padding, dilation, groups):
     y = _native.conv_forward(x, w, b, transpose, stride, padding, output_padding, dilation, groups)   # tcgen05 kernels when the shape allows
     if y is not None:
+        # The kernels compute in NHWC.  Like F.conv2d, the op hands back the memory format of its INPUT: an NCHW-contiguous caller (the unmodified
+        # reference networks: their .view() of activations assumes it, networks.py:659-662) gets an NCHW-contiguous result, a channels_last caller
+        # (the native modules) keeps channels_last and pays no conversion.
+        if x.is_contiguous() and not (x.shape[1] == 1 or (x.shape[2] == 1 and x.shape[3] == 1)):
+            y = y.contiguous()
         return y
     F = torch.nn.functional
     if transpose:

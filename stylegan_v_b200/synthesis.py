@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import conv as _conv
+from . import dense as _dense
 from .modconv import fused_modulated_conv, demod_coefs, prepare_weights, WeightGradBox, WeightGradNode
 from .ops import upfirdn2d as _upfirdn2d
 from .ops import bias_act as _bias_act
@@ -211,7 +212,9 @@ class SynthesisBlock(torch.nn.Module):
         if fused_modconv is None:               # networks.py:232: per-sample-weight conv in eval mode, unless fp16 with a batch
             fused_modconv = (not self.training) and (dtype == torch.float32 or (x is not None and int(x.shape[0]) == 1))
         if self.in_channels == 0:
-            x = self.input(motion_v).contiguous()
+            x = self.input(motion_v)
+            if not x.is_cuda:
+                x = x.contiguous()              # CUDA keeps the NHWC layout of the kernels: the drop-in ops hand back their input's memory format
         else:
             x = _layer_unfused(self.conv0, x.to(dtype), next(w_iter), fused_modconv, conv_clamp=self.conv_clamp, noise_mode=noise_mode)
         x = _layer_unfused(self.conv1, x, next(w_iter), fused_modconv, conv_clamp=self.conv_clamp, noise_mode=noise_mode)
@@ -272,9 +275,13 @@ class SynthesisNetwork(torch.nn.Module):
             w_idx += block.num_conv
         out = {}
         for wi, layers in groups.items():
-            wcat = torch.cat([l.affine.weight for l in layers], dim=0) * layers[0].affine.weight_gain
-            bcat = torch.cat([l.affine.bias for l in layers], dim=0)
-            s = torch.addmm(bcat.unsqueeze(0), ws[:, wi], wcat.t())
+            wcat = torch.cat([l.affine.weight for l in layers], dim=0) if len(layers) > 1 else layers[0].affine.weight
+            bcat = torch.cat([l.affine.bias for l in layers], dim=0) if len(layers) > 1 else layers[0].affine.bias
+            wrow = ws[:, wi].contiguous()
+            if _dense.supported(wrow, wcat):       # tcgen05 contraction, weight gain folded into its weight pass, bias in its epilogue (fp32-grade)
+                s = _dense.linear(wrow, wcat, bcat, layers[0].affine.weight_gain, 1.0)
+            else:
+                s = torch.addmm(bcat.unsqueeze(0), wrow, (wcat * layers[0].affine.weight_gain).t())
             for l, piece in zip(layers, s.split([l.affine.weight.shape[0] for l in layers], dim=1)):
                 out[id(l)] = piece
         return out
