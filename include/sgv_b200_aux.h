@@ -73,6 +73,32 @@ typedef struct sgv_adam_params {
 
 int sgv_adam_ema_step(const sgv_adam_params* p, void* stream);
 
+/* ---- discriminator-side companions (csrc/disc_ops.cu) -------------------------------------------------------------------------
+ * sgv_fromrgb_fwd: the 1x1 `fromrgb` convolution of the first discriminator block with its bias / activation fused
+ *   (src/training/networks.py:447-449,467-470; layers.py:184-197 with <= 4 input channels — a streaming pass, not a tensor-core
+ *   contraction):   y[n, hw, c] = act(sum_j img[n, j, hw] * w[c, j] * weight_gain + bias[c]) * gain
+ *   img [n, img_channels, hw] NCHW (as the frames arrive), w [c, img_channels], y [n, hw, c] NHWC (the layout of the conv that follows);
+ *   c = 4 * (a power of two <= 32); act 1 = linear, 3 = lrelu.
+ * sgv_fromrgb_bwd: from dz = d(loss)/d(pre-activation) [n, hw, c] (sgv_modconv_act_bwd on the saved output gives it, and d bias):
+ *   dimg[n, j, hw] = weight_gain * sum_c dz * w[c, j]   (dimg may be NULL);   dw[c, j] += weight_gain * sum_{n,hw} dz * img   (caller zeroes dw).
+ */
+int sgv_fromrgb_fwd(const float* img, const float* w, const float* bias, float* y, int32_t n, int32_t hw, int32_t c, int32_t img_channels,
+                    float weight_gain, int32_t act, float alpha, float gain, void* stream);
+int sgv_fromrgb_bwd(const float* dz, const float* img, const float* w, float* dimg, float* dw, int32_t n, int32_t hw, int32_t c,
+                    int32_t img_channels, float weight_gain, void* stream);
+
+/* sgv_mbstd_fwd: MinibatchStdLayer (networks.py:492-516) + the channel concat + zero padding of the channel count to `cpad`:
+ *   samples are grouped as n = g * M + m (G = group, M = n / G); with c1 = c / num_channels
+ *     s[m, f]            = mean_{c' < c1, p} sqrt( var_g x[g*M+m, f*c1+c', p] + 1e-8 )
+ *     y[n, p, 0:c]       = x[n, 0:c, p];   y[n, p, c+f] = s[n % M, f];   y[n, p, c+F:cpad] = 0          (y is NHWC [n, hw, cpad])
+ *   x is addressed through element strides (sample, channel, pixel), so NCHW and NHWC inputs both work; sd_mean [M, F] receives s.
+ * sgv_mbstd_bwd: dx[n, p, c] (NHWC [n, hw, c]) = dy[n, p, c] + (sum_{g,p} dy[g*M+m, p, C+f]) / (c1 * hw) * (x - mean_g x) / (G * sd).
+ */
+int sgv_mbstd_fwd(const float* x, int64_t x_stride_n, int64_t x_stride_c, int64_t x_stride_p, float* y, float* sd_mean,
+                  int32_t n, int32_t c, int32_t hw, int32_t cpad, int32_t group, int32_t num_channels, void* stream);
+int sgv_mbstd_bwd(const float* dy, const float* x, int64_t x_stride_n, int64_t x_stride_c, int64_t x_stride_p, float* dx,
+                  int32_t n, int32_t c, int32_t hw, int32_t cpad, int32_t group, int32_t num_channels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

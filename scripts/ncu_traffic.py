@@ -44,7 +44,7 @@ def main(rep, tag):
             for k, v in rec.items():
                 if k == key:
                     u = rec.get(k + ':unit', '')
-                    scale = {'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'byte': 1.0, 'usecond': 1e-3, 'msecond': 1.0, 'nsecond': 1e-6, 'second': 1e3}.get(u, 1.0)
+                    scale = {'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'byte': 1.0, 'usecond': 1e-3, 'us': 1e-3, 'msecond': 1.0, 'ms': 1.0, 'nsecond': 1e-6, 'ns': 1e-6, 'second': 1e3, 's': 1e3}.get(u, 1.0)
                     return v * scale
             return None
         rd, wr = val('dram__bytes_read.sum'), val('dram__bytes_write.sum')

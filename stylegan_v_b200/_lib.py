@@ -133,6 +133,10 @@ SYMBOLS = [
     ('sgv_time_encoder_fwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_vp]),
     ('sgv_time_encoder_bwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_vp]),
     ('sgv_adam_ema_step', c_int, [ctypes.POINTER(AdamParams), c_vp]),
+    ('sgv_fromrgb_fwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_int, c_f32, c_f32, c_vp]),
+    ('sgv_fromrgb_bwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp]),
+    ('sgv_mbstd_fwd', c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    ('sgv_mbstd_bwd', c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
 ]
 
 _lib = None

@@ -17,8 +17,10 @@ inside the node.
 """
 import torch
 
+from . import _lib
 from . import conv as _conv
 from . import native_conv as _native
+from . import precision as _precision
 
 
 def supported(x, w, stride, padding):
@@ -35,23 +37,34 @@ def supported(x, w, stride, padding):
 
 class _FusedConvAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b, stride, padding, act, gain):
+    def forward(ctx, x, w, b, stride, padding, act, gain, weight_gain, add_to):
         x = x.contiguous(memory_format=torch.channels_last)
         k = w.shape[2]
         taps = [(ky, kx) for ky in range(k) for kx in range(k)]
         oh, ow = (x.shape[2] + 2 * padding - k) // stride + 1, (x.shape[3] + 2 * padding - k) // stride + 1
-        y = _conv.igemm_conv(x, _conv.prep_weights(w, taps), [(ky - padding, kx - padding) for ky, kx in taps], out_hw=(oh, ow),
-                             in_stride=stride, bias=b, act=act, gain=gain)
-        # a linear layer's gradient does not need y (the block adds the two branches IN PLACE into the skip branch's output, networks.py:481)
+        offs = [(ky - padding, kx - padding) for ky, kx in taps]
+        x3 = _precision.is_x3()
+        if add_to is None:
+            # the equalised-lr weight gain (layers.py:186) rides on the weight-preparation pass: no scaled weight copy, no multiply in the backward
+            y = _conv.igemm_conv(x, _conv.prep_weights(w, taps, scale=weight_gain, x3=x3), offs, out_hw=(oh, ow), in_stride=stride, bias=b, act=act, gain=gain)
+        else:
+            # residual form  add_to += conv(x, w) * gain  (the block's `y.add_(x)`, networks.py:481-487, folded into the skip branch's launch: the
+            # kernel's TMA reduce-add epilogue accumulates into the other branch's output; the output gain rides on the weights)
+            assert act == 'linear' and b is None and tuple(add_to.shape) == (x.shape[0], w.shape[0], oh, ow)
+            _conv.igemm_conv(x, _conv.prep_weights(w, taps, scale=weight_gain * gain, x3=x3), offs, out_view=add_to, in_stride=stride, accumulate=True)
+            ctx.mark_dirty(add_to)
+            y = add_to
+        # a linear layer's gradient does not need y
         ctx.save_for_backward(x, w, y if act != 'linear' else x.new_empty(0), b if b is not None else x.new_empty(0))
-        ctx.cfg = (stride, padding, act, gain, b is not None)
+        ctx.cfg = (stride, padding, act, gain, b is not None, weight_gain, add_to is not None)
+        ctx.x3 = x3
         return y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         x, w, y, b = ctx.saved_tensors
-        stride, padding, act, gain, has_b = ctx.cfg
+        stride, padding, act, gain, has_b, weight_gain, residual = ctx.cfg
         dy = dy.contiguous(memory_format=torch.channels_last)
         want_db = has_b and ctx.needs_input_grad[2]
         if act == 'linear':
@@ -60,19 +73,113 @@ class _FusedConvAct(torch.autograd.Function):
         else:
             dz, db, _ = _conv.act_bwd(dy, y, b if has_b else None, act, gain, want_db, False)
         gx = gw = None
-        s2, p2 = (stride, stride), (padding, padding)
+        k = w.shape[2]
+        taps = [(ky, kx) for ky in range(k) for kx in range(k)]
         if ctx.needs_input_grad[0]:
-            k = w.shape[2]
+            s2, p2 = (stride, stride), (padding, padding)
             op = tuple(x.shape[i + 2] - (dz.shape[i + 2] - 1) * stride - (1 - 2 * padding) - (k - 1) for i in range(2))   # conv2d_gradfix.py:95-104
-            gx = _native.conv_forward(dz, w, None, True, s2, p2, op, (1, 1), 1)
+            gx = _native.conv_forward(dz, w, None, True, s2, p2, op, (1, 1), 1, weight_scale=weight_gain, x3=ctx.x3)
             assert gx is not None and gx.shape == x.shape
         if ctx.needs_input_grad[1]:
-            gw = _native.conv_weight_grad(dz, x, tuple(w.shape), False, s2, p2, (0, 0), (1, 1), 1)
+            gw = _native.conv_weight_grad(dz, x, tuple(w.shape), False, (stride, stride), (padding, padding), (0, 0), (1, 1), 1, x3=ctx.x3)
             assert gw is not None
-        return gx, gw, db, None, None, None, None
+            if weight_gain != 1:
+                gw = gw * weight_gain
+        return gx, gw, db, None, None, None, None, None, (dy if residual else None)
 
 
-def fused_conv_act(x, w, b=None, stride=1, padding=0, act='linear', gain=1.0):
-    """act(conv2d(x, w, stride, padding) + b) * gain as one autograd node; act in {'linear', 'lrelu'}.  Caller checks supported()."""
+def fused_conv_act(x, w, b=None, stride=1, padding=0, act='linear', gain=1.0, weight_gain=1.0, add_to=None):
+    """act(conv2d(x, w * weight_gain, stride, padding) + b) * gain as one autograd node; act in {'linear', 'lrelu'}.  Caller checks supported().
+    add_to (linear, bias-free layers): the result is ACCUMULATED into that NHWC tensor in place (and returned) — the residual add of a block
+    without a separate pass."""
     assert act in ('linear', 'lrelu')
-    return _FusedConvAct.apply(x, w, b, int(stride), int(padding), act, float(gain))
+    return _FusedConvAct.apply(x, w, b, int(stride), int(padding), act, float(gain), float(weight_gain), add_to)
+
+
+class _FromRgb(torch.autograd.Function):
+    """y (NHWC) = act(conv1x1(img (NCHW, <= 4 channels), w * weight_gain) + b) * gain: one streaming pass each way (csrc/disc_ops.cu)."""
+
+    @staticmethod
+    def forward(ctx, img, w, b, act, gain, weight_gain):
+        img = img.contiguous()
+        N, J, H, W = img.shape
+        O = w.shape[0]
+        y = torch.empty_strided([N, O, H, W], [H * W * O, 1, W * O, O], dtype=torch.float32, device=img.device)
+        w2 = w.reshape(O, J).contiguous()
+        with torch.cuda.device(img.device):
+            _lib.check(_lib.lib().sgv_fromrgb_fwd(img.data_ptr(), w2.data_ptr(), b.data_ptr() if b is not None else None, y.data_ptr(), N, H * W, O, J,
+                                                  float(weight_gain), {'linear': 1, 'lrelu': 3}[act], 0.2, float(gain), _conv._stream(img.device)), 'sgv_fromrgb_fwd')
+        ctx.save_for_backward(img, w2, y if act != 'linear' else img.new_empty(0))
+        ctx.cfg = (act, gain, weight_gain, b is not None, tuple(w.shape))
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        img, w2, y = ctx.saved_tensors
+        act, gain, weight_gain, has_b, w_shape = ctx.cfg
+        N, J, H, W = img.shape
+        O = w2.shape[0]
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        want_db = has_b and ctx.needs_input_grad[2]
+        if act == 'linear':
+            dz = dy * gain if gain != 1 else dy
+            db = dz.sum(dim=[0, 2, 3]) if want_db else None
+        else:
+            dz, db, _ = _conv.act_bwd(dy, y, None, act, gain, want_db, False)
+        dimg = torch.empty_like(img) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros([O, J], dtype=torch.float32, device=img.device)
+        with torch.cuda.device(img.device):
+            _lib.check(_lib.lib().sgv_fromrgb_bwd(dz.data_ptr(), img.data_ptr(), w2.data_ptr(), dimg.data_ptr() if dimg is not None else None, dw.data_ptr(),
+                                                  N, H * W, O, J, float(weight_gain), _conv._stream(img.device)), 'sgv_fromrgb_bwd')
+        return dimg, (dw.reshape(w_shape) if ctx.needs_input_grad[1] else None), db, None, None, None
+
+
+def fromrgb_supported(img, w):
+    o = w.shape[0]
+    return (_native.enabled and img.is_cuda and img.dtype == torch.float32 and w.dtype == torch.float32 and img.ndim == 4 and img.shape[1] <= 4
+            and tuple(w.shape[2:]) == (1, 1) and o % 4 == 0 and o // 4 <= 32 and (o // 4) & (o // 4 - 1) == 0)
+
+
+def fromrgb(img, w, b=None, act='lrelu', gain=1.0, weight_gain=1.0):
+    """The discriminator's first 1x1 layer on the frames (networks.py:467-470): NCHW image in, NHWC activation out.  Caller checks fromrgb_supported()."""
+    return _FromRgb.apply(img, w, b, act, float(gain), float(weight_gain))
+
+
+class _MinibatchStd(torch.autograd.Function):
+    """MinibatchStdLayer + concat (+ zero channels up to `cpad`) -> NHWC [N, cpad, H, W]; csrc/disc_ops.cu.  First order."""
+
+    @staticmethod
+    def forward(ctx, x, group, num_channels, cpad):
+        N, Cc, H, W = x.shape
+        y = torch.empty_strided([N, cpad, H, W], [H * W * cpad, 1, W * cpad, cpad], dtype=torch.float32, device=x.device)
+        sd = torch.empty([N // group, num_channels], dtype=torch.float32, device=x.device)
+        assert x.stride(2) == W * x.stride(3), 'pixels of a sample must be addressable with one stride'
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().sgv_mbstd_fwd(x.data_ptr(), x.stride(0), x.stride(1), x.stride(3), y.data_ptr(), sd.data_ptr(), N, Cc, H * W, cpad,
+                                                group, num_channels, _conv._stream(x.device)), 'sgv_mbstd_fwd')
+        ctx.save_for_backward(x)
+        ctx.cfg = (group, num_channels, cpad)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, = ctx.saved_tensors
+        group, num_channels, cpad = ctx.cfg
+        N, Cc, H, W = x.shape
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_strided([N, Cc, H, W], [H * W * Cc, 1, W * Cc, Cc], dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().sgv_mbstd_bwd(dy.data_ptr(), x.data_ptr(), x.stride(0), x.stride(1), x.stride(3), dx.data_ptr(), N, Cc, H * W, cpad,
+                                                group, num_channels, _conv._stream(x.device)), 'sgv_mbstd_bwd')
+        return dx, None, None, None
+
+
+def minibatch_std_concat(x, group_size, num_channels=1, pad_to=32):
+    """[N, C, H, W] -> NHWC [N, roundup(C + num_channels, pad_to), H, W]: x, the per-group standard-deviation statistic as extra channel(s),
+    zero channels after that (the consumer pads its weight with zero input channels).  CUDA float32; N % G == 0 like the reference's reshape."""
+    N, Cc = x.shape[0], x.shape[1]
+    G = min(group_size, N) if group_size is not None else N
+    cpad = (Cc + num_channels + pad_to - 1) // pad_to * pad_to
+    return _MinibatchStd.apply(x, int(G), int(num_channels), int(cpad))

@@ -1,17 +1,16 @@
-"""Dense layers of the path on the tcgen05 contraction kernels: FullyConnectedLayer (style affines, mapping networks, time-encoder
-predictors; src/training/layers.py:108-138) and EqLRConv1d (the motion trajectory convolutions; layers.py:331-373, motion.py:55-58).
+"""FullyConnectedLayer (src/training/layers.py:108-138) on the tcgen05 contraction kernels: the mapping networks of G and D and the
+discriminator epilogue's dense layers.
 
-The reference runs these as torch.addmm / matmul (cuBLAS) and F.conv1d (cuDNN).  Here both are instances of the implicit-GEMM kernel
-of libsgv_b200 (include/sgv_b200_conv.h) on a channels-last view of the operand, with the equalised-lr weight gain folded into the
-weight preparation pass, bias (+ leaky ReLU) in the epilogue, and the two gradients on the same kernels:
+The reference runs these as torch.addmm / matmul (cuBLAS) + bias_act.  Here a layer is ONE launch of the implicit-GEMM kernel of
+libsgv_b200 (include/sgv_b200_conv.h) on x [M, K] viewed as the NHWC image [M, 1, 1, K] with one tap: the equalised-lr weight gain is
+folded into the weight preparation pass, bias / leaky ReLU / gain run in the epilogue, and both gradients run on the same kernels.
+The generic line form (x [B, C, 1, L], k taps along L) is kept because it is what the kernel computes; k = 1, L = 1 is the dense layer.
 
-    linear   x [M, K]            = NHWC image [M, 1, 1, K]; one tap
-    conv1d   x [B, L, C] (the trajectory as the reference stores it BEFORE its permute to [B, C, L]) = NHWC image [B, 1, L, C]; k taps
-             along W, no padding (motion.py:55-58 use padding 0)
-
-They always run in the fp32-grade `tf32x3` arithmetic, whatever stylegan_v_b200.precision says: their outputs are styles and Fourier
-phases — the time-encoder multiplies them by phase scales up to 64 before sin / cos — where TF32's 1e-3 would be visible in the image,
-and their FLOPs are negligible (the reference computes them in fp32 too).
+Always the fp32-grade `tf32x3` arithmetic, whatever stylegan_v_b200.precision says (the reference computes these layers in fp32 and
+their FLOPs are negligible).  Measured accuracy (tests/test_dense_gpu.py): 7e-6 of fp64 at K = 512, 5e-5 at K = 8192 — the tensor
+core's fp32 accumulation is not round-to-nearest, so the error grows with K.  That is why the TIME ENCODER stays on true-fp32 library
+GEMMs / conv1d (stylegan_v_b200/time_encoder.py: its outputs are multiplied by phase scales up to 64 before sin / cos), and the stacked
+style affines of the synthesis network stay on cuBLAS for speed (stylegan_v_b200/synthesis.py::_all_styles).
 CUDA / float32 only; anything else (CPU tensors, fp16) takes the PyTorch formulation in the calling module, like the reference's ops do.
 """
 import torch
@@ -23,12 +22,6 @@ def _as_image(x2d):
     """[M, K] contiguous -> the same memory as an NHWC [M, K, 1, 1] tensor (channel stride 1, every pixel stride = K)."""
     M, K = x2d.shape
     return x2d.as_strided([M, K, 1, 1], [K, 1, K, K])
-
-
-def _as_line(x3d):
-    """[B, L, C] contiguous -> NHWC [B, C, 1, L]."""
-    B, L, Cc = x3d.shape
-    return x3d.as_strided([B, Cc, 1, L], [L * Cc, 1, L * Cc, Cc])
 
 
 def _nhwc_exact(t):
@@ -101,15 +94,3 @@ def linear(x, weight, bias=None, weight_gain=1.0, bias_gain=1.0, act='linear', g
         b = bias if bias_gain == 1 else bias * bias_gain
     y = _DenseConv.apply(_as_image(x.contiguous()), weight.unsqueeze(2), b, float(weight_gain), act, float(gain))
     return y.reshape(x.shape[0], weight.shape[0])
-
-
-def conv1d_lines(x, weight, bias=None, weight_gain=1.0, bias_gain=1.0, act='linear'):
-    """EqLRConv1d on the trajectory in its storage layout: x [B, L, C_in] -> [B, L - k + 1, C_out] (no padding, stride 1),
-    = F.conv1d(x.permute(0, 2, 1), weight * weight_gain, bias * bias_gain).permute(0, 2, 1) followed by the activation."""
-    assert act in ('linear', 'lrelu') and x.ndim == 3 and weight.ndim == 3
-    b = None
-    if bias is not None:
-        b = bias if bias_gain == 1 else bias * bias_gain
-    y = _DenseConv.apply(_as_line(x.contiguous()), weight, b, float(weight_gain), act, 1.0)
-    B, O, _, Lout = y.shape
-    return y.permute(0, 2, 3, 1).reshape(B, Lout, O)

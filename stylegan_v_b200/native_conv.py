@@ -42,8 +42,10 @@ def _taps(k):
     return [(ky, kx) for ky in range(k) for kx in range(k)]
 
 
-def conv_forward(x, w, b, transpose, stride, padding, output_padding, dilation, groups):
-    """Returns the convolution result (channels_last) or None when the call is outside the native envelope."""
+def conv_forward(x, w, b, transpose, stride, padding, output_padding, dilation, groups, weight_scale=1.0, x3=None):
+    """Returns the convolution result (channels_last) or None when the call is outside the native envelope.
+    weight_scale is folded into the weight-preparation pass (equalised-lr gain without a scaled weight copy); x3 selects the arithmetic
+    mode (None = stylegan_v_b200.precision at call time; autograd nodes pass the mode of their forward pass)."""
     if not _common_ok(x, w, dilation, groups):
         return None
     k = w.shape[2]
@@ -59,7 +61,7 @@ def conv_forward(x, w, b, transpose, stride, padding, output_padding, dilation, 
         oh, ow = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
         if oh < 1 or ow < 1:
             return None
-        wp = _conv.prep_weights(w, taps)
+        wp = _conv.prep_weights(w, taps, scale=weight_scale, x3=x3)
         return _conv.igemm_conv(_nhwc(x), wp, [(ky - p, kx - p) for ky, kx in taps], out_hw=(oh, ow), in_stride=s, bias=b)
     # transposed: weight [Cin, Cout, k, k]
     I, O = w.shape[0], w.shape[1]
@@ -72,7 +74,7 @@ def conv_forward(x, w, b, transpose, stride, padding, output_padding, dilation, 
         oh, ow = H + k - 1 - 2 * p, W + k - 1 - 2 * p
         if oh < 1 or ow < 1:
             return None
-        wp = _conv.prep_weights(w, taps, rows_dim=1, cols_dim=0)
+        wp = _conv.prep_weights(w, taps, rows_dim=1, cols_dim=0, scale=weight_scale, x3=x3)
         return _conv.igemm_conv(_nhwc(x), wp, [(p - ky, p - kx) for ky, kx in taps], out_hw=(oh, ow), bias=b)
     if s == 2 and k == 3 and p == 0:
         op = tuple(output_padding)
@@ -85,12 +87,12 @@ def conv_forward(x, w, b, transpose, stride, padding, output_padding, dilation, 
                 ph_taps = [(ky, kx) for ky in range(a, 3, 2) for kx in range(c, 3, 2)]
                 offs = [(-((ky - a) // 2), -((kx - c) // 2)) for ky, kx in ph_taps]
                 view = u[:, :, a:2 * H + 1:2, c:2 * W + 1:2]
-                _conv.igemm_conv(xn, _conv.prep_weights(w, ph_taps, rows_dim=1, cols_dim=0), offs, out_view=view, bias=b)
+                _conv.igemm_conv(xn, _conv.prep_weights(w, ph_taps, rows_dim=1, cols_dim=0, scale=weight_scale, x3=x3), offs, out_view=view, bias=b)
         return u
     return None
 
 
-def conv_weight_grad(gy, x, w_shape, transpose, stride, padding, output_padding, dilation, groups):
+def conv_weight_grad(gy, x, w_shape, transpose, stride, padding, output_padding, dilation, groups, x3=None):
     """Weight gradient (shape w_shape) of the op above, or None when outside the native envelope."""
     k = w_shape[2]
     if not (enabled and x.is_cuda and x.dtype == torch.float32 and gy.dtype == torch.float32 and groups == 1 and tuple(dilation) == (1, 1)
@@ -104,7 +106,7 @@ def conv_weight_grad(gy, x, w_shape, transpose, stride, padding, output_padding,
         if I % 32 or O % 32 or s not in (1, 2):
             return None
         oh, ow = gy.shape[2], gy.shape[3]
-        dw = _conv.igemm_wgrad(_nhwc(gy), _nhwc(x), [(0, 0)] * len(taps), [(ky - p, kx - p) for ky, kx in taps], (oh, ow), x_stride=s)
+        dw = _conv.igemm_wgrad(_nhwc(gy), _nhwc(x), [(0, 0)] * len(taps), [(ky - p, kx - p) for ky, kx in taps], (oh, ow), x_stride=s, x3=x3)
         return dw.reshape(k, k, O, I).permute(2, 3, 0, 1)
     I, O = w_shape[0], w_shape[1]
     if I % 32 or O % 32:
@@ -112,7 +114,7 @@ def conv_weight_grad(gy, x, w_shape, transpose, stride, padding, output_padding,
     if s == 1:
         # y[Y] = sum_ky x[Y + p - ky] w[ky]  =>  dw[i, o, ky] = sum_Y gy[Y, o] x[Y + p - ky, i]; lattice = gy's extent
         oh, ow = gy.shape[2], gy.shape[3]
-        dw = _conv.igemm_wgrad(_nhwc(gy), _nhwc(x), [(0, 0)] * len(taps), [(p - ky, p - kx) for ky, kx in taps], (oh, ow))
+        dw = _conv.igemm_wgrad(_nhwc(gy), _nhwc(x), [(0, 0)] * len(taps), [(p - ky, p - kx) for ky, kx in taps], (oh, ow), x3=x3)
         return dw.reshape(k, k, O, I).permute(3, 2, 0, 1)
     if s == 2 and k == 3 and p == 0:
         g = _nhwc(gy)
@@ -124,8 +126,8 @@ def conv_weight_grad(gy, x, w_shape, transpose, stride, padding, output_padding,
                     ph_taps = [(ky, kx) for ky in range(a, 3, 2) for kx in range(c, 3, 2)]
                     offs = [(ky // 2, kx // 2) for ky, kx in ph_taps]
                     _conv.igemm_wgrad(xn, g[:, :, a:2 * H + 1:2, c:2 * W + 1:2], [(0, 0)] * len(ph_taps), offs, (H, W),
-                                      out=dwt, slots=[ky * 3 + kx for ky, kx in ph_taps])
+                                      out=dwt, slots=[ky * 3 + kx for ky, kx in ph_taps], x3=x3)
             return dwt.reshape(3, 3, I, O).permute(2, 3, 0, 1)
-        dw = _conv.igemm_wgrad(g, xn, taps, [(0, 0)] * 9, (H, W), g_stride=2)
+        dw = _conv.igemm_wgrad(g, xn, taps, [(0, 0)] * 9, (H, W), g_stride=2, x3=x3)
         return dw.reshape(3, 3, O, I).permute(3, 2, 0, 1)
     return None

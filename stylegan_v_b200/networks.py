@@ -119,22 +119,28 @@ class Conv2dLayer(torch.nn.Module):
             else:
                 self.bias = None
 
-    def forward(self, x, gain=1, fused=False):
-        """fused=True: layers inside the native envelope run as [FIR] + ONE implicit-GEMM launch with the bias / activation epilogue
-        (stylegan_v_b200/dconv.py; first-order differentiable); everything else — and fused=False — is conv2d_resample + bias_act."""
-        w = self.weight * self.weight_gain
+    def forward(self, x, gain=1, fused=False, add_to=None):
+        """fused=True: layers inside the native envelope run as [FIR] + ONE implicit-GEMM launch with the equalised-lr weight gain folded into
+        the weight pass and the bias / activation epilogue (stylegan_v_b200/dconv.py; first-order differentiable); a 1x1 layer on <= 4 input
+        channels (fromrgb) runs as one streaming pass (dconv.fromrgb); everything else — and fused=False — is conv2d_resample + bias_act.
+        add_to (fused, linear, bias-free layers): the result is accumulated in place into that tensor (the block's residual add)."""
         b = self.bias.to(x.dtype) if self.bias is not None else None
         if fused and self.up == 1 and self.down in (1, 2) and self.conv_clamp is None and self.activation in ('linear', 'lrelu'):
             k = self.weight.shape[2]
+            if k == 1 and self.down == 1 and add_to is None and dconv.fromrgb_supported(x, self.weight):
+                return dconv.fromrgb(x, self.weight, b, act=self.activation, gain=self.act_gain * gain, weight_gain=self.weight_gain)
             # down layers (conv2d_resample.py:100-110,119-122): k = 3 -> low-pass at full resolution, then the convolution strides;
             #                                                    k = 1 -> the FIR decimates, then a 1x1 convolution
             stride, pad = (2, 0) if (self.down == 2 and k == 3) else (1, self.padding if self.down == 1 else 0)
-            if dconv.supported(x, w, stride, pad):
+            if dconv.supported(x, self.weight, stride, pad) and (add_to is None or (self.activation == 'linear' and b is None)):
                 if self.down == 2:
                     fw = self.resample_filter.shape[-1]
                     p0, p1 = self.padding + (fw - self.down + 1) // 2, self.padding + (fw - self.down) // 2       # conv2d_resample.py:100-104
                     x = upfirdn2d.upfirdn2d(x, self.resample_filter, down=(1 if k == 3 else 2), padding=[p0, p1, p0, p1])
-                return dconv.fused_conv_act(x, w, b, stride=stride, padding=pad, act=self.activation, gain=self.act_gain * gain)
+                return dconv.fused_conv_act(x, self.weight, b, stride=stride, padding=pad, act=self.activation, gain=self.act_gain * gain,
+                                            weight_gain=self.weight_gain, add_to=add_to)
+        assert add_to is None, 'add_to needs the fused node'
+        w = self.weight * self.weight_gain
         x = conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down, padding=self.padding,
                                             flip_weight=(self.up == 1))
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
@@ -176,18 +182,24 @@ class DiscriminatorBlock(torch.nn.Module):
         if self.in_channels == 0 or self.architecture == 'skip':
             assert img.shape[1] == self.img_channels and img.shape[2] == img.shape[3] == self.resolution
             img = img.to(dtype)
-            if fused and img.is_cuda:
-                # 3-channel NHWC view of the frames (37 MB at 48 x 256^2): the library 1x1 conv then writes its 64-channel output channels_last,
-                # i.e. already in the layout of the fused conv0 that follows — otherwise that 805 MB activation is transposed once forward and
-                # once backward per discriminator pass (profiles/timeline_gd_step_r1.txt: 10.9 ms of strided-copy kernels per G+D step)
+            if fused and img.is_cuda and not dconv.fromrgb_supported(img, self.fromrgb.weight):
+                # library route of the 1x1 layer: a 3-channel NHWC view of the frames makes it write its output channels_last, the layout of the
+                # fused conv0 that follows (the streaming fromrgb kernel does that by itself from the NCHW frames)
                 img = img.contiguous(memory_format=torch.channels_last)
             y = self.fromrgb(img, fused=fused)
             x = x + y if x is not None else y
             img = upfirdn2d.downsample2d(img, self.resample_filter) if self.architecture == 'skip' else None
         if self.architecture == 'resnet':
-            y = self.skip(x, gain=np.sqrt(0.5), fused=fused)
-            x = self.conv1(self.conv0(x, fused=fused), gain=np.sqrt(0.5), fused=fused)
-            x = y.add_(x)
+            x0 = self.conv0(x, fused=fused)
+            if (fused and x.is_cuda and self.skip.bias is None and self.conv1.conv_clamp is None and dconv.supported(x, self.skip.weight, 1, 0)
+                    and dconv.supported(x0, self.conv1.weight, 2, 0)):
+                # residual add folded into the skip branch's launch: its TMA reduce-add epilogue accumulates into conv1's (NHWC) output
+                y = self.conv1(x0, gain=np.sqrt(0.5), fused=True)
+                x = self.skip(x, gain=np.sqrt(0.5), fused=True, add_to=y)
+            else:
+                y = self.skip(x, gain=np.sqrt(0.5), fused=fused)
+                x = self.conv1(x0, gain=np.sqrt(0.5), fused=fused)
+                x = y.add_(x)
         else:
             x = self.conv1(self.conv0(x, fused=fused), fused=fused)
         return x, img
@@ -228,12 +240,22 @@ class DiscriminatorEpilogue(torch.nn.Module):
 
     def forward(self, x, img, cmap, fused=False):
         assert x.shape[1] == self.in_channels and x.shape[2] == x.shape[3] == self.resolution
-        x = x.to(dtype=torch.float32, memory_format=torch.contiguous_format)
-        if self.architecture == 'skip':
-            x = x + self.fromrgb(img.to(dtype=torch.float32, memory_format=torch.contiguous_format))
-        if self.mbstd is not None:
-            x = self.mbstd(x)
-        x = self.conv(x)
+        w = self.conv.weight
+        if (fused and x.is_cuda and x.dtype == torch.float32 and self.architecture != 'skip' and self.mbstd is not None and self.conv.conv_clamp is None
+                and x.shape[0] % min(self.mbstd.group_size or x.shape[0], x.shape[0]) == 0 and w.shape[0] % 64 == 0 and x.shape[1] % 4 == 0):
+            # minibatch-std + concat + zero padding of the 513 channels to 544 in ONE kernel (NHWC), then the 3x3 conv on the tcgen05 kernel with
+            # zero input-channel padding of its weight (instead of the library call a 513-channel contraction needs)
+            xp = dconv.minibatch_std_concat(x, self.mbstd.group_size, self.mbstd.num_channels)
+            wpad = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, xp.shape[1] - w.shape[1]))
+            x = dconv.fused_conv_act(xp, wpad, self.conv.bias, stride=1, padding=1, act=self.conv.activation, gain=self.conv.act_gain,
+                                     weight_gain=self.conv.weight_gain)
+        else:
+            x = x.to(dtype=torch.float32, memory_format=torch.contiguous_format)
+            if self.architecture == 'skip':
+                x = x + self.fromrgb(img.to(dtype=torch.float32, memory_format=torch.contiguous_format))
+            if self.mbstd is not None:
+                x = self.mbstd(x)
+            x = self.conv(x)
         # flatten in (C, H, W) order like the reference, whatever memory format the conv returned
         x = self.out(self.fc(x.contiguous().flatten(1), fused=fused), fused=fused)
         if self.cmap_dim > 0:
@@ -292,6 +314,16 @@ class TemporalDifferenceEncoder(torch.nn.Module):
         diffs = (t[:, 1] - t[:, 0]) if self.sampling_type == 'uniform' else (t[:, 1:] - t[:, :-1]).reshape(-1)
         emb = torch.cat([self.const_embed(diffs.float().round().long()), self.time_encoder(diffs.unsqueeze(1))], dim=1)
         return emb.reshape(B, -1)
+
+
+def _concat_frames(x, num_frames, keep_nhwc=False):
+    """[B*F, C, h, w] -> [B, F*C, h, w] with channel index f * C + c (networks.py:659-662).  For an NHWC activation on the fused path the
+    result is produced NHWC with ONE copy (pixel-major, the frames' channel vectors side by side) instead of NCHW-and-back."""
+    BF, Cc, h, w = x.shape
+    if keep_nhwc and x.is_cuda and x.stride(1) == 1 and Cc > 1:
+        m = x.permute(0, 2, 3, 1).reshape(BF // num_frames, num_frames, h, w, Cc).permute(0, 2, 3, 1, 4).reshape(BF // num_frames, h, w, num_frames * Cc)
+        return m.permute(0, 3, 1, 2)
+    return x.contiguous().reshape(-1, num_frames * Cc, h, w)
 
 
 class Discriminator(torch.nn.Module):
@@ -357,7 +389,7 @@ class Discriminator(torch.nn.Module):
         x = None
         for res in self.block_resolutions:
             if res == self.concat_res:
-                x = x.contiguous().reshape(-1, self.num_frames_per_video * x.shape[1], *x.shape[2:])     # [B, F*C, h, w] in (frame, channel) order
+                x = _concat_frames(x, self.num_frames_per_video, keep_nhwc=fused)     # [B, F*C, h, w] in (frame, channel) order
             x, img = getattr(self, f'b{res}')(x, img, fused=fused)
         cmap = self.mapping(None, c) if c.shape[1] > 0 else None
         return {'image_logits': self.b4(x, img, cmap, fused=fused).squeeze(1)}

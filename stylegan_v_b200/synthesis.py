@@ -18,7 +18,6 @@ import numpy as np
 import torch
 
 from . import conv as _conv
-from . import dense as _dense
 from .modconv import fused_modulated_conv, demod_coefs, prepare_weights, WeightGradBox, WeightGradNode
 from .ops import upfirdn2d as _upfirdn2d
 from .ops import bias_act as _bias_act
@@ -275,13 +274,12 @@ class SynthesisNetwork(torch.nn.Module):
             w_idx += block.num_conv
         out = {}
         for wi, layers in groups.items():
-            wcat = torch.cat([l.affine.weight for l in layers], dim=0) if len(layers) > 1 else layers[0].affine.weight
-            bcat = torch.cat([l.affine.bias for l in layers], dim=0) if len(layers) > 1 else layers[0].affine.bias
-            wrow = ws[:, wi].contiguous()
-            if _dense.supported(wrow, wcat):       # tcgen05 contraction, weight gain folded into its weight pass, bias in its epilogue (fp32-grade)
-                s = _dense.linear(wrow, wcat, bcat, layers[0].affine.weight_gain, 1.0)
-            else:
-                s = torch.addmm(bcat.unsqueeze(0), wrow, (wcat * layers[0].affine.weight_gain).t())
+            # library fp32 GEMM on purpose: measured on the B200 (profiles/launches_r2b_summary.txt) the 14 stacked affine products of a step cost
+            # 0.6 ms on cuBLAS and 1.3 ms as tcgen05 tf32x3 launches of the per-tap kernel (M = 32 rows fill a quarter of one 128-row tile and
+            # the K loop is latency-bound); stylegan_v_b200/dense.py serves the mapping networks and the discriminator's dense layers instead
+            wcat = torch.cat([l.affine.weight for l in layers], dim=0) * layers[0].affine.weight_gain
+            bcat = torch.cat([l.affine.bias for l in layers], dim=0)
+            s = torch.addmm(bcat.unsqueeze(0), ws[:, wi], wcat.t())
             for l, piece in zip(layers, s.split([l.affine.weight.shape[0] for l in layers], dim=1)):
                 out[id(l)] = piece
         return out

@@ -22,7 +22,6 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from . import dense as _dense
 from . import precision as _precision
 
 
@@ -77,12 +76,7 @@ class EqualizedLinear(torch.nn.Module):
         self.weight_gain = lr_multiplier / np.sqrt(in_features)
         self.bias_gain = lr_multiplier
 
-    def forward(self, x, fused=False):
-        """fused=True (callers that need first-order gradients only): the tcgen05 contraction of libsgv_b200 with the weight gain folded
-        into its weight pass and the bias in its epilogue (stylegan_v_b200/dense.py); otherwise the reference's torch.addmm / matmul
-        formulation, differentiable to any order (path-length regularisation differentiates the affines twice)."""
-        if fused and x.ndim == 2 and _dense.supported(x, self.weight):
-            return _dense.linear(x, self.weight, self.bias, self.weight_gain, self.bias_gain)
+    def forward(self, x):
         w = self.weight.to(x.dtype) * self.weight_gain
         if self.bias is None:
             return x.matmul(w.t())
@@ -124,20 +118,10 @@ class EqualizedConv1d(torch.nn.Module):
         self.bias_gain = lr_multiplier
 
     def forward(self, x):
-        """x [B, C, L] (the reference's layout after its permute) -> [B, C_out, L - k + 1]: the library formulation, used for CPU tensors and
-        shapes outside the kernels' envelope."""
         # true fp32: the embedding multiplies these features by phase scales up to 64 and takes sin/cos, so TF32 rounding
         # here (PyTorch's cuDNN default) would show up as ~1e-2 errors in motion_v; the reference trains with allow_tf32=False
         y = _Conv1dFp32Fwd.apply(x, self.weight * self.weight_gain, self.bias * self.bias_gain)
         return F.leaky_relu(y, 0.2)
-
-    def forward_lines(self, x):
-        """x [B, L, C] (the trajectory as stored, no permute) -> [B, L - k + 1, C_out] on the tcgen05 contraction kernel (fp32-grade
-        arithmetic, bias + leaky ReLU in its epilogue, both gradients on the same kernels): stylegan_v_b200/dense.py."""
-        return _dense.conv1d_lines(x, self.weight, self.bias, self.weight_gain, self.bias_gain, act='lrelu')
-
-    def lines_supported(self, x):
-        return x.ndim == 3 and _dense.supported(x, self.weight, act='lrelu')
 
 
 class AlignedTimeEncoder(torch.nn.Module):
@@ -159,12 +143,15 @@ class AlignedTimeEncoder(torch.nn.Module):
         (t, d) itself exactly as MotionMappingNetwork does (motion.py:111-115)."""
         nf = self.freqs.shape[1]
         # one stacked GEMM for the three heads on u_left, one for the aligners on u_right
+        # True-fp32 library GEMMs on purpose (and a true-fp32 library conv1d for the trajectory below): the phases are multiplied by
+        # phase_scales up to 64 before sin / cos, so these products need round-to-nearest fp32 accumulation.  Measured on the B200: with the
+        # tcgen05 tf32x3 kernels (whose tensor-core accumulation is not round-to-nearest: error grows ~K, 4e-5 at K = 5632) motion_v is off
+        # by 2e-3 against the fp32 CPU evaluation; with the library fp32 path by 1e-4 (profiles/dense_precision_r2.txt).
         heads = torch.cat([self.periods_predictor.weight, self.phase_predictor.weight, self.aligners_predictor.weight], dim=0)
         gain = self.periods_predictor.weight_gain
-        on_kernels = u_left.ndim == 2 and _dense.supported(u_left, heads)
-        hl = _dense.linear(u_left, heads, None, gain) if on_kernels else u_left.matmul((heads * gain).t())
+        hl = u_left.matmul((heads * gain).t())
         if motion_z_distance is not None and t.is_cuda and hl.dtype == torch.float32:
-            return _TimeEncoderTail.apply(hl, self.aligners_predictor(u_right, fused=True), t.reshape(-1), self.freqs, self.phase_scales, motion_z_distance)
+            return _TimeEncoderTail.apply(hl, self.aligners_predictor(u_right), t.reshape(-1), self.freqs, self.phase_scales, motion_z_distance)
         periods = hl[:, :nf].tanh() + 1
         phases = hl[:, nf:2 * nf]
         al_left = hl[:, 2 * nf:]
@@ -207,11 +194,7 @@ class MotionMappingNetwork(torch.nn.Module):
         L = self.traj_len(t_max)
         if motion_z is None:
             motion_z = torch.randn(B, L, self.z_dim, device=t.device)
-        traj_in = motion_z[:B, :L, :self.z_dim]
-        if self.conv[0].lines_supported(traj_in) and _dense.supported(traj_in, self.conv[1].weight, act='lrelu'):
-            trajs = self.conv[1].forward_lines(self.conv[0].forward_lines(traj_in))              # [B, L - 20, v_dim], no permutes
-        else:
-            trajs = self.conv(traj_in.permute(0, 2, 1)).permute(0, 2, 1)
+        trajs = self.conv(motion_z[:B, :L, :self.z_dim].permute(0, 2, 1)).permute(0, 2, 1)   # [B, L - 20, v_dim]
         d = self.motion_z_distance
         left = (t / d).floor().long()
         rows = torch.arange(B, device=t.device).unsqueeze(1).expand(B, Fr)
