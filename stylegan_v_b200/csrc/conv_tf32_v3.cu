@@ -56,11 +56,11 @@ struct ConvV3Args
     int debug;      // ablation switches, only honoured by -DSGV_ABLATION builds (profiles/conv_v3_ablation_r1.txt): 1 skip transform, 2 skip epilogue, 4 skip MMAs
 };
 
-template <int BN, int MH, int SA, int SB>
+template <int BN, int MH, int SA, int SB, bool PAIR = false>
 struct ConvV3Smem
 {
     static constexpr int kPatch = (((16 + 2) * (8 * MH + 2) * 128) + 1023) & ~1023;
-    static constexpr int kBTile = BN * 128;
+    static constexpr int kBTile = (PAIR ? BN / 2 : BN) * 128;      // CTA-pair MMAs: each CTA of the pair holds half of the slab's rows
     static constexpr int kBOffset = SA * kPatch;
     static constexpr int kStageOffset = kBOffset + SB * kBTile;      // 2 x 16 KB output staging (128 pixels x 32 channels, 128B-swizzled)
     static constexpr int kBarOffset = kStageOffset + 2 * 16384;
@@ -87,12 +87,21 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvV3Args& p, int group, 
     return c;
 }
 
-template <int BN, int MH, int SA, int SB, int CL>
+// PAIR (needs CL == 2): the two CTAs of a cluster issue their MMAs as ONE tcgen05.mma.cta_group::2 of M = 256 — CTA r supplies the 128 pixel
+// rows of ITS tile (own patches, own staging warps, own accumulator rows in its own TMEM, own epilogue) and rows [r*BN/2, (r+1)*BN/2) of every
+// weight slab, so a CTA reads only half of B from shared memory per instruction (the B-operand traffic that makes the 128 B/clk
+// shared-memory port the limiter in the one-CTA form: DESIGN.md §4).  Only the even CTA (the leader) issues MMAs; synchronisation:
+//   ready_a  (leader's copy, 8 arrivals)   the 4 staging warps of BOTH CTAs arrive here (remote arrive from the odd CTA)
+//   full_b   (leader's copy)               both CTAs' slab TMAs complete their bytes on it (cta_group::2 TMA form); the leader expects both halves
+//   empty_a / empty_b / acc_full           tcgen05.commit.cta_group::2 multicast: one arrival on the barrier in each CTA
+//   acc_empty (leader's copy, 16 arrivals) the 8 epilogue warps of both CTAs
+template <int BN, int MH, int SA, int SB, int CL, bool PAIR>
 __global__ void __launch_bounds__(kV3Threads, 1)
 conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_y, const ConvV3Args p)
 {
-    using L = ConvV3Smem<BN, MH, SA, SB>;
+    static_assert(!PAIR || CL == 2, "CTA-pair MMAs need clusters of exactly two CTAs");
+    using L = ConvV3Smem<BN, MH, SA, SB, PAIR>;
     constexpr int NB = L::kAccBufs;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -117,12 +126,16 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         prefetch_tmap(&tmap_x);
         prefetch_tmap(&tmap_w);
         prefetch_tmap(&tmap_y);
-        for (int s = 0; s < SA; s++) { mbar_init(full_a + s, 1); mbar_init(ready_a + s, 4); mbar_init(empty_a + s, 1); }
-        for (int s = 0; s < SB; s++) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, CL); }   // a slab slot is freed by the MMAs of all CL CTAs
-        for (int s = 0; s < 2; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 8); }
+        for (int s = 0; s < SA; s++) { mbar_init(full_a + s, 1); mbar_init(ready_a + s, PAIR ? 8 : 4); mbar_init(empty_a + s, 1); }
+        for (int s = 0; s < SB; s++) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, PAIR ? 1 : CL); }   // a slab slot is freed by the MMAs of all CL CTAs (pair: by the leader's, multicast)
+        for (int s = 0; s < 2; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, PAIR ? 16 : 8); }
         fence_mbar_init();
     }
-    if (warp == 1) { tmem_alloc(tmem_slot, L::kTmemCols); tmem_relinquish(); }
+    if (warp == 1)
+    {
+        if (PAIR) { tmem_alloc_pair(tmem_slot, L::kTmemCols); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_slot, L::kTmemCols); tmem_relinquish(); }
+    }
     tc_fence_before();
     if (CL > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers are initialised before anything is multicast at them
     tc_fence_after();
@@ -163,6 +176,14 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     for (int t = 0; t < p.ntaps; t++)
                     {
                         mbar_wait(empty_b + sb, pb ^ 1);
+                        if (PAIR)
+                        {
+                            // this CTA's half of the slab rows into ITS shared memory; both halves complete on the leader's barrier
+                            if (crank == 0) mbar_expect_tx(full_b + sb, 2 * L::kBTile);
+                            tma_load_2d_pair(smem + L::kBOffset + sb * L::kBTile, &tmap_w, full_b + sb, kc * 32, p.tap_slab[t] + nb0 + crank * (BN / 2));
+                            if (++sb == SB) { sb = 0; pb ^= 1; }
+                            continue;
+                        }
                         mbar_expect_tx(full_b + sb, L::kBTile);
                         if (CL == 1)
                             tma_load_2d(smem + L::kBOffset + sb * L::kBTile, &tmap_w, full_b + sb, kc * 32, p.tap_slab[t] + nb0);
@@ -179,9 +200,9 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     {
         // ===== MMA issuer: ONE elected thread runs the whole role (no per-tap election / reconvergence), descriptors are built
         //       from a constant high word and a 32-bit low word that only needs integer adds per tap / half / k-step =====
-        if (elect_one())
+        if (elect_one() && (!PAIR || crank == 0))
         {
-            constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
+            constexpr uint32_t idesc = umma_idesc_tf32(PAIR ? 256 : 128, BN);
             const uint64_t proto = umma_desc_k_sw128(0);
             const uint32_t b_hi = (uint32_t)(proto >> 32);
             const uint32_t a_hi = (b_hi & ~0x3FFFu) | (((uint32_t)(p.pw * 128) >> 4) & 0x3FFFu);      // SBO = patch row pitch
@@ -217,13 +238,19 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 #pragma unroll
                                 for (int k = 0; k < 4; k++)
                                     if (!SGV_ABL(p.debug, 4))
-                                        mma_tf32(acc + (uint32_t)(h * BN), desc(a_lo + (uint32_t)(h * 64 + k * 2), a_hi), desc(b_lo + (uint32_t)(k * 2), b_hi), idesc,
-                                                 (kc > 0 || t > 0 || k > 0) ? 1u : 0u);
-                            if (CL == 1) mma_commit(empty_b + sb); else mma_commit_mc(empty_b + sb, kMask);
+                                    {
+                                        if (PAIR) mma_tf32_pair(acc + (uint32_t)(h * BN), desc(a_lo + (uint32_t)(h * 64 + k * 2), a_hi), desc(b_lo + (uint32_t)(k * 2), b_hi), idesc,
+                                                                (kc > 0 || t > 0 || k > 0) ? 1u : 0u);
+                                        else mma_tf32(acc + (uint32_t)(h * BN), desc(a_lo + (uint32_t)(h * 64 + k * 2), a_hi), desc(b_lo + (uint32_t)(k * 2), b_hi), idesc,
+                                                      (kc > 0 || t > 0 || k > 0) ? 1u : 0u);
+                                    }
+                            if (PAIR) mma_commit_pair_mc(empty_b + sb, kMask);
+                            else if (CL == 1) mma_commit(empty_b + sb);
+                            else mma_commit_mc(empty_b + sb, kMask);
                             if (t == t_end - 1)
                             {
-                                mma_commit(empty_a + sa);
-                                if (kc == kchunks - 1 && c == p.ncls - 1) mma_commit(acc_full + buf);
+                                if (PAIR) mma_commit_pair_mc(empty_a + sa, kMask); else mma_commit(empty_a + sa);
+                                if (kc == kchunks - 1 && c == p.ncls - 1) { if (PAIR) mma_commit_pair_mc(acc_full + buf, kMask); else mma_commit(acc_full + buf); }
                             }
                             if (++sb == SB) { sb = 0; pb ^= 1; }
                         }
@@ -291,7 +318,7 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(ready_a + sa);
+                    if (lane == 0) { if (PAIR) mbar_arrive_leader(ready_a + sa); else mbar_arrive(ready_a + sa); }
                     if (++sa == SA) { sa = 0; pa ^= 1; }
                 }
             }
@@ -336,7 +363,7 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         // the accumulator buffer is in registers now: hand it back to the MMA issuer before the stores
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(acc_empty + buf);
+                        if (lane == 0) { if (PAIR) mbar_arrive_leader(acc_empty + buf); else mbar_arrive(acc_empty + buf); }
                     }
                     if (p.red_out)
                     {
@@ -385,21 +412,21 @@ conv_tf32_v3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     }
                 }
             }
-            if (SGV_ABL(p.debug, 2)) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(acc_empty + buf); }
+            if (SGV_ABL(p.debug, 2)) { tc_fence_before(); __syncwarp(); if (lane == 0) { if (PAIR) mbar_arrive_leader(acc_empty + buf); else mbar_arrive(acc_empty + buf); } }
         }
         if (issuer) bulk_wait_all();
     }
 
     tc_fence_before();
     if (CL > 1) cluster_sync_all(); else __syncthreads();      // no CTA leaves while a peer may still multicast into it
-    if (warp == 1) tmem_dealloc(tmem_base, L::kTmemCols);
+    if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem_base, L::kTmemCols); else tmem_dealloc(tmem_base, L::kTmemCols); }
 }
 
-template <int BN, int MH, int SA, int SB, int CL>
+template <int BN, int MH, int SA, int SB, int CL, bool PAIR = false>
 static int launch_v3(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvV3Args& a, cudaStream_t stream)
 {
-    using L = ConvV3Smem<BN, MH, SA, SB>;
-    auto kern = conv_tf32_v3_kernel<BN, MH, SA, SB, CL>;
+    using L = ConvV3Smem<BN, MH, SA, SB, PAIR>;
+    auto kern = conv_tf32_v3_kernel<BN, MH, SA, SB, CL, PAIR>;
     static PerDeviceInt max_clusters;      // co-resident clusters of this variant, per device
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -429,6 +456,19 @@ static int launch_v3(const CUtensorMap& tx, const CUtensorMap& tw, const CUtenso
     return SGV_OK;
 }
 
+// CTA-pair variants (cta_group::2 MMAs): same tiles; the halved slab stages buy deeper slab rings
+static int launch_v3_pair(int bn, int mh, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvV3Args& a, cudaStream_t stream)
+{
+    switch (bn)
+    {
+        case 256: return launch_v3<256, 2, 2, 4, 2, true>(tx, tw, ty, a, stream);     // 84 KB patches + 4 x 16 KB slab halves
+        case 128: return launch_v3<128, 2, 3, 6, 2, true>(tx, tw, ty, a, stream);     // 126 + 6 x 8 KB
+        default:
+            if (mh == 4) return launch_v3<64, 4, 2, 6, 2, true>(tx, tw, ty, a, stream);   // 154 + 6 x 4 KB
+            return launch_v3<64, 2, 3, 8, 2, true>(tx, tw, ty, a, stream);
+    }
+}
+
 template <int CL>
 static int launch_v3_bn(int bn, int mh, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& ty, const ConvV3Args& a, cudaStream_t stream)
 {
@@ -450,8 +490,10 @@ struct V3Tuning
     int max_bn;       // SGV_V3_MAXBN
     int wide_cin;     // SGV_V3_WIDE_CIN: smallest cin that takes the 256-column N tile
     int debug;        // SGV_V3_DEBUG: ablation switches (honoured by -DSGV_ABLATION builds only)
+    int pair;         // SGV_CONV_PAIR=0|1: issue the MMAs of a 2-CTA cluster as tcgen05 cta_group::2 (M = 256, B halved per CTA)
     V3Tuning()
     {
+        pair = env_int("SGV_CONV_PAIR", 0) ? 1 : 0;
         cluster = env_int("SGV_CONV_CLUSTER", 2);
         if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
         mh4 = env_int("SGV_V3_MH4", 1) ? 1 : 0;
@@ -541,9 +583,10 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream, sgv_conv_varia
     int cl = tune.cluster;
     while (cl > 1 && (pixel_tiles % cl != 0 || pixel_tiles / cl * a.ntiles_n < num_sms() / cl)) cl >>= 1;   // small problems: fill the SMs first
     a.total_groups = pixel_tiles / cl * a.ntiles_n;
+    const bool pair = tune.pair && cl == 2;
     if (query)
     {
-        query->kernel = 3; query->bn = bn; query->mh = mh; query->cluster = cl; query->cta_pair = 0; query->x3 = x3 ? 1 : 0;
+        query->kernel = 3; query->bn = bn; query->mh = mh; query->cluster = cl; query->cta_pair = pair ? 1 : 0; query->x3 = x3 ? 1 : 0;
         return SGV_OK;
     }
 
@@ -561,7 +604,7 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream, sgv_conv_varia
     {
         const uint64_t dims[2] = {(uint64_t)p->cin, (uint64_t)slab_rows};
         const uint64_t strides[1] = {(uint64_t)p->cin * 4};
-        const uint32_t box[2] = {32, (uint32_t)(bn / cl)};
+        const uint32_t box[2] = {32, (uint32_t)(bn / cl)};      // cluster of 2 (multicast or CTA pair): each CTA fetches half of the slab rows
         const uint32_t es[2] = {1, 1};
         int rc = make_tmap_f32(&tmw, p->wp, 2, dims, strides, box, es);
         if (rc != SGV_OK) return rc;
@@ -575,6 +618,7 @@ int conv2d_tf32_v3(const sgv_conv_params* p, cudaStream_t stream, sgv_conv_varia
         int rc = make_tmap_f32(&tmy, p->y, 4, dims, strides, box, es);
         if (rc != SGV_OK) return rc;
     }
+    if (pair) return launch_v3_pair(bn, mh, tmx, tmw, tmy, a, stream);
     if (cl == 4) return launch_v3_bn<4>(bn, mh, tmx, tmw, tmy, a, stream);
     if (cl == 2) return launch_v3_bn<2>(bn, mh, tmx, tmw, tmy, a, stream);
     return launch_v3_bn<1>(bn, mh, tmx, tmw, tmy, a, stream);

@@ -7,7 +7,7 @@
 //                            NCHW tensor plus a separate bias_act pass.  The frames stay NCHW (as the data loader / generator deliver
 //                            them), the 64-channel result is written NHWC, i.e. in the layout of the tcgen05 conv that follows.
 //   sgv_mbstd_fwd / _bwd     MinibatchStdLayer (networks.py:492-516) fused with the channel concat that follows it and with the zero
-//                            padding of the channel count to a multiple of 32 (513 -> 544), so that the epilogue's 3x3 convolution
+//                            padding of the channel count to a multiple of 64 (513 -> 576), so that the epilogue's 3x3 convolution
 //                            runs on the tcgen05 kernel instead of the library.
 //
 // Same contract as include/sgv_b200.h (caller-owned buffers, no allocation, no synchronisation, explicit stream, int status).

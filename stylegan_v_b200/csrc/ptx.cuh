@@ -134,6 +134,50 @@ __device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t cta_mask)
                  :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
+// ---- CTA pair (cta_group::2): two CTAs of a cluster (ranks 2i, 2i+1 = the two SMs of a TPC) execute ONE MMA of M = 256: each CTA
+//      supplies its own 128 A rows and HALF of the B columns from the same shared-memory offsets and receives its 128 accumulator rows in
+//      its own TMEM.  PTX forms as in CUTLASS (cute/arch/tmem_allocator_sm100.hpp, mma_sm100_umma.hpp, copy_sm100_tma.hpp, cutlass/arch/barrier.h).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the EVEN CTA of the pair (the MMA leader)
+
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols)   // the same warp of BOTH CTAs, same dst offset
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+// issued by ONE thread of the leader CTA only
+__device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// completion of all MMAs issued so far by this thread -> one arrival on the barrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void mma_commit_pair_mc(uint64_t* bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose byte count completes on the LEADER CTA's mbarrier (same offset)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+// Arrival on the LEADER CTA's copy of a barrier (from either CTA of the pair) — the form CUTLASS' ClusterBarrier::arrive(cta_id) uses.
+// What it orders here: a CTA's staging warps write THEIR OWN shared memory, fence.proxy.async, then arrive; the data is read from that
+// same SM's shared memory by the pair MMA the leader issues after the barrier flips — no data crosses SMs, so no cluster-scope fence
+// (which compiles to MEMBAR.ALL.GPU per arrival) is needed.
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
 // ---- thread-block cluster ----
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {

@@ -37,26 +37,18 @@ def supported(x, w, stride, padding):
 
 class _FusedConvAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b, stride, padding, act, gain, weight_gain, add_to):
+    def forward(ctx, x, w, b, stride, padding, act, gain, weight_gain):
         x = x.contiguous(memory_format=torch.channels_last)
         k = w.shape[2]
         taps = [(ky, kx) for ky in range(k) for kx in range(k)]
         oh, ow = (x.shape[2] + 2 * padding - k) // stride + 1, (x.shape[3] + 2 * padding - k) // stride + 1
         offs = [(ky - padding, kx - padding) for ky, kx in taps]
         x3 = _precision.is_x3()
-        if add_to is None:
-            # the equalised-lr weight gain (layers.py:186) rides on the weight-preparation pass: no scaled weight copy, no multiply in the backward
-            y = _conv.igemm_conv(x, _conv.prep_weights(w, taps, scale=weight_gain, x3=x3), offs, out_hw=(oh, ow), in_stride=stride, bias=b, act=act, gain=gain)
-        else:
-            # residual form  add_to += conv(x, w) * gain  (the block's `y.add_(x)`, networks.py:481-487, folded into the skip branch's launch: the
-            # kernel's TMA reduce-add epilogue accumulates into the other branch's output; the output gain rides on the weights)
-            assert act == 'linear' and b is None and tuple(add_to.shape) == (x.shape[0], w.shape[0], oh, ow)
-            _conv.igemm_conv(x, _conv.prep_weights(w, taps, scale=weight_gain * gain, x3=x3), offs, out_view=add_to, in_stride=stride, accumulate=True)
-            ctx.mark_dirty(add_to)
-            y = add_to
-        # a linear layer's gradient does not need y
+        # the equalised-lr weight gain (layers.py:186) rides on the weight-preparation pass: no scaled weight copy, no multiply in the backward
+        y = _conv.igemm_conv(x, _conv.prep_weights(w, taps, scale=weight_gain, x3=x3), offs, out_hw=(oh, ow), in_stride=stride, bias=b, act=act, gain=gain)
+        # a linear layer's gradient does not need y (the block adds the two branches IN PLACE into the skip branch's output, networks.py:481)
         ctx.save_for_backward(x, w, y if act != 'linear' else x.new_empty(0), b if b is not None else x.new_empty(0))
-        ctx.cfg = (stride, padding, act, gain, b is not None, weight_gain, add_to is not None)
+        ctx.cfg = (stride, padding, act, gain, b is not None, weight_gain)
         ctx.x3 = x3
         return y
 
@@ -64,7 +56,7 @@ class _FusedConvAct(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         x, w, y, b = ctx.saved_tensors
-        stride, padding, act, gain, has_b, weight_gain, residual = ctx.cfg
+        stride, padding, act, gain, has_b, weight_gain = ctx.cfg
         dy = dy.contiguous(memory_format=torch.channels_last)
         want_db = has_b and ctx.needs_input_grad[2]
         if act == 'linear':
@@ -85,15 +77,13 @@ class _FusedConvAct(torch.autograd.Function):
             assert gw is not None
             if weight_gain != 1:
                 gw = gw * weight_gain
-        return gx, gw, db, None, None, None, None, None, (dy if residual else None)
+        return gx, gw, db, None, None, None, None, None
 
 
-def fused_conv_act(x, w, b=None, stride=1, padding=0, act='linear', gain=1.0, weight_gain=1.0, add_to=None):
-    """act(conv2d(x, w * weight_gain, stride, padding) + b) * gain as one autograd node; act in {'linear', 'lrelu'}.  Caller checks supported().
-    add_to (linear, bias-free layers): the result is ACCUMULATED into that NHWC tensor in place (and returned) — the residual add of a block
-    without a separate pass."""
+def fused_conv_act(x, w, b=None, stride=1, padding=0, act='linear', gain=1.0, weight_gain=1.0):
+    """act(conv2d(x, w * weight_gain, stride, padding) + b) * gain as one autograd node; act in {'linear', 'lrelu'}.  Caller checks supported()."""
     assert act in ('linear', 'lrelu')
-    return _FusedConvAct.apply(x, w, b, int(stride), int(padding), act, float(gain), float(weight_gain), add_to)
+    return _FusedConvAct.apply(x, w, b, int(stride), int(padding), act, float(gain), float(weight_gain))
 
 
 class _FromRgb(torch.autograd.Function):
@@ -176,7 +166,7 @@ class _MinibatchStd(torch.autograd.Function):
         return dx, None, None, None
 
 
-def minibatch_std_concat(x, group_size, num_channels=1, pad_to=32):
+def minibatch_std_concat(x, group_size, num_channels=1, pad_to=64):
     """[N, C, H, W] -> NHWC [N, roundup(C + num_channels, pad_to), H, W]: x, the per-group standard-deviation statistic as extra channel(s),
     zero channels after that (the consumer pads its weight with zero input channels).  CUDA float32; N % G == 0 like the reference's reshape."""
     N, Cc = x.shape[0], x.shape[1]

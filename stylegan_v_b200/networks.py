@@ -119,27 +119,25 @@ class Conv2dLayer(torch.nn.Module):
             else:
                 self.bias = None
 
-    def forward(self, x, gain=1, fused=False, add_to=None):
+    def forward(self, x, gain=1, fused=False):
         """fused=True: layers inside the native envelope run as [FIR] + ONE implicit-GEMM launch with the equalised-lr weight gain folded into
         the weight pass and the bias / activation epilogue (stylegan_v_b200/dconv.py; first-order differentiable); a 1x1 layer on <= 4 input
-        channels (fromrgb) runs as one streaming pass (dconv.fromrgb); everything else — and fused=False — is conv2d_resample + bias_act.
-        add_to (fused, linear, bias-free layers): the result is accumulated in place into that tensor (the block's residual add)."""
+        channels (fromrgb) runs as one streaming pass (dconv.fromrgb); everything else — and fused=False — is conv2d_resample + bias_act."""
         b = self.bias.to(x.dtype) if self.bias is not None else None
         if fused and self.up == 1 and self.down in (1, 2) and self.conv_clamp is None and self.activation in ('linear', 'lrelu'):
             k = self.weight.shape[2]
-            if k == 1 and self.down == 1 and add_to is None and dconv.fromrgb_supported(x, self.weight):
+            if k == 1 and self.down == 1 and dconv.fromrgb_supported(x, self.weight):
                 return dconv.fromrgb(x, self.weight, b, act=self.activation, gain=self.act_gain * gain, weight_gain=self.weight_gain)
             # down layers (conv2d_resample.py:100-110,119-122): k = 3 -> low-pass at full resolution, then the convolution strides;
             #                                                    k = 1 -> the FIR decimates, then a 1x1 convolution
             stride, pad = (2, 0) if (self.down == 2 and k == 3) else (1, self.padding if self.down == 1 else 0)
-            if dconv.supported(x, self.weight, stride, pad) and (add_to is None or (self.activation == 'linear' and b is None)):
+            if dconv.supported(x, self.weight, stride, pad):
                 if self.down == 2:
                     fw = self.resample_filter.shape[-1]
                     p0, p1 = self.padding + (fw - self.down + 1) // 2, self.padding + (fw - self.down) // 2       # conv2d_resample.py:100-104
                     x = upfirdn2d.upfirdn2d(x, self.resample_filter, down=(1 if k == 3 else 2), padding=[p0, p1, p0, p1])
                 return dconv.fused_conv_act(x, self.weight, b, stride=stride, padding=pad, act=self.activation, gain=self.act_gain * gain,
-                                            weight_gain=self.weight_gain, add_to=add_to)
-        assert add_to is None, 'add_to needs the fused node'
+                                            weight_gain=self.weight_gain)
         w = self.weight * self.weight_gain
         x = conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=self.resample_filter, up=self.up, down=self.down, padding=self.padding,
                                             flip_weight=(self.up == 1))
@@ -190,16 +188,11 @@ class DiscriminatorBlock(torch.nn.Module):
             x = x + y if x is not None else y
             img = upfirdn2d.downsample2d(img, self.resample_filter) if self.architecture == 'skip' else None
         if self.architecture == 'resnet':
-            x0 = self.conv0(x, fused=fused)
-            if (fused and x.is_cuda and self.skip.bias is None and self.conv1.conv_clamp is None and dconv.supported(x, self.skip.weight, 1, 0)
-                    and dconv.supported(x0, self.conv1.weight, 2, 0)):
-                # residual add folded into the skip branch's launch: its TMA reduce-add epilogue accumulates into conv1's (NHWC) output
-                y = self.conv1(x0, gain=np.sqrt(0.5), fused=True)
-                x = self.skip(x, gain=np.sqrt(0.5), fused=True, add_to=y)
-            else:
-                y = self.skip(x, gain=np.sqrt(0.5), fused=fused)
-                x = self.conv1(x0, gain=np.sqrt(0.5), fused=fused)
-                x = y.add_(x)
+            # (the add stays a separate in-place pass into the LINEAR skip output: conv1's own output must survive unchanged, its backward
+            #  recovers the leaky-ReLU slope from it — an accumulate-epilogue into either branch's buffer was tried and dropped for that reason)
+            y = self.skip(x, gain=np.sqrt(0.5), fused=fused)
+            x = self.conv1(self.conv0(x, fused=fused), gain=np.sqrt(0.5), fused=fused)
+            x = y.add_(x)
         else:
             x = self.conv1(self.conv0(x, fused=fused), fused=fused)
         return x, img
@@ -243,10 +236,12 @@ class DiscriminatorEpilogue(torch.nn.Module):
         w = self.conv.weight
         if (fused and x.is_cuda and x.dtype == torch.float32 and self.architecture != 'skip' and self.mbstd is not None and self.conv.conv_clamp is None
                 and x.shape[0] % min(self.mbstd.group_size or x.shape[0], x.shape[0]) == 0 and w.shape[0] % 64 == 0 and x.shape[1] % 4 == 0):
-            # minibatch-std + concat + zero padding of the 513 channels to 544 in ONE kernel (NHWC), then the 3x3 conv on the tcgen05 kernel with
+            # minibatch-std + concat + zero padding of the 513 channels to 576 in ONE kernel (NHWC), then the 3x3 conv on the tcgen05 kernel with
             # zero input-channel padding of its weight (instead of the library call a 513-channel contraction needs)
-            xp = dconv.minibatch_std_concat(x, self.mbstd.group_size, self.mbstd.num_channels)
+            # (padding to a multiple of 64: the padded count is GEMM-N of the data-gradient contraction)
+            xp = dconv.minibatch_std_concat(x, self.mbstd.group_size, self.mbstd.num_channels, pad_to=64)
             wpad = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, xp.shape[1] - w.shape[1]))
+            assert dconv.supported(xp, wpad, 1, 1)
             x = dconv.fused_conv_act(xp, wpad, self.conv.bias, stride=1, padding=1, act=self.conv.activation, gain=self.conv.act_gain,
                                      weight_gain=self.conv.weight_gain)
         else:

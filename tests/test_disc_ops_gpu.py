@@ -1,5 +1,5 @@
 """Discriminator-side kernels (csrc/disc_ops.cu, stylegan_v_b200/dconv.py) against torch fp64 on the GPU: the streaming `fromrgb` layer, the
-minibatch-std + concat + channel-padding kernel, and the residual add folded into the skip branch's contraction."""
+minibatch-std + concat + channel-padding kernel."""
 import numpy as np
 import pytest
 import torch
@@ -41,7 +41,7 @@ def test_minibatch_std_concat_kernel(N, C, G, nhwc):
         x = x.contiguous(memory_format=torch.channels_last)
     x.requires_grad_(True)
     y = dconv.minibatch_std_concat(x, G, 1)
-    cpad = (C + 1 + 31) // 32 * 32
+    cpad = (C + 1 + 63) // 64 * 64
     assert y.shape == (N, cpad, 4, 4) and y.stride(1) == 1
     x64 = x.detach().double().requires_grad_(True)
     ref = MinibatchStdLayer(G, 1)(x64)                                              # the reference arithmetic (networks.py:499-514) in fp64
@@ -50,24 +50,3 @@ def test_minibatch_std_concat_kernel(N, C, G, nhwc):
     gx, = torch.autograd.grad(y, x, dy)
     rx, = torch.autograd.grad(ref, x64, dy[:, :C + 1].double())
     assert rel_err(gx, rx) < 1e-5
-
-
-def test_residual_add_folded_into_skip_launch():
-    """y1 = conv1-like output; skip(x) accumulates into it in place (TMA reduce-add epilogue): values and all gradients equal the separate add."""
-    g = torch.Generator().manual_seed(3)
-    N, Ci, Co, H = 4, 64, 128, 16
-    x = torch.randn(N, Ci, H, H, generator=g).cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
-    w = torch.randn(Co, Ci, 1, 1, generator=g).cuda().requires_grad_(True)
-    base = torch.randn(N, Co, H, H, generator=g).cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
-    wg, gain = 1 / np.sqrt(Ci), float(np.sqrt(0.5))
-    y1 = base * 1.0                                                                   # a non-leaf tensor to accumulate into
-    out = dconv.fused_conv_act(x, w, None, stride=1, padding=0, act='linear', gain=gain, weight_gain=wg, add_to=y1)
-    assert out.data_ptr() == y1.data_ptr()
-    dy = torch.randn(out.shape, generator=g).cuda()
-    got = torch.autograd.grad(out, [x, w, base], dy)
-    x64, w64, b64 = (t.detach().double().requires_grad_(True) for t in (x, w, base))
-    r = b64 + F.conv2d(x64, w64 * wg) * gain
-    ref = torch.autograd.grad(r, [x64, w64, b64], dy.double())
-    assert rel_err(out, r) < 1e-3
-    for a, e, n in zip(got, ref, ('dx', 'dw', 'dbase')):
-        assert rel_err(a, e) < 2e-3, (n, rel_err(a, e))
