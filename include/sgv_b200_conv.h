@@ -141,7 +141,8 @@ typedef struct sgv_wgrad_params {
 
 int sgv_conv2d_wgrad_tf32(const sgv_wgrad_params* p, void* stream);
 
-/* Variant query for the weight gradient (see sgv_conv2d_tf32_variant): kernel = 1 per-tap kernel, 2 grouped-tap kernel; nt = N tile
+/* Variant query for the weight gradient (see sgv_conv2d_tf32_variant): kernel = 1 per-tap kernel, 2 grouped-tap kernel, 3 stacked-M kernel for 64 output
+ * channels (wgrad_tf32_s64.cu); nt = N tile
  * (input channels per CTA), stages = pipeline depth, ksplit = split-K factor, passes = launches issued (3 in tf32x3 mode). */
 typedef struct sgv_wgrad_variant { int32_t kernel, nt, stages, ksplit, passes; } sgv_wgrad_variant;
 int sgv_conv2d_wgrad_tf32_variant(const sgv_wgrad_params* p, sgv_wgrad_variant* out);

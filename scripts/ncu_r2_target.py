@@ -1,6 +1,6 @@
 """Target for `ncu --set full` (round 2): the hot kernels at their BASELINE configs[1] shapes, in a FIXED order so that scripts/ncu_traffic.py
 can name each captured launch.  Each kernel is launched twice (the first warms caches / attributes); capture with
-  ncu --set full --clock-control none --import-source on -k regex:'conv_tf32_v3|wgrad_tf32_v2|fir_nhwc_tma44' -o gpurun_out/ncu_r2 python scripts/ncu_r2_target.py
+  ncu --set full --clock-control none --import-source on -k regex:'conv_tf32_v3|wgrad_tf32_v2|wgrad_tf32_s64|fir_nhwc_tma44' -o gpurun_out/ncu_r2 python scripts/ncu_r2_target.py
 Order of the captured names (second launch of each pair is the one summarised): see ORDER below."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

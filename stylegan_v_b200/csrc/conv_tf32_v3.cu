@@ -490,10 +490,12 @@ struct V3Tuning
     int max_bn;       // SGV_V3_MAXBN
     int wide_cin;     // SGV_V3_WIDE_CIN: smallest cin that takes the 256-column N tile
     int debug;        // SGV_V3_DEBUG: ablation switches (honoured by -DSGV_ABLATION builds only)
-    int pair;         // SGV_CONV_PAIR=0|1: issue the MMAs of a 2-CTA cluster as tcgen05 cta_group::2 (M = 256, B halved per CTA)
+    int pair;         // SGV_CONV_PAIR=0: clusters of 2 share slabs by TMA multicast instead of issuing tcgen05 cta_group::2 MMAs (M = 256, B halved per CTA)
     V3Tuning()
     {
-        pair = env_int("SGV_CONV_PAIR", 0) ? 1 : 0;
+        // default ON: measured on the B200 (profiles/conv_pair_probe_r2_*.jsonl) bit-identical results and 0.215 -> 0.212 / 0.197 -> 0.178 /
+        // 0.213 -> 0.191 / 0.297 -> 0.267 ms for the 512 / 256 / 128 / 64-channel conv1 layers of the 256^2 network at 32 frames
+        pair = env_int("SGV_CONV_PAIR", 1) ? 1 : 0;
         cluster = env_int("SGV_CONV_CLUSTER", 2);
         if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 2;
         mh4 = env_int("SGV_V3_MH4", 1) ? 1 : 0;

@@ -42,28 +42,41 @@ __global__ void __launch_bounds__(kDiscThreads) fromrgb_fwd_kernel(FromRgbArgs p
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
     const long long total = (long long)p.n * p.hw;
-    for (long long px = (long long)blockIdx.x * p.lanes + lane; px < total; px += (long long)gridDim.x * p.lanes)
+    const long long stride = (long long)gridDim.x * p.lanes;
+    // four pixels per trip: the image loads of all four are issued before any store (the kernel is a pure stream: 12 B in, 4 * c B out per pixel)
+    for (long long px0 = (long long)blockIdx.x * p.lanes + lane; px0 < total; px0 += 4 * stride)
     {
-        const int n = (int)(px / p.hw), q = (int)(px - (long long)n * p.hw);
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* ip = p.img + (long long)n * p.j * p.hw + q;
+        float x[4][4];
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (j < p.j)
-            {
-                const float x = __ldg(ip + (long long)j * p.hw);
-#pragma unroll
-                for (int e = 0; e < 4; e++) v[e] = fmaf(x, wr[e][j], v[e]);
-            }
-        float o[4] = {v[0] + b.x, v[1] + b.y, v[2] + b.z, v[3] + b.w};
-#pragma unroll
-        for (int e = 0; e < 4; e++)
+        for (int u = 0; u < 4; u++)
         {
-            float f = o[e];
-            if (p.act == 3) f = f > 0.f ? f : f * p.alpha;
-            o[e] = f * p.gain;
+            const long long px = px0 + u * stride;
+            const bool ok = px < total;
+            const int n = ok ? (int)(px / p.hw) : 0, q = ok ? (int)(px - (long long)n * p.hw) : 0;
+            const float* ip = p.img + (long long)n * p.j * p.hw + q;
+#pragma unroll
+            for (int j = 0; j < 4; j++) x[u][j] = (ok && j < p.j) ? __ldg(ip + (long long)j * p.hw) : 0.f;
         }
-        __stcs(reinterpret_cast<float4*>(p.y + px * p.c + c0), make_float4(o[0], o[1], o[2], o[3]));
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+        {
+            const long long px = px0 + u * stride;
+            if (px >= total) continue;
+            float o[4] = {b.x, b.y, b.z, b.w};
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) v[e] = fmaf(x[u][j], wr[e][j], v[e]);
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+            {
+                float f = v[e] + o[e];
+                if (p.act == 3) f = f > 0.f ? f : f * p.alpha;
+                o[e] = f * p.gain;
+            }
+            __stcs(reinterpret_cast<float4*>(p.y + px * p.c + c0), make_float4(o[0], o[1], o[2], o[3]));
+        }
     }
 }
 
@@ -82,40 +95,52 @@ __global__ void __launch_bounds__(kDiscThreads) fromrgb_bwd_kernel(FromRgbArgs p
     const long long total = (long long)p.n * p.hw;
     const long long stride = (long long)gridDim.x * p.lanes;
     const long long iters = (total + stride - 1) / stride;             // uniform trip count: the shuffles below need whole warps
-    for (long long it = 0; it < iters; it++)
+    for (long long it0 = 0; it0 < iters; it0 += 4)
     {
-        const long long px = (long long)blockIdx.x * p.lanes + lane + it * stride;
-        const bool ok = active && px < total;
-        float r[4] = {0.f, 0.f, 0.f, 0.f};
-        if (ok)
+        // four pixels per trip: all loads (4 x 128-bit gradient + 4 x j image scalars) are in flight before the arithmetic starts
+        float4 d[4]; float x[4][4]; bool ok[4]; long long pxs[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
         {
-            const int n = (int)(px / p.hw), q = (int)(px - (long long)n * p.hw);
-            const float4 d = __ldcs(reinterpret_cast<const float4*>(p.dz + px * p.c + c0));
-            const float dv[4] = {d.x, d.y, d.z, d.w};
+            pxs[u] = (long long)blockIdx.x * p.lanes + lane + (it0 + u) * stride;
+            ok[u] = active && (it0 + u) < iters && pxs[u] < total;
+            d[u] = ok[u] ? __ldcs(reinterpret_cast<const float4*>(p.dz + pxs[u] * p.c + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int n = ok[u] ? (int)(pxs[u] / p.hw) : 0, q = ok[u] ? (int)(pxs[u] - (long long)n * p.hw) : 0;
             const float* ip = p.img + (long long)n * p.j * p.hw + q;
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (j < p.j)
-                {
-                    const float x = __ldg(ip + (long long)j * p.hw);
+            for (int j = 0; j < 4; j++) x[u][j] = (ok[u] && j < p.j) ? __ldg(ip + (long long)j * p.hw) : 0.f;
+        }
+        float r[4][4];
 #pragma unroll
-                    for (int e = 0; e < 4; e++) { acc[e][j] = fmaf(dv[e], x, acc[e][j]); r[j] = fmaf(dv[e], wr[e][j], r[j]); }
-                }
+        for (int u = 0; u < 4; u++)
+        {
+            const float dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+            {
+                r[u][j] = 0.f;
+#pragma unroll
+                for (int e = 0; e < 4; e++) { acc[e][j] = fmaf(dv[e], x[u][j], acc[e][j]); r[u][j] = fmaf(dv[e], wr[e][j], r[u][j]); }
+            }
         }
         if (p.dimg)
         {
-            // reduce over the cvecs threads of the pixel (cvecs is a power of two <= 32: a pixel's threads sit in one warp)
+            // reduce over the cvecs threads of a pixel (cvecs is a power of two <= 32: a pixel's threads sit in one warp)
             for (int o = p.cvecs >> 1; o > 0; o >>= 1)
 #pragma unroll
-                for (int j = 0; j < 4; j++) r[j] += __shfl_down_sync(0xffffffffu, r[j], o, 32);
-            if (ok && cv == 0)
-            {
-                const int n = (int)(px / p.hw), q = (int)(px - (long long)n * p.hw);
-                float* op = p.dimg + (long long)n * p.j * p.hw + q;
+                for (int u = 0; u < 4; u++)
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (j < p.j) op[(long long)j * p.hw] = r[j];
-            }
+                    for (int j = 0; j < 4; j++) r[u][j] += __shfl_down_sync(0xffffffffu, r[u][j], o, 32);
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (ok[u] && cv == 0)
+                {
+                    const int n = (int)(pxs[u] / p.hw), q = (int)(pxs[u] - (long long)n * p.hw);
+                    float* op = p.dimg + (long long)n * p.j * p.hw + q;
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (j < p.j) op[(long long)j * p.hw] = r[u][j];
+                }
         }
     }
     // block reduction of the weight-gradient partials over the pixel lanes, then one atomic per (c, j)

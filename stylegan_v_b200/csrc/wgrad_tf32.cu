@@ -25,6 +25,7 @@ using namespace ptx;
 
 // g_lo / x_lo: stage the TF32 residual tf32(v - tf32(v)) of that operand instead of tf32(v) (one pass of the tf32x3 mode)
 int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, int g_lo, int x_lo, cudaStream_t stream, sgv_wgrad_variant* query);
+int conv2d_wgrad_tf32_s64(const sgv_wgrad_params* p, int g_lo, int x_lo, cudaStream_t stream, sgv_wgrad_variant* query);     // wgrad_tf32_s64.cu
 
 constexpr int kWgThreads = 192;
 constexpr int kWgM = 128;
@@ -296,6 +297,8 @@ static int wgrad_pass(const sgv_wgrad_params* p, int g_lo, int x_lo, cudaStream_
     static const bool force_v1 = env_int("SGV_WGRAD_V1", 0) != 0;
     if (!force_v1)
     {
+        rc = conv2d_wgrad_tf32_s64(p, g_lo, x_lo, stream, query);        // 64 output channels, full 3x3: stacked-M kernel
+        if (rc != SGV_ERR_UNSUPPORTED) return rc;
         rc = conv2d_wgrad_tf32_v2(p, g_lo, x_lo, stream, query);
         if (rc != SGV_ERR_UNSUPPORTED) return rc;
     }

@@ -101,7 +101,8 @@ def test_stride2_input(N, Cin, Cout, h):
     assert rel_err(y, ref) < 2e-5
 
 
-@pytest.mark.parametrize('N,Cin,Cout,H', [(2, 64, 128, 16), (3, 32, 64, 12), (8, 64, 64, 4), (2, 256, 128, 8), (1, 128, 32, 20)])
+@pytest.mark.parametrize('N,Cin,Cout,H', [(2, 64, 128, 16), (3, 32, 64, 12), (8, 64, 64, 4), (2, 256, 128, 8), (1, 128, 32, 20),
+                                        (3, 64, 64, 20), (2, 128, 64, 33), (1, 64, 64, 9), (2, 64, 64, 64)])      # last four: the stacked-M kernel (64 output channels)
 def test_wgrad_stride1(N, Cin, Cout, H):
     g_ = torch.Generator().manual_seed(N + Cin)
     x = torch.randn(N, Cin, H, H, generator=g_).cuda()
@@ -109,6 +110,8 @@ def test_wgrad_stride1(N, Cin, Cout, H):
     s = (torch.rand(N, Cin, generator=g_) + 0.5).cuda()
     d = (torch.rand(N, Cout, generator=g_) + 0.5).cuda()
     taps = C.TAPS_3x3
+    q = C.igemm_wgrad(_cl(gy), _cl(x), [(0, 0)] * 9, [(ky - 1, kx - 1) for ky, kx in taps], (H, H), g_scale=d, x_scale=s, x3=False, query=True)
+    assert q['kernel'] == (3 if (Cout == 64 and Cin % 64 == 0 and H >= 8) else 2 if H >= 8 else 1), q
     dw = C.igemm_wgrad(_cl(gy), _cl(x), [(0, 0)] * 9, [(ky - 1, kx - 1) for ky, kx in taps], (H, H), g_scale=d, x_scale=s)
     xs = tf32_round(x * s[:, :, None, None]).double().requires_grad_(False)
     gs = tf32_round(gy * d[:, :, None, None]).double()

