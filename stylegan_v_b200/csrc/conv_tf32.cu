@@ -16,6 +16,11 @@
 //   warp 1     allocates TMEM, issues tcgen05.mma.kind::tf32 (one elected thread, 4 x K=8 per k-step) with the
 //              accumulator in TMEM, releases stages with tcgen05.commit -> empty[stage].
 //
+// Split-K (small planes: the 4x4 ... 16x16 layers have only 4-64 pixel tiles but K = 9 * 512 ... 9 * 1024): the launch is a thread-block
+// cluster of KS CTAs per output tile along gridDim.z; CTA r walks k-steps [r*S/KS, (r+1)*S/KS) into its own TMEM accumulator, the
+// non-leader CTAs park their partial tile in their (now idle) pipeline stages, and after a cluster barrier the leader adds them through
+// distributed shared memory (ld.shared::cluster) before its epilogue — no workspace, no second launch, no atomics (deterministic order).
+//
 // Replaces cuDNN for the reference's conv2d_gradfix.conv2d / conv_transpose2d on the hot-path shapes
 // (conv2d_gradfix.py:35-43) plus the x*styles, *dcoefs and bias_act passes around it (networks.py:64-74,141-143).
 #include "common.cuh"
@@ -87,7 +92,12 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int ox0 = tile_x * p.tw, oy0 = tile_y * p.th;
     const int nb0 = blockIdx.y * BN;                 // first output channel of this CTA
     const int kchunks = p.cin / kBK;
-    const int ksteps = kchunks * p.ntaps * p.parts;
+    const int tp_per_chunk = p.ntaps * p.parts;
+    const int ksteps_total = kchunks * tp_per_chunk;
+    // split-K over the CTAs of the cluster (gridDim.z = cluster size; 1 = no split)
+    const int ks_n = (int)gridDim.z, ks_r = (int)blockIdx.z;
+    const int k_begin = (int)(((long long)ksteps_total * ks_r) / ks_n), k_end = (int)(((long long)ksteps_total * (ks_r + 1)) / ks_n);
+    const int ksteps = k_end - k_begin;
 
     if (threadIdx.x == 0)
     {
@@ -113,10 +123,10 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if (elect_one())
         {
             int stage = 0; uint32_t phase = 0;
-            for (int kc = 0; kc < kchunks; kc++)
-                for (int t = 0; t < p.ntaps; t++)
-                    for (int part = 0; part < p.parts; part++)
+            for (int ks = k_begin; ks < k_end; ks++)
                     {
+                        const int kc = ks / tp_per_chunk, tp = ks - kc * tp_per_chunk;
+                        const int t = tp / p.parts, part = tp - t * p.parts;
                         mbar_wait(empty_bar + stage, phase ^ 1);
                         uint8_t* sa = smem + stage * L::kStageBytes;
                         uint8_t* sb = sa + kATileBytes;
@@ -168,21 +178,20 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         {
             int stage = 0; uint32_t phase = 0;
             float sv[kBK];
-            for (int kc = 0; kc < kchunks; kc++)
+#pragma unroll
+            for (int j = 0; j < kBK; j++) sv[j] = 1.f;
+            int cur_kc = -1;
             {
-                if (p.a_scale)
+                for (int ks = k_begin; ks < k_end; ks++)
                 {
-                    const float4* sp = reinterpret_cast<const float4*>(p.a_scale + (long long)nc * p.cin + kc * kBK);
+                    const int kc = ks / tp_per_chunk, tp = ks - kc * tp_per_chunk;
+                    if (kc != cur_kc && p.a_scale)
+                    {
+                        const float4* sp = reinterpret_cast<const float4*>(p.a_scale + (long long)nc * p.cin + kc * kBK);
 #pragma unroll
-                    for (int j = 0; j < kBK / 4; j++) { float4 v = __ldg(sp + j); sv[4 * j] = v.x; sv[4 * j + 1] = v.y; sv[4 * j + 2] = v.z; sv[4 * j + 3] = v.w; }
-                }
-                else
-                {
-#pragma unroll
-                    for (int j = 0; j < kBK; j++) sv[j] = 1.f;
-                }
-                for (int tp = 0; tp < p.ntaps * p.parts; tp++)
-                {
+                        for (int j = 0; j < kBK / 4; j++) { float4 v = __ldg(sp + j); sv[4 * j] = v.x; sv[4 * j + 1] = v.y; sv[4 * j + 2] = v.z; sv[4 * j + 3] = v.w; }
+                    }
+                    cur_kc = kc;
                     const bool lo_part = (p.parts == 3) && (tp % 3 == 1);
                     mbar_wait(full_bar + stage, phase);
                     const uint32_t arow = smem_u32(smem + stage * L::kStageBytes) + (uint32_t)row * 128u;
@@ -217,9 +226,40 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
         }
 
-        // ---- epilogue ----
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
+        // ---- split-K: non-leader CTAs park their partial tile [128 rows][BN] in their idle pipeline stages ----
+        if (ksteps > 0) { mbar_wait(accum_bar, 0); tc_fence_after(); }
+        if (ks_n > 1 && ks_r != 0)
+        {
+#pragma unroll 1
+            for (int cc = 0; cc < BN / 32; cc++)
+            {
+                uint32_t v[32];
+                if (ksteps > 0) { tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v); tmem_ld_wait(); }
+                else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = 0u;
+                }
+                const uint32_t dst = smem_u32(smem) + (uint32_t)row * (uint32_t)(BN * 4) + (uint32_t)(cc * 128);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    sts128(dst + (uint32_t)(((j + row) & 7) << 4), make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+            }
+        }
+    }
+    if (ks_n > 1) { tc_fence_before(); cluster_sync_all(); tc_fence_after(); }      // partial tiles are visible cluster-wide
+    if (warp >= 2 && ks_r == 0)
+    {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int box_hw = p.th * p.tw;
+        const int tn_i = row / box_hw;
+        const int rem = row - tn_i * box_hw;
+        const int ty = rem / p.tw, tx = rem - ty * p.tw;
+        const int n = n0 + tn_i;
+        const int oy = oy0 + ty, ox = ox0 + tx;
+        const bool valid = (n < p.n) && (oy < p.out_h) && (ox < p.out_w);
+        const int nc = n < p.n ? n : p.n - 1;
+        // ---- epilogue (leader CTA of the split-K cluster) ----
         float* yrow = p.y + (long long)nc * p.osn + (long long)oy * p.osy + (long long)ox * p.osx + nb0;
         const float* osc = p.o_scale ? p.o_scale + (long long)nc * p.cout + nb0 : nullptr;
         const float* bia = p.bias ? p.bias + nb0 : nullptr;
@@ -230,6 +270,18 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
             tmem_ld_wait();
+            for (int r = 1; r < ks_n; r++)
+            {
+                // partial tile of CTA r of the cluster (same layout, same rotation of the 16-byte chunks as it was written with)
+                const uint32_t src = mapa_cluster(smem_u32(smem) + (uint32_t)row * (uint32_t)(BN * 4) + (uint32_t)(cc * 128), (uint32_t)r);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                {
+                    const float4 t4 = ld_dsmem128(src + (uint32_t)(((j + row) & 7) << 4));
+                    v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + t4.x); v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + t4.y);
+                    v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + t4.z); v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + t4.w);
+                }
+            }
             if (p.red_out)
             {
                 // fused style-gradient reduction (see conv_tf32_v3.cu); a warp's 32 rows may straddle samples when the box spills
@@ -283,7 +335,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (ks_n > 1) cluster_sync_all(); else __syncthreads();      // no CTA leaves while the leader may still read its shared memory
     if (warp == 1) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
 }
 
@@ -386,7 +438,19 @@ static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvA
     using L = ConvSmem<BN, STAGES>;
     auto kern = conv_tf32_kernel<BN, STAGES>;
     SGV_OPT_IN_SMEM(kern, L::kTotal);
-    kern<<<grid, kConvThreads, L::kTotal, stream>>>(tx, tw, a);
+    if (grid.z > 1)
+    {
+        // split-K: the gridDim.z CTAs of an output tile form a thread-block cluster (partial tiles are reduced through distributed shared memory)
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = grid.z;
+        cfg.gridDim = grid; cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = stream;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        SGV_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tx, tw, a));
+    }
+    else
+        kern<<<grid, kConvThreads, L::kTotal, stream>>>(tx, tw, a);
     SGV_LAUNCH_OK("conv_tf32_kernel");
     return SGV_OK;
 }
@@ -536,9 +600,18 @@ static int conv2d_tf32_dispatch(const sgv_conv_params* p, cudaStream_t stream, s
     int bn = (p->cout % 256 == 0) ? 256 : (p->cout % 128 == 0) ? 128 : (p->cout % 64 == 0) ? 64 : p->cout;
     while (bn > 64 && p->cout % (bn / 2) == 0 && mtiles_total * (p->cout / bn) < num_sms()) bn /= 2;
 
+    // split-K over a cluster of 2 / 4 / 8 CTAs when the output tiles alone leave most SMs idle (the 4x4 ... 16x16 planes: 4-64 tiles, K up to
+    // 9 * 1024): every CTA keeps >= 16 k-steps, and the partial tile must fit the pipeline stages it is parked in
+    static const int split_k = env_int("SGV_CONV_SPLITK", 1);
+    int ks = 1;
+    {
+        const int ctas = mtiles_total * (p->cout / bn);
+        const int ksteps_total = (p->cin / kBK) * p->ntaps * a.parts;
+        while (split_k && ks < 8 && ctas * ks * 2 <= num_sms() && ksteps_total / (ks * 2) >= 16) ks *= 2;
+    }
     if (query)
     {
-        query->kernel = 1; query->bn = bn; query->mh = 1; query->cluster = 1; query->cta_pair = 0; query->x3 = x3 ? 1 : 0;
+        query->kernel = 1; query->bn = bn; query->mh = 1; query->cluster = ks; query->cta_pair = 0; query->x3 = x3 ? 1 : 0;
         return SGV_OK;
     }
     CUtensorMap tmx, tmw;
@@ -561,7 +634,7 @@ static int conv2d_tf32_dispatch(const sgv_conv_params* p, cudaStream_t stream, s
         rc = make_tmap_f32(&tmw, p->wp, 2, dims, strides, box, es);
         if (rc != SGV_OK) return rc;
     }
-    dim3 grid((unsigned)(a.tiles_x * a.tiles_y * a.tiles_nb), (unsigned)(p->cout / bn), 1);
+    dim3 grid((unsigned)(a.tiles_x * a.tiles_y * a.tiles_nb), (unsigned)(p->cout / bn), (unsigned)ks);
     switch (bn)
     {
         case 256: return launch_conv<256, 4>(tmx, tmw, a, grid, stream);

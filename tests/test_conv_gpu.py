@@ -68,6 +68,36 @@ def test_conv1x1_and_modulated_epilogue():
     assert rel_err(y1, ref1) < 2e-5
 
 
+@pytest.mark.parametrize('N,Cin,Cout,H', [(32, 1024, 512, 4), (32, 512, 512, 8), (4, 512, 128, 8), (2, 256, 64, 6)])
+def test_small_planes_split_k_cluster(N, Cin, Cout, H):
+    """The 4x4 ... 16x16 layers (b4.conv1: 1024 -> 512 on 4x4 planes) have few output tiles and a long contraction: the per-tap kernel
+    splits K over a thread-block cluster and reduces the partial tiles through distributed shared memory.  Same results as the
+    one-CTA form (checked against fp64 on the same rounded operands), epilogue and fused d(styles) reduction included."""
+    g = torch.Generator().manual_seed(H * 7 + N)
+    x = torch.randn(N, Cin, H, H, generator=g).cuda()
+    w = torch.randn(Cout, Cin, 3, 3, generator=g).cuda()
+    s = (torch.randn(N, Cin, generator=g) + 1).cuda()
+    d = (torch.rand(N, Cout, generator=g) + 0.5).cuda() / np.sqrt(Cin * 9)
+    b = torch.randn(Cout, generator=g).cuda()
+    taps, offs = C.conv3x3_taps()
+    wp = C.prep_weights(w, taps, x3=False)
+    kw = dict(a_scale=s, o_scale=d, bias=b, act='lrelu', gain=float(np.sqrt(2)))
+    v = C.igemm_conv(_cl(x), wp, offs, query=True, **kw)
+    assert v['kernel'] == 1 and v['cluster'] >= 2, v
+    y = C.igemm_conv(_cl(x), wp, offs, **kw)
+    xs = tf32_round(x * s[:, :, None, None])
+    ref = F.conv2d(xs.double(), tf32_round(w).double(), padding=1) * d.double()[:, :, None, None] + b.double()[None, :, None, None]
+    ref = F.leaky_relu(ref, 0.2) * np.sqrt(2)
+    assert rel_err(y, ref) < 2e-5
+    # data-gradient form: raw accumulator times o_scale, with the fused reduction against a tensor shaped like the output
+    rx = _cl(torch.randn(N, Cout, H, H, generator=g).cuda())
+    red = torch.zeros(N, Cout, device='cuda')
+    y2 = C.igemm_conv(_cl(x), wp, offs, o_scale=d, red_x=rx, red_out=red)
+    raw = F.conv2d(tf32_round(x).double(), tf32_round(w).double(), padding=1)
+    assert rel_err(y2, raw * d.double()[:, :, None, None]) < 2e-5
+    assert rel_err(red, (raw * rx.double()).sum(dim=[2, 3])) < 1e-4
+
+
 def test_transposed_conv_as_four_phases():
     """conv_transpose2d(stride 2, pad 0) written as 4 polyphase stride-1 launches into one [2h+1, 2w+1] tensor."""
     g = torch.Generator().manual_seed(3)
