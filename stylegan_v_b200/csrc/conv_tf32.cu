@@ -594,21 +594,25 @@ static int conv2d_tf32_dispatch(const sgv_conv_params* p, cudaStream_t stream, s
     a.tw = tw; a.th = th; a.tn = tn;
     a.tiles_x = ceil_div(p->out_w, tw); a.tiles_y = ceil_div(p->out_h, th); a.tiles_nb = ceil_div(p->n, tn);
 
-    // widest N tile that still gives the grid about one CTA per SM: the 4x4 / 8x8 layers have only 4-16 pixel tiles, and a
-    // 256-wide tile would leave them on 8-32 CTAs walking K = 9216 serially (b4.conv1: 198 us on 8 CTAs)
-    const int mtiles_total = a.tiles_x * a.tiles_y * a.tiles_nb;
-    int bn = (p->cout % 256 == 0) ? 256 : (p->cout % 128 == 0) ? 128 : (p->cout % 64 == 0) ? 64 : p->cout;
-    while (bn > 64 && p->cout % (bn / 2) == 0 && mtiles_total * (p->cout / bn) < num_sms()) bn /= 2;
-
-    // split-K over a cluster of 2 / 4 / 8 CTAs when the output tiles alone leave most SMs idle (the 4x4 ... 16x16 planes: 4-64 tiles, K up to
-    // 9 * 1024): every CTA keeps >= 16 k-steps, and the partial tile must fit the pipeline stages it is parked in
+    // N tile and split-K factor.  A k-step of this kernel costs about the same whatever the N tile (its pace is set by the staging pass over
+    // the 128-row A tile: measured ~950 clk per k-step at N = 64), so the WIDEST tile that divides cout does the most work per step, and the
+    // SMs that the few pixel tiles of the 4x4 ... 8x8 planes leave idle are filled by splitting K over a thread-block cluster of 2 / 4 / 8
+    // CTAs (>= 16 k-steps each; partial tiles are reduced through distributed shared memory, see the kernel).  Only when even 8-way split-K
+    // leaves more than half of the SMs idle is the tile narrowed.  Measured (profiles/bench_conv_small_r2.jsonl): b4.conv1 0.127 -> 0.048 ms.
     static const int split_k = env_int("SGV_CONV_SPLITK", 1);
+    const int mtiles_total = a.tiles_x * a.tiles_y * a.tiles_nb;
+    const int ksteps_all = (p->cin / kBK) * p->ntaps * a.parts;
+    int bn = (p->cout % 256 == 0) ? 256 : (p->cout % 128 == 0) ? 128 : (p->cout % 64 == 0) ? 64 : p->cout;
     int ks = 1;
+    for (;;)
     {
         const int ctas = mtiles_total * (p->cout / bn);
-        const int ksteps_total = (p->cin / kBK) * p->ntaps * a.parts;
-        while (split_k && ks < 8 && ctas * ks * 2 <= num_sms() && ksteps_total / (ks * 2) >= 16) ks *= 2;
+        ks = 1;
+        while (split_k && ks < 8 && ctas * ks * 2 <= num_sms() && ksteps_all / (ks * 2) >= 16) ks *= 2;
+        if (ctas * ks * 2 > num_sms() || bn <= 64 || p->cout % (bn / 2) != 0) break;
+        bn /= 2;
     }
+
     if (query)
     {
         query->kernel = 1; query->bn = bn; query->mh = 1; query->cluster = ks; query->cta_pair = 0; query->x3 = x3 ? 1 : 0;

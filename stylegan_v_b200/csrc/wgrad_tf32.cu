@@ -377,21 +377,28 @@ struct Wg2Args
     int debug;      // ablation switches, only honoured by -DSGV_ABLATION builds (profiles/wgrad_ablation_r1.txt): 1 skip transform, 2 skip epilogue, 4 skip MMAs
 };
 
-template <int NT, int STAGES>
+template <int NT, int STAGES, bool PAIR = false>
 struct Wg2Smem
 {
     static constexpr int kXBlock = 10 * 4 * 128;                  // one 32-channel block of the (8+2) x 4 patch (5120 B, multiple of the 512 B swizzle atom)
-    static constexpr int kXTile = ((NT / 32) * kXBlock + 1023) & ~1023;
+    static constexpr int kNLocal = PAIR ? NT / 2 : NT;            // CTA pair: each CTA holds (stages, reads) half of the N tile's channel blocks
+    static constexpr int kXTile = ((kNLocal / 32) * kXBlock + 1023) & ~1023;
     static constexpr int kStage = kW2GTile + kXTile;
     static constexpr int kBarOffset = STAGES * kStage;
     static constexpr int kTotal = kBarOffset + (3 * STAGES + 1) * 8 + 16 + 1024;
 };
 
-template <int NT, int STAGES>
+// PAIR: the CTAs (2i, 2i+1) of a 2-CTA cluster own the output-channel tiles (mt, mt + 1) of the SAME input-channel tile and tap group and
+// issue ONE tcgen05.mma.cta_group::2 of M = 256 per k-row: each CTA supplies its own gradient tile (A) and HALF of the input patch's channel
+// blocks (B) — half the patch TMA, half the staging work and half the B-operand reads per CTA (the shared-memory port is this kernel's
+// limiter: DESIGN.md §4).  Leader-issued MMAs, remote barrier arrivals and multicast commits as in conv_tf32_v3.cu.
+template <int NT, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(kWg2Threads, 1)
 wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x, const Wg2Args p)
 {
-    using L = Wg2Smem<NT, STAGES>;
+    using L = Wg2Smem<NT, STAGES, PAIR>;
+    constexpr int NL = L::kNLocal;
+    const int crank = PAIR ? (int)cluster_ctarank() : 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
@@ -410,20 +417,24 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
     const int kt1 = min(kt0 + per, p.ktiles);
     const int ksteps = kt1 - kt0;
     const int xblock = p.pw * 4 * 128;                         // bytes of one 32-channel block of the patch
-    const uint32_t x_bytes = (uint32_t)(xblock * (NT / 32));
+    const uint32_t x_bytes = (uint32_t)(xblock * (NL / 32));
 
     if (threadIdx.x == 0)
     {
         prefetch_tmap(&tmap_g);
         prefetch_tmap(&tmap_x);
-        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 1); mbar_init(ready_bar + s, 8); mbar_init(empty_bar + s, 1); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(full_bar + s, 1); mbar_init(ready_bar + s, PAIR ? 16 : 8); mbar_init(empty_bar + s, 1); }
         mbar_init(accum_bar, 1);
         fence_mbar_init();
     }
     constexpr int kCols = (kW2MaxGroupTaps * NT) <= 256 ? 256 : 512;
-    if (warp == 1) { tmem_alloc(tmem_slot, kCols); tmem_relinquish(); }
+    if (warp == 1)
+    {
+        if (PAIR) { tmem_alloc_pair(tmem_slot, kCols); tmem_relinquish_pair(); }
+        else { tmem_alloc(tmem_slot, kCols); tmem_relinquish(); }
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -444,15 +455,15 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
                     uint8_t* sg = smem + stage * L::kStage;
                     mbar_expect_tx(full_bar + stage, kW2GTile + x_bytes);
                     tma_load_5d(sg, &tmap_g, full_bar + stage, 0, px0, py0, n, m0 / 32);
-                    tma_load_5d(sg + kW2GTile, &tmap_x, full_bar + stage, 0, px0 + p.dx_min, py0 + p.grp_dy[grp], n, c0 / 32);
+                    tma_load_5d(sg + kW2GTile, &tmap_x, full_bar + stage, 0, px0 + p.dx_min, py0 + p.grp_dy[grp], n, c0 / 32 + crank * (NL / 32));
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
         else if (warp == 1)
         {
-            constexpr uint32_t idesc = umma_idesc_tf32(kWgM, NT, 1, 1);
-            if (elect_one())      // one thread runs the whole issue loop (no per-step election / reconvergence)
+            constexpr uint32_t idesc = umma_idesc_tf32(PAIR ? 2 * kWgM : kWgM, NT, 1, 1);
+            if (elect_one() && crank == 0)      // one thread (of the leader CTA) runs the whole issue loop (no per-step election / reconvergence)
             {
                 int stage = 0; uint32_t phase = 0;
                 for (int ks = 0; ks < ksteps; ks++)
@@ -469,11 +480,12 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
                             if (SGV_ABL(p.debug, 4)) continue;
                             const uint64_t da = umma_desc_mn_sw128_32b(sg + k * 1024, 32 * 128, 512);
                             const uint64_t db = umma_desc_mn_sw128_32b(sx + (uint32_t)(p.grp_col[grp][t] + k * p.pw) * 128u, (uint32_t)xblock, 512);
-                            mma_tf32(tmem_base + (uint32_t)(t * NT), da, db, idesc, (ks > 0 || k > 0) ? 1u : 0u);
+                            if (PAIR) mma_tf32_pair(tmem_base + (uint32_t)(t * NT), da, db, idesc, (ks > 0 || k > 0) ? 1u : 0u);
+                            else mma_tf32(tmem_base + (uint32_t)(t * NT), da, db, idesc, (ks > 0 || k > 0) ? 1u : 0u);
                         }
                     }
-                    mma_commit(empty_bar + stage);
-                    if (ks == ksteps - 1) mma_commit(accum_bar);
+                    if (PAIR) mma_commit_pair_mc(empty_bar + stage, 3); else mma_commit(empty_bar + stage);
+                    if (ks == ksteps - 1) { if (PAIR) mma_commit_pair_mc(accum_bar, 3); else mma_commit(accum_bar); }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -486,7 +498,7 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
             // are reloaded only when the sample index changes.
             const int tid = threadIdx.x - 64;                   // 0..255
             const int xrows_blk = p.pw * 4;
-            const int total_rows = 128 + xrows_blk * (NT / 32);
+            const int total_rows = 128 + xrows_blk * (NL / 32);
             float sv[2][32];
             int cur_n = -1;
             const FastDiv div_plane((uint32_t)(p.tiles_x * p.tiles_y));
@@ -501,7 +513,7 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
                 if (act[s])
                 {
                     if (rr[s] < 128) { const int ch = m0 + (rr[s] >> 5) * 32; act[s] = ch < p.cout && !p.g_ready; if (p.g_scale) { sbase[s] = p.g_scale + ch; sstride[s] = p.cout; } }
-                    else { const int ch = c0 + ((rr[s] - 128) / xrows_blk) * 32; act[s] = ch < p.cin && !p.x_ready; if (p.x_scale) { sbase[s] = p.x_scale + ch; sstride[s] = p.cin; } }
+                    else { const int ch = c0 + crank * NL + ((rr[s] - 128) / xrows_blk) * 32; act[s] = ch < p.cin && !p.x_ready; if (p.x_scale) { sbase[s] = p.x_scale + ch; sstride[s] = p.cin; } }
                 }
 #pragma unroll
                 for (int j = 0; j < 32; j++) sv[s][j] = 1.f;
@@ -557,7 +569,7 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(ready_bar + stage);
+                    if (lane == 0) { if (PAIR) mbar_arrive_leader(ready_bar + stage); else mbar_arrive(ready_bar + stage); }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -589,17 +601,28 @@ wgrad_tf32_v2_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_co
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, kCols);
+    if (PAIR) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem_base, kCols); else tmem_dealloc(tmem_base, kCols); }
 }
 
-template <int NT, int STAGES>
+template <int NT, int STAGES, bool PAIR = false>
 static int launch_wgrad_v2(const CUtensorMap& tg, const CUtensorMap& tx, const Wg2Args& a, dim3 grid, cudaStream_t stream)
 {
-    using L = Wg2Smem<NT, STAGES>;
-    auto kern = wgrad_tf32_v2_kernel<NT, STAGES>;
+    using L = Wg2Smem<NT, STAGES, PAIR>;
+    auto kern = wgrad_tf32_v2_kernel<NT, STAGES, PAIR>;
     SGV_OPT_IN_SMEM(kern, L::kTotal);
-    kern<<<grid, kWg2Threads, L::kTotal, stream>>>(tg, tx, a);
+    if (PAIR)
+    {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.gridDim = grid; cfg.blockDim = dim3(kWg2Threads); cfg.dynamicSmemBytes = L::kTotal; cfg.stream = stream;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        SGV_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tg, tx, a));
+    }
+    else
+        kern<<<grid, kWg2Threads, L::kTotal, stream>>>(tg, tx, a);
     SGV_LAUNCH_OK("wgrad_tf32_v2_kernel");
     return SGV_OK;
 }
@@ -649,9 +672,13 @@ int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, int g_lo, int x_lo, cudaStre
     a.g_ready = p->g_ready && !p->g_scale && !p->precision; a.x_ready = p->x_ready && !p->x_scale && !p->precision;
     a.g_lo = g_lo; a.x_lo = x_lo;
 
+    // CTA pairs (tcgen05 cta_group::2): two output-channel tiles of the same (input-channel tile, tap group, K split) — needs an even number of
+    // M tiles (adjacent blockIdx.x = adjacent M tiles form the cluster) and the 128-column N tile; SGV_WGRAD_PAIR=0 disables
+    static const int pair_ok = env_int("SGV_WGRAD_PAIR", 1);
+    const bool pair = pair_ok && nt == 128 && a.mtiles % 2 == 0 && p->cout % 256 == 0;
     if (query)
     {
-        query->kernel = 2; query->nt = nt; query->stages = nt == 128 ? 5 : nt == 64 ? 7 : 8; query->ksplit = a.ksplit; query->passes = 1;
+        query->kernel = 2; query->nt = nt; query->stages = nt == 128 ? (pair ? 6 : 5) : nt == 64 ? 7 : 8; query->ksplit = a.ksplit; query->passes = 1;
         return SGV_OK;
     }
     CUtensorMap tg, tx;
@@ -662,7 +689,7 @@ int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, int g_lo, int x_lo, cudaStre
         const bool view = p->x_stride_x != 0;
         const uint64_t strides[4] = {(uint64_t)(view ? p->x_stride_x : p->cin) * 4, (uint64_t)(view ? p->x_stride_y : (int64_t)p->xw * p->cin) * 4,
                                      (uint64_t)(view ? p->x_stride_n : (int64_t)p->xh * p->xw * p->cin) * 4, 128};
-        const uint32_t box[5] = {32, (uint32_t)a.pw, 4, 1, (uint32_t)(nt / 32)};
+        const uint32_t box[5] = {32, (uint32_t)a.pw, 4, 1, (uint32_t)((pair ? nt / 2 : nt) / 32)};
         const uint32_t es[5] = {1, 1, 1, 1, 1};
         rc = make_tmap_f32(&tx, p->x, 5, dims, strides, box, es, /*atom32=*/true);
         if (rc != SGV_OK) return rc;
@@ -670,7 +697,7 @@ int conv2d_wgrad_tf32_v2(const sgv_wgrad_params* p, int g_lo, int x_lo, cudaStre
     dim3 grid((unsigned)(a.mtiles * (p->cin / nt)), (unsigned)ksplit, (unsigned)a.ngroups);
     switch (nt)
     {
-        case 128: return launch_wgrad_v2<128, 5>(tg, tx, a, grid, stream);
+        case 128: return pair ? launch_wgrad_v2<128, 6, true>(tg, tx, a, grid, stream) : launch_wgrad_v2<128, 5>(tg, tx, a, grid, stream);
         case 64:  return launch_wgrad_v2<64, 7>(tg, tx, a, grid, stream);
         default:  return launch_wgrad_v2<32, 8>(tg, tx, a, grid, stream);
     }

@@ -79,8 +79,11 @@ def conv_forward(x, w, b, transpose, stride, padding, output_padding, dilation, 
     if s == 2 and k == 3 and p == 0:
         op = tuple(output_padding)
         oh, ow = 2 * H + 1 + op[0], 2 * W + 1 + op[1]
-        alloc = torch.zeros if op != (0, 0) else torch.empty
-        u = alloc([N, O, oh, ow], dtype=torch.float32, device=x.device).contiguous(memory_format=torch.channels_last)
+        # allocated channels_last directly (an NCHW allocation + .contiguous(channels_last) is a full-size copy of an uninitialised tensor:
+        # 0.8 GB per call for the 256^2 discriminator layers — found in the round-2 G+D timeline)
+        u = torch.empty([N, O, oh, ow], dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+        if op != (0, 0):
+            u.zero_()           # the polyphase launches below do not cover the output-padding row / column
         xn = _nhwc(x)
         for a in (0, 1):
             for c in (0, 1):

@@ -106,7 +106,8 @@ def test_weight_gradient_variants_of_the_benchmark(shape, nt):
     offs = [(ky - 1, kx - 1) for ky, kx in C.TAPS_3x3]
     v = C.igemm_wgrad(_cl(gy), _cl(x), [(0, 0)] * 9, offs, (H, H), x_scale=s, g_ready=True, x3=False, query=True)
     # 64 output channels: the stacked-M kernel (wgrad_tf32_s64.cu, kernel 3); otherwise the grouped-tap kernel (kernel 2)
-    assert (v['kernel'], v['nt'], v['stages']) == ((3, 64, 5) if Cout == 64 else (2, nt, 5)), v
+    # ... with CTA pairs (tcgen05 cta_group::2, 6 stages) when there are two output-channel tiles to pair
+    assert (v['kernel'], v['nt'], v['stages']) == ((3, 64, 5) if Cout == 64 else (2, nt, 6 if Cout % 256 == 0 else 5)), v
     dw = C.igemm_wgrad(_cl(gy), _cl(x), [(0, 0)] * 9, offs, (H, H), x_scale=s, g_ready=True, x3=False)
     got = dw.reshape(3, 3, Cout, Cin).permute(2, 3, 0, 1)
     w = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float64, device='cuda', requires_grad=True)
