@@ -99,6 +99,51 @@ int sgv_mbstd_fwd(const float* x, int64_t x_stride_n, int64_t x_stride_c, int64_
 int sgv_mbstd_bwd(const float* dy, const float* x, int64_t x_stride_n, int64_t x_stride_c, int64_t x_stride_p, float* dx,
                   int32_t n, int32_t c, int32_t hw, int32_t cpad, int32_t group, int32_t num_channels, void* stream);
 
+/* ---- exact-fp32 dense layers (csrc/dense_f32.cu) --------------------------------------------------------------------------------
+ * Replace torch.addmm / matmul (+ bias_act) of FullyConnectedLayer / EqualizedLinear (src/training/layers.py:108-138: style affines,
+ * mapping networks, discriminator dense layers, time-encoder heads) and F.conv1d of EqualizedConv1d (layers.py:331-373; as a GEMM over
+ * windows).  Plain fp32 FMAs with round-to-nearest accumulation (CUDA cores): these GEMMs have M = batch rows and feed sin / cos.
+ *
+ *   fwd     y[m, n]   = act(w_gain * sum_k A[m, k] * w[n, k] + b_gain * bias[n]) * gain            act: 1 linear, 3 lrelu(alpha)
+ *   dgrad   dA[m, k] += w_gain * sum_n dz[m, n] * w[n, k]        (atomic adds: the caller zero-fills dA or passes a running gradient)
+ *   wgrad   dW[n, k]  = w_gain * sum_m dz[m, n] * A[m, k];   db[n] = b_gain * sum_m dz[m, n]      (accumulate != 0: added to dW / db)
+ *           with dz[m, n] = dy[m, n] * gain * (act == lrelu && y[m, n] <= 0 ? alpha : 1)   — the gradients read dy and the saved y.
+ *
+ * Addressing of A: row m starts at  a + (a_row_off ? a_row_off[m] : m * lda) + group offset.  a_row_off (device array, elements) makes rows
+ * overlapping WINDOWS: the valid conv1d of z [B, L, C] with kt taps is this GEMM with row (b, q) -> offset (b * L + q) * C, k = kt * C
+ * and the weight re-ordered to [n, kt * C].  Column groups (device arrays group_col [groups + 1], ascending multiples of 8, and group_off
+ * [groups], elements): columns [group_col[g], group_col[g+1]) read A (fwd, wgrad) / write dA (dgrad) displaced by group_off[g] — one
+ * launch for all style affines of the synthesis network, group g = the layers fed by ws[:, g, :] (networks.py:350-357).
+ * Every row / group offset, lda, ldda and k are multiples of 4 elements and a, w, dA, dW 16-byte aligned (16-byte vector loads).
+ */
+typedef struct sgv_dense_params {
+    const float*   a;                /* A operand (fwd, wgrad) */
+    const int64_t* a_row_off;        /* NULL, or [m] element offsets of the rows (device memory) */
+    int64_t        lda;
+    const float*   w;                /* [n, k] row-major */
+    const float*   bias;             /* [n] or NULL */
+    float*         y;                /* [m, n] with row stride ldy: output of fwd, saved output for the gradients (lrelu) */
+    int64_t        ldy;
+    int32_t        m, n, k;
+    float          w_gain, b_gain;
+    int32_t        act;
+    float          alpha, gain;
+    int32_t        groups;           /* 0 = none */
+    const int32_t* group_col;
+    const int64_t* group_off;
+    const float*   dy;               /* gradients: d(loss)/dy, row stride lddy */
+    int64_t        lddy;
+    float*         da;               /* dgrad output, row stride ldda */
+    int64_t        ldda;
+    float*         dw;               /* wgrad output [n, k] */
+    float*         db;               /* wgrad: [n] or NULL */
+    int32_t        accumulate;
+} sgv_dense_params;
+
+int sgv_dense_f32_fwd(const sgv_dense_params* p, void* stream);
+int sgv_dense_f32_dgrad(const sgv_dense_params* p, void* stream);
+int sgv_dense_f32_wgrad(const sgv_dense_params* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,7 +30,7 @@ def main():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     for name, cin, cout, res in shapes:
-        if only and only != name and not (only == 'main4' and res >= 32):
+        if only and only != name and not (only == 'main4' and res >= 32) and not (only == 'small' and res <= 16):
             continue
         x = torch.randn(N, cin, res, res, device='cuda').contiguous(memory_format=torch.channels_last)
         w = torch.randn(cout, cin, 3, 3, device='cuda')

@@ -100,7 +100,17 @@ class AdamParams(ctypes.Structure):
     ]
 
 
-STRUCTS = {'sgv_upfirdn2d_params': UpfirdnParams, 'sgv_bias_act_params': BiasActParams, 'sgv_conv_params': ConvParams,
+class DenseParams(ctypes.Structure):
+    """struct sgv_dense_params (include/sgv_b200_aux.h)"""
+    _fields_ = [
+        ('a', c_vp), ('a_row_off', c_vp), ('lda', c_i64), ('w', c_vp), ('bias', c_vp), ('y', c_vp), ('ldy', c_i64),
+        ('m', c_int), ('n', c_int), ('k', c_int), ('w_gain', c_f32), ('b_gain', c_f32), ('act', c_int), ('alpha', c_f32), ('gain', c_f32),
+        ('groups', c_int), ('group_col', c_vp), ('group_off', c_vp),
+        ('dy', c_vp), ('lddy', c_i64), ('da', c_vp), ('ldda', c_i64), ('dw', c_vp), ('db', c_vp), ('accumulate', c_int),
+    ]
+
+
+STRUCTS = {'sgv_dense_params': DenseParams, 'sgv_upfirdn2d_params': UpfirdnParams, 'sgv_bias_act_params': BiasActParams, 'sgv_conv_params': ConvParams,
            'sgv_wgrad_params': WgradParams, 'sgv_adam_params': AdamParams, 'sgv_conv_variant': ConvVariant, 'sgv_wgrad_variant': WgradVariant}
 
 # every symbol include/sgv_b200*.h declares: (name, restype, argtypes)
@@ -137,6 +147,9 @@ SYMBOLS = [
     ('sgv_fromrgb_bwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp]),
     ('sgv_mbstd_fwd', c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     ('sgv_mbstd_bwd', c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    ('sgv_dense_f32_fwd', c_int, [ctypes.POINTER(DenseParams), c_vp]),
+    ('sgv_dense_f32_dgrad', c_int, [ctypes.POINTER(DenseParams), c_vp]),
+    ('sgv_dense_f32_wgrad', c_int, [ctypes.POINTER(DenseParams), c_vp]),
 ]
 
 _lib = None

@@ -17,9 +17,10 @@
 //              accumulator in TMEM, releases stages with tcgen05.commit -> empty[stage].
 //
 // Split-K (small planes: the 4x4 ... 16x16 layers have only 4-64 pixel tiles but K = 9 * 512 ... 9 * 1024): the launch is a thread-block
-// cluster of KS CTAs per output tile along gridDim.z; CTA r walks k-steps [r*S/KS, (r+1)*S/KS) into its own TMEM accumulator, the
-// non-leader CTAs park their partial tile in their (now idle) pipeline stages, and after a cluster barrier the leader adds them through
-// distributed shared memory (ld.shared::cluster) before its epilogue — no workspace, no second launch, no atomics (deterministic order).
+// cluster of KS CTAs per output tile along gridDim.z; CTA r walks k-steps [r*S/KS, (r+1)*S/KS) into its own TMEM accumulator, every CTA
+// parks the column chunks it does not own in its (now idle) pipeline stages, and after a cluster barrier CTA r sums chunk cc (cc % KS == r)
+// over the cluster through distributed shared memory (ld.shared::cluster) and runs the epilogue for it — a reduce-scatter: no workspace,
+// no second launch, no atomics, fixed summation order.
 //
 // Replaces cuDNN for the reference's conv2d_gradfix.conv2d / conv_transpose2d on the hot-path shapes
 // (conv2d_gradfix.py:35-43) plus the x*styles, *dcoefs and bias_act passes around it (networks.py:64-74,141-143).
@@ -226,13 +227,15 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
         }
 
-        // ---- split-K: non-leader CTAs park their partial tile [128 rows][BN] in their idle pipeline stages ----
+        // ---- split-K: every CTA of the cluster parks the 32-column chunks of its partial tile [128 rows][BN] that ANOTHER CTA owns
+        //      (chunk cc belongs to CTA cc % KS) in its now idle pipeline stages ----
         if (ksteps > 0) { mbar_wait(accum_bar, 0); tc_fence_after(); }
-        if (ks_n > 1 && ks_r != 0)
+        if (ks_n > 1)
         {
 #pragma unroll 1
             for (int cc = 0; cc < BN / 32; cc++)
             {
+                if (cc % ks_n == ks_r) continue;
                 uint32_t v[32];
                 if (ksteps > 0) { tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v); tmem_ld_wait(); }
                 else {
@@ -247,7 +250,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
     }
     if (ks_n > 1) { tc_fence_before(); cluster_sync_all(); tc_fence_after(); }      // partial tiles are visible cluster-wide
-    if (warp >= 2 && ks_r == 0)
+    if (warp >= 2)
     {
         const int q = warp & 3;
         const int row = q * 32 + lane;
@@ -259,7 +262,9 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int oy = oy0 + ty, ox = ox0 + tx;
         const bool valid = (n < p.n) && (oy < p.out_h) && (ox < p.out_w);
         const int nc = n < p.n ? n : p.n - 1;
-        // ---- epilogue (leader CTA of the split-K cluster) ----
+        // ---- epilogue; under split-K a reduce-scatter: each CTA sums and finishes the column chunks it owns, reading the other CTAs' parts of
+        //      them through distributed shared memory (the serial chain per CTA is KS times shorter than a reduction in one leader CTA:
+        //      b4.conv1 with 8-way split measured 0.099 ms with the leader-only reduction) ----
         float* yrow = p.y + (long long)nc * p.osn + (long long)oy * p.osy + (long long)ox * p.osx + nb0;
         const float* osc = p.o_scale ? p.o_scale + (long long)nc * p.cout + nb0 : nullptr;
         const float* bia = p.bias ? p.bias + nb0 : nullptr;
@@ -267,19 +272,26 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll 1
         for (int cc = 0; cc < BN / 32; cc++)
         {
+            if (ks_n > 1 && cc % ks_n != ks_r) continue;
             uint32_t v[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
-            tmem_ld_wait();
-            for (int r = 1; r < ks_n; r++)
+            if (ksteps > 0) { tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v); tmem_ld_wait(); }
+            else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = 0u;
+            }
+            for (int r = 0; r < ks_n; r++)
             {
+                if (r == ks_r) continue;
                 // partial tile of CTA r of the cluster (same layout, same rotation of the 16-byte chunks as it was written with)
                 const uint32_t src = mapa_cluster(smem_u32(smem) + (uint32_t)row * (uint32_t)(BN * 4) + (uint32_t)(cc * 128), (uint32_t)r);
+                float4 t4[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) t4[j] = ld_dsmem128(src + (uint32_t)(((j + row) & 7) << 4));
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                 {
-                    const float4 t4 = ld_dsmem128(src + (uint32_t)(((j + row) & 7) << 4));
-                    v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + t4.x); v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + t4.y);
-                    v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + t4.z); v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + t4.w);
+                    v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + t4[j].x); v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + t4[j].y);
+                    v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + t4[j].z); v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + t4[j].w);
                 }
             }
             if (p.red_out)
@@ -612,6 +624,11 @@ static int conv2d_tf32_dispatch(const sgv_conv_params* p, cudaStream_t stream, s
         if (ctas * ks * 2 > num_sms() || bn <= 64 || p->cout % (bn / 2) != 0) break;
         bn /= 2;
     }
+
+    // tuning overrides (read once; used by scripts/bench_conv.py sweeps): force the N tile and / or the split factor when they are legal
+    static const int force_bn = env_int("SGV_CONV_V1_BN", 0), force_ks = env_int("SGV_CONV_V1_KS", 0);
+    if (force_bn > 0 && force_bn <= 256 && p->cout % force_bn == 0 && (force_bn & (force_bn - 1)) == 0 && force_bn >= 32) bn = force_bn;
+    if (force_ks > 0 && force_ks <= 8 && (force_ks & (force_ks - 1)) == 0 && ksteps_all / force_ks >= 1) ks = force_ks;
 
     if (query)
     {

@@ -36,9 +36,9 @@ class FullyConnectedLayer(torch.nn.Module):
         self.bias_gain = lr_multiplier
 
     def forward(self, x, fused=False):
-        """fused=True (first-order callers): ONE tcgen05 contraction with the weight gain folded into its weight pass and bias / leaky ReLU /
-        gain in its epilogue (stylegan_v_b200/dense.py, fp32-grade arithmetic); otherwise the reference's addmm / matmul + bias_act
-        formulation, differentiable to any order (the R1 penalty differentiates the discriminator's dense layers twice)."""
+        """fused=True (first-order callers): ONE launch of the exact-fp32 dense kernel with the weight gain, bias, leaky ReLU and gain in its
+        epilogue (stylegan_v_b200/dense.py -> csrc/dense_f32.cu); otherwise the reference's addmm / matmul + bias_act formulation,
+        differentiable to any order (the R1 penalty differentiates the discriminator's dense layers twice)."""
         if fused and x.ndim == 2 and self.activation in ('linear', 'lrelu') and _dense.supported(x, self.weight, self.activation):
             return _dense.linear(x, self.weight, self.bias, self.weight_gain, self.bias_gain, act=self.activation,
                                  gain=bias_act.activation_funcs[self.activation].def_gain)

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import conv as _conv
+from . import dense as _dense
 from .modconv import fused_modulated_conv, demod_coefs, prepare_weights, WeightGradBox, WeightGradNode
 from .ops import upfirdn2d as _upfirdn2d
 from .ops import bias_act as _bias_act
@@ -261,22 +262,40 @@ class SynthesisNetwork(torch.nn.Module):
                    resample_filter=tuple(cfg.resample_filter), use_noise=bool(getattr(cfg, 'use_noise', False)))
 
     def _all_styles(self, ws):
-        """Evaluates every style affine of the forward pass with one stacked GEMM per distinct w index.
-        Layer l of block b reads ws[:, w_idx(b) + l] (networks.py:350-357); layers sharing a w row share a GEMM."""
+        """Evaluates every style affine of the forward pass (networks.py:124-126,159-160 for all layers) up front.
+        Layer l of block b reads ws[:, w_idx(b) + l] (networks.py:350-357).  CUDA fp32: ONE launch of the exact-fp32 dense kernel for all
+        layers — the affine weights are stacked along the output dimension in w-index order and column group g reads ws[:, g, :]
+        (stylegan_v_b200/dense.py::stacked_affine; the tcgen05 kernels are the wrong tool here: M = 32 rows fill a quarter of one 128-row
+        tile and the K = 512 loop is latency-bound — 1.3 ms per step measured against 0.6 ms for cuBLAS, profiles/launches_r2b_summary.txt).
+        Otherwise one library GEMM per distinct w index."""
         groups = {}
         w_idx = 0
-        order = []
         for res in self.block_resolutions:
             block = getattr(self, f'b{res}')
             for j, layer in enumerate(block.layers()):
                 groups.setdefault(w_idx + j, []).append(layer)
-                order.append((res, layer))
             w_idx += block.num_conv
         out = {}
+        order = sorted(groups)
+        first = groups[order[0]][0].affine
+        if ws.is_cuda and ws.dtype == torch.float32 and first.weight.dtype == torch.float32 and ws.shape[2] % 4 == 0 \
+                and all(l.affine.weight.shape[0] % 8 == 0 for wi in order for l in groups[wi]):
+            layers = [l for wi in order for l in groups[wi]]
+            key = (str(ws.device), ws.shape[1], ws.shape[2])
+            if getattr(self, '_affine_groups_key', None) != key:
+                col, c = [0], 0
+                for wi in order:
+                    c += sum(l.affine.weight.shape[0] for l in groups[wi])
+                    col.append(c)
+                self._affine_groups = _dense.make_groups(col, order, ws.shape[2], ws.device)
+                self._affine_groups_key = key
+            wcat = torch.cat([l.affine.weight for l in layers], dim=0)
+            bcat = torch.cat([l.affine.bias for l in layers], dim=0)
+            s = _dense.stacked_affine(ws, wcat, bcat, self._affine_groups, first.weight_gain)
+            for l, piece in zip(layers, s.split([l.affine.weight.shape[0] for l in layers], dim=1)):
+                out[id(l)] = piece
+            return out
         for wi, layers in groups.items():
-            # library fp32 GEMM on purpose: measured on the B200 (profiles/launches_r2b_summary.txt) the 14 stacked affine products of a step cost
-            # 0.6 ms on cuBLAS and 1.3 ms as tcgen05 tf32x3 launches of the per-tap kernel (M = 32 rows fill a quarter of one 128-row tile and
-            # the K loop is latency-bound); stylegan_v_b200/dense.py serves the mapping networks and the discriminator's dense layers instead
             wcat = torch.cat([l.affine.weight for l in layers], dim=0) * layers[0].affine.weight_gain
             bcat = torch.cat([l.affine.bias for l in layers], dim=0)
             s = torch.addmm(bcat.unsqueeze(0), ws[:, wi], wcat.t())

@@ -22,6 +22,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
+from . import dense as _dense
 from . import precision as _precision
 
 
@@ -77,6 +78,8 @@ class EqualizedLinear(torch.nn.Module):
         self.bias_gain = lr_multiplier
 
     def forward(self, x):
+        if x.ndim == 2 and _dense.supported(x, self.weight):
+            return _dense.linear(x, self.weight, self.bias, self.weight_gain, self.bias_gain)      # exact-fp32 kernel, gains + bias in the epilogue
         w = self.weight.to(x.dtype) * self.weight_gain
         if self.bias is None:
             return x.matmul(w.t())
@@ -142,14 +145,17 @@ class AlignedTimeEncoder(torch.nn.Module):
         With `motion_z_distance` (d) given, CUDA inputs run the fused tail kernel, which derives t_left / t_right / alpha from
         (t, d) itself exactly as MotionMappingNetwork does (motion.py:111-115)."""
         nf = self.freqs.shape[1]
-        # one stacked GEMM for the three heads on u_left, one for the aligners on u_right
-        # True-fp32 library GEMMs on purpose (and a true-fp32 library conv1d for the trajectory below): the phases are multiplied by
-        # phase_scales up to 64 before sin / cos, so these products need round-to-nearest fp32 accumulation.  Measured on the B200: with the
-        # tcgen05 tf32x3 kernels (whose tensor-core accumulation is not round-to-nearest: error grows ~K, 4e-5 at K = 5632) motion_v is off
-        # by 2e-3 against the fp32 CPU evaluation; with the library fp32 path by 1e-4 (profiles/dense_precision_r2.txt).
+        # one stacked GEMM for the three heads on u_left, one for the aligners on u_right.  Exact fp32 on purpose (csrc/dense_f32.cu; the
+        # reference's library GEMMs for CPU tensors): the phases are multiplied by phase_scales up to 64 before sin / cos, so these products and
+        # the trajectory conv1d below need round-to-nearest fp32 accumulation.  Measured on the B200 (profiles/dense_precision_r2.txt): with
+        # the tcgen05 tf32x3 kernels, whose accumulator truncates (error ~K, 4e-5 at K = 5632), motion_v is off by 2e-3 against the fp32 CPU
+        # evaluation; in fp32 by 1e-4.
         heads = torch.cat([self.periods_predictor.weight, self.phase_predictor.weight, self.aligners_predictor.weight], dim=0)
         gain = self.periods_predictor.weight_gain
-        hl = u_left.matmul((heads * gain).t())
+        if _dense.supported(u_left, heads):
+            hl = _dense.linear(u_left, heads, None, gain)
+        else:
+            hl = u_left.matmul((heads * gain).t())
         if motion_z_distance is not None and t.is_cuda and hl.dtype == torch.float32:
             return _TimeEncoderTail.apply(hl, self.aligners_predictor(u_right), t.reshape(-1), self.freqs, self.phase_scales, motion_z_distance)
         periods = hl[:, :nf].tanh() + 1
@@ -194,12 +200,35 @@ class MotionMappingNetwork(torch.nn.Module):
         L = self.traj_len(t_max)
         if motion_z is None:
             motion_z = torch.randn(B, L, self.z_dim, device=t.device)
-        trajs = self.conv(motion_z[:B, :L, :self.z_dim].permute(0, 2, 1)).permute(0, 2, 1)   # [B, L - 20, v_dim]
         d = self.motion_z_distance
         left = (t / d).floor().long()
-        rows = torch.arange(B, device=t.device).unsqueeze(1).expand(B, Fr)
-        u_left = trajs[rows, left].reshape(B * Fr, -1)
-        u_right = trajs[rows, left + 1].reshape(B * Fr, -1)
+        z = motion_z[:B, :L, :self.z_dim]
+        c0, c1 = self.conv[0], self.conv[1]
+        k = c0.weight.shape[2]
+        if z.is_cuda and z.dtype == torch.float32 and not z.requires_grad and c0.weight.shape[1] % 4 == 0 and c1.weight.shape[1] % 4 == 0:
+            # the two valid conv1d layers as exact-fp32 GEMMs over windows of the [B, L, C] sequence (stylegan_v_b200/dense.py), evaluated only
+            # where the result is read: a frame needs trajectory positions left, left + 1 = 2 outputs of layer 2 = k + 1 outputs of layer 1.
+            # With many frames per clip the windows overlap enough that the whole trajectory is cheaper; then every position is computed once.
+            C = z.shape[2]
+            z = z.contiguous()
+            if Fr * (k + 1) <= L - k + 1:
+                left = left.clamp(0, L - 2 * k)                                      # (the reference would raise on an out-of-range index)
+                base = ((torch.arange(B, device=t.device).unsqueeze(1) * L + left) * C).reshape(-1)
+                y1 = _dense.conv1d_slabs(z, base, k + 1, c0.weight, c0.bias, c0.weight_gain, c0.bias_gain, 'lrelu')          # [B*F, k+1, C]
+                y2 = _dense.conv1d_slabs(y1, None, 2, c1.weight, c1.bias, c1.weight_gain, c1.bias_gain, 'lrelu')             # [B*F, 2, v]
+                u_left, u_right = y2[:, 0], y2[:, 1]
+            else:
+                base = torch.arange(B, device=t.device) * (L * C)
+                y1 = _dense.conv1d_slabs(z, base, L - k + 1, c0.weight, c0.bias, c0.weight_gain, c0.bias_gain, 'lrelu')      # [B, L-k+1, C]
+                trajs = _dense.conv1d_slabs(y1, None, L - 2 * k + 2, c1.weight, c1.bias, c1.weight_gain, c1.bias_gain, 'lrelu')
+                rows = torch.arange(B, device=t.device).unsqueeze(1).expand(B, Fr)
+                u_left = trajs[rows, left].reshape(B * Fr, -1)
+                u_right = trajs[rows, left + 1].reshape(B * Fr, -1)
+        else:
+            trajs = self.conv(z.permute(0, 2, 1)).permute(0, 2, 1)                   # [B, L - 20, v_dim]
+            rows = torch.arange(B, device=t.device).unsqueeze(1).expand(B, Fr)
+            u_left = trajs[rows, left].reshape(B * Fr, -1)
+            u_right = trajs[rows, left + 1].reshape(B * Fr, -1)
         if t.is_cuda and (t.dtype == torch.float32 or not t.dtype.is_floating_point):
             # fused tail: remainder / neighbour positions / alpha are derived from (t, d) inside the kernel (exact for integer frame indices too)
             v = self.time_encoder(t.reshape(-1).to(torch.float32), u_left, u_right, None, None, None, motion_z_distance=d)
