@@ -647,6 +647,67 @@ __global__ void __launch_bounds__(256, 2) fir_nhwc_tma44(const __grid_constant__
     }
 }
 
+// Zero-insertion x2 with 4x4 taps on channels_last tensors, even leading pads: the ADJOINT of the discriminator's decimating FIR
+// (conv2d_resample.py:100-110 forward with down = 2 -> upfirdn2d.py:205-213 backward: up = 2, pad0 = 2) — 5.1 ms of a G + D step on the
+// general kernel below (one output per thread, runtime tap loops: 21 % of the HBM rate, profiles/timeline_gd_step_r2h.txt).
+// A thread owns 4 channels of a 2x2 output quad: with an even pad the quad (2qy + a, 2qx + b) reads the 3x3 input window starting at
+// (qy - pad_y0/2, qx - pad_x0/2); output parity a uses window rows a, a + 1 with taps 3 - a, 1 - a (mirrored when flip).  9 vector loads
+// for 4 vector stores; per output the taps are accumulated rows-then-columns ascending with the same FMAs as fir_nhwc_any and out-of-range
+// taps are skipped, not added as zeros => identical bits.
+__global__ void __launch_bounds__(256) fir_nhwc_up2_44(FirArgs p, long long total, int qw, int qh)
+{
+    __shared__ float sf[16];
+    if (threadIdx.x < 16)
+    {
+        const int fy = threadIdx.x >> 2, fx = threadIdx.x & 3;
+        sf[threadIdx.x] = p.f[(p.flip ? 3 - fx : fx) * p.fsx + (p.flip ? 3 - fy : fy) * p.fsy];
+    }
+    __syncthreads();
+    const int cvecs = p.in_c / 4;
+    const int sx = -(p.pad_x0 / 2), sy = -(p.pad_y0 / 2);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    {
+        long long r = idx;
+        const int cv = (int)(r % cvecs); r /= cvecs;
+        const int qx = (int)(r % qw); r /= qw;
+        const int qy = (int)(r % qh);
+        const int n = (int)(r / qh);
+        const int c0 = cv * 4;
+        const int ix0 = qx + sx, iy0 = qy + sy;
+        const float* xb = (const float*)p.x + n * p.isn + c0;
+        float4 win[3][3];
+        bool rok[3], cok[3];
+#pragma unroll
+        for (int w = 0; w < 3; w++) { rok[w] = (iy0 + w >= 0) && (iy0 + w < p.in_h); cok[w] = (ix0 + w >= 0) && (ix0 + w < p.in_w); }
+#pragma unroll
+        for (int wy = 0; wy < 3; wy++)
+#pragma unroll
+            for (int wx = 0; wx < 3; wx++)
+            {
+                vzero(win[wy][wx]);
+                if (rok[wy] && cok[wx]) win[wy][wx] = __ldg(reinterpret_cast<const float4*>(xb + (iy0 + wy) * p.isy + (ix0 + wx) * p.isx));
+            }
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+            {
+                const int oy = 2 * qy + a, ox = 2 * qx + b;
+                if (oy >= p.out_h || ox >= p.out_w) continue;
+                float4 acc; vzero(acc);
+#pragma unroll
+                for (int ty = 0; ty < 2; ty++)
+                {
+                    if (!rok[a + ty]) continue;
+#pragma unroll
+                    for (int tx = 0; tx < 2; tx++)
+                        if (cok[b + tx]) vfma(acc, win[a + ty][b + tx], sf[(3 - a - 2 * ty) * 4 + (3 - b - 2 * tx)]);
+                }
+                nhwc_store<4, true>(p, acc, n, c0, oy, ox);
+            }
+    }
+}
+
 // General channels_last kernel (any up/down/filter), one output pixel x VEC channels per thread.
 template <int VEC>
 __global__ void __launch_bounds__(256) fir_nhwc_any(FirArgs p, long long total)
@@ -859,6 +920,16 @@ extern "C" int sgv_upfirdn2d(const sgv_upfirdn2d_params* p, void* stream_)
                 else SGV_NHWC_FAST(1, 2);
 #undef SGV_NHWC_FAST
                 SGV_LAUNCH_OK("fir_nhwc_fast");
+                return SGV_OK;
+            }
+            if (v4 && a.upx == 2 && a.upy == 2 && a.downx == 1 && a.downy == 1 && a.f_w == 4 && a.f_h == 4
+                && a.pad_x0 >= 0 && a.pad_y0 >= 0 && a.pad_x0 % 2 == 0 && a.pad_y0 % 2 == 0)
+            {
+                const int qw = (ow + 1) / 2, qh = (oh + 1) / 2;
+                const long long quads = (long long)a.in_n * qh * qw * cvecs;
+                const unsigned gq = (unsigned)min((long long)sms * 32, (quads + 255) / 256);
+                fir_nhwc_up2_44<<<gq, 256, 0, stream>>>(a, quads, qw, qh);
+                SGV_LAUNCH_OK("fir_nhwc_up2_44");
                 return SGV_OK;
             }
             const long long work = (long long)a.in_n * oh * ow * cvecs;

@@ -67,6 +67,11 @@ SHAPES = [
     (2, 64, 65, 65, 1, 1, [1, 1, 1, 1], False, 4),       # channels_last + C % 32 == 0: the TMA-fed persistent kernel, 2 channel blocks
     (3, 32, 40, 52, 1, 1, [2, 2, 2, 2], True, 4),        # its backward geometry, ragged tiles in both directions
     (1, 96, 33, 100, 1, 1, [2, 1, 1, 2], False, 1),      # 3 channel blocks, asymmetric padding
+    (2, 8, 32, 32, 2, 1, [2, 1, 2, 1], True, 1),         # backward of the D skip FIR: zero insertion x2, channels_last quad kernel
+    (1, 12, 17, 9, 2, 1, [2, 1, 2, 1], False, 4),        # same kernel, odd extents
+    (1, 4, 1, 1, 2, 1, [2, 1, 2, 1], True, 1),           # 1 x 1 input: every tap row / column clipped somewhere
+    (1, 4, 6, 5, 2, 1, [4, 0, 0, 3], False, 1),          # even leading pads 4 / 0, odd output extents
+    (1, 4, 6, 5, 2, 1, [3, 2, 1, 2], False, 1),          # odd leading pads: stays on the general channels_last kernel
 ]
 
 
