@@ -255,10 +255,47 @@ def run_gd_step(args):
             graph = None
             torch.cuda.synchronize()
 
+    split = None
+    if not args.no_graph and world > 1:
+        # N > 1: the gradient exchange sits between the phases, so each main phase (loss + backward into the flat gradient buffer) is its own
+        # graph and the NCCL all-reduce + fused update run between the replays.  All ranks must agree on the mode: a rank whose capture failed
+        # would otherwise issue a different sequence of collectives.
+        zeros_c = torch.zeros(B, 0, device=dev)
+        g_part = lambda: tp.backward_gmain(s_z, zeros_c, s_t)
+        d_part = lambda: tp.backward_dmain(s_real, zeros_c, s_t, s_z, zeros_c, s_t)
+        ok = torch.ones(1, device=dev)
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    g_part(); tp.finish_g(); d_part(); tp.finish_d()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            gG, gD = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
+            with torch.cuda.graph(gG):
+                s_lg = g_part()
+            with torch.cuda.graph(gD, pool=gG.pool()):
+                s_ld = d_part()
+            graph_launches = _lib.launch_count() - l0
+            split = (gG, gD, s_lg, s_ld)
+        except Exception as e:
+            sys.stderr.write(f'[bench] rank {rank}: per-phase CUDA graph capture failed ({type(e).__name__}: {e}); eager launches\n')
+            ok.zero_()
+            torch.cuda.synchronize()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0:
+            split = None
+
     def step():
         if graph is not None:
             graph.replay()
             return s_loss
+        if split is not None:
+            gG, gD, s_lg, s_ld = split
+            gG.replay(); tp.finish_g(); gD.replay(); tp.finish_d()
+            return torch.stack([s_lg, s_ld])
         return compute()
 
     def timed(fn, steps, warmup):
@@ -288,6 +325,8 @@ def run_gd_step(args):
     ms_total, launches = timed(step, args.steps, args.warmup)
     if graph is not None:
         launches = graph_launches * args.steps
+    elif split is not None:
+        launches += graph_launches * args.steps          # the replayed phases + the update launches counted live
     clocks = sampler.stop() if rank == 0 else None
 
     def e2e_step():
@@ -302,7 +341,8 @@ def run_gd_step(args):
                     dtype='tf32 (fp32 storage, TF32 tensor-core products, fp32 accumulate)', data='synthetic',
                     config=dict(workload='BASELINE configs[2]: 256x256 G+D training step fwd+bwd (Gmain + Dmain, no reg), 3 frames/clip, 16 clips/GPU, '
                                          'all-reduce + fused Adam/EMA update per phase', clips_per_gpu=B, frames_per_clip=Fr, parallelism=f'dp{world}',
-                                cuda_graph=graph is not None, fused_discriminator_layers=bool(train_step.FUSED_DISCRIMINATOR),
+                                cuda_graph=(graph is not None) or ('per phase, all-reduce + update between replays' if split is not None else False),
+                                fused_discriminator_layers=bool(train_step.FUSED_DISCRIMINATOR),
                                 l2='per-step activation working set >> 126 MB L2; no explicit flush',
                                 G_params=int(tp.G_state.numel), D_params=int(tp.D_state.numel)),
                     e2e=dict(value=frames / (ms_e2e / args.steps * 1e-3), unit='frames/s',

@@ -144,6 +144,21 @@ int sgv_dense_f32_fwd(const sgv_dense_params* p, void* stream);
 int sgv_dense_f32_dgrad(const sgv_dense_params* p, void* stream);
 int sgv_dense_f32_wgrad(const sgv_dense_params* p, void* stream);
 
+/* ---- demodulation coefficients (csrc/demod.cu) -----------------------------------------------------------------------------------
+ * dcoefs[n, o] = rsqrt(sum_{i, k} (w[o, i, k] * styles[n, i])^2 + eps)     (src/training/networks.py:57-59), evaluated as
+ * rsqrt(sum_i styles[n, i]^2 * wsq[o, i] + eps) with wsq[o, i] = sum_k w[o, i, k]^2 formed on the fly; w [o, i, taps] (taps = 9 only),
+ * styles [n, i] with row stride styles_stride (elements, multiple of 4), dcoefs [n, o] dense; exact fp32.
+ * Gradients from d_dcoefs = d(loss)/d(dcoefs), with g = -0.5 * dcoefs^3 * d_dcoefs:
+ *   sgv_demod_bwd_styles   d_styles[n, i] += 2 * styles[n, i] * sum_o g[n, o] * wsq[o, i]        (atomic adds into the caller's buffer)
+ *   sgv_demod_bwd_weight   dw[o, i, k]     = 2 * w[o, i, k] * sum_n g[n, o] * styles[n, i]^2     (dw dense, same shape as w)
+ */
+int sgv_demod_fwd(const float* w, const float* styles, int64_t styles_stride, float* dcoefs, int32_t n, int32_t o, int32_t i, int32_t taps,
+                  float eps, void* stream);
+int sgv_demod_bwd_styles(const float* w, const float* styles, int64_t styles_stride, const float* dcoefs, const float* d_dcoefs,
+                         float* d_styles, int64_t d_styles_stride, int32_t n, int32_t o, int32_t i, int32_t taps, void* stream);
+int sgv_demod_bwd_weight(const float* w, const float* styles, int64_t styles_stride, const float* dcoefs, const float* d_dcoefs,
+                         float* dw, int32_t n, int32_t o, int32_t i, int32_t taps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,16 @@ def main():
         med, best = timeit(lambda: U.upfirdn2d(x, f, **kw))
         out.append(dict(kernel=name, shape=list(shape), ms=med, ms_best=best, gbs=nbytes / med / 1e6, frac_of_measured_peak=nbytes / med / 1e6 / peak))
         del x, y
+    # the same D-side geometries channels_last (what the fused discriminator runs), and the adjoint of the decimating FIR (zero insertion x2)
+    for name, shape, kw in [('fir_down2_nhwc', (32, 64, 256, 256), dict(down=2, padding=1)), ('fir_blur_pad2_nhwc', (32, 64, 256, 256), dict(padding=2)),
+                            ('fir_up2_adjoint_nhwc', (32, 64, 128, 128), dict(up=2, padding=[2, 1, 2, 1], flip_filter=True)),
+                            ('fir_up2_adjoint_nhwc_128ch', (32, 128, 64, 64), dict(up=2, padding=[2, 1, 2, 1], flip_filter=True))]:
+        x = torch.randn(shape, device=dev).contiguous(memory_format=torch.channels_last)
+        y = U.upfirdn2d(x, f, **kw)
+        nbytes = (x.numel() + y.numel()) * 4
+        med, best = timeit(lambda: U.upfirdn2d(x, f, **kw))
+        out.append(dict(kernel=name, shape=list(shape), ms=med, ms_best=best, gbs=nbytes / med / 1e6, frac_of_measured_peak=nbytes / med / 1e6 / peak))
+        del x, y
     for name, shape, cl in [('bias_act_b256_nchw', (32, 64, 256, 256), False), ('bias_act_b256_nhwc', (32, 64, 256, 256), True)]:
         x = torch.randn(shape, device=dev)
         if cl:

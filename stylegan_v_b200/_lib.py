@@ -150,6 +150,9 @@ SYMBOLS = [
     ('sgv_dense_f32_fwd', c_int, [ctypes.POINTER(DenseParams), c_vp]),
     ('sgv_dense_f32_dgrad', c_int, [ctypes.POINTER(DenseParams), c_vp]),
     ('sgv_dense_f32_wgrad', c_int, [ctypes.POINTER(DenseParams), c_vp]),
+    ('sgv_demod_fwd', c_int, [c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp]),
+    ('sgv_demod_bwd_styles', c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp]),
+    ('sgv_demod_bwd_weight', c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
 ]
 
 _lib = None

@@ -606,23 +606,28 @@ static int conv2d_tf32_dispatch(const sgv_conv_params* p, cudaStream_t stream, s
     a.tw = tw; a.th = th; a.tn = tn;
     a.tiles_x = ceil_div(p->out_w, tw); a.tiles_y = ceil_div(p->out_h, th); a.tiles_nb = ceil_div(p->n, tn);
 
-    // N tile and split-K factor.  A k-step of this kernel costs about the same whatever the N tile (its pace is set by the staging pass over
-    // the 128-row A tile: measured ~950 clk per k-step at N = 64), so the WIDEST tile that divides cout does the most work per step, and the
-    // SMs that the few pixel tiles of the 4x4 ... 8x8 planes leave idle are filled by splitting K over a thread-block cluster of 2 / 4 / 8
-    // CTAs (>= 16 k-steps each; partial tiles are reduced through distributed shared memory, see the kernel).  Only when even 8-way split-K
-    // leaves more than half of the SMs idle is the tile narrowed.  Measured (profiles/bench_conv_small_r2.jsonl): b4.conv1 0.127 -> 0.048 ms.
+    // N tile and split-K factor for the few pixel tiles of the 4x4 ... 16x16 planes (K = 9 * 512 ... 9 * 1024): K is split over a thread-block
+    // cluster of KS <= 4 CTAs (>= 16 k-steps each; partial tiles are reduce-scattered through distributed shared memory, see the kernel) and the
+    // N tile is chosen so that CTAs x KS fills the SMs in ONE wave as far as possible; ties go to the wider tile (a k-step costs about the same
+    // whatever the N tile: its pace is set by the staging pass over the 128-row A tile).  Measured sweep (profiles/bench_conv_small_r2j.jsonl,
+    // 32 frames): b4.conv1 (4 pixel tiles) 0.0455 ms at (64, 4), 0.060 at (256, 4), 0.070-0.088 at KS = 8; b8.conv1 (16 tiles) 0.0475 ms at
+    // (256, 4) = (128, 2), 0.066 at (128, 4) (two waves), 0.13 at KS = 8 (clusters of 8 schedule poorly and lengthen the reduction).
     static const int split_k = env_int("SGV_CONV_SPLITK", 1);
     const int mtiles_total = a.tiles_x * a.tiles_y * a.tiles_nb;
     const int ksteps_all = (p->cin / kBK) * p->ntaps * a.parts;
     int bn = (p->cout % 256 == 0) ? 256 : (p->cout % 128 == 0) ? 128 : (p->cout % 64 == 0) ? 64 : p->cout;
     int ks = 1;
-    for (;;)
     {
-        const int ctas = mtiles_total * (p->cout / bn);
-        ks = 1;
-        while (split_k && ks < 8 && ctas * ks * 2 <= num_sms() && ksteps_all / (ks * 2) >= 16) ks *= 2;
-        if (ctas * ks * 2 > num_sms() || bn <= 64 || p->cout % (bn / 2) != 0) break;
-        bn /= 2;
+        int best_bn = bn, best_ks = 1, best_fill = -1;
+        for (int cand = bn; cand >= 64 && p->cout % cand == 0; cand /= 2)
+        {
+            const int ctas = mtiles_total * (p->cout / cand);
+            int k = 1;
+            while (split_k && k < 4 && ctas * k * 2 <= num_sms() && ksteps_all / (k * 2) >= 16) k *= 2;
+            const int fill = ctas * k <= num_sms() ? ctas * k : 0;          // more than one wave: never better than the wider tile
+            if (fill > best_fill) { best_fill = fill; best_bn = cand; best_ks = k; }
+        }
+        bn = best_bn; ks = best_ks;
     }
 
     // tuning overrides (read once; used by scripts/bench_conv.py sweeps): force the N tile and / or the split factor when they are legal

@@ -25,6 +25,7 @@ import os
 import numpy as np
 import torch
 
+from . import _lib
 from . import conv as _conv
 from . import plugin as _plugin
 
@@ -34,8 +35,50 @@ _OFFS3_DGRAD = [(1 - ky, 1 - kx) for ky, kx in _TAPS3]        # its adjoint
 _FIR_1331 = None
 
 
+class _Demod(torch.autograd.Function):
+    """dcoefs from (weight, styles) in one launch, both gradients in one launch each (csrc/demod.cu).  First order."""
+
+    @staticmethod
+    def forward(ctx, weight, styles):
+        O, I = weight.shape[0], weight.shape[1]
+        N = styles.shape[0]
+        if styles.stride(1) != 1 or styles.stride(0) % 4 != 0 or styles.data_ptr() % 16 != 0:
+            styles = styles.contiguous()
+        w = weight.contiguous()
+        dc = torch.empty([N, O], dtype=torch.float32, device=weight.device)
+        with torch.cuda.device(weight.device):
+            _lib.check(_lib.lib().sgv_demod_fwd(w.data_ptr(), styles.data_ptr(), styles.stride(0), dc.data_ptr(), N, O, I, 9, 1e-8,
+                                                _conv._stream(weight.device)), 'sgv_demod_fwd')
+        ctx.save_for_backward(w, styles, dc)
+        return dc
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, ddc):
+        w, styles, dc = ctx.saved_tensors
+        O, I = w.shape[0], w.shape[1]
+        N = styles.shape[0]
+        ddc = ddc.contiguous()
+        dw = ds = None
+        L, st = _lib.lib(), _conv._stream(w.device)
+        with torch.cuda.device(w.device):
+            if ctx.needs_input_grad[0]:
+                dw = torch.empty_like(w)
+                _lib.check(L.sgv_demod_bwd_weight(w.data_ptr(), styles.data_ptr(), styles.stride(0), dc.data_ptr(), ddc.data_ptr(), dw.data_ptr(),
+                                                  N, O, I, 9, st), 'sgv_demod_bwd_weight')
+            if ctx.needs_input_grad[1]:
+                ds = torch.zeros([N, I], dtype=torch.float32, device=w.device)
+                _lib.check(L.sgv_demod_bwd_styles(w.data_ptr(), styles.data_ptr(), styles.stride(0), dc.data_ptr(), ddc.data_ptr(), ds.data_ptr(), I,
+                                                  N, O, I, 9, st), 'sgv_demod_bwd_styles')
+        return dw, ds
+
+
 def demod_coefs(weight, styles):
-    """dcoefs[n,o] = rsqrt(sum_{i,k} (W[o,i,k] * s[n,i])^2 + 1e-8)   (networks.py:57-59) without materialising [N,O,I,k,k]."""
+    """dcoefs[n,o] = rsqrt(sum_{i,k} (W[o,i,k] * s[n,i])^2 + 1e-8)   (networks.py:57-59) without materialising [N,O,I,k,k].
+    CUDA fp32 3x3 weights: one launch (and one per gradient) of csrc/demod.cu; otherwise differentiable torch ops on [O, I]-sized tensors."""
+    if (weight.is_cuda and weight.dtype == torch.float32 and styles.dtype == torch.float32 and tuple(weight.shape[2:]) == (3, 3)
+            and weight.shape[1] % 4 == 0):
+        return _Demod.apply(weight, styles)
     wsq = weight.square().sum(dim=[2, 3])                  # [O, I]
     return (styles.square() @ wsq.t() + 1e-8).rsqrt()      # [N, O]
 

@@ -77,9 +77,12 @@ class EqualizedLinear(torch.nn.Module):
         self.weight_gain = lr_multiplier / np.sqrt(in_features)
         self.bias_gain = lr_multiplier
 
-    def forward(self, x):
-        if x.ndim == 2 and _dense.supported(x, self.weight):
-            return _dense.linear(x, self.weight, self.bias, self.weight_gain, self.bias_gain)      # exact-fp32 kernel, gains + bias in the epilogue
+    def forward(self, x, fused=False):
+        """fused=True (first-order callers: the motion encoder, whose nodes are never on a path that is differentiated twice): one launch of
+        the exact-fp32 dense kernel with gains + bias in its epilogue; default: the reference's addmm / matmul formulation, differentiable to
+        any order (the style affines sit between ws and the image, which path-length regularisation differentiates twice, loss.py:101-119)."""
+        if fused and x.ndim == 2 and _dense.supported(x, self.weight):
+            return _dense.linear(x, self.weight, self.bias, self.weight_gain, self.bias_gain)
         w = self.weight.to(x.dtype) * self.weight_gain
         if self.bias is None:
             return x.matmul(w.t())
@@ -157,7 +160,7 @@ class AlignedTimeEncoder(torch.nn.Module):
         else:
             hl = u_left.matmul((heads * gain).t())
         if motion_z_distance is not None and t.is_cuda and hl.dtype == torch.float32:
-            return _TimeEncoderTail.apply(hl, self.aligners_predictor(u_right), t.reshape(-1), self.freqs, self.phase_scales, motion_z_distance)
+            return _TimeEncoderTail.apply(hl, self.aligners_predictor(u_right, fused=True), t.reshape(-1), self.freqs, self.phase_scales, motion_z_distance)
         periods = hl[:, :nf].tanh() + 1
         phases = hl[:, nf:2 * nf]
         al_left = hl[:, 2 * nf:]

@@ -164,6 +164,26 @@ class TrainingPhases:
             return v.get(name, v['Gmain'])
         return v
 
+    # The two main phases up to (not including) the gradient exchange: loss + backward into the flat gradient buffer.  Separate entry points so that
+    # a caller can replay each as a CUDA graph and keep the NCCL all-reduce + update (`finish_g` / `finish_d`) between the replays (bench.py, N > 1).
+    def backward_gmain(self, z, c, t, **synthesis_kwargs):
+        self._grad_mode(True)
+        loss = generator_main_loss(self.G, self.D, z, c, t, **self.aug, **synthesis_kwargs)
+        loss.backward()
+        return loss.detach()
+
+    def backward_dmain(self, real_img, real_c, real_t, z, c, t, **synthesis_kwargs):
+        self._grad_mode(False)
+        loss_gen, loss_real = discriminator_main_loss(self.G, self.D, real_img, real_c, real_t, z, c, t, **self.aug, **synthesis_kwargs)
+        (loss_gen + loss_real).backward()
+        return (loss_gen + loss_real).detach()
+
+    def finish_g(self, ema=True):
+        self._finish(self.G_state, self.G_opt, ema_beta=self.ema_beta() if ema else None)
+
+    def finish_d(self):
+        self._finish(self.D_state, self.D_opt)
+
     def step(self, real_img, real_t, z, t, c=None, real_c=None, **synthesis_kwargs):
         """One iteration: real_img [B*F, 3, R, R], real_t [B, F]; generator latents z [B, z_dim] and times t [B, F].
 
@@ -183,11 +203,8 @@ class TrainingPhases:
         do_dreg = self.run_dreg and self.it % self.D_reg_interval == 0
         ema_beta = self.ema_beta()                                                   # from the pre-increment image count
         # ---- G phases
-        self._grad_mode(True)
         pz, pc, pt = pick('Gmain')
-        loss = generator_main_loss(self.G, self.D, pz, pc, pt, **self.aug, **synthesis_kwargs)
-        loss.backward()
-        out['Gmain'] = loss.detach()
+        out['Gmain'] = self.backward_gmain(pz, pc, pt, **synthesis_kwargs)
         self._finish(self.G_state, self.G_opt, ema_beta=None if do_greg else ema_beta)
         if do_greg:
             pz, pc, pt = pick('Greg')
@@ -196,11 +213,8 @@ class TrainingPhases:
             out['Greg'] = loss.detach()
             self._finish(self.G_state, self.G_opt, ema_beta=ema_beta)
         # ---- D phases
-        self._grad_mode(False)
         pz, pc, pt = pick('Dmain')
-        loss_gen, loss_real = discriminator_main_loss(self.G, self.D, real_img, real_c, real_t, pz, pc, pt, **self.aug, **synthesis_kwargs)
-        (loss_gen + loss_real).backward()
-        out['Dmain'] = (loss_gen + loss_real).detach()
+        out['Dmain'] = self.backward_dmain(real_img, real_c, real_t, pz, pc, pt, **synthesis_kwargs)
         self._finish(self.D_state, self.D_opt)
         if do_dreg:
             loss = discriminator_r1_loss(self.D, real_img, real_c, real_t, self.r1_gamma, **self.aug)

@@ -154,3 +154,25 @@ def test_module_routes():
     n2 = _lib.launch_count()
     ws = mp(torch.randn(8, 512, device='cuda'), torch.zeros(8, 0, device='cuda'))
     assert ws.shape == (8, 14, 512) and _lib.launch_count() - n2 >= 2
+
+
+@pytest.mark.parametrize('N,O,I', [(32, 512, 512), (5, 64, 64), (3, 12, 20), (33, 256, 128)])
+def test_demod_coefs_vs_fp64(N, O, I):
+    """Demodulation coefficients (networks.py:57-59) and their gradients from csrc/demod.cu against the materialised fp64 formula; styles are
+    a column slice of a wider tensor like the stacked affine output."""
+    from stylegan_v_b200.modconv import demod_coefs
+    g = torch.Generator().manual_seed(N + O)
+    w = torch.randn(O, I, 3, 3, generator=g).cuda().requires_grad_(True)
+    wide = (torch.randn(N, I + 16, generator=g) + 1).cuda().requires_grad_(True)
+    s = wide[:, 8:8 + I]
+    n0 = _lib.launch_count()
+    dc = demod_coefs(w, s)
+    ddc = torch.randn(N, O, generator=g).cuda()
+    gw, gs = torch.autograd.grad(dc, [w, wide], ddc)
+    assert _lib.launch_count() - n0 == 3
+    wd, sd = w.detach().double().requires_grad_(True), wide.detach().double().requires_grad_(True)
+    wm = wd.unsqueeze(0) * sd[:, 8:8 + I].reshape(N, 1, I, 1, 1)
+    ref = (wm.square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt()
+    rw, rs = torch.autograd.grad(ref, [wd, sd], ddc.double())
+    assert rel_err(dc, ref) < BAR
+    assert rel_err(gw, rw) < 5e-6 and rel_err(gs, rs) < 5e-6, (rel_err(gw, rw), rel_err(gs, rs))
