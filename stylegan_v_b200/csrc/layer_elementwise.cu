@@ -324,6 +324,63 @@ __global__ void __launch_bounds__(kEwThreads) torgb_fwd_kernel(ToRgbArgs p)
     }
 }
 
+// ToRGB forward for the wide layers (C = 256 / 512 at 4x4 ... 64x64): a WARP owns a pixel, lane l covers channel vectors l, l + 32, ... (K per
+// lane), four pixels in flight per warp, one shuffle reduction per pixel and no block barrier.  (The generic kernel above spreads a pixel over
+// 2-4 warps and meets at two __syncthreads per pixel: 0.2 of the step's 0.35 ms of ToRGB forward went into 20 % of its bytes.)
+template <int K>
+__global__ void __launch_bounds__(kEwThreads) torgb_fwd_wide_kernel(ToRgbArgs p, int chunks)
+{
+    const EwGeom g = p.g;
+    const int n = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kWarps = kEwThreads / 32;
+    const float4* wm = reinterpret_cast<const float4*>(p.wmod + (long long)n * 3 * g.c);
+    float4 w0[K], w1[K], w2[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { w0[k] = __ldg(wm + lane + 32 * k); w1[k] = __ldg(wm + g.cvecs + lane + 32 * k); w2[k] = __ldg(wm + 2 * g.cvecs + lane + 32 * k); }
+    const float b0 = p.bias ? p.bias[0] : 0.f, b1 = p.bias ? p.bias[1] : 0.f, b2 = p.bias ? p.bias[2] : 0.f;
+    const long long base = (long long)n * g.hw * g.c;
+    const int stride = kWarps * chunks;
+    constexpr int U = K >= 4 ? 2 : 4;                       // pixels in flight per warp: U * K 16-byte loads per lane
+    for (int p0 = chunk * kWarps + warp; p0 < g.hw; p0 += U * stride)
+    {
+        float4 v[U][K];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+        {
+            const int px = p0 + u * stride;
+#pragma unroll
+            for (int k = 0; k < K; k++)
+                v[u][k] = px < g.hw ? __ldcs(reinterpret_cast<const float4*>(p.x + base + (long long)px * g.c) + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+        {
+            float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; k++)
+            {
+                r0 += v[u][k].x * w0[k].x + v[u][k].y * w0[k].y + v[u][k].z * w0[k].z + v[u][k].w * w0[k].w;
+                r1 += v[u][k].x * w1[k].x + v[u][k].y * w1[k].y + v[u][k].z * w1[k].z + v[u][k].w * w1[k].w;
+                r2 += v[u][k].x * w2[k].x + v[u][k].y * w2[k].y + v[u][k].z * w2[k].z + v[u][k].w * w2[k].w;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                r0 += __shfl_down_sync(0xffffffffu, r0, o);
+                r1 += __shfl_down_sync(0xffffffffu, r1, o);
+                r2 += __shfl_down_sync(0xffffffffu, r2, o);
+            }
+            const int px = p0 + u * stride;
+            if (lane == 0 && px < g.hw)
+            {
+                float* yo = p.y + (long long)n * 3 * g.hw + px;
+                yo[0] = r0 + b0; yo[g.hw] = r1 + b1; yo[2 * g.hw] = r2 + b2;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kEwThreads) torgb_bwd_kernel(ToRgbArgs p)
 {
     extern __shared__ float sacc[];            // [3][c]
@@ -458,6 +515,18 @@ extern "C" int sgv_torgb_fwd(const float* x, const float* wmod, const float* bia
     rc = make_geom(&a.g, n, hw, c);
     if (rc != SGV_OK) return rc;
     SGV_CHECK_ARG(a.g.cvecs <= 32 ? ((a.g.cvecs & (a.g.cvecs - 1)) == 0) : (a.g.cvecs % 32 == 0), "channel count %d not supported by torgb", c);
+    if (a.g.cvecs == 64 || a.g.cvecs == 128)
+    {
+        // wide layers: a warp per pixel; CTAs per sample so that the grid covers the SMs about four times (at least one pixel per warp)
+        int chunks = ceil_div(4 * num_sms(), n);
+        const int maxc = ceil_div(hw, kEwThreads / 32);
+        if (chunks > maxc) chunks = maxc;
+        if (chunks < 1) chunks = 1;
+        if (a.g.cvecs == 64) torgb_fwd_wide_kernel<2><<<(unsigned)(n * chunks), kEwThreads, 0, (cudaStream_t)stream_>>>(a, chunks);
+        else torgb_fwd_wide_kernel<4><<<(unsigned)(n * chunks), kEwThreads, 0, (cudaStream_t)stream_>>>(a, chunks);
+        SGV_LAUNCH_OK("torgb_fwd_wide_kernel");
+        return SGV_OK;
+    }
     torgb_fwd_kernel<<<(unsigned)(n * a.g.chunks), kEwThreads, 0, (cudaStream_t)stream_>>>(a);
     SGV_LAUNCH_OK("torgb_fwd_kernel");
     return SGV_OK;

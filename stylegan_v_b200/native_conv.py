@@ -109,6 +109,19 @@ def conv_weight_grad(gy, x, w_shape, transpose, stride, padding, output_padding,
         if I % 32 or O % 32 or s not in (1, 2):
             return None
         oh, ow = gy.shape[2], gy.shape[3]
+        if s == 2 and k == 3 and ow >= 8 and oh >= 4:
+            # stride 2 (the discriminator's down layers): x[2 oy + ky - p] = x_phase(a)[oy + (ky - p - a) / 2] with a = (ky - p) mod 2, so each of
+            # the four pixel-parity views of x is a STRIDE-1 weight gradient over its 4 / 2 / 2 / 1 taps — and runs on the grouped-tap kernel
+            # (one patch per dy row) instead of nine per-tap passes of the strided kernel (0.87 ms -> see profiles/timeline_gd_step_r2*.txt for
+            # 64 -> 128 channels at 128^2 x 48 frames).  The four calls accumulate into their tap slots of one buffer.
+            g, xn = _nhwc(gy), _nhwc(x)
+            dwt = torch.zeros([9, O, I], dtype=torch.float32, device=x.device)
+            for a in (0, 1):
+                for c in (0, 1):
+                    ph = [(ky, kx) for ky, kx in taps if (ky - p) % 2 == a and (kx - p) % 2 == c]
+                    offs = [((ky - p - a) // 2, (kx - p - c) // 2) for ky, kx in ph]
+                    _conv.igemm_wgrad(g, xn[:, :, a::2, c::2], [(0, 0)] * len(ph), offs, (oh, ow), out=dwt, slots=[ky * 3 + kx for ky, kx in ph], x3=x3)
+            return dwt.reshape(3, 3, O, I).permute(2, 3, 0, 1)
         dw = _conv.igemm_wgrad(_nhwc(gy), _nhwc(x), [(0, 0)] * len(taps), [(ky - p, kx - p) for ky, kx in taps], (oh, ow), x_stride=s, x3=x3)
         return dw.reshape(k, k, O, I).permute(2, 3, 0, 1)
     I, O = w_shape[0], w_shape[1]

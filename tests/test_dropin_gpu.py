@@ -29,7 +29,7 @@ CASES = [
     # transpose, Cin, Cout, k, stride, padding, H
     (False, 64, 64, 3, 1, 1, 16), (False, 32, 128, 1, 1, 0, 12), (False, 64, 64, 3, 2, 0, 17), (False, 64, 128, 3, 2, 1, 16),
     (True, 64, 64, 3, 2, 0, 8), (True, 64, 64, 3, 2, 0, 5), (True, 64, 32, 3, 1, 1, 12),
-    (False, 64, 64, 3, 2, 1, 40), (True, 64, 128, 3, 2, 0, 16),
+    (False, 64, 64, 3, 2, 1, 40), (True, 64, 128, 3, 2, 0, 16), (False, 64, 128, 3, 2, 0, 65), (False, 128, 256, 3, 2, 0, 33),
 ]
 
 
@@ -58,6 +58,28 @@ def test_conv2d_gradfix_native_matches_fp64(transpose, ci, co, k, s, p, H):
     gx, gw = torch.autograd.grad(y, [x, w], gy)
     rx, rw = torch.autograd.grad(ref, [xd, wd], gy.double())
     assert rel_err(gx, rx) < 1e-3 and rel_err(gw, rw) < 1e-3
+
+
+def test_stride2_weight_gradient_runs_on_the_grouped_tap_kernel():
+    """The discriminator's down layers (3x3, stride 2 on the blurred input): the weight gradient is issued as four pixel-parity stride-1 calls,
+    each of which the library serves with the grouped-tap kernel (variant 2), not the per-tap kernel (variant 1)."""
+    from stylegan_v_b200 import conv as C
+    x = torch.randn(4, 64, 65, 65, device='cuda').contiguous(memory_format=torch.channels_last)
+    g = torch.randn(4, 128, 32, 32, device='cuda').contiguous(memory_format=torch.channels_last)
+    seen = []
+    orig = C.igemm_wgrad
+
+    def spy(g_, x_, tg, tx, hw, **kw):
+        seen.append(orig(g_, x_, tg, tx, hw, **{**kw, 'query': True, 'out': None, 'slots': None})['kernel'])
+        return orig(g_, x_, tg, tx, hw, **kw)
+    C.igemm_wgrad = spy
+    try:
+        dw = native_conv.conv_weight_grad(g, x, (128, 64, 3, 3), False, (2, 2), (0, 0), (0, 0), (1, 1), 1)
+    finally:
+        C.igemm_wgrad = orig
+    assert seen == [2, 2, 2, 2], seen
+    ref, = torch.autograd.grad(F.conv2d(x.double(), (w := torch.zeros(128, 64, 3, 3, device='cuda', dtype=torch.double, requires_grad=True)), stride=2), w, g.double())
+    assert rel_err(dw, ref) < 1e-3
 
 
 def test_unsupported_shapes_fall_back_to_library():

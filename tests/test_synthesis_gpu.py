@@ -189,7 +189,7 @@ def test_config5_1024_forward_runs():
 def test_layer_elementwise_kernels():
     from stylegan_v_b200 import conv as C
     gen = torch.Generator().manual_seed(3)
-    for (N, Cc, H) in ((3, 64, 9), (2, 512, 4), (2, 128, 16), (1, 1024, 4), (2, 16, 8)):
+    for (N, Cc, H) in ((3, 64, 9), (2, 512, 4), (2, 128, 16), (1, 1024, 4), (2, 16, 8), (2, 256, 19), (3, 512, 33)):
         cl = lambda t: t.cuda().contiguous(memory_format=torch.channels_last)
         dy = cl(torch.randn(N, Cc, H, H, generator=gen)); v = torch.randn(N, Cc, H, H, generator=gen)
         bias = torch.randn(Cc, generator=gen).cuda(); gain = float(np.sqrt(2))
