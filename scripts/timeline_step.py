@@ -87,3 +87,27 @@ hist = collections.Counter()
 for d, a, b in gaps:
     hist[min(int(d // 1000), 20)] += 1      # microsecond buckets
 print('gap length histogram (us: count):', dict(sorted(hist.items())))
+# ---- where the step is SERIAL: time during which exactly one activity is in flight, grouped by that activity; and the tail of the step ----
+edges = []
+for i, (s, e, name, stream, kind) in enumerate(ks):
+    edges.append((s, 1, i)); edges.append((e, -1, i))
+edges.sort()
+live = set(); alone = collections.defaultdict(float); multi = 0.0; prev = edges[0][0]
+for tt, d, i in edges:
+    if tt > prev and live:
+        if len(live) == 1:
+            alone[ks[next(iter(live))][2].split('(')[0][:70]] += tt - prev
+        else:
+            multi += tt - prev
+    prev = tt
+    (live.add if d > 0 else live.discard)(i)
+print(f'time with >= 2 activities in flight {multi / 1e3:.3f} ms; time with exactly one, by kernel:')
+for k, v in sorted(alone.items(), key=lambda kv: -kv[1])[:25]:
+    print(f'  {v / 1e3:8.3f} ms  {k}')
+streams = collections.defaultdict(float)
+for s, e, name, stream, kind in ks:
+    streams[stream] += e - s
+print('busy time per stream:', {str(k): round(v / 1e3, 3) for k, v in streams.items()})
+print('last 60 activities (start offset from the end of the step in us, duration us, stream, name):')
+for s, e, name, stream, kind in sorted(ks, key=lambda k: k[1])[-60:]:
+    print(f'  {(s - t1) / 1e3:9.1f} {(e - s) / 1e3:8.1f}  {stream}  {name.split("(")[0][:80]}')

@@ -120,3 +120,103 @@ def test_unmodified_reference_generator_and_discriminator_on_dropin_ops(tmp_path
     for k, cs in x1['cos'].items():
         if not k.endswith('bias'):
             assert cs > 0.99, (k, cs)
+
+
+_LOSS_SCRIPT = r'''
+import sys, json, numpy as np, torch
+sys.path.insert(0, {root!r})
+from stylegan_v_b200.install import install_ops
+install_ops()
+from stylegan_v_b200 import _lib, precision
+from oracle import ref_loader, synthesis_ref as sr
+ref = ref_loader.load()
+from stylegan_v_b200.ops import conv2d_gradfix
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+# the reference draws its motion noise with torch.randn on the compute device (motion.py:83); route every draw through ONE CPU generator so that
+# the CPU and the CUDA evaluation see the same numbers (the reference code itself is untouched)
+_gen = torch.Generator()
+_randn = torch.randn
+def randn(*size, **kw):
+    dev = kw.pop('device', None)
+    kw.pop('generator', None)
+    out = _randn(*size, generator=_gen, **kw)
+    return out.to(dev) if dev is not None else out
+torch.randn = randn
+
+cfg = sr.SynthesisConfig(img_resolution=32, w_dim=64, channel_base=2048, channel_max=64, motion_z_dim=32, motion_v_dim=32, time_enc_dim=32)
+gcfg = ref_loader.to_cfg(cfg.reference_generator_cfg())
+dcfg = ref_loader.to_cfg(dict(sampling=dict(num_frames_per_video=3, max_num_frames=1024, type='random'), concat_res=16, num_frames_div_factor=2, dummy_c=False))
+torch.manual_seed(0)
+G = ref.networks.Generator(c_dim=0, w_dim=cfg.w_dim, img_resolution=32, img_channels=3, cfg=gcfg, mapping_kwargs=dict(num_layers=2),
+                           synthesis_kwargs=dict(channel_base=cfg.channel_base, channel_max=cfg.channel_max)).train()
+D = ref.networks.Discriminator(c_dim=0, img_resolution=32, img_channels=3, channel_base=2048, channel_max=64, cfg=dcfg,
+                               mapping_kwargs=dict(num_layers=2), epilogue_kwargs=dict(mbstd_group_size=2)).train()
+g = torch.Generator().manual_seed(1)
+B, Fr = 2, 3
+real = _randn(B, Fr, 3, 32, 32, generator=g).clamp(-1, 1)
+real_t = torch.tensor([[0.0, 4.0, 20.0], [30.0, 31.0, 33.0]])
+gen_t = torch.tensor([[2.0, 10.0, 11.0], [500.0, 516.0, 530.0]])
+z = _randn(B, cfg.w_dim, generator=g)
+c = torch.zeros(B, 0)
+PHASES = [('Gmain', 'G', 1), ('Dmain', 'D', 1), ('Dreg', 'D', 16)]
+
+
+def run(dev):
+    Gd, Dd = G.to(dev), D.to(dev)
+    loss = ref.loss.StyleGAN2Loss(cfg=None, device=dev, G_mapping=Gd.mapping, G_synthesis=Gd.synthesis, D=Dd, style_mixing_prob=0.0, r1_gamma=0.5, pl_weight=0.0)
+    w0 = Gd.mapping.w_avg.clone()
+    out = {{}}
+    for phase, which, gain in PHASES:
+        module = Gd if which == 'G' else Dd
+        Gd.requires_grad_(which == 'G'); Dd.requires_grad_(which == 'D')
+        for p in module.parameters():
+            p.grad = None
+        _gen.manual_seed(100)
+        loss.accumulate_gradients(phase=phase, real_img=real.to(dev), real_c=c.to(dev), real_t=real_t.to(dev), gen_z=z.to(dev), gen_c=c.to(dev), gen_t=gen_t.to(dev), sync=True, gain=gain)
+        Gd.mapping.w_avg.copy_(w0)
+        for n, p in module.named_parameters():
+            if p.grad is not None and p.grad.numel() >= 64 and not n.endswith('bias'):
+                out[phase + ':' + n] = p.grad.double().cpu().clone()
+    return out
+
+
+cpu = run(torch.device('cpu'))
+conv2d_gradfix.enabled = True
+n0 = _lib.launch_count()
+with precision.precision('tf32x3'):
+    gpu = run(torch.device('cuda', 0))
+torch.cuda.synchronize()
+rep = dict(launches=_lib.launch_count() - n0, grads=len(cpu))
+worst = {{}}
+for k in cpu:
+    a, b = gpu[k], cpu[k]
+    rel = float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    cs = float(torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0))
+    ph = k.split(':')[0]
+    w = worst.setdefault(ph, dict(rel=0.0, cos=1.0, n=0))
+    w['rel'] = max(w['rel'], rel); w['cos'] = min(w['cos'], cs); w['n'] += 1
+    if rel == w['rel']:
+        w['worst'] = k
+rep['worst'] = worst
+print('REPORT ' + json.dumps(rep))
+'''
+
+
+def test_unmodified_reference_loss_phases_on_dropin_ops():
+    """SURVEY §2 row 11: `StyleGAN2Loss` stays the reference's.  Its `accumulate_gradients` (loss.py:73-173) — Gmain, Dmain and the R1 phase, which
+    differentiates the discriminator twice — runs unmodified on the drop-in ops on cuda:0 (fp32-grade mode) and must reproduce the gradients of
+    its own CPU evaluation for every weight of the trained network."""
+    code = _LOSS_SCRIPT.format(root=ROOT)
+    env = dict(os.environ)
+    env.pop('SGV_PRECISION', None)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    rep = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('REPORT ')][-1][len('REPORT '):])
+    assert rep['launches'] > 300 and rep['grads'] > 40, rep
+    for phase, w in rep['worst'].items():
+        # bars: direction to 0.995 and max-norm error 8e-2 per tensor (measured values are printed by the failure message; the fp32-grade mode's
+        # weight gradients carry leaky-ReLU slope flips of any non-bit-equal forward, tests/test_precision_gpu.py)
+        assert w['n'] > 5 and w['cos'] > 0.995 and w['rel'] < 8e-2, (phase, w)
+    print('reference loss phases on the drop-in ops:', rep)
