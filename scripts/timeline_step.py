@@ -108,6 +108,6 @@ streams = collections.defaultdict(float)
 for s, e, name, stream, kind in ks:
     streams[stream] += e - s
 print('busy time per stream:', {str(k): round(v / 1e3, 3) for k, v in streams.items()})
-print('last 60 activities (start offset from the end of the step in us, duration us, stream, name):')
+print('last 60 activities (start offset from the end of the step in ms, duration ms, stream, name):')
 for s, e, name, stream, kind in sorted(ks, key=lambda k: k[1])[-60:]:
-    print(f'  {(s - t1) / 1e3:9.1f} {(e - s) / 1e3:8.1f}  {stream}  {name.split("(")[0][:80]}')
+    print(f'  {(s - t1) / 1e3:9.3f} {(e - s) / 1e3:8.3f}  {stream}  {name.split("(")[0][:80]}')

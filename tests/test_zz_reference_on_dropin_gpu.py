@@ -216,7 +216,7 @@ def test_unmodified_reference_loss_phases_on_dropin_ops():
     rep = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('REPORT ')][-1][len('REPORT '):])
     assert rep['launches'] > 300 and rep['grads'] > 40, rep
     for phase, w in rep['worst'].items():
-        # bars: direction to 0.995 and max-norm error 8e-2 per tensor (measured values are printed by the failure message; the fp32-grade mode's
-        # weight gradients carry leaky-ReLU slope flips of any non-bit-equal forward, tests/test_precision_gpu.py)
-        assert w['n'] > 5 and w['cos'] > 0.995 and w['rel'] < 8e-2, (phase, w)
+        # measured on the B200 (call M of round 2): worst max-norm error 1.7e-4 (Gmain) / 3.9e-4 (Dmain) / 7.7e-5 (Dreg), cosine 1 - 1e-8; bars 2e-3 / 0.9999
+        # (the fp32-grade mode; leaky-ReLU slope flips of a non-bit-equal forward are what the margin is for, tests/test_precision_gpu.py)
+        assert w['n'] > 5 and w['cos'] > 0.9999 and w['rel'] < 2e-3, (phase, w)
     print('reference loss phases on the drop-in ops:', rep)
