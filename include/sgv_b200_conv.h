@@ -177,6 +177,13 @@ int sgv_modconv_act_bwd_ex(const float* dy, const float* y, const float* bias, f
 int sgv_modconv_scale_reduce(const float* dxs, const float* x, const float* s, float* dx, float* ds,
                              int32_t n, int32_t hw, int32_t c, void* stream);
 int sgv_torgb_fwd(const float* x, const float* wmod, const float* bias, float* y, int32_t n, int32_t hw, int32_t c, void* stream);
+/* ToRGB modulated weights (networks.py:159-160):  wmod[n, j, c] = w[j, c] * styles[n, c] * gain   (w [img_channels <= 4, c]; styles [n, c] with row
+ * stride styles_stride), and both gradients in one launch:  d_styles[n, c] = gain * sum_j dwmod[n, j, c] * w[j, c]  (dense [n, c]; may be NULL),
+ * dw[j, c] = gain * sum_n dwmod[n, j, c] * styles[n, c]  (may be NULL). */
+int sgv_torgb_wmod_fwd(const float* w, const float* styles, int64_t styles_stride, float* wmod, int32_t n, int32_t c, int32_t img_channels,
+                       float gain, void* stream);
+int sgv_torgb_wmod_bwd(const float* dwmod, const float* w, const float* styles, int64_t styles_stride, float* d_styles, float* dw,
+                       int32_t n, int32_t c, int32_t img_channels, float gain, void* stream);
 int sgv_torgb_bwd(const float* dy, const float* x, const float* wmod, float* dx, float* dwmod, int32_t n, int32_t hw, int32_t c, void* stream);
 
 #ifdef __cplusplus

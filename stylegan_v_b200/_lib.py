@@ -140,6 +140,8 @@ SYMBOLS = [
     ('sgv_modconv_scale_reduce', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     ('sgv_torgb_fwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     ('sgv_torgb_bwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
+    ('sgv_torgb_wmod_fwd', c_int, [c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_int, c_f32, c_vp]),
+    ('sgv_torgb_wmod_bwd', c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_f32, c_vp]),
     ('sgv_time_encoder_fwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_vp]),
     ('sgv_time_encoder_bwd', c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_f32, c_vp]),
     ('sgv_adam_ema_step', c_int, [ctypes.POINTER(AdamParams), c_vp]),

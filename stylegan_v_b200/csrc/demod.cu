@@ -53,10 +53,22 @@ __device__ __forceinline__ float4 wsq4(const float* wp)
 }
 
 // ---- forward: CTA = 8 output channels x 32 samples; warp = 8 samples; lane = 4 consecutive input channels per 128-wide trip ----
+// wsq of the CTA's 8 output channels is formed ONCE, cooperatively (every thread: I / 64 items of 9 independent 16-byte loads), into shared
+// memory; the four warps then read it as LDS.128.  (First version: every warp recomputed wsq from global memory inside the reduction loop —
+// 4x redundant, dependent loads: 20 us per 512 x 512 layer, 28 us for the style gradient; the kernels sit in the serial head / tail of the step.)
 __global__ void __launch_bounds__(kDemodThreads) demod_fwd_kernel(const DemodArgs p)
 {
+    extern __shared__ __align__(16) float wsq_s[];          // [8][i]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int o0 = blockIdx.x * 8;
+    const int ivecs = p.i >> 2;
+    for (int item = threadIdx.x; item < 8 * ivecs; item += kDemodThreads)
+    {
+        const int c = item / ivecs, iv = item - c * ivecs;
+        const float4 q = wsq4(p.w + ((long long)min(o0 + c, p.o - 1) * p.i + iv * 4) * kDemodTaps);
+        *reinterpret_cast<float4*>(wsq_s + c * p.i + iv * 4) = q;
+    }
+    __syncthreads();
     const int n0 = blockIdx.y * 32 + warp * 8;
     if (n0 >= p.n) return;
     float acc[8][8];
@@ -74,7 +86,7 @@ __global__ void __launch_bounds__(kDemodThreads) demod_fwd_kernel(const DemodArg
             s2[r] = make_float4(t.x * t.x, t.y * t.y, t.z * t.z, t.w * t.w);
         }
 #pragma unroll
-        for (int c = 0; c < 8; c++) wq[c] = wsq4(p.w + ((long long)min(o0 + c, p.o - 1) * p.i + i0) * kDemodTaps);
+        for (int c = 0; c < 8; c++) wq[c] = *reinterpret_cast<const float4*>(wsq_s + c * p.i + i0);
 #pragma unroll
         for (int r = 0; r < 8; r++)
 #pragma unroll
@@ -109,11 +121,14 @@ __device__ __forceinline__ float demod_g(const DemodArgs& p, int n, int o)
 }
 
 // ---- d styles: CTA = 32 samples x 128 input channels over one slice of the output channels; lane = 4 consecutive input channels ----
+// per chunk of 32 output channels the CTA stages g [32 samples][32] and wsq [32][128 input channels] in shared memory cooperatively
 __global__ void __launch_bounds__(kDemodThreads) demod_bwd_styles_kernel(const DemodArgs p)
 {
     __shared__ __align__(16) float gs[32][36];
+    __shared__ __align__(16) float wq_s[32][128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i0 = blockIdx.x * 128 + lane * 4;
+    const int ib = blockIdx.x * 128;
+    const int i0 = ib + lane * 4;
     const int n0 = blockIdx.y * 32;
     const int chunk = ((p.o + p.osplit - 1) / p.osplit + 31) & ~31;
     const int ob = (int)blockIdx.z * chunk, oe = min(p.o, ob + chunk);
@@ -132,11 +147,18 @@ __global__ void __launch_bounds__(kDemodThreads) demod_bwd_styles_kernel(const D
             const int n = n0 + srow, o = oc + sseg + j;
             gs[srow][sseg + j] = (n < p.n && o < oe) ? demod_g(p, n, o) : 0.f;
         }
-        __syncthreads();
-        const int olim = min(32, oe - oc);
-        for (int j = 0; j < olim; j++)
+        for (int item = threadIdx.x; item < 32 * 32; item += kDemodThreads)
         {
-            const float4 wq = iok ? wsq4(p.w + ((long long)(oc + j) * p.i + i0) * kDemodTaps) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int ol = item >> 5, iv = item & 31;
+            const int o = oc + ol, ii = ib + iv * 4;
+            const float4 q = (o < oe && ii < p.i) ? wsq4(p.w + ((long long)o * p.i + ii) * kDemodTaps) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(&wq_s[ol][iv * 4]) = q;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < 32; j++)
+        {
+            const float4 wq = *reinterpret_cast<const float4*>(&wq_s[j][lane * 4]);
 #pragma unroll
             for (int r = 0; r < 8; r++)
             {
@@ -158,7 +180,8 @@ __global__ void __launch_bounds__(kDemodThreads) demod_bwd_styles_kernel(const D
     }
 }
 
-// ---- d weight: CTA = 8 output channels x 512 input channels; warp = 128 input channels; lane = 4 consecutive; loop over all samples ----
+// ---- d weight: CTA = 8 output channels x 512 input channels; warp = 128 input channels; lane = 4 consecutive; loop over all samples;
+//      the epilogue (read w, scale, write dw: 9 + 9 vector accesses per output channel) is rolled two channels at a time ----
 __global__ void __launch_bounds__(kDemodThreads) demod_bwd_weight_kernel(const DemodArgs p)
 {
     __shared__ __align__(16) float gs[32][8];
@@ -201,7 +224,7 @@ __global__ void __launch_bounds__(kDemodThreads) demod_bwd_weight_kernel(const D
         }
     }
     if (!iok) return;
-#pragma unroll
+#pragma unroll 2
     for (int c = 0; c < 8; c++)
     {
         if (o0 + c >= p.o) break;
@@ -247,7 +270,9 @@ extern "C" int sgv_demod_fwd(const float* w, const float* styles, int64_t styles
     if (rc != SGV_OK) return rc;
     a.dc = dcoefs; a.eps = eps;
     dim3 grid((unsigned)ceil_div(o, 8), (unsigned)ceil_div(n, 32));
-    demod_fwd_kernel<<<grid, kDemodThreads, 0, (cudaStream_t)stream_>>>(a);
+    const size_t smem = (size_t)8 * i * sizeof(float);
+    SGV_CHECK_ARG(smem <= 48 * 1024, "sgv_demod_fwd: at most 1536 input channels (got %d)", i);
+    demod_fwd_kernel<<<grid, kDemodThreads, smem, (cudaStream_t)stream_>>>(a);
     SGV_LAUNCH_OK("demod_fwd_kernel");
     return SGV_OK;
 }

@@ -447,6 +447,46 @@ static int make_geom(EwGeom* g, int n, int hw, int c)
     return SGV_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// ToRGB modulated weights (networks.py:159-160: styles = affine(w) * weight_gain; the 1x1 modulated conv without demodulation multiplies the
+// [3, C] weight by them): wmod[n, j, c] = w[j, c] * s[n, c] * gain, and both gradients in ONE launch.  Per layer and step this replaces 2
+// (forward) + 6 (autograd) element-wise / reduction launches on [N, 3, C]-sized tensors that sat in the serial tail of the step.
+__global__ void __launch_bounds__(128) torgb_wmod_fwd_kernel(const float* __restrict__ w, const float* __restrict__ s, long long lds, float* __restrict__ wmod,
+                                                             int n, int c, int j, float gain)
+{
+    const int ci = blockIdx.x * 128 + threadIdx.x, ni = blockIdx.y;
+    if (ci >= c) return;
+    const float sv = __ldg(s + (long long)ni * lds + ci) * gain;
+    for (int jj = 0; jj < j; jj++) wmod[((long long)ni * j + jj) * c + ci] = __ldg(w + (long long)jj * c + ci) * sv;
+}
+
+// thread = one channel: ds[n, c] = gain * sum_j dwmod[n, j, c] * w[j, c];  dw[j, c] = gain * sum_n dwmod[n, j, c] * s[n, c]      (j <= 4)
+__global__ void __launch_bounds__(128) torgb_wmod_bwd_kernel(const float* __restrict__ dwmod, const float* __restrict__ w, const float* __restrict__ s, long long lds,
+                                                             float* __restrict__ ds, float* __restrict__ dw, int n, int c, int j, float gain)
+{
+    const int ci = blockIdx.x * 128 + threadIdx.x;
+    if (ci >= c) return;
+    float wv[4], acc[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) { wv[jj] = jj < j ? __ldg(w + (long long)jj * c + ci) : 0.f; acc[jj] = 0.f; }
+    for (int ni = 0; ni < n; ni++)
+    {
+        const float sv = __ldg(s + (long long)ni * lds + ci);
+        float d = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++)
+            if (jj < j)
+            {
+                const float g = __ldg(dwmod + ((long long)ni * j + jj) * c + ci);
+                d = fmaf(g, wv[jj], d);
+                acc[jj] = fmaf(g, sv, acc[jj]);
+            }
+        if (ds) ds[(long long)ni * c + ci] = d * gain;
+    }
+    if (dw)
+        for (int jj = 0; jj < j; jj++) dw[(long long)jj * c + ci] = acc[jj] * gain;
+}
+
 } // namespace sgv
 
 extern "C" int sgv_modconv_act_bwd_ex(const float* dy, const float* y, const float* bias, float* dz, float* db, float* dd,
@@ -545,5 +585,30 @@ extern "C" int sgv_torgb_bwd(const float* dy, const float* x, const float* wmod,
     if (rc != SGV_OK) return rc;
     torgb_bwd_kernel<<<(unsigned)(n * a.g.chunks), kEwThreads, 3 * c * sizeof(float), (cudaStream_t)stream_>>>(a);
     SGV_LAUNCH_OK("torgb_bwd_kernel");
+    return SGV_OK;
+}
+
+extern "C" int sgv_torgb_wmod_fwd(const float* w, const float* styles, int64_t styles_stride, float* wmod, int32_t n, int32_t c, int32_t img_channels,
+                                  float gain, void* stream_)
+{
+    using namespace sgv;
+    SGV_CHECK_ARG(w && styles && wmod && n >= 1 && c >= 1 && img_channels >= 1 && img_channels <= 4, "sgv_torgb_wmod_fwd: bad argument");
+    int rc = sgv_device_check();
+    if (rc != SGV_OK) return rc;
+    dim3 grid((unsigned)ceil_div(c, 128), (unsigned)n);
+    torgb_wmod_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream_>>>(w, styles, styles_stride, wmod, n, c, img_channels, gain);
+    SGV_LAUNCH_OK("torgb_wmod_fwd_kernel");
+    return SGV_OK;
+}
+
+extern "C" int sgv_torgb_wmod_bwd(const float* dwmod, const float* w, const float* styles, int64_t styles_stride, float* d_styles, float* dw,
+                                  int32_t n, int32_t c, int32_t img_channels, float gain, void* stream_)
+{
+    using namespace sgv;
+    SGV_CHECK_ARG(dwmod && w && styles && (d_styles || dw) && n >= 1 && c >= 1 && img_channels >= 1 && img_channels <= 4, "sgv_torgb_wmod_bwd: bad argument");
+    int rc = sgv_device_check();
+    if (rc != SGV_OK) return rc;
+    torgb_wmod_bwd_kernel<<<(unsigned)ceil_div(c, 128), 128, 0, (cudaStream_t)stream_>>>(dwmod, w, styles, styles_stride, d_styles, dw, n, c, img_channels, gain);
+    SGV_LAUNCH_OK("torgb_wmod_bwd_kernel");
     return SGV_OK;
 }

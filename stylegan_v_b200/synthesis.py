@@ -17,6 +17,7 @@ import os
 import numpy as np
 import torch
 
+from . import _lib
 from . import conv as _conv
 from . import dense as _dense
 from .modconv import fused_modulated_conv, demod_coefs, prepare_weights, WeightGradBox, WeightGradNode
@@ -109,6 +110,38 @@ class _ToRGB(torch.autograd.Function):
         return dx, dwmod, dy.sum(dim=[0, 2, 3])
 
 
+class _ToRgbWmod(torch.autograd.Function):
+    """wmod[n, j, c] = weight[j, c] * styles[n, c] * gain (networks.py:159-160) and both gradients: csrc/layer_elementwise.cu.  First order."""
+
+    @staticmethod
+    def forward(ctx, weight, styles, gain):
+        J, C = weight.shape[0], weight.shape[1]
+        N = styles.shape[0]
+        w2 = weight.reshape(J, C).contiguous()
+        wmod = torch.empty([N, J, C], dtype=torch.float32, device=styles.device)
+        with torch.cuda.device(styles.device):
+            _lib.check(_lib.lib().sgv_torgb_wmod_fwd(w2.data_ptr(), styles.data_ptr(), styles.stride(0), wmod.data_ptr(), N, C, J, gain,
+                                                     _conv._stream(styles.device)), 'sgv_torgb_wmod_fwd')
+        ctx.save_for_backward(w2, styles)
+        ctx.cfg = (gain, tuple(weight.shape))
+        return wmod
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dwmod):
+        w2, styles = ctx.saved_tensors
+        gain, w_shape = ctx.cfg
+        J, C = w2.shape
+        N = styles.shape[0]
+        dwmod = dwmod.contiguous()
+        ds = torch.empty([N, C], dtype=torch.float32, device=styles.device) if ctx.needs_input_grad[1] else None
+        dw = torch.empty([J, C], dtype=torch.float32, device=styles.device) if ctx.needs_input_grad[0] else None
+        with torch.cuda.device(styles.device):
+            _lib.check(_lib.lib().sgv_torgb_wmod_bwd(dwmod.data_ptr(), w2.data_ptr(), styles.data_ptr(), styles.stride(0), ds.data_ptr() if ds is not None else None,
+                                                     dw.data_ptr() if dw is not None else None, N, C, J, gain, _conv._stream(styles.device)), 'sgv_torgb_wmod_bwd')
+        return (dw.reshape(w_shape) if dw is not None else None), ds, None
+
+
 class ToRGBLayer(torch.nn.Module):
     """1x1 modulated conv to RGB without demodulation + bias (networks.py:148-163).  With 3 output channels this is
     memory-bound; it runs as one batched [HW, C] x [C, 3] product per sample straight from the NHWC activations."""
@@ -122,6 +155,8 @@ class ToRGBLayer(torch.nn.Module):
 
     def plan(self, styles):
         C = self.weight.shape[1]
+        if styles.is_cuda and styles.dtype == torch.float32 and self.weight.dtype == torch.float32 and self.weight.shape[0] <= 4 and styles.stride(1) == 1:
+            return dict(wmod=_ToRgbWmod.apply(self.weight, styles, float(self.weight_gain)))          # [N, 3, C]: one launch, one in the backward
         return dict(wmod=self.weight.reshape(1, -1, C) * (styles * self.weight_gain).unsqueeze(1))   # [N, 3, C]  (tiny, differentiable torch ops)
 
     def forward(self, x, w=None, styles=None, plan=None):

@@ -219,3 +219,21 @@ def test_layer_elementwise_kernels():
                 assert rel_err(dz2, dz2_ref) < 1e-6 and rel_err(db2, dz2_ref.sum([0, 2, 3])) < 1e-5
                 assert rel_err(dd2, (dz2_ref * v.cuda().double()).sum([2, 3])) < 1e-4
                 assert rel_err(dwm2, torch.einsum('njhw,nchw->njc', g3.double(), y.double())) < 1e-5
+
+
+def test_torgb_modulated_weight_node():
+    """wmod = weight * styles * gain of the ToRGB layers (networks.py:159-160) as one launch + one backward launch vs the torch formula; styles is
+    a column slice of the stacked affine output."""
+    from stylegan_v_b200.synthesis import _ToRgbWmod
+    gen = torch.Generator().manual_seed(5)
+    for N, C in ((32, 512), (3, 64), (5, 200)):
+        w = torch.randn(3, C, 1, 1, generator=gen).cuda().requires_grad_(True)
+        wide = torch.randn(N, C + 24, generator=gen).cuda().requires_grad_(True)
+        s = wide[:, 8:8 + C]
+        gain = 1 / np.sqrt(C)
+        got = _ToRgbWmod.apply(w, s, float(gain))
+        ref = w.reshape(1, 3, C) * (s * gain).unsqueeze(1)
+        dy = torch.randn(N, 3, C, generator=gen).cuda()
+        gw, gs = torch.autograd.grad(got, [w, wide], dy)
+        rw, rs = torch.autograd.grad(ref, [w, wide], dy)
+        assert rel_err(got, ref) < 1e-6 and rel_err(gw, rw) < 1e-5 and rel_err(gs, rs) < 1e-5
