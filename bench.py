@@ -520,6 +520,7 @@ def main():
     ap.add_argument('--res', type=int, default=256, help='synthesis_fwd: 256 (BASELINE configs[1], 32 frames) or 1024 (configs[4], 8 frames, fmaps 1)')
     ap.add_argument('--precision', default='tf32', choices=['tf32', 'tf32x3'], help='arithmetic mode of the headline number (the other mode is measured beside it)')
     ap.add_argument('--no-second-mode', action='store_true', help='skip the measurement of the other arithmetic mode')
+    ap.add_argument('--no-overlap', action='store_true', help='N > 1: one gradient all-reduce after the graph replay instead of the early bucket inside the graph')
     ap.add_argument('--ref-frames', type=int, default=8, help='--impl reference: frames per sampled CPU step (of the 32 of a step)')
     ap.add_argument('--workload', default='synthesis', choices=['synthesis', 'gd_step', 'synthesis_fwd', 'full_loop'],
                     help="synthesis = BASELINE metric (256x256 SynthesisNetwork fwd+bwd, configs[1] batch); gd_step = configs[2] (G+D training step, no reg)")
@@ -557,8 +558,27 @@ def main():
     net = SynthesisNetwork(img_resolution=RES).to(dev).train()
     # parameters / gradients / Adam moments in flat buffers: one all-reduce (N > 1) and one fused nan_to_num + Adam launch per step
     # (training_loop.py:381-386 semantics; lr as train.py:160).  --no-optimizer times forward + backward alone.
-    state = FlatModuleState(list(net.parameters()))
+    # N > 1: the 3x3 convolution weights (70 % of the gradient bytes) come FIRST in the flat buffer: their weight-gradient kernels are the last
+    # tensor-core kernels of the backward pass, but ~0.7 ms of small kernels follow them (demodulation / affine / motion-encoder gradients,
+    # profiles/timeline_r2m_serial.txt), so their all-reduce is issued — inside the captured graph — the moment the last of them has been
+    # accumulated and runs under that tail; only the rest of the buffer is reduced after the backward pass.  (--no-overlap: one collective.)
+    params = list(net.parameters())
+    overlap = world > 1 and not args.no_overlap and not args.no_graph
+    early = [p for p in params if p.ndim == 4 and p.shape[-1] == 3] if overlap else []
+    early_ids = {id(p) for p in early}
+    state = FlatModuleState(early + [p for p in params if id(p) not in early_ids])
+    early_numel = state.offsets[len(early)] if early else 0
     state.broadcast(0)                         # ... and rank 0's parameters are broadcast like the reference's "Distribute across GPUs" (training_loop.py:215-232)
+    bucket = dict(armed=False, left=0, work=None)
+
+    def _early_ready(_p):
+        if not bucket['armed']:
+            return
+        bucket['left'] -= 1
+        if bucket['left'] == 0:
+            bucket['work'] = dist.all_reduce(state.grad[:early_numel], op=dist.ReduceOp.SUM, async_op=True)
+    for p in early:
+        p.register_post_accumulate_grad_hook(_early_ready)
     opt = None if args.no_optimizer else FusedAdamEMA(state, lr=0.0025, betas=(0.0, 0.99), eps=1e-8)
     torch.manual_seed(1 + rank)                # per-rank latents (each rank works on its own 32 frames)
     N = FRAMES_PER_GPU
@@ -577,7 +597,13 @@ def main():
         ws = ws.requires_grad_(True)
         img = net(ws, t, motion_z=mz)
         loss = (img * dimg).sum()
+        if bucket['armed']:
+            bucket['left'], bucket['work'] = len(early), None
         loss.backward()
+        if bucket['armed']:
+            assert bucket['work'] is not None, 'the early gradient bucket never became ready'
+            bucket['work'].wait()                                                  # stream-level wait (capturable)
+            dist.all_reduce(state.grad[early_numel:], op=dist.ReduceOp.SUM)        # the rest: affines, biases, motion encoder
         return loss
 
     # The step (about 1000 kernel launches: forward + backward of 20 fused layers) is captured ONCE into a CUDA graph and replayed:
@@ -588,8 +614,10 @@ def main():
         """The step in one arithmetic mode of the contractions (stylegan_v_b200.precision): 'tf32' or the fp32-grade 'tf32x3'.  The mode is
         read when the kernels are issued, i.e. at capture time; a replay needs no context."""
         graph, graph_launches, s_loss = None, 0, None
+        in_graph_reduce = False
         if not args.no_graph:
             try:
+                bucket['armed'] = overlap                   # the collectives are captured with the step
                 with precision.precision(mode):
                     side = torch.cuda.Stream()
                     side.wait_stream(torch.cuda.current_stream())
@@ -603,11 +631,31 @@ def main():
                     with torch.cuda.graph(graph):
                         s_loss = step_compute(s_ws.detach(), s_t, s_mz)
                     graph_launches = _lib.launch_count() - l0
+                in_graph_reduce = overlap
             except Exception as e:      # capture is an optimisation, not a requirement
-                if rank == 0:
-                    sys.stderr.write(f'[bench] CUDA graph capture failed ({type(e).__name__}: {e}); falling back to eager launches\n')
+                sys.stderr.write(f'[bench] rank {rank}: CUDA graph capture failed ({type(e).__name__}: {e}); falling back\n')
                 graph = None
                 torch.cuda.synchronize()
+            bucket['armed'] = False
+            if overlap:
+                # every rank must issue the same collectives: if the capture with NCCL inside failed anywhere, all ranks re-capture without it
+                ok = torch.tensor([1.0 if graph is not None else 0.0], device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if float(ok.item()) == 0.0:
+                    in_graph_reduce = False
+                    graph = None
+                    try:
+                        with precision.precision(mode):
+                            torch.cuda.synchronize()
+                            graph = torch.cuda.CUDAGraph()
+                            l0 = _lib.launch_count()
+                            with torch.cuda.graph(graph):
+                                s_loss = step_compute(s_ws.detach(), s_t, s_mz)
+                            graph_launches = _lib.launch_count() - l0
+                    except Exception as e:
+                        sys.stderr.write(f'[bench] rank {rank}: CUDA graph capture failed again ({type(e).__name__}: {e}); eager launches\n')
+                        graph = None
+                        torch.cuda.synchronize()
         state.zero_grad()                          # warm-up / capture passes accumulated into the buffer
 
         def step(ws, t, mz):
@@ -619,15 +667,16 @@ def main():
             else:
                 with precision.precision(mode):
                     loss = step_compute(ws, t, mz)
-            state.all_reduce()                     # SUM over ranks; the 1/world of the average is applied inside the update kernel
+            if not (in_graph_reduce and graph is not None):
+                state.all_reduce()                 # SUM over ranks; the 1/world of the average is applied inside the update kernel
             if opt is not None:
                 opt.step(zero_grad=True)
             elif world > 1:
                 state.grad.div_(world)
             return loss
-        return step, graph, graph_launches
+        return step, graph, graph_launches, in_graph_reduce
 
-    step, graph, graph_launches = build_step(args.precision)
+    step, graph, graph_launches, reduce_in_graph = build_step(args.precision)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -673,7 +722,7 @@ def main():
     other_mode = 'tf32x3' if args.precision == 'tf32' else 'tf32'
     other = None
     if not args.no_second_mode:
-        step2, graph2, launches2 = build_step(other_mode)
+        step2, graph2, launches2, _ = build_step(other_mode)
         k2 = max(3, args.steps // 2)
         ms2, l2 = timed(lambda: step2(s_ws if graph2 is not None else d_ws.detach(), s_t if graph2 is not None else d_t, s_mz if graph2 is not None else d_mz), k2, 3)
         other = dict(dtype=DTYPES[other_mode], value=N * world / (ms2 / k2 * 1e-3), unit='frames/s', ms_per_step=ms2 / k2, steps=k2, warmup=3,
@@ -796,7 +845,8 @@ def main():
                 data='synthetic',
                 config=dict(workload='256x256 SynthesisNetwork forward+backward' + (' + fused nan_to_num/Adam update of all parameters' if opt is not None else '') +
                                      ', 32 frames/GPU (32 latents x 1 frame), fmaps 0.5, random-init weights', optimizer_step=opt is not None,
-                            frames_per_gpu=N, parallelism=f'dp{world}', cuda_graph=graph is not None, l2='activation working set per step (>= 134 MB per layer at res >= 64, ~6 GB total) exceeds the 126 MB L2; no explicit flush',
+                            frames_per_gpu=N, parallelism=f'dp{world}', cuda_graph=graph is not None,
+                            gradient_all_reduce=('none (1 GPU)' if world == 1 else 'conv-weight bucket inside the graph under the backward tail + rest after it' if reduce_in_graph else 'one collective after the graph replay'), l2='activation working set per step (>= 134 MB per layer at res >= 64, ~6 GB total) exceeds the 126 MB L2; no explicit flush',
                             conv_gflop_per_frame_fwd=conv_gflop_fwd),
                 e2e=dict(value=e2e_value, unit='frames/s', h2d_bytes_per_step=(h_ws.numel() + h_t.numel() + h_mz.numel()) * 4, d2h_bytes_per_step=4),
                 gpu_launches=launches, clocks=clocks, roofline=roofline, upfirdn2d=upfirdn, optimizer=optimizer, cpu_baseline=cpu_baseline,
