@@ -733,9 +733,19 @@ def main():
     frames = N * world
     value = frames / (ms_step * 1e-3)
     e2e_value = frames / (ms_e2e / args.steps * 1e-3)
+    def leave():
+        """End of a rank's work.  When NCCL collectives were captured into the step's CUDA graph, tearing the process group down (here, or from
+        interpreter shutdown) blocked for minutes on this stack (round-2 call O: the result line was printed, the ranks never exited) — the
+        graphs hold communicator work the destructor waits for.  Those runs drop the graphs and leave through os._exit after flushing."""
+        if world == 1:
+            return
+        torch.cuda.synchronize()
+        if reduce_in_graph:
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        leave()
         return
 
     peaks = load_peaks()
@@ -853,8 +863,7 @@ def main():
                 model_tflops_fwd_bwd=3 * conv_gflop_fwd * frames / ms_step / world, reference_cuda_kernels=ref_cuda)
     line[other_mode] = other      # the same step in the other arithmetic mode, measured beside the headline
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 if __name__ == '__main__':
