@@ -562,23 +562,10 @@ def main():
     # tensor-core kernels of the backward pass, but ~0.7 ms of small kernels follow them (demodulation / affine / motion-encoder gradients,
     # profiles/timeline_r2m_serial.txt), so their all-reduce is issued — inside the captured graph — the moment the last of them has been
     # accumulated and runs under that tail; only the rest of the buffer is reduced after the backward pass.  (--no-overlap: one collective.)
-    params = list(net.parameters())
     overlap = world > 1 and not args.no_overlap and not args.no_graph
-    early = [p for p in params if p.ndim == 4 and p.shape[-1] == 3] if overlap else []
-    early_ids = {id(p) for p in early}
-    state = FlatModuleState(early + [p for p in params if id(p) not in early_ids])
-    early_numel = state.offsets[len(early)] if early else 0
+    state = FlatModuleState(list(net.parameters()), early=(lambda p: p.ndim == 4 and p.shape[-1] == 3) if overlap else None)
     state.broadcast(0)                         # ... and rank 0's parameters are broadcast like the reference's "Distribute across GPUs" (training_loop.py:215-232)
-    bucket = dict(armed=False, left=0, work=None)
-
-    def _early_ready(_p):
-        if not bucket['armed']:
-            return
-        bucket['left'] -= 1
-        if bucket['left'] == 0:
-            bucket['work'] = dist.all_reduce(state.grad[:early_numel], op=dist.ReduceOp.SUM, async_op=True)
-    for p in early:
-        p.register_post_accumulate_grad_hook(_early_ready)
+    bucket = dict(armed=False)                 # whether the step being built carries its collectives (stylegan_v_b200/optim.py: begin / finish_backward)
     opt = None if args.no_optimizer else FusedAdamEMA(state, lr=0.0025, betas=(0.0, 0.99), eps=1e-8)
     torch.manual_seed(1 + rank)                # per-rank latents (each rank works on its own 32 frames)
     N = FRAMES_PER_GPU
@@ -598,12 +585,10 @@ def main():
         img = net(ws, t, motion_z=mz)
         loss = (img * dimg).sum()
         if bucket['armed']:
-            bucket['left'], bucket['work'] = len(early), None
+            state.begin_backward()
         loss.backward()
         if bucket['armed']:
-            assert bucket['work'] is not None, 'the early gradient bucket never became ready'
-            bucket['work'].wait()                                                  # stream-level wait (capturable)
-            dist.all_reduce(state.grad[early_numel:], op=dist.ReduceOp.SUM)        # the rest: affines, biases, motion encoder
+            state.finish_backward()            # waits for the conv-weight bucket (stream-level, capturable), reduces the rest: affines, biases, motion encoder
         return loss
 
     # The step (about 1000 kernel launches: forward + backward of 20 fused layers) is captured ONCE into a CUDA graph and replayed:

@@ -32,8 +32,17 @@ class FlatModuleState:
     After construction `p.data` and `p.grad` of every parameter are views into `self.param` / `self.grad`
     (values preserved), `p_ema.data` into `self.ema`."""
 
-    def __init__(self, params, ema_params=None, process_group=None):
-        self.params = [p for p in params]
+    def __init__(self, params, ema_params=None, process_group=None, early=None):
+        """early: optional predicate on a parameter.  Parameters it selects are placed FIRST in the flat buffers (`early_numel` elements) and form
+        a gradient bucket that `begin_backward()` / `finish_backward()` all-reduce as soon as the last of them has received its gradient,
+        i.e. while the rest of the backward pass still runs (the reference's DDP buckets overlap the same way, training_loop.py:215-232)."""
+        params = [p for p in params]
+        self._early_params = [p for p in params if early is not None and early(p)]
+        if self._early_params:
+            assert ema_params is None, 'the early bucket re-orders the parameters; give EMA parameters in the same (re-ordered) order via state.params'
+            ids = {id(p) for p in self._early_params}
+            params = self._early_params + [p for p in params if id(p) not in ids]
+        self.params = params
         assert self.params, 'no parameters'
         dev = self.params[0].device
         assert all(p.dtype == torch.float32 and p.device == dev for p in self.params), 'all parameters must be float32 on one device'
@@ -59,6 +68,41 @@ class FlatModuleState:
                 view = self.ema[o:o + p.numel()].view_as(p)
                 view.copy_(p.data)
                 p.data = view
+
+        self.early_numel = self.offsets[len(self._early_params)] if 0 < len(self._early_params) < len(self.params) else (off if self._early_params else 0)
+        self._bucket = dict(armed=False, left=0, work=None)
+        if self._early_params:
+            for p in self._early_params:
+                p.register_post_accumulate_grad_hook(self._early_ready)
+
+    # ---- overlapped gradient exchange: early bucket during the backward pass, the rest after it ----
+    def _early_ready(self, _p):
+        b = self._bucket
+        if not b['armed']:
+            return
+        b['left'] -= 1
+        if b['left'] == 0:
+            b['work'] = dist.all_reduce(self.grad[:self.early_numel], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def begin_backward(self):
+        """Arm the early bucket for ONE backward pass (no-op without an early bucket or with one rank).  Returns whether it is armed."""
+        b = self._bucket
+        b['armed'] = bool(self._early_params) and self.world_size() > 1
+        b['left'], b['work'] = len(self._early_params), None
+        return b['armed']
+
+    def finish_backward(self):
+        """After the backward pass: wait for the early bucket (a stream-level wait on CUDA: capturable in a CUDA graph together with the
+        collectives) and reduce the rest of the buffer.  Without an armed bucket: the plain single all-reduce."""
+        b = self._bucket
+        if not b['armed']:
+            return self.all_reduce()
+        b['armed'] = False
+        assert b['work'] is not None, 'the early gradient bucket never became ready (a selected parameter received no gradient)'
+        b['work'].wait()
+        if self.early_numel < self.numel:
+            dist.all_reduce(self.grad[self.early_numel:], op=dist.ReduceOp.SUM, group=self.group)
+        return None
 
     def zero_grad(self):
         self.grad.zero_()
