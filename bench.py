@@ -591,7 +591,7 @@ def main():
             state.finish_backward()            # waits for the conv-weight bucket (stream-level, capturable), reduces the rest: affines, biases, motion encoder
         return loss
 
-    # The step (about 1000 kernel launches: forward + backward of 20 fused layers) is captured ONCE into a CUDA graph and replayed:
+    # The step (about 670 kernel launches: forward + backward of 20 fused layers) is captured ONCE into a CUDA graph and replayed:
     # the GPU then never waits for the Python/ctypes launch path.  The gradient all-reduce (N > 1) is issued after each replay.
     s_ws, s_t, s_mz = d_ws.clone(), d_t.clone(), d_mz.clone()      # static graph inputs
 
