@@ -155,12 +155,14 @@ __global__ void __launch_bounds__(kDenseThreads) dense_dgrad_kernel(const DenseA
             dzs[srow][sseg + j] = (m < p.m && n < ne) ? dense_dz(p, m, n) : 0.f;
         }
         __syncthreads();
-        const int nlim = min(32, ne - nc);
-        for (int j = 0; j < nlim; j += 4)
-        {
-            float4 wv[4];
+        // 8 weight rows (16-byte loads) in flight per lane; columns past the slice read as zero (their dz entries are zero as well)
 #pragma unroll
-            for (int jj = 0; jj < 4; jj++)
+        for (int j = 0; j < 32; j += 8)
+        {
+            if (nc + j >= ne) break;
+            float4 wv[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++)
             {
                 const int n = nc + j + jj;
                 wv[jj] = (kok && n < ne) ? __ldg(reinterpret_cast<const float4*>(p.w + (long long)n * p.k + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -168,8 +170,10 @@ __global__ void __launch_bounds__(kDenseThreads) dense_dgrad_kernel(const DenseA
 #pragma unroll
             for (int r = 0; r < 8; r++)
             {
-                const float4 d = *reinterpret_cast<const float4*>(&dzs[warp * 8 + r][j]);
-                fma4(acc[r], d.x, wv[0]); fma4(acc[r], d.y, wv[1]); fma4(acc[r], d.z, wv[2]); fma4(acc[r], d.w, wv[3]);
+                const float4 d0 = *reinterpret_cast<const float4*>(&dzs[warp * 8 + r][j]);
+                const float4 d1 = *reinterpret_cast<const float4*>(&dzs[warp * 8 + r][j + 4]);
+                fma4(acc[r], d0.x, wv[0]); fma4(acc[r], d0.y, wv[1]); fma4(acc[r], d0.z, wv[2]); fma4(acc[r], d0.w, wv[3]);
+                fma4(acc[r], d1.x, wv[4]); fma4(acc[r], d1.y, wv[5]); fma4(acc[r], d1.z, wv[6]); fma4(acc[r], d1.w, wv[7]);
             }
         }
     }
@@ -185,28 +189,31 @@ __global__ void __launch_bounds__(kDenseThreads) dense_dgrad_kernel(const DenseA
     }
 }
 
-// ---- weight gradient: CTA = 8 weight rows x 512 k; warp = 128 k; lane = 4 consecutive k; loop over all A rows ----
+// ---- weight gradient: CTA = NC weight rows x 512 k; warp = 128 k; lane = 4 consecutive k; loop over all A rows ----
+// NC = 16 when the reduction is long (many A rows: the conv1d-as-windows layers): every A row is then re-read by half as many CTAs — the
+// kernel is bound by that L2 traffic (M = 384, K = 5632, N = 512: 92 us at NC = 8, profiles/timeline_r2m_serial.txt).
+template <int NC>
 __global__ void __launch_bounds__(kDenseThreads) dense_wgrad_kernel(const DenseArgs p)
 {
-    __shared__ __align__(16) float dzs[kDenseRows][kDenseCols];
+    __shared__ __align__(16) float dzs[kDenseRows][NC];
     __shared__ long long roff[kDenseRows];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.y * kDenseCols;
+    const int n0 = blockIdx.y * NC;
     const int k0 = blockIdx.x * 512 + warp * 128 + lane * 4;
     const bool kok = k0 < p.k;
     const long long goff = dense_group_offset(p, n0);
-    float4 acc[8];
+    float4 acc[NC];
 #pragma unroll
-    for (int c = 0; c < 8; c++) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < NC; c++) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     float bsum = 0.f;
 
     for (int mc = 0; mc < p.m; mc += kDenseRows)
     {
         __syncthreads();
 #pragma unroll
-        for (int e = 0; e < 2; e++)
+        for (int e = 0; e < kDenseRows * NC / kDenseThreads; e++)
         {
-            const int idx = threadIdx.x * 2 + e, r = idx >> 3, c = idx & 7;
+            const int idx = threadIdx.x * (kDenseRows * NC / kDenseThreads) + e, r = idx / NC, c = idx % NC;
             const int m = mc + r, n = n0 + c;
             dzs[r][c] = (m < p.m && n < p.n) ? dense_dz(p, m, n) : 0.f;
         }
@@ -223,19 +230,21 @@ __global__ void __launch_bounds__(kDenseThreads) dense_wgrad_kernel(const DenseA
             for (int r = 0; r < rows; r++)
             {
                 const float4 av = __ldg(reinterpret_cast<const float4*>(p.a + roff[r] + k0));
-                const float4 d0 = *reinterpret_cast<const float4*>(&dzs[r][0]);
-                const float4 d1 = *reinterpret_cast<const float4*>(&dzs[r][4]);
-                fma4(acc[0], d0.x, av); fma4(acc[1], d0.y, av); fma4(acc[2], d0.z, av); fma4(acc[3], d0.w, av);
-                fma4(acc[4], d1.x, av); fma4(acc[5], d1.y, av); fma4(acc[6], d1.z, av); fma4(acc[7], d1.w, av);
+#pragma unroll
+                for (int c4 = 0; c4 < NC / 4; c4++)
+                {
+                    const float4 d = *reinterpret_cast<const float4*>(&dzs[r][c4 * 4]);
+                    fma4(acc[c4 * 4 + 0], d.x, av); fma4(acc[c4 * 4 + 1], d.y, av); fma4(acc[c4 * 4 + 2], d.z, av); fma4(acc[c4 * 4 + 3], d.w, av);
+                }
             }
         }
-        if (p.db && blockIdx.x == 0 && warp == 0 && lane < kDenseCols)
+        if (p.db && blockIdx.x == 0 && warp == 0 && lane < NC)
             for (int r = 0; r < rows; r++) bsum += dzs[r][lane];
     }
     if (kok)
     {
 #pragma unroll
-        for (int c = 0; c < 8; c++)
+        for (int c = 0; c < NC; c++)
         {
             if (n0 + c >= p.n) break;
             float4* dst = reinterpret_cast<float4*>(p.dw + (long long)(n0 + c) * p.k + k0);
@@ -244,7 +253,7 @@ __global__ void __launch_bounds__(kDenseThreads) dense_wgrad_kernel(const DenseA
             *dst = o;
         }
     }
-    if (p.db && blockIdx.x == 0 && warp == 0 && lane < kDenseCols && n0 + lane < p.n)
+    if (p.db && blockIdx.x == 0 && warp == 0 && lane < NC && n0 + lane < p.n)
     {
         const float o = bsum * p.b_gain;
         p.db[n0 + lane] = p.accumulate ? p.db[n0 + lane] + o : o;
@@ -330,8 +339,18 @@ extern "C" int sgv_dense_f32_wgrad(const sgv_dense_params* p, void* stream_)
     SGV_CHECK_ARG(p->act == 1 || p->y != nullptr, "sgv_dense_f32_wgrad: lrelu needs the saved output y");
     rc = sgv_device_check();
     if (rc != SGV_OK) return rc;
-    dim3 grid((unsigned)ceil_div(p->k, 512), (unsigned)ceil_div(p->n, kDenseCols));
-    dense_wgrad_kernel<<<grid, kDenseThreads, 0, (cudaStream_t)stream_>>>(a);
+    // 16 weight rows per CTA when the reduction is long and the grid still covers the SMs (group boundaries are multiples of 8 columns, so
+    // grouped launches keep 8)
+    if (p->m >= 128 && p->groups == 0 && p->n % 16 == 0 && ceil_div(p->k, 512) * (p->n / 16) >= num_sms())
+    {
+        dim3 grid((unsigned)ceil_div(p->k, 512), (unsigned)(p->n / 16));
+        dense_wgrad_kernel<16><<<grid, kDenseThreads, 0, (cudaStream_t)stream_>>>(a);
+    }
+    else
+    {
+        dim3 grid((unsigned)ceil_div(p->k, 512), (unsigned)ceil_div(p->n, kDenseCols));
+        dense_wgrad_kernel<8><<<grid, kDenseThreads, 0, (cudaStream_t)stream_>>>(a);
+    }
     SGV_LAUNCH_OK("dense_wgrad_kernel");
     return SGV_OK;
 }

@@ -18,7 +18,7 @@ BAR = 2e-6
 
 @pytest.mark.parametrize('M,K,O,act,bias', [(32, 512, 512, 'linear', True), (48, 512, 1536, 'linear', True), (7, 64, 64, 'lrelu', True),
                                             (96, 8192, 512, 'lrelu', True), (33, 512, 1024, 'linear', False), (2, 512, 32, 'linear', True),
-                                            (5, 512, 1, 'linear', True), (70, 36, 13, 'lrelu', True)])
+                                            (5, 512, 1, 'linear', True), (70, 36, 13, 'lrelu', True), (200, 4096, 512, 'lrelu', True)])
 def test_linear_vs_fp64(M, K, O, act, bias):
     g = torch.Generator().manual_seed(M + K)
     x = torch.randn(M, K, generator=g).cuda().requires_grad_(True)
