@@ -6,8 +6,8 @@ Reference sequence per phase (src/training/training_loop.py:381-386,392-400):
     for p_ema, p in zip(G_ema.parameters(), G.parameters()): p_ema.copy_(p.lerp(p_ema, ema_beta))    # after the G phase
 
 `FlatModuleState` re-homes every parameter of a module (and, optionally, of its EMA twin) as a view into one flat fp32
-buffer, with gradients in a matching flat buffer — the buffer the data-parallel all-reduce runs on (stylegan_v_b200/ddp.py
-semantics: SUM over ranks; the 1/world_size is folded into the update kernel).  `FusedAdamEMA.step()` is then a single
+buffer, with gradients in a matching flat buffer — the buffer the data-parallel all-reduce runs on (the reference: torch DDP over NCCL,
+training_loop.py:215-232; here SUM over ranks, the 1/world_size is folded into the update kernel).  `FusedAdamEMA.step()` is then a single
 `sgv_adam_ema_step` launch (csrc/optim_step.cu).  There is no CPU implementation: CPU tensors raise.
 """
 import ctypes

@@ -1,42 +1,8 @@
-"""world_size-2 gloo test of the gradient exchange used by bench.py / training at N > 1 GPUs."""
+"""world_size-2 gloo tests of the gradient exchange used by bench.py / training at N > 1 GPUs (stylegan_v_b200/optim.py::FlatModuleState)."""
 import os
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
-
-
-def _worker(rank, world, port, out):
-    os.environ['MASTER_ADDR'] = '127.0.0.1'
-    os.environ['MASTER_PORT'] = str(port)
-    dist.init_process_group('gloo', rank=rank, world_size=world)
-    from stylegan_v_b200.ddp import FlatGradReducer
-    torch.manual_seed(0)
-    lin = torch.nn.Linear(5, 3)
-    conv = torch.nn.Conv2d(2, 2, 3)
-    params = list(lin.parameters()) + list(conv.parameters())
-    red = FlatGradReducer(params)
-    red.zero()
-    x = torch.full((4, 5), float(rank + 1))
-    y = lin(x).sum() + conv(torch.ones(1, 2, 5, 5) * (rank + 1)).sum()
-    y.backward()
-    # grads were accumulated directly into the flat buffer
-    assert params[0].grad.data_ptr() == red.flat.data_ptr()
-    local = red.flat.clone()
-    red.all_reduce()
-    gathered = [torch.zeros_like(local) for _ in range(world)]
-    dist.all_gather(gathered, local)
-    expect = sum(gathered) / world
-    ok = torch.allclose(red.flat, expect) and not torch.allclose(local, expect)
-    out[rank] = bool(ok)
-    dist.destroy_process_group()
-
-
-def test_flat_grad_reducer_world2():
-    mgr = mp.Manager()
-    out = mgr.dict()
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
-    assert out[0] and out[1]
 
 
 def _worker_flat_state(rank, world, port, out):
