@@ -176,6 +176,21 @@ class AlignedTimeEncoder(torch.nn.Module):
         return emb(t) - remove + add
 
 
+def trajectory_slabs(left, B, Fr, L, k, C):
+    """Which slabs of the [B, L, C] noise sequence the two valid conv1d layers (k taps each) must be evaluated on so that trajectory positions
+    left and left + 1 of every frame exist (motion.py:100-115).  Returns (windows, left, base):
+      windows = True   one slab of k + 1 layer-1 outputs (2 k input positions) per FRAME, starting at input position left[b, f]:
+                       base[b * Fr + f] = (b * L + left) * C element offsets; chosen while Fr * (k + 1) <= L - k + 1, i.e. while the windows
+                       are cheaper than the whole trajectory;
+      windows = False  one slab per CLIP covering the whole sequence: base[b] = b * L * C.
+    left is clamped into [0, L - 2 k] (the last position whose right neighbour exists; the reference would raise on an out-of-range index)."""
+    dev = left.device
+    if Fr * (k + 1) <= L - k + 1:
+        left = left.clamp(0, L - 2 * k)
+        return True, left, ((torch.arange(B, device=dev).unsqueeze(1) * L + left) * C).reshape(-1)
+    return False, left, torch.arange(B, device=dev) * (L * C)
+
+
 class MotionMappingNetwork(torch.nn.Module):
     def __init__(self, z_dim=512, v_dim=512, kernel_size=11, motion_z_distance=16, time_enc_dim=256,
                  min_period_len=16, max_period_len=1024, max_num_frames=1024):
@@ -214,14 +229,12 @@ class MotionMappingNetwork(torch.nn.Module):
             # With many frames per clip the windows overlap enough that the whole trajectory is cheaper; then every position is computed once.
             C = z.shape[2]
             z = z.contiguous()
-            if Fr * (k + 1) <= L - k + 1:
-                left = left.clamp(0, L - 2 * k)                                      # (the reference would raise on an out-of-range index)
-                base = ((torch.arange(B, device=t.device).unsqueeze(1) * L + left) * C).reshape(-1)
+            windows, left, base = trajectory_slabs(left, B, Fr, L, k, C)
+            if windows:
                 y1 = _dense.conv1d_slabs(z, base, k + 1, c0.weight, c0.bias, c0.weight_gain, c0.bias_gain, 'lrelu')          # [B*F, k+1, C]
                 y2 = _dense.conv1d_slabs(y1, None, 2, c1.weight, c1.bias, c1.weight_gain, c1.bias_gain, 'lrelu')             # [B*F, 2, v]
                 u_left, u_right = y2[:, 0], y2[:, 1]
             else:
-                base = torch.arange(B, device=t.device) * (L * C)
                 y1 = _dense.conv1d_slabs(z, base, L - k + 1, c0.weight, c0.bias, c0.weight_gain, c0.bias_gain, 'lrelu')      # [B, L-k+1, C]
                 trajs = _dense.conv1d_slabs(y1, None, L - 2 * k + 2, c1.weight, c1.bias, c1.weight_gain, c1.bias_gain, 'lrelu')
                 rows = torch.arange(B, device=t.device).unsqueeze(1).expand(B, Fr)

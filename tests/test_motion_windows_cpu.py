@@ -1,0 +1,62 @@
+"""Host logic of the motion encoder's window formulation (stylegan_v_b200/time_encoder.py::trajectory_slabs + the slab semantics of
+stylegan_v_b200/dense.py::conv1d_slabs), emulated with torch ops on CPU: evaluating the two valid conv1d layers only on the slabs must give the
+trajectory codes the full conv1d formulation (the reference's, layers.py:356-373 / motion.py:100-115) gathers.  The CUDA kernels themselves are
+checked against the same formulation in tests/test_dense_gpu.py."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from stylegan_v_b200.time_encoder import MotionMappingNetwork, trajectory_slabs
+
+
+def slabs_ref(src, base, P, conv):
+    """What dense.conv1d_slabs computes: row (g, p) = the contiguous [k, C] window of `src` starting at element base[g] + p * C, against the
+    conv1d weight re-ordered to [O, k * C]; gains, bias and leaky ReLU as EqualizedConv1d applies them."""
+    C = src.shape[-1]
+    O, _, k = conv.weight.shape
+    flat = src.reshape(-1)
+    if base is None:
+        base = torch.arange(src.shape[0]) * ((P + k - 1) * C)
+    rows = torch.stack([flat[int(b) + p * C: int(b) + (p + k) * C] for b in base for p in range(P)])
+    wr = conv.weight.permute(0, 2, 1).reshape(O, k * C) * conv.weight_gain
+    y = F.leaky_relu(rows @ wr.t() + conv.bias * conv.bias_gain, 0.2)
+    return y.reshape(len(base), P, O)
+
+
+@pytest.mark.parametrize('frames', [1, 3, 16])
+def test_window_formulation_equals_full_trajectory(frames):
+    torch.manual_seed(frames)
+    enc = MotionMappingNetwork(z_dim=32, v_dim=32, kernel_size=11, motion_z_distance=16, time_enc_dim=16, max_num_frames=1024).double()
+    B = 3
+    L = enc.traj_len()
+    t = torch.randint(0, 1000, (B, frames)).double()
+    t[0, 0] = 0.0
+    t[-1, -1] = 1023.0                                                # first and last admissible positions
+    z = torch.randn(B, L, 32, dtype=torch.float64)
+    k, d = 11, enc.motion_z_distance
+    left = (t / d).floor().long()
+    # the reference formulation: full conv1d over the sequence, then gather
+    trajs = enc.conv(z.permute(0, 2, 1)).permute(0, 2, 1)
+    rows = torch.arange(B).unsqueeze(1).expand(B, frames)
+    want_l, want_r = trajs[rows, left].reshape(B * frames, -1), trajs[rows, left + 1].reshape(B * frames, -1)
+    windows, left2, base = trajectory_slabs(left, B, frames, L, k, 32)
+    assert windows == (frames * (k + 1) <= L - k + 1)
+    if windows:
+        assert base.shape == (B * frames,) and torch.equal(left2, left)          # admissible positions are not clamped
+        y1 = slabs_ref(z, base, k + 1, enc.conv[0])
+        y2 = slabs_ref(y1, None, 2, enc.conv[1])
+        got_l, got_r = y2[:, 0], y2[:, 1]
+    else:
+        assert base.shape == (B,)
+        y1 = slabs_ref(z, base, L - k + 1, enc.conv[0])
+        tr = slabs_ref(y1, None, L - 2 * k + 2, enc.conv[1])
+        assert torch.allclose(tr, trajs, atol=1e-10)
+        got_l, got_r = tr[rows, left].reshape(B * frames, -1), tr[rows, left + 1].reshape(B * frames, -1)
+    assert torch.allclose(got_l, want_l, atol=1e-10) and torch.allclose(got_r, want_r, atol=1e-10)
+
+
+def test_window_positions_are_clamped_into_the_sequence():
+    left = torch.tensor([[-3, 0], [70, 500]])
+    windows, clamped, base = trajectory_slabs(left, 2, 2, 86, 11, 8)
+    assert windows and clamped.min() == 0 and clamped.max() == 86 - 22
+    assert int(base.max()) + (2 * 11) * 8 <= 2 * 86 * 8               # the last window ends inside the [B, L, C] buffer
