@@ -296,6 +296,24 @@ class SynthesisNetwork(torch.nn.Module):
                    min_period_len=cfg.min_period_len, max_period_len=cfg.max_period_len, max_num_frames=cfg.max_num_frames,
                    resample_filter=tuple(cfg.resample_filter), use_noise=bool(getattr(cfg, 'use_noise', False)))
 
+    def affine_layout(self):
+        """Which w row every style affine reads, and the column layout of the stacked affine product: returns (groups, order, layers, col) with
+        groups {w index: [layers]}, order = the w indices ascending, layers = all layers in that order, col[g] .. col[g + 1] = the columns of the
+        stacked output that belong to order[g].  Layer l of block b reads ws[:, w_idx(b) + l], and a block's ToRGB shares its row with the next
+        block's first conv (networks.py:350-357)."""
+        groups, w_idx = {}, 0
+        for res in self.block_resolutions:
+            block = getattr(self, f'b{res}')
+            for j, layer in enumerate(block.layers()):
+                groups.setdefault(w_idx + j, []).append(layer)
+            w_idx += block.num_conv
+        order = sorted(groups)
+        layers = [l for wi in order for l in groups[wi]]
+        col = [0]
+        for wi in order:
+            col.append(col[-1] + sum(l.affine.weight.shape[0] for l in groups[wi]))
+        return groups, order, layers, col
+
     def _all_styles(self, ws):
         """Evaluates every style affine of the forward pass (networks.py:124-126,159-160 for all layers) up front.
         Layer l of block b reads ws[:, w_idx(b) + l] (networks.py:350-357).  CUDA fp32: ONE launch of the exact-fp32 dense kernel for all
@@ -303,25 +321,13 @@ class SynthesisNetwork(torch.nn.Module):
         (stylegan_v_b200/dense.py::stacked_affine; the tcgen05 kernels are the wrong tool here: M = 32 rows fill a quarter of one 128-row
         tile and the K = 512 loop is latency-bound — 1.3 ms per step measured against 0.6 ms for cuBLAS, profiles/launches_r2b_summary.txt).
         Otherwise one library GEMM per distinct w index."""
-        groups = {}
-        w_idx = 0
-        for res in self.block_resolutions:
-            block = getattr(self, f'b{res}')
-            for j, layer in enumerate(block.layers()):
-                groups.setdefault(w_idx + j, []).append(layer)
-            w_idx += block.num_conv
+        groups, order, layers, col = self.affine_layout()
         out = {}
-        order = sorted(groups)
-        first = groups[order[0]][0].affine
+        first = layers[0].affine
         if ws.is_cuda and ws.dtype == torch.float32 and first.weight.dtype == torch.float32 and ws.shape[2] % 4 == 0 \
-                and all(l.affine.weight.shape[0] % 8 == 0 for wi in order for l in groups[wi]):
-            layers = [l for wi in order for l in groups[wi]]
+                and all(l.affine.weight.shape[0] % 8 == 0 for l in layers):
             key = (str(ws.device), ws.shape[1], ws.shape[2])
             if getattr(self, '_affine_groups_key', None) != key:
-                col, c = [0], 0
-                for wi in order:
-                    c += sum(l.affine.weight.shape[0] for l in groups[wi])
-                    col.append(c)
                 self._affine_groups = _dense.make_groups(col, order, ws.shape[2], ws.device)
                 self._affine_groups_key = key
             wcat = torch.cat([l.affine.weight for l in layers], dim=0)

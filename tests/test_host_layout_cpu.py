@@ -1,4 +1,4 @@
-"""Host logic of the motion encoder's window formulation (stylegan_v_b200/time_encoder.py::trajectory_slabs + the slab semantics of
+"""Host logic of the one-launch formulations: the motion encoder's window formulation (stylegan_v_b200/time_encoder.py::trajectory_slabs + the slab semantics of
 stylegan_v_b200/dense.py::conv1d_slabs), emulated with torch ops on CPU: evaluating the two valid conv1d layers only on the slabs must give the
 trajectory codes the full conv1d formulation (the reference's, layers.py:356-373 / motion.py:100-115) gathers.  The CUDA kernels themselves are
 checked against the same formulation in tests/test_dense_gpu.py."""
@@ -60,3 +60,28 @@ def test_window_positions_are_clamped_into_the_sequence():
     windows, clamped, base = trajectory_slabs(left, 2, 2, 86, 11, 8)
     assert windows and clamped.min() == 0 and clamped.max() == 86 - 22
     assert int(base.max()) + (2 * 11) * 8 <= 2 * 86 * 8               # the last window ends inside the [B, L, C] buffer
+
+
+def test_stacked_affine_layout_equals_per_layer_affines():
+    """SynthesisNetwork.affine_layout (the column groups of the one-launch stacked affine product, stylegan_v_b200/dense.py::stacked_affine):
+    evaluating group g as ws[:, order[g]] @ wcat[col[g]:col[g+1]].T must give every layer the style its own affine computes from the w row the
+    reference feeds it (networks.py:350-357: block b, layer l reads ws[:, w_idx(b) + l])."""
+    from stylegan_v_b200.synthesis import SynthesisNetwork
+    torch.manual_seed(0)
+    net = SynthesisNetwork(w_dim=64, img_resolution=32, channel_base=2048, channel_max=64, motion_z_dim=32, motion_v_dim=32, time_enc_dim=16).double()
+    groups, order, layers, col = net.affine_layout()
+    assert order == list(range(net.num_ws)) and all(c % 8 == 0 for c in col) and len(col) == len(order) + 1
+    ws = torch.randn(3, net.num_ws, 64, dtype=torch.float64)
+    wcat = torch.cat([l.affine.weight for l in layers]) * layers[0].affine.weight_gain
+    bcat = torch.cat([l.affine.bias for l in layers])
+    stacked = torch.cat([ws[:, order[g]] @ wcat[col[g]:col[g + 1]].t() + bcat[col[g]:col[g + 1]] for g in range(len(order))], dim=1)
+    pieces = dict(zip([id(l) for l in layers], stacked.split([l.affine.weight.shape[0] for l in layers], dim=1)))
+    w_idx = 0
+    for res in net.block_resolutions:
+        block = getattr(net, f'b{res}')
+        for j, layer in enumerate(block.layers()):
+            assert torch.allclose(pieces[id(layer)], layer.affine(ws[:, w_idx + j]), atol=1e-12), (res, j)
+        w_idx += block.num_conv
+    # and the network's own evaluation (library branch on CPU) agrees
+    lib = net._all_styles(ws)
+    assert all(torch.allclose(lib[id(l)], pieces[id(l)], atol=1e-12) for l in layers)
