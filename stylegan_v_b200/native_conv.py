@@ -95,6 +95,19 @@ def conv_forward(x, w, b, transpose, stride, padding, output_padding, dilation, 
     return None
 
 
+def stride2_phases(k, p):
+    """Pixel-parity decomposition of a stride-2 correlation with a k x k kernel and padding p: x[2 o + t - p] = x_phase(a)[o + (t - p - a) / 2]
+    with a = (t - p) mod 2.  Returns [(a, c, offsets, slots)]: for the view x[:, :, a::2, c::2] the taps (ky, kx) that fall on it, as stride-1
+    pixel offsets into that view and as their slots ky * k + kx in the [k * k, O, I] result."""
+    out = []
+    for a in (0, 1):
+        for c in (0, 1):
+            ph = [(ky, kx) for ky in range(k) for kx in range(k) if (ky - p) % 2 == a and (kx - p) % 2 == c]
+            if ph:
+                out.append((a, c, [((ky - p - a) // 2, (kx - p - c) // 2) for ky, kx in ph], [ky * k + kx for ky, kx in ph]))
+    return out
+
+
 def conv_weight_grad(gy, x, w_shape, transpose, stride, padding, output_padding, dilation, groups, x3=None):
     """Weight gradient (shape w_shape) of the op above, or None when outside the native envelope."""
     k = w_shape[2]
@@ -116,11 +129,8 @@ def conv_weight_grad(gy, x, w_shape, transpose, stride, padding, output_padding,
             # 64 -> 128 channels at 128^2 x 48 frames).  The four calls accumulate into their tap slots of one buffer.
             g, xn = _nhwc(gy), _nhwc(x)
             dwt = torch.zeros([9, O, I], dtype=torch.float32, device=x.device)
-            for a in (0, 1):
-                for c in (0, 1):
-                    ph = [(ky, kx) for ky, kx in taps if (ky - p) % 2 == a and (kx - p) % 2 == c]
-                    offs = [((ky - p - a) // 2, (kx - p - c) // 2) for ky, kx in ph]
-                    _conv.igemm_wgrad(g, xn[:, :, a::2, c::2], [(0, 0)] * len(ph), offs, (oh, ow), out=dwt, slots=[ky * 3 + kx for ky, kx in ph], x3=x3)
+            for a, c, offs, slots in stride2_phases(k, p):
+                _conv.igemm_wgrad(g, xn[:, :, a::2, c::2], [(0, 0)] * len(offs), offs, (oh, ow), out=dwt, slots=slots, x3=x3)
             return dwt.reshape(3, 3, O, I).permute(2, 3, 0, 1)
         dw = _conv.igemm_wgrad(_nhwc(gy), _nhwc(x), [(0, 0)] * len(taps), [(ky - p, kx - p) for ky, kx in taps], (oh, ow), x_stride=s, x3=x3)
         return dw.reshape(k, k, O, I).permute(2, 3, 0, 1)

@@ -85,3 +85,35 @@ def test_stacked_affine_layout_equals_per_layer_affines():
     # and the network's own evaluation (library branch on CPU) agrees
     lib = net._all_styles(ws)
     assert all(torch.allclose(lib[id(l)], pieces[id(l)], atol=1e-12) for l in layers)
+
+
+@pytest.mark.parametrize('H,p', [(17, 0), (16, 1), (9, 0), (12, 1)])
+def test_stride2_weight_gradient_phases(H, p):
+    """native_conv.stride2_phases: the weight gradient of a stride-2 3x3 convolution as four stride-1 weight gradients over the pixel-parity
+    views of the input (what the discriminator's down layers issue on the GPU).  The stride-1 contraction dw[t] = sum g[y, x] * view[y + dy,
+    x + dx] (zero outside the view — the TMA's out-of-bounds fill) is emulated with torch ops and compared with autograd through F.conv2d."""
+    from stylegan_v_b200.native_conv import stride2_phases
+    torch.manual_seed(H + p)
+    N, I, O, k = 2, 3, 4, 3
+    x = torch.randn(N, I, H, H, dtype=torch.float64)
+    w = torch.zeros(O, I, k, k, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(x, w, stride=2, padding=p)
+    g = torch.randn_like(y)
+    want, = torch.autograd.grad(y, w, g)
+    oh, ow = g.shape[2:]
+    dwt = torch.zeros(k * k, O, I, dtype=torch.float64)
+    seen = []
+    for a, c, offs, slots in stride2_phases(k, p):
+        view = x[:, :, a::2, c::2]
+        vh, vw = view.shape[2:]
+        for (dy, dx), slot in zip(offs, slots):
+            ys, xs = torch.arange(oh) + dy, torch.arange(ow) + dx
+            oky, okx = (ys >= 0) & (ys < vh), (xs >= 0) & (xs < vw)
+            sub = view[:, :, ys[oky]][:, :, :, xs[okx]]
+            tmp = torch.zeros(N, I, oh, ow, dtype=torch.float64)                 # positions outside the view stay zero (the TMA's fill)
+            tmp[:, :, oky.nonzero().squeeze(1)[:, None], okx.nonzero().squeeze(1)[None, :]] = sub
+            dwt[slot] = torch.einsum('noyx,niyx->oi', g, tmp)
+            seen.append(slot)
+    assert sorted(seen) == list(range(k * k))                            # every tap exactly once
+    got = dwt.reshape(k, k, O, I).permute(2, 3, 0, 1)
+    assert torch.allclose(got, want, atol=1e-10)
